@@ -1,0 +1,403 @@
+/*
+ * isof_oracle.c -- CPU restatement of the isONform hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (isonform_b200/) never links, imports or calls it.
+ *
+ * What is restated, and where it comes from (file:line relative to the reference tree):
+ *   - isof_oracle_pyhash          CPython 3.12 hash(str) under PYTHONHASHSEED=0 == SipHash-1-3 with a
+ *                                 zero key over the ASCII bytes (third-party: CPython Python/pyhash.c,
+ *                                 3.11+ `siphash13`).  Used by main:85,94 as the minimizer order.
+ *                                 PINNED: tests compare with the running interpreter's hash().
+ *   - isof_oracle_minimizers      get_kmer_minimizers, main:81-110 (+ rindex main:72-79), restated
+ *                                 literally (deque window, stale minimizer_pos).  PINNED by executing
+ *                                 the reference (tests/golden/minimizers_*.json).
+ *   - isof_oracle_pairs / spans   minimizers_comb_iterator main:215-224,
+ *                                 get_minimizer_combinations_database main:174-212 and
+ *                                 find_most_supported_span main:308-338 restated over integer k-mer
+ *                                 ids.  PINNED by executing the reference.
+ *   - isof_oracle_sg_align        consensus.parasail_alignment, modules/consensus.py:55-67, i.e.
+ *                                 parasail.sg_trace_scan_16/_32 + result.cigar.  Third-party
+ *                                 (PyPI parasail >=1.3.3 / jeffdaily/parasail 2.x), source NOT under
+ *                                 the reference tree and not installable here.
+ *                                 *** PARITY UNPINNED *** : restated from the library's published
+ *                                 algorithm (Gotoh affine semi-global, all four end gaps free,
+ *                                 trace table + cigar walk); every tie-break lives in
+ *                                 isof_tiebreak_t below so it can be re-validated on a host that
+ *                                 has parasail.
+ *
+ * Build: see oracle/Makefile (gcc -O3 -march=native -fopenmp -shared -fPIC).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#if defined(__GNUC__)
+#define ISOF_API __attribute__((visibility("default")))
+#else
+#define ISOF_API
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* SipHash-1-3, zero key  (CPython Python/pyhash.c `siphash13`)                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+#define ROTL64(x, b) (uint64_t)(((x) << (b)) | ((x) >> (64 - (b))))
+#define SIPROUND(v0, v1, v2, v3)                                                                  \
+    do {                                                                                          \
+        v0 += v1; v1 = ROTL64(v1, 13); v1 ^= v0; v0 = ROTL64(v0, 32);                             \
+        v2 += v3; v3 = ROTL64(v3, 16); v3 ^= v2;                                                  \
+        v0 += v3; v3 = ROTL64(v3, 21); v3 ^= v0;                                                  \
+        v2 += v1; v1 = ROTL64(v1, 17); v1 ^= v2; v2 = ROTL64(v2, 32);                             \
+    } while (0)
+
+ISOF_API int64_t isof_oracle_pyhash(const uint8_t *s, int64_t len)
+{
+    if (len <= 0) return 0;                       /* hash("") == 0 */
+    uint64_t k0 = 0, k1 = 0;                      /* PYTHONHASHSEED=0 */
+    uint64_t b = (uint64_t)len << 56;
+    uint64_t v0 = k0 ^ 0x736f6d6570736575ULL;
+    uint64_t v1 = k1 ^ 0x646f72616e646f6dULL;
+    uint64_t v2 = k0 ^ 0x6c7967656e657261ULL;
+    uint64_t v3 = k1 ^ 0x7465646279746573ULL;
+    int64_t n = len;
+    const uint8_t *p = s;
+    while (n >= 8) {
+        uint64_t mi = 0;
+        for (int q = 0; q < 8; ++q) mi |= (uint64_t)p[q] << (8 * q);   /* little endian */
+        v3 ^= mi;
+        SIPROUND(v0, v1, v2, v3);
+        v0 ^= mi;
+        p += 8; n -= 8;
+    }
+    uint64_t t = 0;
+    for (int q = 0; q < (int)n; ++q) t |= (uint64_t)p[q] << (8 * q);
+    b |= t;
+    v3 ^= b;
+    SIPROUND(v0, v1, v2, v3);
+    v0 ^= b;
+    v2 ^= 0xff;
+    SIPROUND(v0, v1, v2, v3);
+    SIPROUND(v0, v1, v2, v3);
+    SIPROUND(v0, v1, v2, v3);
+    uint64_t h = (v0 ^ v1) ^ (v2 ^ v3);
+    int64_t x = (int64_t)h;
+    if (x == -1) x = -2;                          /* CPython reserves -1 for errors */
+    return x;
+}
+
+/* hash(seq[i:i+k]) with Python slice truncation */
+static int64_t slice_hash(const uint8_t *seq, int64_t n, int64_t i, int k)
+{
+    if (i >= n) return 0;
+    int64_t len = (i + k <= n) ? k : (n - i);
+    return isof_oracle_pyhash(seq + i, len);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* get_kmer_minimizers  (main:81-110)                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Returns the number of minimizers; writes at most `cap` positions (the k-mer string is
+ * seq[pos:pos+k], rebuilt by the caller).  Literal restatement: the window is a ring buffer of
+ * the last w+1 hashes, minimizer_pos is only refreshed in the recompute branch. */
+ISOF_API int64_t isof_oracle_minimizers(const uint8_t *seq, int64_t n, int k, int w_size,
+                                        int32_t *out_pos, int64_t cap)
+{
+    int w = w_size - k;
+    if (w < 0) return -1;
+    int W = w + 1;
+    int64_t *win = (int64_t *)malloc(sizeof(int64_t) * (size_t)W);
+    int64_t cnt = 0;
+    /* window_kmers = deque(hash(seq[i:i+k]) for i in range(w+1)) */
+    for (int i = 0; i < W; ++i) win[i] = slice_hash(seq, n, i, k);
+    int64_t curr_min = win[0];
+    for (int i = 1; i < W; ++i) if (win[i] < curr_min) curr_min = win[i];
+    int64_t minimizer_pos = 0;
+    for (int i = 0; i < W; ++i) if (win[i] == curr_min) minimizer_pos = i;   /* rindex: last */
+    if (cnt < cap) out_pos[cnt] = (int32_t)minimizer_pos;
+    ++cnt;
+    int head = 0;                                   /* index of the oldest element */
+    for (int64_t i = w + 1; i < n - k; ++i) {
+        int64_t new_kmer = slice_hash(seq, n, i, k);
+        int64_t discarded = win[head];
+        win[head] = new_kmer;
+        head = (head + 1) % W;                      /* oldest is now win[head] == position i-w */
+        if (curr_min == discarded && minimizer_pos < i - w) {
+            curr_min = win[head];
+            for (int q = 1; q < W; ++q) {
+                int64_t v = win[(head + q) % W];
+                if (v < curr_min) curr_min = v;
+            }
+            int last = 0;
+            for (int q = 0; q < W; ++q) if (win[(head + q) % W] == curr_min) last = q;
+            minimizer_pos = last + i - w;
+            if (cnt < cap) out_pos[cnt] = (int32_t)minimizer_pos;
+            ++cnt;
+        } else if (new_kmer < curr_min) {
+            curr_min = new_kmer;
+            if (cnt < cap) out_pos[cnt] = (int32_t)i;   /* minimizer_pos deliberately not updated */
+            ++cnt;
+        }
+    }
+    free(win);
+    return cnt;
+}
+
+/* Batch form used by the CPU baseline: reads concatenated, off[R+1]; out_off[R+1] filled. */
+ISOF_API int64_t isof_oracle_minimizers_batch(const uint8_t *cat, const int64_t *off, int R, int k,
+                                              int w_size, int32_t *out_pos, int64_t *out_off,
+                                              int64_t cap, int threads)
+{
+    /* two passes so that the output is packed in read order regardless of thread schedule */
+    int64_t *cnt = (int64_t *)calloc((size_t)R + 1, sizeof(int64_t));
+    int32_t **tmp = (int32_t **)calloc((size_t)R, sizeof(int32_t *));
+    (void)threads;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (int r = 0; r < R; ++r) {
+        int64_t n = off[r + 1] - off[r];
+        int64_t c = n > 0 ? n : 1;
+        tmp[r] = (int32_t *)malloc(sizeof(int32_t) * (size_t)c);
+        cnt[r] = isof_oracle_minimizers(cat + off[r], n, k, w_size, tmp[r], c);
+    }
+    int64_t tot = 0;
+    for (int r = 0; r < R; ++r) {
+        out_off[r] = tot;
+        int64_t c = cnt[r] < 0 ? 0 : cnt[r];
+        if (tot + c <= cap) memcpy(out_pos + tot, tmp[r], sizeof(int32_t) * (size_t)c);
+        tot += c;
+        free(tmp[r]);
+    }
+    out_off[R] = tot;
+    free(tmp); free(cnt);
+    return tot;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* parasail sg_trace + cigar  (modules/consensus.py:55-67)  *** PARITY UNPINNED ***             */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Every tie-break of the restatement, in one place.  Defaults = the library as restated
+ * (see DESIGN.md "parasail tie-break table"). */
+typedef struct {
+    /* H source on ties.  0: DIAG > F(walks query i) > E(walks ref j).  1: DIAG > E > F. */
+    int32_t h_e_before_f;
+    /* gap state on ties open==extend.  0: extend (open only if strictly greater).  1: open. */
+    int32_t gap_open_on_tie;
+    /* end cell.  0: last ROW first (smallest j, strict >), then last COLUMN only if strictly
+     * greater (smallest i); equal score and end_ref==m-1 takes the smaller i.
+     * 1: last COLUMN first (smallest i), then last row only if strictly greater (smallest j). */
+    int32_t end_col_first;
+} isof_tiebreak_t;
+
+/* BAM op codes used in the run encoding (len << 4 | op), as parasail's cigar->seq does. */
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_EQ = 7, OP_X = 8 };
+
+/* parasail_matrix_create("ACGT", match, mismatch): case-insensitive, everything outside the
+ * alphabet maps to the wildcard row/column which scores 0. */
+static inline int base_code(uint8_t c)
+{
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+static inline int upc(uint8_t c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+#define T_SRC_DIAG 3
+#define T_SRC_F 2       /* parasail "DEL": walks the query axis i -> SAM 'I' */
+#define T_SRC_E 1       /* parasail "INS": walks the ref axis j   -> SAM 'D' */
+#define T_E_EXT 1       /* bit0: E(i,j) came from E(i,j-1)-ext  */
+#define T_F_EXT 2       /* bit1: F(i,j) came from F(i-1,j)-ext  */
+
+/*
+ * s1 = query (rows i), s2 = ref (columns j).  Outputs: score, end_query, end_ref (0-based cell),
+ * cigar runs in alignment order.  Returns the number of runs (>=0), -1 on bad input, -2 if
+ * cigar_cap is too small (n_runs still the true count via *n_runs_out).
+ */
+ISOF_API int32_t isof_oracle_sg_align_tb(const uint8_t *s1, int32_t n, const uint8_t *s2, int32_t m,
+                                         int32_t match, int32_t mismatch, int32_t open, int32_t ext,
+                                         const isof_tiebreak_t *tbk, int32_t *score_out,
+                                         int32_t *end_q_out, int32_t *end_r_out, uint32_t *cigar,
+                                         int32_t cigar_cap, int32_t *n_runs_out)
+{
+    if (n <= 0 || m <= 0) return -1;               /* parasail rejects empty sequences */
+    isof_tiebreak_t tb = {0, 0, 0};
+    if (tbk) tb = *tbk;
+    const int32_t NEG = -(1 << 29);
+    int32_t S[5][5];
+    for (int a = 0; a < 5; ++a)
+        for (int b = 0; b < 5; ++b)
+            S[a][b] = (a == 4 || b == 4) ? 0 : (a == b ? match : mismatch);
+
+    uint8_t *trace = (uint8_t *)malloc((size_t)n * (size_t)m);
+    int32_t *H = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1));   /* previous row, H[j+1]=H(i-1,j) */
+    int32_t *F = (int32_t *)malloc(sizeof(int32_t) * (size_t)m);         /* F(i-1,j) */
+    uint8_t *c2 = (uint8_t *)malloc((size_t)m);
+    if (!trace || !H || !F || !c2) { free(trace); free(H); free(F); free(c2); return -3; }
+    for (int j = 0; j < m; ++j) { c2[j] = (uint8_t)base_code(s2[j]); F[j] = NEG; }
+    for (int j = 0; j <= m; ++j) H[j] = 0;                                /* free begin gaps */
+
+    int32_t best_row = NEG, best_row_j = 0;     /* over the last row    */
+    int32_t best_col = NEG, best_col_i = 0;     /* over the last column */
+
+    for (int i = 0; i < n; ++i) {
+        const int32_t *Srow = S[base_code(s1[i])];
+        int32_t Hdiag = 0;            /* H(i-1,-1) = 0 */
+        int32_t Hleft = 0;            /* H(i,-1)   = 0 */
+        int32_t Eleft = NEG;          /* E(i,-1)        */
+        uint8_t *trow = trace + (size_t)i * (size_t)m;
+        for (int j = 0; j < m; ++j) {
+            int32_t Hup = H[j + 1];
+            int32_t e_opn = Hleft - open, e_ext = Eleft - ext;
+            int32_t f_opn = Hup - open, f_ext = F[j] - ext;
+            uint8_t t = 0;
+            int32_t E, Fv;
+            if (tb.gap_open_on_tie ? (e_opn >= e_ext) : (e_opn > e_ext)) E = e_opn; else { E = e_ext; t |= T_E_EXT; }
+            if (tb.gap_open_on_tie ? (f_opn >= f_ext) : (f_opn > f_ext)) Fv = f_opn; else { Fv = f_ext; t |= T_F_EXT; }
+            int32_t Hd = Hdiag + Srow[c2[j]];
+            int32_t Hv = Hd;
+            if (E > Hv) Hv = E;
+            if (Fv > Hv) Hv = Fv;
+            int src;
+            if (Hv == Hd) src = T_SRC_DIAG;
+            else if (tb.h_e_before_f) src = (Hv == E) ? T_SRC_E : T_SRC_F;
+            else src = (Hv == Fv) ? T_SRC_F : T_SRC_E;
+            trow[j] = (uint8_t)(t | (src << 2));
+            Hdiag = Hup;
+            H[j + 1] = Hv;          /* row i overwrites row i-1 */
+            F[j] = Fv;
+            Hleft = Hv;
+            Eleft = E;
+        }
+        H[0] = 0;
+        /* last column */
+        if (H[m] > best_col) { best_col = H[m]; best_col_i = i; }
+    }
+    for (int j = 0; j < m; ++j)
+        if (H[j + 1] > best_row) { best_row = H[j + 1]; best_row_j = j; }
+
+    int32_t score, eq, er;
+    if (!tb.end_col_first) {
+        score = best_row; eq = n - 1; er = best_row_j;
+        if (best_col > score) { score = best_col; eq = best_col_i; er = m - 1; }
+        else if (best_col == score && er == m - 1 && best_col_i < eq) eq = best_col_i;
+    } else {
+        score = best_col; eq = best_col_i; er = m - 1;
+        if (best_row > score) { score = best_row; eq = n - 1; er = best_row_j; }
+    }
+    *score_out = score; *end_q_out = eq; *end_r_out = er;
+
+    /* ---- cigar walk (reverse), run-length encoded on the fly ---- */
+    int32_t nr = 0;                 /* runs emitted (reverse order) */
+    uint32_t cur_op = 0xffffffffu, cur_len = 0;
+    uint32_t *rev = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + m + 2));
+#define PUSH(op, len)                                                                              \
+    do {                                                                                           \
+        if ((len) > 0) {                                                                           \
+            if (cur_op == (uint32_t)(op)) cur_len += (uint32_t)(len);                              \
+            else { if (cur_len) rev[nr++] = (cur_len << 4) | cur_op; cur_op = (op); cur_len = (len); } \
+        }                                                                                          \
+    } while (0)
+    int32_t i = eq, j = er;
+    if (eq + 1 == n) PUSH(OP_D, m - 1 - j);        /* unaligned ref tail   */
+    else PUSH(OP_I, n - 1 - i);                    /* unaligned query tail */
+    int where = T_SRC_DIAG;
+    while (i >= 0 || j >= 0) {
+        if (i < 0) { PUSH(OP_D, j + 1); break; }
+        if (j < 0) { PUSH(OP_I, i + 1); break; }
+        uint8_t t = trace[(size_t)i * (size_t)m + (size_t)j];
+        if (where == T_SRC_DIAG) {
+            int src = t >> 2;
+            if (src == T_SRC_DIAG) {
+                PUSH(upc(s1[i]) == upc(s2[j]) ? OP_EQ : OP_X, 1);
+                --i; --j;
+            } else where = src;
+        } else if (where == T_SRC_E) {
+            PUSH(OP_D, 1); --j;
+            where = (t & T_E_EXT) ? T_SRC_E : T_SRC_DIAG;
+        } else {
+            PUSH(OP_I, 1); --i;
+            where = (t & T_F_EXT) ? T_SRC_F : T_SRC_DIAG;
+        }
+    }
+    if (cur_len) rev[nr++] = (cur_len << 4) | cur_op;
+#undef PUSH
+    *n_runs_out = nr;
+    int32_t rc = nr;
+    if (nr > cigar_cap) rc = -2;
+    else for (int q = 0; q < nr; ++q) cigar[q] = rev[nr - 1 - q];
+    free(rev); free(trace); free(H); free(F); free(c2);
+    return rc;
+}
+
+ISOF_API int32_t isof_oracle_sg_align(const uint8_t *s1, int32_t n, const uint8_t *s2, int32_t m,
+                                      int32_t match, int32_t mismatch, int32_t open, int32_t ext,
+                                      int32_t *score_out, int32_t *end_q_out, int32_t *end_r_out,
+                                      uint32_t *cigar, int32_t cigar_cap, int32_t *n_runs_out)
+{
+    return isof_oracle_sg_align_tb(s1, n, s2, m, match, mismatch, open, ext, NULL, score_out,
+                                   end_q_out, end_r_out, cigar, cigar_cap, n_runs_out);
+}
+
+/*
+ * Batch over a sequence pool (cat/off) and index pairs; the CPU baseline of bench.py.
+ * cigar_off[P+1] is filled with exclusive prefix sums; runs that do not fit `cigar_cap` are
+ * counted but not written.  Returns total runs, or <0 on error.
+ */
+ISOF_API int64_t isof_oracle_sg_align_pairs(const uint8_t *cat, const int64_t *off, const int32_t *ia,
+                                            const int32_t *ib, int64_t P, int32_t match,
+                                            int32_t mismatch, int32_t open, int32_t ext,
+                                            int32_t *score, int32_t *end_q, int32_t *end_r,
+                                            uint32_t *cigar, int64_t *cigar_off, int64_t cigar_cap,
+                                            int threads)
+{
+    uint32_t **runs = (uint32_t **)calloc((size_t)P, sizeof(uint32_t *));
+    int32_t *nr = (int32_t *)calloc((size_t)P, sizeof(int32_t));
+    int err = 0;
+    (void)threads;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int64_t p = 0; p < P; ++p) {
+        int32_t n = (int32_t)(off[ia[p] + 1] - off[ia[p]]);
+        int32_t m = (int32_t)(off[ib[p] + 1] - off[ib[p]]);
+        int32_t cap = n + m + 2;
+        runs[p] = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)cap);
+        int32_t rc = isof_oracle_sg_align(cat + off[ia[p]], n, cat + off[ib[p]], m, match, mismatch,
+                                          open, ext, &score[p], &end_q[p], &end_r[p], runs[p], cap,
+                                          &nr[p]);
+        if (rc < 0) err = 1;
+    }
+    int64_t tot = 0;
+    for (int64_t p = 0; p < P; ++p) {
+        cigar_off[p] = tot;
+        if (!err && cigar && tot + nr[p] <= cigar_cap)
+            memcpy(cigar + tot, runs[p], sizeof(uint32_t) * (size_t)nr[p]);
+        tot += nr[p];
+        free(runs[p]);
+    }
+    cigar_off[P] = tot;
+    free(runs); free(nr);
+    return err ? -1 : tot;
+}
+
+ISOF_API int32_t isof_oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
