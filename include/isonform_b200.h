@@ -1,0 +1,163 @@
+/*
+ * isonform_b200.h -- C ABI of libisonform_b200.so, the B200 (sm_100a) implementation of isONform's
+ * data-parallel hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (aljpetri/isONform v0.3.9) is pure Python and has no FFI of its own; the seams this
+ * library replaces are module-level Python functions.  Each entry point
+ * cites the reference interface it stands in for (file:line relative to the reference tree).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative isof_status; isof_last_error(ctx) gives text.
+ *   - the caller owns every buffer; the library owns only `ctx` (device scratch, one CUDA stream).
+ *   - one ctx per (process, GPU); calls on a ctx are stream-ordered and not thread-safe.
+ *   - "_dev" variants take DEVICE pointers for all array arguments and do not synchronise the stream
+ *     except where documented; the others take HOST pointers, copy in/out and synchronise.
+ *   - there is no CPU fallback: without a CUDA device isof_init fails with ISOF_ERR_CUDA.
+ */
+#ifndef ISONFORM_B200_H
+#define ISONFORM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ISOF_API __attribute__((visibility("default")))
+#else
+#define ISOF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct isof_ctx isof_ctx;
+
+typedef enum {
+    ISOF_OK = 0,
+    ISOF_ERR_CUDA = -1,       /* CUDA runtime error (text in isof_last_error)                     */
+    ISOF_ERR_ARG = -2,        /* bad argument (empty sequence, k > 64*8, w_size < k, ...)         */
+    ISOF_ERR_CAPACITY = -3,   /* an output buffer is too small; required size reported            */
+    ISOF_ERR_NOMEM = -4,      /* a single work item does not fit the scratch budget               */
+    ISOF_ERR_RANGE = -5       /* scores would overflow the 32-bit tagged representation           */
+} isof_status;
+
+/* CIGAR run encoding: (length << 4) | op, BAM op codes, as parasail's Cigar.seq. */
+enum { ISOF_CIGAR_M = 0, ISOF_CIGAR_I = 1, ISOF_CIGAR_D = 2, ISOF_CIGAR_EQ = 7, ISOF_CIGAR_X = 8 };
+
+/* number of int32 features per pair written by isof_sg_features_* (see below) */
+#define ISOF_N_FEATURES 12
+
+/* ------------------------------------------------------------------------------------------ */
+/* context                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+ISOF_API int isof_version(void);
+/* Creates the context on CUDA device `device`.  Fails (ISOF_ERR_CUDA) when no device is present. */
+ISOF_API int isof_init(int device, isof_ctx **ctx);
+ISOF_API int isof_destroy(isof_ctx *ctx);
+ISOF_API const char *isof_last_error(const isof_ctx *ctx);
+/* Use an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream, so that
+ * the caller's CUDA events bracket the library's kernels.  NULL restores the ctx-owned stream. */
+ISOF_API int isof_set_stream(isof_ctx *ctx, void *cuda_stream);
+/* Upper bound for the alignment trace scratch in bytes (default: 40% of free device memory). */
+ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
+
+/* Per-ctx counters, reset by isof_profile_reset.  Kernel times are measured with CUDA events on the
+ * ctx stream around each launch when profiling is enabled (isof_profile_enable(ctx,1)); enabling
+ * it adds one event pair per launch and a synchronise in isof_profile_get. */
+typedef struct {
+    int64_t launches;            /* kernels launched by this library                            */
+    int64_t dp_launches;         /* launches of the alignment DP kernel                          */
+    double dp_ms;                /* summed device time of the DP kernel                          */
+    double traceback_ms;         /* summed device time of the traceback + cigar kernels          */
+    double minimizer_ms;         /* summed device time of the minimizer kernels                  */
+    double other_ms;             /* planning / encoding / span kernels                           */
+    int64_t dp_cells;            /* sum len(s1)*len(s2) over aligned pairs                       */
+    int64_t dp_cells_padded;     /* cells actually updated (stripe padding included)             */
+    int64_t trace_bytes;         /* trace bytes written by the DP kernel                         */
+    int64_t h2d_bytes, d2h_bytes;
+} isof_profile;
+ISOF_API int isof_profile_enable(isof_ctx *ctx, int on);
+ISOF_API int isof_profile_reset(isof_ctx *ctx);
+ISOF_API int isof_profile_get(isof_ctx *ctx, isof_profile *out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (a) minimizers                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Replaces get_minimizers_and_positions / get_kmer_minimizers (main:159-171, main:81-110).
+ *   bases      concatenated ASCII reads (any byte values; hashed as CPython hashes str under
+ *              PYTHONHASHSEED=0, i.e. SipHash-1-3 with a zero key, main:85,94)
+ *   read_off   n_reads+1 offsets into `bases`
+ *   k, w_size  the reference's k_size and w_size (window holds w_size-k+1 k-mers)
+ *   out_pos    minimizer start positions, reads back to back (the k-mer string is
+ *              read[pos:pos+k], rebuilt by the caller exactly like main:89,104,109)
+ *   out_off    n_reads+1 offsets into out_pos
+ *   n_out      total minimizers; on ISOF_ERR_CAPACITY the size out_pos must have
+ */
+ISOF_API int isof_minimizers_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                          int32_t k, int32_t w_size, int32_t *out_pos, int64_t out_cap, int64_t *out_off,
+                          int64_t *n_out);
+/* Device-pointer variant; *n_out is a HOST pointer (one 8-byte read-back, synchronises). */
+ISOF_API int isof_minimizers_batch_dev(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                              int64_t n_bases, int32_t k, int32_t w_size, int32_t *out_pos, int64_t out_cap,
+                              int64_t *out_off, int64_t *n_out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (b) semi-global affine alignment with traceback                                            */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Replaces consensus.parasail_alignment (modules/consensus.py:55-67): parasail.matrix_create("ACGT",
+ * match, mismatch) + parasail.sg_trace_scan_16/_32(s1, s2, open, ext) + result.cigar, for a batch of
+ * pairs drawn from a sequence pool.  s1 = pool[pair_a[p]] is the query (CIGAR 'I' consumes it),
+ * s2 = pool[pair_b[p]] the reference ('D' consumes it).  Call sites in the reference:
+ * SimplifyGraph.py:644 (2,-8,12,1), IsoformGeneration.py:381 (2,-2,12,1), reached again from
+ * batch_merging_parallel.py:193.
+ *   seq_cat/seq_off   concatenated ASCII sequences and n_seqs+1 offsets
+ *   score,end_q,end_r per pair: score, 0-based end cell (parasail's end_query / end_ref)
+ *   cigar_runs        (len<<4|op) runs of all pairs back to back, alignment order, end gaps included
+ *   cigar_off         n_pairs+1 offsets into cigar_runs (filled even on ISOF_ERR_CAPACITY)
+ *   cigar_runs may be NULL (cigar_cap 0) when only scores/end cells are wanted: cigar_off is still filled.
+ * Empty sequences are rejected (ISOF_ERR_ARG), as parasail does.
+ */
+ISOF_API int isof_sg_align_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs,
+                        const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs, int32_t match,
+                        int32_t mismatch, int32_t gap_open, int32_t gap_ext, int32_t *score, int32_t *end_q,
+                        int32_t *end_r, uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off);
+/* Device-pointer variant; `n_bases` = seq_off[n_seqs].  *n_runs_total is a HOST pointer. */
+ISOF_API int isof_sg_align_pairs_dev(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs,
+                            int64_t n_bases, const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs,
+                            int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext, int32_t *score,
+                            int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs, int64_t cigar_cap,
+                            int64_t *cigar_off, int32_t *features, int32_t delta_len, int64_t *n_runs_total);
+/*
+ * The SURVEY.md section 8b form: two concatenations, pair p = (s1[p], s2[p]).
+ */
+ISOF_API int isof_sg_align_batch(isof_ctx *ctx, const uint8_t *s1_cat, const int64_t *s1_off, const uint8_t *s2_cat,
+                        const int64_t *s2_off, int32_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                        int32_t gap_ext, int32_t *score, int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs,
+                        int64_t cigar_cap, int64_t *cigar_off);
+/*
+ * Fused epilogue: alignment + the integer features the reference derives from the CIGAR and the
+ * aligned strings to decide bubble popping (parse_cigar_diversity, SimplifyGraph.py:175-196) and
+ * isoform merging (find_first_significant_match / parse_cigar_diversity_isoform_level_new,
+ * IsoformGeneration.py:251-320,370-397).  The float comparisons stay on the host (python), fed by
+ * these integers.  features[p*ISOF_N_FEATURES + ...]:
+ *   0 alen          alignment columns            1 n_runs
+ *   2 nonmatch      sum of non-'=' run lengths   3 max_nonmatch_run
+ *   4 start_match   first column of a 30-column window with >=22 equal columns, -1 if none
+ *   5 end_match     the same on the reversed alignment, -1 if none
+ *   6 structural    1 if a non-match run longer than delta_len lies between first and last match
+ *   7 miss_runs     number of non-match runs (<= delta_len) between first and last match
+ *   8 before_match  9 before_nomatch  10 after_match  11 after_nomatch   (IsoformGeneration.py:266-289)
+ * cigar_runs/cigar_off may be NULL when only features are wanted.
+ */
+ISOF_API int isof_sg_features_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs,
+                           const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs, int32_t match,
+                           int32_t mismatch, int32_t gap_open, int32_t gap_ext, int32_t delta_len, int32_t *score,
+                           int32_t *features, uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISONFORM_B200_H */

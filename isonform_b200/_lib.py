@@ -1,0 +1,253 @@
+"""ctypes binding of libisonform_b200.so (include/isonform_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present the
+product raises.  `Context` is one (process, GPU) handle; host-array methods take numpy arrays,
+`*_dev` methods take raw device pointers (e.g. ``torch.Tensor.data_ptr()``).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libisonform_b200.so")
+
+N_FEATURES = 12
+OPS = {0: "M", 1: "I", 2: "D", 7: "=", 8: "X"}
+_OP_CHARS = np.full(16, ord("?"), dtype=np.uint8)
+for _k, _v in OPS.items():
+    _OP_CHARS[_k] = ord(_v)
+
+ISOF_OK, ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_NOMEM, ERR_RANGE = 0, -1, -2, -3, -4, -5
+
+
+class IsofError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("isonform_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Profile(C.Structure):
+    _fields_ = [("launches", C.c_int64), ("dp_launches", C.c_int64), ("dp_ms", C.c_double),
+                ("traceback_ms", C.c_double), ("minimizer_ms", C.c_double), ("other_ms", C.c_double),
+                ("dp_cells", C.c_int64), ("dp_cells_padded", C.c_int64), ("trace_bytes", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget",
+           "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_minimizers_batch",
+           "isof_minimizers_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
+           "isof_sg_features_pairs"]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no CUDA call yet).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError("libisonform_b200.so is not built: run `python -m isonform_b200.build` "
+                          "(needs nvcc; there is no CPU fallback)")
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.isof_version.restype = C.c_int
+    L.isof_init.argtypes = [C.c_int, C.POINTER(vp)]
+    L.isof_destroy.argtypes = [vp]
+    L.isof_last_error.argtypes = [vp]
+    L.isof_last_error.restype = C.c_char_p
+    L.isof_set_stream.argtypes = [vp, vp]
+    L.isof_set_trace_budget.argtypes = [vp, C.c_size_t]
+    L.isof_profile_enable.argtypes = [vp, C.c_int]
+    L.isof_profile_reset.argtypes = [vp]
+    L.isof_profile_get.argtypes = [vp, C.POINTER(Profile)]
+    L.isof_minimizers_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp, C.POINTER(i64)]
+    L.isof_minimizers_batch_dev.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, i64, vp, C.POINTER(i64)]
+    L.isof_sg_align_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp]
+    L.isof_sg_align_pairs_dev.argtypes = [vp, vp, vp, i32, i64, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64,
+                                          vp, vp, i32, C.POINTER(i64)]
+    L.isof_sg_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp]
+    L.isof_sg_features_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp]
+    for name in EXPORTS:
+        getattr(L, name)
+        if name not in ("isof_last_error",):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def pack_sequences(seqs):
+    """list[str|bytes] -> (uint8 cat, int64 off)."""
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=off[1:])
+    cat = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(cat), off
+
+
+def runs_to_string(runs):
+    return "".join("%d%s" % (int(r) >> 4, OPS[int(r) & 15]) for r in runs)
+
+
+def runs_to_tuples(runs):
+    return [(int(r) >> 4, OPS[int(r) & 15]) for r in runs]
+
+
+class Context:
+    """One GPU context.  Not thread-safe; calls are stream-ordered."""
+
+    def __init__(self, device=0):
+        self._L = load()
+        h = C.c_void_p()
+        rc = self._L.isof_init(int(device), C.byref(h))
+        if rc != ISOF_OK:
+            raise IsofError(rc, "isof_init(device=%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.isof_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != ISOF_OK and rc not in allow:
+            raise IsofError(rc, (self._L.isof_last_error(self._h) or b"").decode())
+        return rc
+
+    # ------------------------------------------------------------------ plumbing
+    def set_stream(self, cuda_stream):
+        self._check(self._L.isof_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_trace_budget(self, nbytes):
+        self._check(self._L.isof_set_trace_budget(self._h, int(nbytes)))
+
+    def profile_enable(self, on=True):
+        self._check(self._L.isof_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._check(self._L.isof_profile_reset(self._h))
+
+    def profile(self):
+        p = Profile()
+        self._check(self._L.isof_profile_get(self._h, C.byref(p)))
+        return p.as_dict()
+
+    # ------------------------------------------------------------------ (a) minimizers
+    def minimizers_batch(self, cat, off, k, w_size):
+        """(positions int32, offsets int64[R+1]) for concatenated reads."""
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        R = len(off) - 1
+        # ~0.15 minimizers per base on random sequence; grow on ISOF_ERR_CAPACITY
+        cap = max(int(cat.size) // 3 + 4 * R + 64, 64)
+        out_off = np.empty(R + 1, dtype=np.int64)
+        n_out = C.c_int64(0)
+        while True:
+            out = np.empty(cap, dtype=np.int32)
+            rc = self._L.isof_minimizers_batch(self._h, cat.ctypes.data, off.ctypes.data, R, k, w_size, out.ctypes.data,
+                                               cap, out_off.ctypes.data, C.byref(n_out))
+            if rc == ERR_CAPACITY:
+                cap = int(n_out.value)
+                continue
+            self._check(rc)
+            return out[:n_out.value], out_off
+
+    def minimizers_batch_dev(self, d_bases, d_off, n_reads, n_bases, k, w_size, d_out_pos, out_cap, d_out_off):
+        n_out = C.c_int64(0)
+        self._check(self._L.isof_minimizers_batch_dev(self._h, d_bases, d_off, n_reads, n_bases, k, w_size, d_out_pos,
+                                                      out_cap, d_out_off, C.byref(n_out)))
+        return int(n_out.value)
+
+    # ------------------------------------------------------------------ (b) alignment
+    def sg_align_pairs(self, cat, off, pair_a, pair_b, match=2, mismatch=-2, gap_open=12, gap_ext=1, want_cigar=True,
+                       features_delta_len=None, cigar_cap=None):
+        """Returns dict(score, end_q, end_r, cigar_off, cigar (uint32 runs or None), features or None)."""
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+        pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+        P = len(pa)
+        if len(pb) != P:
+            raise ValueError("pair_a and pair_b differ in length")
+        score = np.empty(P, np.int32)
+        coff = np.zeros(P + 1, np.int64)
+        feats = None
+        if cigar_cap is None:
+            if want_cigar and P:
+                lens = np.diff(off)
+                # a typical alignment of similar sequences has far fewer runs than n+m; start small
+                cap = int(min((lens[pa] + lens[pb] + 2).sum(), max(64 * P, 1 << 16)))
+            else:
+                cap = 0
+        else:
+            cap = int(cigar_cap)
+        while True:
+            cig = np.empty(max(cap, 1), np.uint32) if want_cigar else None
+            cig_ptr = cig.ctypes.data if want_cigar else None
+            if features_delta_len is None:
+                eq = np.empty(P, np.int32)
+                er = np.empty(P, np.int32)
+                rc = self._L.isof_sg_align_pairs(self._h, cat.ctypes.data, off.ctypes.data, len(off) - 1, pa.ctypes.data,
+                                                 pb.ctypes.data, P, match, mismatch, gap_open, gap_ext, score.ctypes.data,
+                                                 eq.ctypes.data, er.ctypes.data, cig_ptr, cap if want_cigar else 0,
+                                                 coff.ctypes.data)
+            else:
+                eq = er = None
+                feats = np.empty((P, N_FEATURES), np.int32)
+                rc = self._L.isof_sg_features_pairs(self._h, cat.ctypes.data, off.ctypes.data, len(off) - 1,
+                                                    pa.ctypes.data, pb.ctypes.data, P, match, mismatch, gap_open, gap_ext,
+                                                    int(features_delta_len), score.ctypes.data, feats.ctypes.data,
+                                                    cig_ptr, cap if want_cigar else 0, coff.ctypes.data)
+            if rc == ERR_CAPACITY and want_cigar:
+                cap = int(coff[P])
+                continue
+            self._check(rc)
+            break
+        return {"score": score, "end_q": eq, "end_r": er, "cigar_off": coff,
+                "cigar": (cig[:coff[P]] if want_cigar else None), "features": feats}
+
+    def sg_align_batch(self, s1_list, s2_list, match=2, mismatch=-2, gap_open=12, gap_ext=1):
+        """The SURVEY 8b concatenated form (isof_sg_align_batch)."""
+        c1, o1 = pack_sequences(s1_list)
+        c2, o2 = pack_sequences(s2_list)
+        P = len(s1_list)
+        score = np.empty(P, np.int32); eq = np.empty(P, np.int32); er = np.empty(P, np.int32)
+        coff = np.zeros(P + 1, np.int64)
+        cap = int((np.diff(o1) + np.diff(o2) + 2).sum()) if P else 1
+        cig = np.empty(max(cap, 1), np.uint32)
+        self._check(self._L.isof_sg_align_batch(self._h, c1.ctypes.data, o1.ctypes.data, c2.ctypes.data, o2.ctypes.data, P,
+                                                match, mismatch, gap_open, gap_ext, score.ctypes.data, eq.ctypes.data,
+                                                er.ctypes.data, cig.ctypes.data, cap, coff.ctypes.data))
+        return {"score": score, "end_q": eq, "end_r": er, "cigar_off": coff, "cigar": cig[:coff[P]]}
+
+    def sg_align_pairs_dev(self, d_cat, d_off, n_seqs, n_bases, d_pa, d_pb, P, match, mismatch, gap_open, gap_ext, d_score,
+                           d_endq, d_endr, d_cigar, cigar_cap, d_cigar_off, d_features=None, delta_len=0):
+        total = C.c_int64(0)
+        self._check(self._L.isof_sg_align_pairs_dev(self._h, d_cat, d_off, n_seqs, n_bases, d_pa, d_pb, P, match, mismatch,
+                                                    gap_open, gap_ext, d_score, d_endq, d_endr, d_cigar, cigar_cap,
+                                                    d_cigar_off, d_features, delta_len, C.byref(total)))
+        return int(total.value)
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context per device (created on first use)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", os.environ.get("ISOF_DEVICE", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

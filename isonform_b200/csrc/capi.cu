@@ -1,0 +1,258 @@
+// capi.cu -- the extern "C" boundary declared in include/isonform_b200.h.
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+int flush_timers(isof_ctx *ctx)
+{
+    if (ctx->timed.empty()) return ISOF_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        switch (t.slot) {
+            case SLOT_DP: ctx->prof.dp_ms += ms; break;
+            case SLOT_TB: ctx->prof.traceback_ms += ms; break;
+            case SLOT_MIN: ctx->prof.minimizer_ms += ms; break;
+            default: ctx->prof.other_ms += ms; break;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    ctx->timed.clear();
+    return ISOF_OK;
+}
+
+int h2d(isof_ctx *ctx, DevBuf &b, const void *src, size_t bytes)
+{
+    TRY(dev_reserve(ctx, b, bytes + 16));
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof.h2d_bytes += (int64_t)bytes;
+    return ISOF_OK;
+}
+
+int d2h(isof_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes && dst) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst) ctx->prof.d2h_bytes += (int64_t)bytes;
+    return ISOF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int isof_version(void) { return ISOF_VERSION; }
+
+int isof_init(int device, isof_ctx **out)
+{
+    if (!out) return ISOF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return ISOF_ERR_CUDA;                 // no CPU fallback: the caller must fail loudly
+    }
+    isof_ctx *ctx = new isof_ctx();
+    ctx->device = device;
+    memset(&ctx->prof, 0, sizeof(ctx->prof));
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    ctx->pinned_cap = 4096;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_cap) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
+    *out = ctx;
+    return ISOF_OK;
+}
+
+int isof_destroy(isof_ctx *ctx)
+{
+    if (!ctx) return ISOF_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    flush_timers(ctx);
+    DevBuf *bufs[] = {&ctx->b_codes, &ctx->b_seqflags, &ctx->b_pn, &ctx->b_pm, &ctx->b_paoff, &ctx->b_pboff, &ctx->b_ptrace,
+                      &ctx->b_scan_tmp, &ctx->b_bnd, &ctx->b_trace, &ctx->b_nruns, &ctx->b_counters, &ctx->b_misc,
+                      &ctx->b_runoff, &ctx->b_status, &ctx->b_h_bases, &ctx->b_h_off, &ctx->b_h_pa, &ctx->b_h_pb,
+                      &ctx->b_h_score, &ctx->b_h_endq, &ctx->b_h_endr, &ctx->b_h_cig, &ctx->b_h_cigoff, &ctx->b_h_feat,
+                      &ctx->b_m_hash, &ctx->b_m_tmp, &ctx->b_m_cnt, &ctx->b_m_off};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return ISOF_OK;
+}
+
+const char *isof_last_error(const isof_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+int isof_set_stream(isof_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    flush_timers(ctx);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ISOF_OK;
+}
+
+int isof_set_trace_budget(isof_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->trace_budget = bytes;
+    return ISOF_OK;
+}
+
+int isof_profile_enable(isof_ctx *ctx, int on)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    flush_timers(ctx);
+    ctx->profiling = on != 0;
+    return ISOF_OK;
+}
+
+int isof_profile_reset(isof_ctx *ctx)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    flush_timers(ctx);
+    memset(&ctx->prof, 0, sizeof(ctx->prof));
+    return ISOF_OK;
+}
+
+int isof_profile_get(isof_ctx *ctx, isof_profile *out)
+{
+    if (!ctx || !out) return ISOF_ERR_ARG;
+    TRY(flush_timers(ctx));
+    *out = ctx->prof;
+    return ISOF_OK;
+}
+
+// ------------------------------------------------------------------------------------------ (a)
+int isof_minimizers_batch_dev(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                              int64_t n_bases, int32_t k, int32_t w_size, int32_t *out_pos, int64_t out_cap,
+                              int64_t *out_off, int64_t *n_out)
+{
+    if (!ctx || !n_out) return ISOF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return isof_minimizers_core(ctx, bases, read_off, n_reads, n_bases, k, w_size, out_pos, out_cap, out_off, n_out);
+}
+
+int isof_minimizers_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads, int32_t k,
+                          int32_t w_size, int32_t *out_pos, int64_t out_cap, int64_t *out_off, int64_t *n_out)
+{
+    if (!ctx || !read_off || !out_off || !n_out || n_reads < 0) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_bases = read_off[n_reads];
+    if (read_off[0] != 0 || n_bases < 0) return isof_fail(ctx, ISOF_ERR_ARG, "read_off must start at 0 and be non-decreasing");
+    TRY(h2d(ctx, ctx->b_h_bases, bases, (size_t)n_bases));
+    TRY(h2d(ctx, ctx->b_h_off, read_off, sizeof(int64_t) * (size_t)(n_reads + 1)));
+    // device outputs: worst case one minimizer per base + one per read
+    const int64_t cap_dev = std::max<int64_t>(std::min<int64_t>(out_cap, n_bases + n_reads), 1);
+    TRY(dev_reserve(ctx, ctx->b_h_cig, sizeof(int32_t) * (size_t)cap_dev));
+    TRY(dev_reserve(ctx, ctx->b_h_cigoff, sizeof(int64_t) * (size_t)(n_reads + 1)));
+    int rc = isof_minimizers_core(ctx, (const uint8_t *)ctx->b_h_bases.p, (const int64_t *)ctx->b_h_off.p, n_reads, n_bases,
+                                  k, w_size, (int32_t *)ctx->b_h_cig.p, cap_dev, (int64_t *)ctx->b_h_cigoff.p, n_out);
+    if (rc != ISOF_OK && rc != ISOF_ERR_CAPACITY) return rc;
+    TRY(d2h(ctx, out_off, ctx->b_h_cigoff.p, sizeof(int64_t) * (size_t)(n_reads + 1)));
+    if (rc == ISOF_OK) TRY(d2h(ctx, out_pos, ctx->b_h_cig.p, sizeof(int32_t) * (size_t)*n_out));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ (b)
+int isof_sg_align_pairs_dev(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, int64_t n_bases,
+                            const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs, int32_t match, int32_t mismatch,
+                            int32_t gap_open, int32_t gap_ext, int32_t *score, int32_t *end_q, int32_t *end_r,
+                            uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off, int32_t *features,
+                            int32_t delta_len, int64_t *n_runs_total)
+{
+    if (!ctx || !score || !end_q || !end_r) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return isof_sg_align_core(ctx, seq_cat, seq_off, n_seqs, n_bases, pair_a, pair_b, n_pairs, match, mismatch, gap_open,
+                              gap_ext, score, end_q, end_r, cigar_runs, cigar_cap, cigar_off, features, delta_len,
+                              n_runs_total);
+}
+
+static int align_host(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, const int32_t *pair_a,
+                      const int32_t *pair_b, int64_t P, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
+                      int32_t delta_len, int32_t *score, int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs,
+                      int64_t cigar_cap, int64_t *cigar_off, int32_t *features)
+{
+    if (!ctx || !seq_off || n_seqs < 0 || P < 0) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_bases = seq_off[n_seqs];
+    if (seq_off[0] != 0 || n_bases < 0) return isof_fail(ctx, ISOF_ERR_ARG, "seq_off must start at 0");
+    if (P == 0) { if (cigar_off) cigar_off[0] = 0; return ISOF_OK; }
+    if (!pair_a || !pair_b) return isof_fail(ctx, ISOF_ERR_ARG, "null pair list");
+    TRY(h2d(ctx, ctx->b_h_bases, seq_cat, (size_t)n_bases));
+    TRY(h2d(ctx, ctx->b_h_off, seq_off, sizeof(int64_t) * (size_t)(n_seqs + 1)));
+    TRY(h2d(ctx, ctx->b_h_pa, pair_a, sizeof(int32_t) * (size_t)P));
+    TRY(h2d(ctx, ctx->b_h_pb, pair_b, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_h_score, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_h_endq, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_h_endr, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_h_cigoff, sizeof(int64_t) * (size_t)(P + 1)));
+    if (cigar_runs && cigar_cap > 0) TRY(dev_reserve(ctx, ctx->b_h_cig, sizeof(uint32_t) * (size_t)cigar_cap));
+    if (features) TRY(dev_reserve(ctx, ctx->b_h_feat, sizeof(int32_t) * (size_t)P * ISOF_N_FEATURES));
+    int64_t total = 0;
+    uint32_t *d_cig = (cigar_runs && cigar_cap > 0) ? (uint32_t *)ctx->b_h_cig.p : nullptr;
+    int rc = isof_sg_align_core(ctx, (const uint8_t *)ctx->b_h_bases.p, (const int64_t *)ctx->b_h_off.p, n_seqs, n_bases,
+                                (const int32_t *)ctx->b_h_pa.p, (const int32_t *)ctx->b_h_pb.p, P, match, mismatch, gap_open,
+                                gap_ext, (int32_t *)ctx->b_h_score.p, (int32_t *)ctx->b_h_endq.p, (int32_t *)ctx->b_h_endr.p,
+                                d_cig, cigar_cap, (int64_t *)ctx->b_h_cigoff.p,
+                                features ? (int32_t *)ctx->b_h_feat.p : nullptr, delta_len, &total);
+    if (rc != ISOF_OK && rc != ISOF_ERR_CAPACITY) return rc;
+    TRY(d2h(ctx, score, ctx->b_h_score.p, sizeof(int32_t) * (size_t)P));
+    TRY(d2h(ctx, end_q, ctx->b_h_endq.p, sizeof(int32_t) * (size_t)P));
+    TRY(d2h(ctx, end_r, ctx->b_h_endr.p, sizeof(int32_t) * (size_t)P));
+    TRY(d2h(ctx, cigar_off, ctx->b_h_cigoff.p, sizeof(int64_t) * (size_t)(P + 1)));
+    if (features) TRY(d2h(ctx, features, ctx->b_h_feat.p, sizeof(int32_t) * (size_t)P * ISOF_N_FEATURES));
+    if (d_cig && rc == ISOF_OK) TRY(d2h(ctx, cigar_runs, d_cig, sizeof(uint32_t) * (size_t)total));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int isof_sg_align_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, const int32_t *pair_a,
+                        const int32_t *pair_b, int64_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                        int32_t gap_ext, int32_t *score, int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs,
+                        int64_t cigar_cap, int64_t *cigar_off)
+{
+    if (!score || !end_q || !end_r) return isof_fail(ctx, ISOF_ERR_ARG, "null output");
+    return align_host(ctx, seq_cat, seq_off, n_seqs, pair_a, pair_b, n_pairs, match, mismatch, gap_open, gap_ext, 0, score,
+                      end_q, end_r, cigar_runs, cigar_cap, cigar_off, nullptr);
+}
+
+int isof_sg_features_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs,
+                           const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs, int32_t match, int32_t mismatch,
+                           int32_t gap_open, int32_t gap_ext, int32_t delta_len, int32_t *score, int32_t *features,
+                           uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off)
+{
+    if (!score || !features) return isof_fail(ctx, ISOF_ERR_ARG, "null output");
+    return align_host(ctx, seq_cat, seq_off, n_seqs, pair_a, pair_b, n_pairs, match, mismatch, gap_open, gap_ext, delta_len,
+                      score, nullptr, nullptr, cigar_runs, cigar_cap, cigar_off, features);
+}
+
+int isof_sg_align_batch(isof_ctx *ctx, const uint8_t *s1_cat, const int64_t *s1_off, const uint8_t *s2_cat,
+                        const int64_t *s2_off, int32_t n_pairs, int32_t match, int32_t mismatch, int32_t gap_open,
+                        int32_t gap_ext, int32_t *score, int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs,
+                        int64_t cigar_cap, int64_t *cigar_off)
+{
+    if (!ctx || !s1_off || !s2_off || n_pairs < 0) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    // build a pool: [s1 sequences..., s2 sequences...]
+    const int64_t n1 = s1_off[n_pairs], n2 = s2_off[n_pairs];
+    std::vector<uint8_t> cat((size_t)(n1 + n2));
+    if (n1) memcpy(cat.data(), s1_cat, (size_t)n1);
+    if (n2) memcpy(cat.data() + n1, s2_cat, (size_t)n2);
+    std::vector<int64_t> off((size_t)2 * n_pairs + 1);
+    for (int32_t p = 0; p <= n_pairs; ++p) off[p] = s1_off[p];
+    for (int32_t p = 0; p <= n_pairs; ++p) off[(size_t)n_pairs + p] = n1 + s2_off[p];
+    std::vector<int32_t> pa((size_t)n_pairs), pb((size_t)n_pairs);
+    for (int32_t p = 0; p < n_pairs; ++p) { pa[p] = p; pb[p] = n_pairs + p; }
+    return isof_sg_align_pairs(ctx, cat.data(), off.data(), 2 * n_pairs, pa.data(), pb.data(), n_pairs, match, mismatch,
+                               gap_open, gap_ext, score, end_q, end_r, cigar_runs, cigar_cap, cigar_off);
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// common.cuh -- context, error handling and small device helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/isonform_b200.h"
+
+#define ISOF_VERSION 100
+
+struct DevBuf {            // grow-only device scratch
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct isof_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    size_t trace_budget = 0;          // bytes; 0 = decide at first use
+    bool profiling = false;
+    isof_profile prof;
+    // pending (start, stop, slot) event pairs when profiling
+    struct Timed { cudaEvent_t a, b; int slot; };
+    std::vector<Timed> timed;
+    // scratch
+    DevBuf b_codes, b_seqflags, b_pn, b_pm, b_paoff, b_pboff, b_ptrace, b_scan_tmp, b_bnd, b_trace, b_nruns,
+        b_counters, b_misc, b_runoff, b_status;
+    DevBuf b_h_bases, b_h_off, b_h_pa, b_h_pb, b_h_score, b_h_endq, b_h_endr, b_h_cig, b_h_cigoff, b_h_feat;
+    DevBuf b_m_hash, b_m_tmp, b_m_cnt, b_m_off;
+    void *pinned = nullptr;           // small pinned staging for scalar read-backs
+    size_t pinned_cap = 0;
+};
+
+enum { SLOT_DP = 0, SLOT_TB = 1, SLOT_MIN = 2, SLOT_OTHER = 3 };
+
+static inline int isof_fail(isof_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                        \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return isof_fail((ctx), ISOF_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__,      \
+                             __LINE__, cudaGetErrorString(e__));                                   \
+    } while (0)
+
+static inline int dev_reserve(isof_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return ISOF_OK;
+    if (b.p) { CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return isof_fail(ctx, ISOF_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return ISOF_OK;
+}
+
+#define TRY(x)                                                                                     \
+    do {                                                                                           \
+        int rc__ = (x);                                                                            \
+        if (rc__ != ISOF_OK) return rc__;                                                          \
+    } while (0)
+
+// Launch bookkeeping: counts the launch and, when profiling, brackets it with events.
+struct LaunchTimer {
+    isof_ctx *ctx;
+    int slot;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchTimer(isof_ctx *c, int s) : ctx(c), slot(s)
+    {
+        ctx->prof.launches++;
+        if (slot == SLOT_DP) ctx->prof.dp_launches++;
+        if (ctx->profiling) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~LaunchTimer()
+    {
+        if (ctx->profiling) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->timed.push_back({a, b, slot});
+        }
+    }
+};
+
+// internal entry points implemented in the .cu files
+int isof_minimizers_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_off, int32_t R, int64_t n_bases,
+                         int32_t k, int32_t w_size, int32_t *d_out_pos, int64_t out_cap, int64_t *d_out_off,
+                         int64_t *h_n_out);
+int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off, int32_t n_seqs, int64_t n_bases,
+                       const int32_t *d_pa, const int32_t *d_pb, int64_t P, int32_t match, int32_t mismatch,
+                       int32_t gap_open, int32_t gap_ext, int32_t *d_score, int32_t *d_endq, int32_t *d_endr,
+                       uint32_t *d_cigar, int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_features,
+                       int32_t delta_len, int64_t *h_total_runs);

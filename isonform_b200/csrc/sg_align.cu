@@ -1,0 +1,622 @@
+// sg_align.cu -- kernel (b): batched semi-global affine-gap alignment with full traceback,
+// CIGAR-compatible with the parasail.sg_trace_scan_16/_32 call behind
+// consensus.parasail_alignment (reference modules/consensus.py:55-67).
+//
+// DP kernel (sg_dp_kernel): one warp per pair, anti-diagonal wavefront.  The query (rows) is cut
+// into stripes of 256 rows; lane l owns 8 consecutive rows and, at step t, the column j = t - l.
+// Per step a lane receives H/F of the row above from lane l-1 (one shuffle each), keeps H(i,j-1),
+// E(i,j-1) of its rows in registers and emits one 32-bit trace word (8 rows x 4 bits).
+// Scores are held as 16*score + tag: the low 4 bits carry the provenance of a value so that the
+// DPX max instructions (VIADDMNMX / VIMNMX3) resolve every tie exactly like the restated library
+// (DIAG > F > E; gap extension wins a tie against gap opening) and the trace nibble falls out of
+// the winning operands' tags without a single compare instruction:
+//     E candidates:  open -> ..0100   extend -> ..0101      (bit0 = E came from extension)
+//     F candidates:  open -> ..1000   extend -> ..1010      (bit1 = F came from extension)
+//     diagonal:                ..1100
+//     nibble = [src1 src0 f_ext e_ext],  src: 3 diag, 2 F (consumes query, 'I'), 1 E (consumes ref, 'D')
+// Trace layout per pair: word[(stripe*(m+31) + t)*32 + lane]  -> every step is one coalesced 128 B
+// store.  The bottom row of a stripe (H,F per column) goes through a per-warp global line buffer.
+//
+// Traceback kernel: one thread per pair walks the trace from the end cell and writes the CIGAR
+// runs backwards into the tail of the pair's own trace region, so the runs end up in alignment
+// order and a coalesced copy moves them to the caller's buffer.
+#include "common.cuh"
+#include <cub/device/device_scan.cuh>
+#include <climits>
+
+namespace {
+
+constexpr int R = 8;                 // rows per lane
+constexpr int SROWS = 32 * R;        // rows per stripe
+constexpr int TAG_BITS = 4;
+constexpr int NEGV = -(1 << 29);     // "minus infinity", a clean multiple of 16
+constexpr int CODE_SHIFT = 12;       // base codes live at bits 12..14 of a register
+constexpr int TRACE_SLACK = 64;      // spare words at the end of every trace region
+constexpr int DP_WARPS = 8;          // warps per CTA of the DP kernel
+
+struct AlignParams {
+    const uint8_t *cat;        // ASCII pool
+    const uint8_t *codes;      // 0..3 ACGT (case-insensitive), 4 anything else
+    const int64_t *seq_off;
+    const int32_t *pa, *pb;
+    const int32_t *pn, *pm;
+    const uint8_t *pwild;
+    const int64_t *ptrace;     // P+1 word offsets (global, exclusive scan)
+    int64_t chunk_base;        // word offset of this chunk's first pair
+    uint32_t *trace;
+    int2 *bnd;
+    int64_t bnd_stride;        // int2 elements per warp
+    int32_t *score, *endq, *endr, *nruns;
+    int c_eo, c_ee, c_fo, c_fe, c_sm, c_sx;
+};
+
+__device__ __forceinline__ int base_code(uint8_t c)
+{
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+// warp per sequence: codes + "has a non-ACGT character" flag
+__global__ void encode_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ off, int n_seqs,
+                              uint8_t *__restrict__ codes, uint8_t *__restrict__ flags)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < n_seqs; s += nwarps) {
+        const int64_t b = off[s], e = off[s + 1];
+        int wild = 0;
+        for (int64_t x = b + lane; x < e; x += 32) {
+            int c = base_code(cat[x]);
+            codes[x] = (uint8_t)c;
+            wild |= (c == 4);
+        }
+        wild = __any_sync(0xffffffffu, wild);
+        if (lane == 0) flags[s] = (uint8_t)wild;
+    }
+}
+
+// per pair: lengths, wildcard flag, trace words; misc[0]=error flags, misc[1]=max m, misc[2..3]=cells
+__global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const uint8_t *__restrict__ flags,
+                            const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, int64_t P,
+                            int32_t *__restrict__ pn, int32_t *__restrict__ pm, uint8_t *__restrict__ pwild,
+                            int64_t *__restrict__ words, unsigned long long *__restrict__ misc)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cells = 0, padded = 0;
+    int mm = 0;
+    if (p < P) {
+        int a = pa[p], b = pb[p];
+        int n = 0, m = 0;
+        int64_t w = TRACE_SLACK;
+        if (a < 0 || a >= n_seqs || b < 0 || b >= n_seqs) atomicOr(&misc[0], 1ull);
+        else {
+            n = (int)(off[a + 1] - off[a]);
+            m = (int)(off[b + 1] - off[b]);
+            if (n <= 0 || m <= 0) { atomicOr(&misc[0], 2ull); n = m = 0; }
+            else {
+                int ns = (n + SROWS - 1) / SROWS;
+                w = (int64_t)ns * (m + 31) * 32 + TRACE_SLACK;
+                cells = (unsigned long long)n * m;
+                padded = (unsigned long long)ns * SROWS * m;
+                pwild[p] = flags[a] | flags[b];
+                mm = m;
+            }
+        }
+        pn[p] = n; pm[p] = m;
+        words[p] = w;
+    }
+    // block reduce the statistics
+    for (int d = 16; d; d >>= 1) {
+        cells += __shfl_down_sync(0xffffffffu, cells, d);
+        padded += __shfl_down_sync(0xffffffffu, padded, d);
+        mm = max(mm, __shfl_down_sync(0xffffffffu, mm, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cells) { atomicAdd(&misc[2], cells); atomicAdd(&misc[3], padded); }
+        if (mm) atomicMax(&misc[1], (unsigned long long)mm);
+    }
+    if (p == P) words[P] = 0;
+}
+
+// chunk_start[c] = first pair whose trace offset is >= c*budget   (c = 0..n_chunks)
+__global__ void chunk_bounds_kernel(const int64_t *__restrict__ ptrace, int64_t P, int64_t budget, int n_chunks,
+                                    int64_t *__restrict__ chunk_start)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chunks) return;
+    if (c == n_chunks) { chunk_start[c] = P; return; }
+    int64_t target = (int64_t)c * budget;
+    int64_t lo = 0, hi = P;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (ptrace[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    chunk_start[c] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DP
+// ---------------------------------------------------------------------------------------------
+template <bool WILD>
+__device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int n = P.pn[p], m = P.pm[p];
+    const uint8_t *__restrict__ q = P.codes + P.seq_off[P.pa[p]];
+    const uint8_t *__restrict__ rf = P.codes + P.seq_off[P.pb[p]];
+    uint32_t *__restrict__ trace = P.trace + (P.ptrace[p] - P.chunk_base);
+    const int T = m + 31;
+    const int nstripes = (n + SROWS - 1) / SROWS;
+    const int last_lane = ((n - 1) % SROWS) / R, last_r = (n - 1) % R;
+    const int c_eo = P.c_eo, c_ee = P.c_ee, c_fo = P.c_fo, c_fe = P.c_fe, c_sm = P.c_sm, c_sx = P.c_sx;
+    int best_col = INT_MIN, best_col_i = 0, best_row = INT_MIN, best_row_j = 0;
+
+    for (int s = 0; s < nstripes; ++s) {
+        const int i0 = s * SROWS + lane * R;
+        int qc[R], Hl[R], El[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            qc[r] = (i0 + r < n) ? ((int)q[i0 + r] << CODE_SHIFT) : 0;
+            Hl[r] = 0;           // H(i,-1) = 0: free leading gap
+            El[r] = NEGV;
+        }
+        const bool has_prev = s > 0, has_next = s + 1 < nstripes, is_last = !has_next;
+        int diag0 = 0;           // H(i0-1, j-1); H(.,-1) = 0
+        int Hbot = 0, Fbot = NEGV;
+        int rc_next = (lane == 0) ? ((int)rf[0] << CODE_SHIFT) : 0;
+        int2 b_next = make_int2(0, NEGV);
+        if (has_prev && lane == 0) b_next = __ldcg(&bnd[0]);
+        uint32_t *tp = trace + (size_t)s * T * 32 + lane;
+
+        for (int t = 0; t < T; ++t, tp += 32) {
+            const int j = t - lane;
+            const int rc = rc_next;
+            const int2 bu = b_next;
+            {   // prefetch the next column's reference base / boundary cell
+                const int jn = j + 1;
+                if ((unsigned)jn < (unsigned)m) {
+                    rc_next = (int)rf[jn] << CODE_SHIFT;
+                    if (has_prev && lane == 0) b_next = __ldcg(&bnd[jn]);
+                }
+            }
+            int hu = __shfl_up_sync(FULL, Hbot, 1);
+            int fu = __shfl_up_sync(FULL, Fbot, 1);
+            if (lane == 0) { hu = bu.x; fu = bu.y; }
+            if ((unsigned)j < (unsigned)m) {
+                int up = hu, fup = fu, diag = diag0;
+                diag0 = hu;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int left = Hl[r];
+                    const int Ee = El[r] + c_ee;
+                    const int E = __viaddmax_s32(left, c_eo, Ee);
+                    const int Fe = fup + c_fe;
+                    const int F = __viaddmax_s32(up, c_fo, Fe);
+                    const int y = qc[r] ^ rc ^ (3 << CODE_SHIFT);
+                    int sc = __viaddmax_s32(y, c_sm, c_sx);
+                    if (WILD) { if ((qc[r] | rc) & (4 << CODE_SHIFT)) sc = 12; }
+                    const int Hd = diag + sc;
+                    const int H = __vimax3_s32(Hd, F, E);
+                    uint32_t nib = ((uint32_t)H & ~1u) | ((uint32_t)E & 1u);
+                    nib = (nib & ~2u) | ((uint32_t)F & 2u);
+                    acc |= (nib & 15u) << (4 * r);
+                    const int Hc = H & ~15;
+                    diag = left;
+                    Hl[r] = Hc;
+                    El[r] = E & ~15;
+                    up = Hc;
+                    fup = F & ~15;
+                }
+                Hbot = up; Fbot = fup;
+                *tp = acc;
+                if (has_next && lane == 31) bnd[j] = make_int2(Hbot, Fbot);
+                if (j == m - 1) {                      // last column: smallest i wins ties
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (i0 + r < n && Hl[r] > best_col) { best_col = Hl[r]; best_col_i = i0 + r; }
+                }
+                if (is_last && lane == last_lane) {    // last row: smallest j wins ties
+                    int hv = Hl[0];
+#pragma unroll
+                    for (int r = 1; r < R; ++r) if (r == last_r) hv = Hl[r];
+                    if (hv > best_row) { best_row = hv; best_row_j = j; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // ---- end cell (restated library order: last row first, last column only if strictly greater)
+    best_row = __shfl_sync(FULL, best_row, last_lane);
+    best_row_j = __shfl_sync(FULL, best_row_j, last_lane);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        int ov = __shfl_xor_sync(FULL, best_col, d);
+        int oi = __shfl_xor_sync(FULL, best_col_i, d);
+        if (ov > best_col || (ov == best_col && oi < best_col_i)) { best_col = ov; best_col_i = oi; }
+    }
+    if (lane == 0) {
+        int sc = best_row, eq = n - 1, er = best_row_j;
+        if (best_col > sc) { sc = best_col; eq = best_col_i; er = m - 1; }
+        else if (best_col == sc && er == m - 1 && best_col_i < eq) eq = best_col_i;
+        P.score[p] = sc >> TAG_BITS;
+        P.endq[p] = eq;
+        P.endr[p] = er;
+    }
+}
+
+__global__ void __launch_bounds__(DP_WARPS * 32)
+sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsigned long long *__restrict__ counter)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int2 *bnd = P.bnd + (size_t)(blockIdx.x * DP_WARPS + warp) * P.bnd_stride;
+    for (;;) {
+        unsigned long long tkt = 0;
+        if (lane == 0) tkt = atomicAdd(counter, 1ull);
+        tkt = __shfl_sync(0xffffffffu, tkt, 0);
+        const int64_t p = start + (int64_t)tkt;
+        if (p >= end) break;
+        if (P.pwild[p]) dp_pair<true>(P, p, lane, bnd);
+        else dp_pair<false>(P, p, lane, bnd);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// traceback -> reversed runs at the tail of the trace region
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int upc(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+__global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, const int64_t end)
+{
+    const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= end) return;
+    const int n = P.pn[p], m = P.pm[p];
+    const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
+    const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
+    const uint32_t *trace = P.trace + (P.ptrace[p] - P.chunk_base);
+    uint32_t *tail = P.trace + (P.ptrace[p + 1] - P.chunk_base);     // runs go to tail[-1], tail[-2], ...
+    const int T = m + 31;
+    int i = P.endq[p], j = P.endr[p];
+    int nr = 0;
+    uint32_t cur_op = 0xffu, cur_len = 0;
+#define PUSH(op, len)                                                                              \
+    do {                                                                                           \
+        if ((len) > 0) {                                                                           \
+            if (cur_op == (uint32_t)(op)) cur_len += (uint32_t)(len);                              \
+            else {                                                                                 \
+                if (cur_len) { ++nr; tail[-nr] = (cur_len << 4) | cur_op; }                        \
+                cur_op = (op); cur_len = (len);                                                    \
+            }                                                                                      \
+        }                                                                                          \
+    } while (0)
+    if (i + 1 == n) PUSH(ISOF_CIGAR_D, m - 1 - j);
+    else PUSH(ISOF_CIGAR_I, n - 1 - i);
+    int where = 3;
+    while (i >= 0 || j >= 0) {
+        if (i < 0) { PUSH(ISOF_CIGAR_D, j + 1); break; }
+        if (j < 0) { PUSH(ISOF_CIGAR_I, i + 1); break; }
+        const int s = i >> 8, l = (i >> 3) & 31, r = i & 7;
+        const uint32_t word = __ldcg(&trace[((size_t)s * T + (j + l)) * 32 + l]);
+        const int nib = (word >> (4 * r)) & 15;
+        if (where == 3) {
+            const int src = nib >> 2;
+            if (src == 3) {
+                PUSH(upc(s1[i]) == upc(s2[j]) ? ISOF_CIGAR_EQ : ISOF_CIGAR_X, 1);
+                --i; --j;
+            } else where = src;
+        } else if (where == 1) {          // E: consumes the reference -> 'D'
+            PUSH(ISOF_CIGAR_D, 1);
+            --j;
+            where = (nib & 1) ? 1 : 3;
+        } else {                          // F: consumes the query -> 'I'
+            PUSH(ISOF_CIGAR_I, 1);
+            --i;
+            where = (nib & 2) ? 2 : 3;
+        }
+    }
+    if (cur_len) { ++nr; tail[-nr] = (cur_len << 4) | cur_op; }
+#undef PUSH
+    P.nruns[p] = nr;
+}
+
+// local exclusive offsets (within the chunk) come from cub; *run_base is the running total
+__global__ void cigar_copy_kernel(const AlignParams P, const int64_t start, const int64_t end,
+                                  const int64_t *__restrict__ local_off, const int64_t *__restrict__ run_base,
+                                  uint32_t *__restrict__ cigar, int64_t cigar_cap, int64_t *__restrict__ cigar_off)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t p = start + warp;
+    if (p >= end) return;
+    const int64_t dst = *run_base + local_off[p - start];
+    const int nr = P.nruns[p];
+    if (lane == 0 && cigar_off) cigar_off[p] = dst;
+    if (!cigar) return;
+    const uint32_t *src = P.trace + (P.ptrace[p + 1] - P.chunk_base) - nr;
+    for (int x = lane; x < nr; x += 32)
+        if (dst + x < cigar_cap) cigar[dst + x] = src[x];
+}
+
+__global__ void advance_base_kernel(int64_t *run_base, const int64_t *local_off, const int32_t *nruns, int64_t start,
+                                    int64_t end, int64_t *cigar_off, int64_t P)
+{
+    if (end > start) *run_base += local_off[end - 1 - start] + nruns[end - 1];
+    if (cigar_off && end == P) cigar_off[P] = *run_base;
+}
+
+__global__ void nruns_to_i64_kernel(const int32_t *nruns, int64_t start, int64_t count, int64_t *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = nruns[start + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused epilogue: integer features of the reference's CIGAR decisions (one thread per pair)
+// ---------------------------------------------------------------------------------------------
+__global__ void sg_features_kernel(const AlignParams P, const int64_t start, const int64_t end, int delta_len,
+                                   int32_t *__restrict__ feat)
+{
+    const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= end) return;
+    const int n = P.pn[p], m = P.pm[p];
+    const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
+    const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
+    const int nr = P.nruns[p];
+    const uint32_t *runs = P.trace + (P.ptrace[p + 1] - P.chunk_base) - nr;
+    int32_t *f = feat + p * ISOF_N_FEATURES;
+    // pass 1: parse_cigar_diversity features (SimplifyGraph.py:175-196)
+    int alen = 0, nonmatch = 0, maxrun = 0;
+    for (int x = 0; x < nr; ++x) {
+        const uint32_t rr = runs[x];
+        const int len = (int)(rr >> 4), op = (int)(rr & 15);
+        alen += len;
+        if (op != ISOF_CIGAR_EQ && op != ISOF_CIGAR_M) { nonmatch += len; maxrun = max(maxrun, len); }
+    }
+    // pass 2: find_first_significant_match forward (IsoformGeneration.py:370-377): window 30, > 0.7
+    const int WIN = 30, NEED = 22;
+    int start_match = -1, end_match = -1;
+    {
+        int qi = 0, ri = 0, col = 0;
+        uint32_t bits = 0;
+        for (int x = 0; x < nr && start_match < 0; ++x) {
+            const uint32_t rr = runs[x];
+            const int len = (int)(rr >> 4), op = (int)(rr & 15);
+            for (int y = 0; y < len; ++y) {
+                int eq;
+                if (op == ISOF_CIGAR_EQ || op == ISOF_CIGAR_X || op == ISOF_CIGAR_M) { eq = s1[qi] == s2[ri]; ++qi; ++ri; }
+                else if (op == ISOF_CIGAR_I) { eq = s1[qi] == '-'; ++qi; }
+                else { eq = s2[ri] == '-'; ++ri; }
+                bits = ((bits << 1) | (uint32_t)eq) & 0x3fffffffu;
+                if (col >= WIN - 1 && __popc(bits) >= NEED) { start_match = col - (WIN - 1); break; }
+                ++col;
+            }
+        }
+    }
+    {
+        int qi = n - 1, ri = m - 1, col = 0;
+        uint32_t bits = 0;
+        for (int x = nr - 1; x >= 0 && end_match < 0; --x) {
+            const uint32_t rr = runs[x];
+            const int len = (int)(rr >> 4), op = (int)(rr & 15);
+            for (int y = 0; y < len; ++y) {
+                int eq;
+                if (op == ISOF_CIGAR_EQ || op == ISOF_CIGAR_X || op == ISOF_CIGAR_M) { eq = s1[qi] == s2[ri]; --qi; --ri; }
+                else if (op == ISOF_CIGAR_I) { eq = s1[qi] == '-'; --qi; }
+                else { eq = s2[ri] == '-'; --ri; }
+                bits = ((bits << 1) | (uint32_t)eq) & 0x3fffffffu;
+                if (col >= WIN - 1 && __popc(bits) >= NEED) { end_match = col - (WIN - 1); break; }
+                ++col;
+            }
+        }
+    }
+    // pass 3: parse_cigar_diversity_isoform_level_new integers (IsoformGeneration.py:251-289)
+    int structural = 0, miss_runs = 0, bm = 0, bn = 0, am = 0, an = 0;
+    if (start_match >= 0 && end_match >= 0) {
+        const int first = start_match, last = alen - end_match;
+        int pos = 0;
+        for (int x = 0; x < nr; ++x) {
+            const uint32_t rr = runs[x];
+            const int len = (int)(rr >> 4), op = (int)(rr & 15);
+            const int st = pos;
+            pos += len;
+            if (op != ISOF_CIGAR_EQ && op != ISOF_CIGAR_M) {
+                if (st < first) { if (op != ISOF_CIGAR_D) bn += len; }
+                else if (st >= last || st + len >= last) { if (op != ISOF_CIGAR_D) an += len; }
+                else if (len > delta_len) structural = 1;
+                else ++miss_runs;
+            } else {
+                if (st < first) bm += len;
+                else if (st >= last) am += len;
+            }
+        }
+    }
+    f[0] = alen; f[1] = nr; f[2] = nonmatch; f[3] = maxrun; f[4] = start_match; f[5] = end_match;
+    f[6] = structural; f[7] = miss_runs; f[8] = bm; f[9] = bn; f[10] = am; f[11] = an;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host-side orchestration (all pointers are device pointers)
+// ---------------------------------------------------------------------------------------------
+int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off, int32_t n_seqs, int64_t n_bases,
+                       const int32_t *d_pa, const int32_t *d_pb, int64_t P, int32_t match, int32_t mismatch,
+                       int32_t gap_open, int32_t gap_ext, int32_t *d_score, int32_t *d_endq, int32_t *d_endr,
+                       uint32_t *d_cigar, int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_features,
+                       int32_t delta_len, int64_t *h_total_runs)
+{
+    cudaStream_t st = ctx->stream;
+    if (h_total_runs) *h_total_runs = 0;
+    if (P < 0 || n_seqs < 0) return isof_fail(ctx, ISOF_ERR_ARG, "negative count");
+    if (match - mismatch > 256 || match - mismatch < 0 || gap_open < 0 || gap_ext < 0 ||
+        std::abs(match) > 1024 || std::abs(mismatch) > 1024 || gap_open > 4096 || gap_ext > 4096)
+        return isof_fail(ctx, ISOF_ERR_RANGE, "scoring parameters outside the supported range");
+    if (P == 0) {
+        if (d_cigar_off) CUDA_TRY(ctx, cudaMemsetAsync(d_cigar_off, 0, sizeof(int64_t), st));
+        return ISOF_OK;
+    }
+    // ---- scratch
+    TRY(dev_reserve(ctx, ctx->b_codes, (size_t)n_bases + 16));
+    TRY(dev_reserve(ctx, ctx->b_seqflags, (size_t)n_seqs + 16));
+    TRY(dev_reserve(ctx, ctx->b_pn, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_pm, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_status, (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_paoff, sizeof(int64_t) * (size_t)(P + 1)));      // trace words per pair
+    TRY(dev_reserve(ctx, ctx->b_ptrace, sizeof(int64_t) * (size_t)(P + 1)));     // exclusive scan
+    TRY(dev_reserve(ctx, ctx->b_nruns, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_runoff, sizeof(int64_t) * (size_t)(P + 1)));
+    TRY(dev_reserve(ctx, ctx->b_pboff, sizeof(int64_t) * (size_t)(P + 1)));      // nruns as int64
+    TRY(dev_reserve(ctx, ctx->b_misc, 64));
+    uint8_t *codes = (uint8_t *)ctx->b_codes.p, *flags = (uint8_t *)ctx->b_seqflags.p;
+    int32_t *pn = (int32_t *)ctx->b_pn.p, *pm = (int32_t *)ctx->b_pm.p, *nruns = (int32_t *)ctx->b_nruns.p;
+    uint8_t *pwild = (uint8_t *)ctx->b_status.p;
+    int64_t *words = (int64_t *)ctx->b_paoff.p, *ptrace = (int64_t *)ctx->b_ptrace.p;
+    int64_t *runoff = (int64_t *)ctx->b_runoff.p, *nruns64 = (int64_t *)ctx->b_pboff.p;
+    unsigned long long *misc = (unsigned long long *)ctx->b_misc.p;   // [0] err [1] max m [2] cells [3] padded [4] run_base
+    CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 64, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
+
+    {
+        LaunchTimer t(ctx, SLOT_OTHER);
+        int blocks = std::min((n_seqs * 32 + 255) / 256, ctx->sm_count * 8);
+        encode_kernel<<<std::max(blocks, 1), 256, 0, st>>>(d_cat, d_off, n_seqs, codes, flags);
+    }
+    {
+        LaunchTimer t(ctx, SLOT_OTHER);
+        plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
+                                                                      words, misc);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, words, ptrace, P + 1, st);
+    TRY(dev_reserve(ctx, ctx->b_scan_tmp, tmp_bytes));
+    {
+        LaunchTimer t(ctx, SLOT_OTHER);
+        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, words, ptrace, P + 1, st));
+    }
+    // ---- read back the plan summary
+    unsigned long long *pin = (unsigned long long *)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(pin, misc, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(pin + 4, ptrace + P, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (pin[0] & 1) return isof_fail(ctx, ISOF_ERR_ARG, "pair index outside the sequence pool");
+    if (pin[0] & 2) return isof_fail(ctx, ISOF_ERR_ARG, "empty sequence in a pair (parasail rejects it too)");
+    const int max_m = (int)pin[1];
+    const int64_t total_words = (int64_t)pin[4];
+    ctx->prof.dp_cells += (int64_t)pin[2];
+    ctx->prof.dp_cells_padded += (int64_t)pin[3];
+    ctx->prof.trace_bytes += (total_words - (int64_t)TRACE_SLACK * P) * 4;
+    if ((int64_t)max_m * 16 * (std::abs(match) + std::abs(mismatch) + gap_ext) + 16LL * gap_open > (1LL << 28))
+        return isof_fail(ctx, ISOF_ERR_RANGE, "sequence too long for the 32-bit tagged score range");
+
+    // ---- trace budget / chunks
+    if (ctx->trace_budget == 0) {
+        size_t fr = 0, tot = 0;
+        CUDA_TRY(ctx, cudaMemGetInfo(&fr, &tot));
+        ctx->trace_budget = (size_t)(0.40 * (double)(fr + ctx->b_trace.cap));
+        if (ctx->trace_budget < (64u << 20)) ctx->trace_budget = 64u << 20;
+    }
+    int64_t budget_words = (int64_t)(ctx->trace_budget / 4);
+    if (budget_words > total_words) budget_words = total_words;
+    if (budget_words < 1) budget_words = 1;
+    const int n_chunks = (int)(total_words / budget_words) + 1;
+    TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2));
+    int64_t *chunk_start_d = (int64_t *)ctx->b_counters.p;
+    unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);
+    CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2), st));
+    {
+        LaunchTimer t(ctx, SLOT_OTHER);
+        chunk_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(ptrace, P, budget_words, n_chunks, chunk_start_d);
+    }
+    std::vector<int64_t> chunk_start((size_t)n_chunks + 1), chunk_base((size_t)n_chunks + 1);
+    CUDA_TRY(ctx, cudaMemcpyAsync(chunk_start.data(), chunk_start_d, sizeof(int64_t) * (size_t)(n_chunks + 1),
+                                  cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    // the largest chunk decides the scratch size: offsets of chunk starts are needed on the host
+    std::vector<int64_t> start_off((size_t)n_chunks + 1);
+    for (int c = 0; c <= n_chunks; ++c) {
+        // ptrace[chunk_start[c]] -- fetch individually (n_chunks is small)
+        CUDA_TRY(ctx, cudaMemcpyAsync(&start_off[c], ptrace + chunk_start[c], 8, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int64_t max_chunk_words = 0;
+    for (int c = 0; c < n_chunks; ++c) max_chunk_words = std::max(max_chunk_words, start_off[c + 1] - start_off[c]);
+    if ((size_t)max_chunk_words * 4 > ctx->b_trace.cap) {
+        int rc = dev_reserve(ctx, ctx->b_trace, (size_t)max_chunk_words * 4);
+        if (rc != ISOF_OK)
+            return isof_fail(ctx, ISOF_ERR_NOMEM, "trace scratch of %lld bytes does not fit (largest pair/chunk)",
+                             (long long)max_chunk_words * 4);
+    }
+    const int occ_blocks = ctx->sm_count * 4;           // DP_WARPS*32 threads each
+    const int64_t bnd_stride = ((int64_t)max_m + 64) & ~63LL;
+    TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
+
+    AlignParams A;
+    A.cat = d_cat; A.codes = codes; A.seq_off = d_off; A.pa = d_pa; A.pb = d_pb; A.pn = pn; A.pm = pm; A.pwild = pwild;
+    A.ptrace = ptrace; A.trace = (uint32_t *)ctx->b_trace.p; A.bnd = (int2 *)ctx->b_bnd.p; A.bnd_stride = bnd_stride;
+    A.score = d_score; A.endq = d_endq; A.endr = d_endr; A.nruns = nruns;
+    const int S = 1 << TAG_BITS;
+    A.c_eo = -gap_open * S + 4;
+    A.c_ee = -gap_ext * S + 5;
+    A.c_fo = -gap_open * S + 8;
+    A.c_fe = -gap_ext * S + 10;
+    A.c_sm = match * S + 12 - (3 << CODE_SHIFT);
+    A.c_sx = mismatch * S + 12;
+    int64_t *run_base = (int64_t *)(misc + 4);
+    CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
+
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t ps = chunk_start[c], pe = chunk_start[c + 1];
+        if (pe <= ps) continue;
+        const int64_t cnt = pe - ps;
+        A.chunk_base = start_off[c];
+        {
+            LaunchTimer t(ctx, SLOT_DP);
+            int blocks = (int)std::min<int64_t>((cnt + DP_WARPS - 1) / DP_WARPS, occ_blocks);
+            sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, st>>>(A, ps, pe, counters + c);
+        }
+        {
+            LaunchTimer t(ctx, SLOT_TB);
+            sg_traceback_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, st>>>(A, ps, pe);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        if (d_features) {
+            LaunchTimer t(ctx, SLOT_TB);
+            sg_features_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, st>>>(A, ps, pe, delta_len, d_features);
+        }
+        {
+            LaunchTimer t(ctx, SLOT_TB);
+            nruns_to_i64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(nruns, ps, cnt, nruns64);
+        }
+        size_t tb2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, nruns64, runoff, cnt, st);
+        TRY(dev_reserve(ctx, ctx->b_scan_tmp, tb2));
+        {
+            LaunchTimer t(ctx, SLOT_TB);
+            CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tb2, nruns64, runoff, cnt, st));
+        }
+        {
+            LaunchTimer t(ctx, SLOT_TB);
+            cigar_copy_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, st>>>(A, ps, pe, runoff, run_base, d_cigar,
+                                                                                 cigar_cap, d_cigar_off);
+        }
+        {
+            LaunchTimer t(ctx, SLOT_TB);
+            advance_base_kernel<<<1, 1, 0, st>>>(run_base, runoff, nruns, ps, pe, d_cigar_off, P);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    int64_t *pin64 = (int64_t *)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(pin64, run_base, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (h_total_runs) *h_total_runs = pin64[0];
+    if (d_cigar && pin64[0] > cigar_cap)
+        return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap,
+                         (long long)pin64[0]);
+    return ISOF_OK;
+}

@@ -1,0 +1,236 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs, and against the committed golden fixtures."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import lcg, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from isonform_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _rand_dna(rng, n, alphabet="ACGT"):
+    return "".join(alphabet[int(x)] for x in rng.integers(0, len(alphabet), size=n))
+
+
+# ------------------------------------------------------------------------------- minimizers
+def test_minimizers_golden(ctx):
+    from isonform_b200 import hotpath
+    g = load_golden("minimizers.json")
+    by_kw = {}
+    for c in g["cases"]:
+        by_kw.setdefault((c["k"], c["w"]), []).append(c)
+    for (k, w), cases in by_kw.items():
+        got = hotpath.minimizer_positions_batch([c["seq"] for c in cases], k, w, ctx)
+        for c, pos in zip(cases, got):
+            assert pos.tolist() == c["pos"], c["name"]
+
+
+def test_minimizers_kat3_digest(ctx):
+    from isonform_b200 import hotpath
+    g = load_golden("minimizers.json")["kat3"]
+    pos = hotpath.minimizer_positions_batch([lcg(g["n"], g["seed"])], g["k"], g["w"], ctx)[0].tolist()
+    assert len(pos) == g["count"]
+    assert hashlib.sha256(",".join(map(str, pos)).encode()).hexdigest()[:16] == g["sha256_16"]
+
+
+def test_minimizers_vs_oracle_ragged(ctx):
+    from isonform_b200 import hotpath
+    rng = np.random.default_rng(17)
+    seqs = []
+    for i in range(300):
+        n = int(rng.integers(0, 1500)) if i % 7 else int(rng.integers(0, 60))
+        alpha = ["ACGT", "AC", "ACGTN", "A"][i % 4] if i % 5 == 0 else "ACGT"
+        seqs.append(_rand_dna(rng, n, alpha))
+    seqs += ["", "A", "ACGT" * 300, ("ACGTTGCA" * 40)[:255], ("ACGTTGCA" * 40)[:256], ("ACGTTGCA" * 40)[:257]]
+    for (k, w) in [(20, 31), (9, 20), (13, 13), (31, 100)]:
+        got = hotpath.minimizer_positions_batch(seqs, k, w, ctx)
+        for s, pos in zip(seqs, got):
+            assert pos.tolist() == oracle.minimizers(s, k, w).tolist(), (k, w, len(s))
+
+
+def test_minimizers_dict_interface(ctx):
+    from isonform_b200 import hotpath
+    s = lcg(200, 42)
+    reads = {1: ("a", s, "I" * 200), 2: ("b", s[:90] + s[95:], "I" * 195)}
+    M = hotpath.get_minimizers_and_positions(reads, 31, 20, "lex", ctx)
+    assert [p for _, p in M[1]] == [9, 13, 16, 19, 29, 40, 43, 54, 60, 68, 75, 76, 86, 94, 100, 108, 118, 121, 131,
+                                    139, 142, 152, 157, 158, 170, 171]
+    assert all(kmer == reads[r][1][p:p + 20] for r in M for kmer, p in M[r])
+    assert M == oracle.get_minimizers_and_positions(reads, 31, 20, "lex")
+    assert hotpath.get_kmer_minimizers(s, 9, 20, ctx) == oracle.get_kmer_minimizers(s, 9, 20)
+
+
+def test_minimizers_empty_batch(ctx):
+    pos, off = ctx.minimizers_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64), 20, 31)
+    assert len(pos) == 0 and off.tolist() == [0]
+
+
+# ------------------------------------------------------------------------------- alignment
+def _check_pairs(ctx, seqs, pa, pb, params):
+    from isonform_b200 import hotpath
+    res = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
+    for p in range(len(pa)):
+        sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params)
+        got = res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]]
+        assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er), (p, len(seqs[pa[p]]), len(seqs[pb[p]]))
+        assert got.tolist() == runs.tolist(), (p, oracle.cigar_runs_to_string(got), oracle.cigar_runs_to_string(runs))
+
+
+def test_align_golden_decisions(ctx):
+    from isonform_b200 import hotpath
+    g = load_golden("decisions.json")
+    for rec in g["pairs"]:
+        a1, a2, cig, tup, score = hotpath.parasail_alignment(rec["s1"], rec["s2"], 2, -8, 12, 1, ctx)
+        assert (cig, score) == (rec["bubble"]["cigar"], rec["bubble"]["score"]), rec["name"]
+        assert hashlib.sha256(a1.encode()).hexdigest()[:12] == rec["bubble"]["a1_sha"]
+        assert hashlib.sha256(a2.encode()).hexdigest()[:12] == rec["bubble"]["a2_sha"]
+        assert hotpath.parse_cigar_diversity(tup, 0.20, 5) == rec["bubble"]["pop_d5"]
+        a1, a2, cig, tup, score = hotpath.parasail_alignment(rec["s1"], rec["s2"], 2, -2, 12, 1, ctx)
+        assert (cig, score) == (rec["iso"]["cigar"], rec["iso"]["score"]), rec["name"]
+        assert hotpath.find_first_significant_match(a1, a2, 30, 0.7) == rec["iso"]["start_match"]
+        assert hotpath.find_first_significant_match(a1[::-1], a2[::-1], 30, 0.7) == rec["iso"]["end_match"]
+        for dl, d in ((5, 0.15), (10, 0.15), (5, 0.1)):
+            assert hotpath.align_to_merge(rec["s1"], rec["s2"], d, dl, 30, 50, ctx) == rec["iso"]["merge_dl%d_d%s" % (dl, d)], rec["name"]
+
+
+def test_align_golden_gates(ctx):
+    from isonform_b200 import hotpath
+    g = load_golden("decisions.json")
+    for gt in g["gates"]:
+        pop, aligned = hotpath.bubble_decisions([gt["s1"], gt["s2"]], [0], [1], gt["delta_len"], ctx)
+        assert (bool(pop[0]), bool(aligned[0])) == (gt["pop"], gt["aligned"])
+
+
+def test_align_random_shapes_vs_oracle(ctx):
+    rng = np.random.default_rng(23)
+    seqs, pa, pb = [], [], []
+    shapes = [(1, 1), (1, 40), (40, 1), (7, 9), (8, 8), (31, 33), (255, 256), (256, 255), (257, 300), (300, 257),
+              (511, 513), (513, 40), (40, 513), (1000, 1100), (64, 2000), (2000, 64)]
+    for (n, m) in shapes:
+        for rep in range(3):
+            x = _rand_dna(rng, max(n, m))
+            if rep == 0:
+                a, b = _rand_dna(rng, n), _rand_dna(rng, m)
+            else:
+                from isonform_b200 import synth
+                y = synth.mutate(rng, x, 0.05 * rep)
+                a, b = x[:n], (y + _rand_dna(rng, m))[:m]
+            seqs += [a, b]
+            pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    for params in [(2, -8, 12, 1), (2, -2, 12, 1), (1, -1, 2, 1), (3, -4, 5, 2), (2, -2, 1, 1)]:
+        _check_pairs(ctx, seqs, pa, pb, params)
+
+
+def test_align_tie_heavy_vs_oracle(ctx):
+    """Low-complexity sequences and small gap costs maximise ties in every max of the recurrence."""
+    rng = np.random.default_rng(29)
+    seqs, pa, pb = [], [], []
+    for i in range(150):
+        alpha = ["AC", "A", "ACG", "AAC"][i % 4]
+        seqs += [_rand_dna(rng, int(rng.integers(1, 70)), alpha), _rand_dna(rng, int(rng.integers(1, 70)), alpha)]
+        pa.append(2 * i); pb.append(2 * i + 1)
+    for params in [(2, -2, 2, 1), (1, -1, 1, 1), (2, -2, 12, 1), (2, -8, 12, 1), (1, -3, 2, 2), (2, -2, 0, 0)]:
+        _check_pairs(ctx, seqs, pa, pb, params)
+
+
+def test_align_wildcards_and_case(ctx):
+    rng = np.random.default_rng(31)
+    seqs, pa, pb = [], [], []
+    for i in range(40):
+        a = _rand_dna(rng, int(rng.integers(5, 300)), "ACGTN")
+        b = _rand_dna(rng, int(rng.integers(5, 300)), "ACGTNacgtX")
+        seqs += [a, b]; pa.append(2 * i); pb.append(2 * i + 1)
+    seqs += ["X" * 40, lcg(45, 42)]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    _check_pairs(ctx, seqs, pa, pb, (2, -8, 12, 1))
+    _check_pairs(ctx, seqs, pa, pb, (2, -2, 12, 1))
+
+
+def test_align_all_pairs_pool_and_chunking(ctx):
+    """An all-pairs job over a small pool with a tiny trace budget: many chunks, same answers."""
+    from isonform_b200 import synth
+    rng = np.random.default_rng(37)
+    base = _rand_dna(rng, 600)
+    seqs = [synth.mutate(rng, base, 0.04) for _ in range(14)]
+    ia, ib = np.triu_indices(len(seqs), 1)
+    ctx.set_trace_budget(2 << 20)
+    try:
+        _check_pairs(ctx, seqs, ia.tolist(), ib.tolist(), (2, -2, 12, 1))
+    finally:
+        ctx.set_trace_budget(0)
+
+
+def test_align_features_vs_oracle(ctx):
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(41)
+    seqs, pa, pb = [], [], []
+    for i in range(60):
+        ln = int(rng.integers(20, 900))
+        x = _rand_dna(rng, ln)
+        y = synth.mutate(rng, x, [0.0, 0.01, 0.05, 0.12][i % 4])
+        if i % 3 == 0 and ln > 100:
+            c = ln // 2; y = y[:c] + y[c + int(rng.integers(3, 30)):]
+        if i % 4 == 1:
+            y = _rand_dna(rng, int(rng.integers(0, 70))) + y
+        if i % 5 == 2:
+            x = x + _rand_dna(rng, int(rng.integers(0, 70)))
+        seqs += [x, y or "A"]; pa.append(2 * i); pb.append(2 * i + 1)
+    for dl in (5, 10):
+        res = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx, want_cigar=True, features_delta_len=dl)
+        merge = hotpath._merge_from_features(res["features"], 0.15, dl, 30, 50)
+        for p in range(len(pa)):
+            s1, s2 = seqs[pa[p]], seqs[pb[p]]
+            a1, a2, cig, tup, score = oracle.parasail_alignment(s1, s2, 2, -2, 12, 1)
+            f = res["features"][p]
+            assert oracle.cigar_runs_to_string(res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]]) == cig
+            sm = oracle.find_first_significant_match(a1, a2, 30, 0.7)
+            em = oracle.find_first_significant_match(a1[::-1], a2[::-1], 30, 0.7)
+            alen = sum(l for l, _ in tup)
+            assert (int(f[0]), int(f[1]), int(f[4]), int(f[5])) == (alen, len(tup), sm, em)
+            assert int(f[2]) == sum(l for l, o in tup if o != "=") and int(f[3]) == max([l for l, o in tup if o != "="] + [0])
+            if sm >= 0 and em >= 0:
+                brk, miss_runs, bm, bn, am, an, _ = oracle.isoform_features(tup, dl, sm, alen - em)
+                assert [int(v) for v in f[6:12]] == [brk, miss_runs, bm, bn, am, an]
+            assert bool(merge[p]) == oracle.align_to_merge(s1, s2, 0.15, dl, 30, 50)
+        pop = hotpath._pop_from_features(res["features"], 0.20, dl)
+        for p in range(len(pa)):
+            tup = oracle.cigar_runs_to_tuples(res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]])
+            assert bool(pop[p]) == oracle.parse_cigar_diversity(tup, 0.20, dl)
+
+
+def test_align_batch_form_and_errors(ctx):
+    from isonform_b200 import _lib, hotpath
+    s = lcg(120, 42)
+    res = ctx.sg_align_batch([s, s[30:90], s], [s, s, s[30:90]])
+    cigs = [oracle.cigar_runs_to_string(res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]]) for p in range(3)]
+    assert cigs == ["120=", "30D60=30D", "30I60=30I"] and res["score"].tolist() == [240, 120, 120]
+    with pytest.raises(ValueError):
+        hotpath.parasail_alignment("", "ACGT", ctx=ctx)
+    with pytest.raises(_lib.IsofError):
+        hotpath.align_pairs(["ACGT", ""], [0], [1], ctx=ctx)
+    with pytest.raises(_lib.IsofError):
+        hotpath.align_pairs(["ACGT", "AC"], [0], [5], ctx=ctx)
+
+
+def test_align_score_only_and_capacity_retry(ctx):
+    from isonform_b200 import hotpath
+    rng = np.random.default_rng(43)
+    seqs = [_rand_dna(rng, 50) for _ in range(8)]
+    ia, ib = np.triu_indices(8, 1)
+    full = hotpath.align_pairs(seqs, ia, ib, ctx=ctx)
+    score_only = hotpath.align_pairs(seqs, ia, ib, ctx=ctx, want_cigar=False)
+    assert score_only["cigar"] is None and score_only["score"].tolist() == full["score"].tolist()
+    assert score_only["cigar_off"].tolist() == full["cigar_off"].tolist()
+    cat, off = hotpath.pack_sequences(seqs)
+    small = ctx.sg_align_pairs(cat, off, ia, ib, cigar_cap=3)      # forces ISOF_ERR_CAPACITY + retry
+    assert small["cigar"].tolist() == full["cigar"].tolist()
