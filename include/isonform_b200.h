@@ -80,6 +80,11 @@ typedef struct {
 ISOF_API int isof_profile_enable(isof_ctx *ctx, int on);
 ISOF_API int isof_profile_reset(isof_ctx *ctx);
 ISOF_API int isof_profile_get(isof_ctx *ctx, isof_profile *out);
+/* Measures the INT32 ALU-pipe peak of this GPU with a register-only micro-kernel of independent
+ * VIADDMNMX (DPX add+max) chains, the instruction the DP kernel is built from: lane-operations per
+ * second.  Denominator of the integer roofline reported by bench.py (there is no published or
+ * driver-measured INT32 figure).  Takes ~20 ms. */
+ISOF_API int isof_int32_peak(isof_ctx *ctx, double *lane_ops_per_s);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (a) minimizers                                                                             */

@@ -38,7 +38,7 @@ class Profile(C.Structure):
 
 
 EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget",
-           "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_minimizers_batch",
+           "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs"]
 
@@ -65,6 +65,7 @@ def load():
     L.isof_profile_enable.argtypes = [vp, C.c_int]
     L.isof_profile_reset.argtypes = [vp]
     L.isof_profile_get.argtypes = [vp, C.POINTER(Profile)]
+    L.isof_int32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.isof_minimizers_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_minimizers_batch_dev.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_sg_align_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp]
@@ -144,6 +145,12 @@ class Context:
         self._check(self._L.isof_profile_get(self._h, C.byref(p)))
         return p.as_dict()
 
+    def int32_peak(self):
+        """Measured INT32 ALU-pipe peak (lane-ops/s) of this GPU -- the integer roofline denominator."""
+        v = C.c_double(0)
+        self._check(self._L.isof_int32_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     # ------------------------------------------------------------------ (a) minimizers
     def minimizers_batch(self, cat, off, k, w_size):
         """(positions int32, offsets int64[R+1]) for concatenated reads."""
@@ -187,8 +194,11 @@ class Context:
         if cigar_cap is None:
             if want_cigar and P:
                 lens = np.diff(off)
+                ns = max(len(lens), 1)
                 # a typical alignment of similar sequences has far fewer runs than n+m; start small
-                cap = int(min((lens[pa] + lens[pb] + 2).sum(), max(64 * P, 1 << 16)))
+                # (out-of-range indices are reported by the library, not here)
+                worst = int((lens[np.clip(pa, 0, ns - 1)] + lens[np.clip(pb, 0, ns - 1)] + 2).sum()) if len(lens) else 1
+                cap = int(min(worst, max(64 * P, 1 << 16)))
             else:
                 cap = 0
         else:

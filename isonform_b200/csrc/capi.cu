@@ -39,9 +39,52 @@ int d2h(isof_ctx *ctx, void *dst, const void *src, size_t bytes)
     return ISOF_OK;
 }
 
+__global__ void __launch_bounds__(256) alu_peak_kernel(int *out, int iters, int c1, int c2)
+{
+    int a[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a[u] = threadIdx.x * 17 + u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a[u] = __viaddmax_s32(a[u], c1, c2 + u);
+    }
+    int s = 0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s ^= a[u];
+    if (s == 0x7fffffff) out[0] = s;          // keeps the chains alive, practically never taken
+}
+
 }  // namespace
 
 extern "C" {
+
+int isof_int32_peak(isof_ctx *ctx, double *lane_ops_per_s)
+{
+    if (!ctx || !lane_ops_per_s) return ISOF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(dev_reserve(ctx, ctx->b_misc, 64));
+    const int blocks = ctx->sm_count * 8, iters = 4096;
+    cudaEvent_t a, b;
+    CUDA_TRY(ctx, cudaEventCreate(&a));
+    CUDA_TRY(ctx, cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(ctx, cudaEventRecord(a, ctx->stream));
+        alu_peak_kernel<<<blocks, 256, 0, ctx->stream>>>((int *)ctx->b_misc.p, iters, -3, 5);
+        CUDA_TRY(ctx, cudaEventRecord(b, ctx->stream));
+        CUDA_TRY(ctx, cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double ops = (double)blocks * 256.0 * iters * 16.0 / (ms * 1e-3);
+        if (rep > 0 && ops > best) best = ops;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    ctx->prof.launches += 4;
+    *lane_ops_per_s = best;
+    return ISOF_OK;
+}
+
 
 int isof_version(void) { return ISOF_VERSION; }
 
