@@ -109,6 +109,38 @@ ISOF_API int isof_minimizers_batch_dev(isof_ctx *ctx, const uint8_t *bases, cons
                               int64_t *out_off, int64_t *n_out);
 
 /* ------------------------------------------------------------------------------------------ */
+/* (c) minimizer-pair database + span search                                                  */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * Replaces, for one batch, minimizers_comb_iterator (main:215-224),
+ * get_minimizer_combinations_database (main:174-212) and find_most_supported_span (main:308-338).
+ * Input: the reads and their minimizers (min_pos/min_off exactly as isof_minimizers_batch returns).
+ * A record g is one (anchor, partner) pair of one read with x_low < p2-p1 <= x_high; records come in
+ * the reference's insertion order (reads in batch order, anchors left to right, partners farthest
+ * first).  Outputs (arrays of capacity rec_cap; bucket_off needs rec_cap+1):
+ *   rec_read (0-based read index; the reference's r_id is rec_read+1), rec_p1, rec_p2
+ *   rec_bucket      bucket (= distinct (kmer1,kmer2) pair) of the record
+ *   rec_count       find_most_supported_span's instance count for the record: 1 + number of
+ *                   OTHER-read records of the bucket with |span difference| < delta_len, or 0 when
+ *                   the reference emits no interval (bucket < 3 records, polyA pair, > 3*n_reads)
+ *   sorted_rec      record indices grouped by bucket, reference insertion order inside a bucket
+ *   bucket_off      n_buckets+1 offsets into sorted_rec;  bucket_dropped: 1 if the reference deletes
+ *                   the bucket (polyA/polyA pair, over-abundant)
+ * On ISOF_ERR_CAPACITY *n_rec holds the needed rec_cap.
+ */
+ISOF_API int isof_spans_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                              const int32_t *min_pos, const int64_t *min_off, int32_t k, int32_t x_low, int32_t x_high,
+                              int32_t delta_len, int64_t rec_cap, int32_t *rec_read, int32_t *rec_p1, int32_t *rec_p2,
+                              int32_t *rec_count, int32_t *rec_bucket, int32_t *sorted_rec, int32_t *bucket_off,
+                              uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets);
+/* Device-pointer variant (n_rec / n_buckets are HOST pointers; two scalar read-backs). */
+ISOF_API int isof_spans_batch_dev(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                                  const int32_t *min_pos, const int64_t *min_off, int64_t n_min, int32_t k, int32_t x_low,
+                                  int32_t x_high, int32_t delta_len, int64_t rec_cap, int32_t *rec_read, int32_t *rec_p1,
+                                  int32_t *rec_p2, int32_t *rec_count, int32_t *rec_bucket, int32_t *sorted_rec,
+                                  int32_t *bucket_off, uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets);
+
+/* ------------------------------------------------------------------------------------------ */
 /* (b) semi-global affine alignment with traceback                                            */
 /* ------------------------------------------------------------------------------------------ */
 /*

@@ -39,7 +39,7 @@ class Profile(C.Structure):
 
 EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
-           "isof_minimizers_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
+           "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs"]
 
 _lib = None
@@ -68,6 +68,10 @@ def load():
     L.isof_int32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.isof_minimizers_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_minimizers_batch_dev.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, i64, vp, C.POINTER(i64)]
+    L.isof_spans_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   C.POINTER(i64), C.POINTER(i64)]
+    L.isof_spans_batch_dev.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       C.POINTER(i64), C.POINTER(i64)]
     L.isof_sg_align_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp]
     L.isof_sg_align_pairs_dev.argtypes = [vp, vp, vp, i32, i64, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64,
                                           vp, vp, i32, C.POINTER(i64)]
@@ -176,6 +180,46 @@ class Context:
         self._check(self._L.isof_minimizers_batch_dev(self._h, d_bases, d_off, n_reads, n_bases, k, w_size, d_out_pos,
                                                       out_cap, d_out_off, C.byref(n_out)))
         return int(n_out.value)
+
+    # ------------------------------------------------------------------ (c) pair database + span search
+    def spans_batch(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len):
+        """dict of numpy arrays, see isof_spans_batch in include/isonform_b200.h."""
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        min_pos = np.ascontiguousarray(min_pos, dtype=np.int32)
+        min_off = np.ascontiguousarray(min_off, dtype=np.int64)
+        R = len(off) - 1
+        cap = max(8 * len(min_pos) + 64, 64)
+        n_rec, n_b = C.c_int64(0), C.c_int64(0)
+        while True:
+            a = {name: np.empty(cap, np.int32) for name in ("rec_read", "rec_p1", "rec_p2", "rec_count", "rec_bucket",
+                                                            "sorted_rec")}
+            boff = np.zeros(cap + 1, np.int32)
+            bdrop = np.zeros(cap, np.uint8)
+            rc = self._L.isof_spans_batch(self._h, cat.ctypes.data, off.ctypes.data, R, min_pos.ctypes.data,
+                                          min_off.ctypes.data, k, x_low, x_high, delta_len, cap, a["rec_read"].ctypes.data,
+                                          a["rec_p1"].ctypes.data, a["rec_p2"].ctypes.data, a["rec_count"].ctypes.data,
+                                          a["rec_bucket"].ctypes.data, a["sorted_rec"].ctypes.data, boff.ctypes.data,
+                                          bdrop.ctypes.data, C.byref(n_rec), C.byref(n_b))
+            if rc == ERR_CAPACITY:
+                cap = int(n_rec.value)
+                continue
+            self._check(rc)
+            break
+        G, B = int(n_rec.value), int(n_b.value)
+        out = {k_: v[:G] for k_, v in a.items()}
+        out["bucket_off"] = boff[:B + 1]
+        out["bucket_dropped"] = bdrop[:B]
+        return out
+
+    def spans_batch_dev(self, d_bases, d_off, n_reads, d_min_pos, d_min_off, n_min, k, x_low, x_high, delta_len, rec_cap,
+                        d_rec_read, d_rec_p1, d_rec_p2, d_rec_count, d_rec_bucket, d_sorted_rec, d_bucket_off, d_bucket_dropped):
+        n_rec, n_b = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.isof_spans_batch_dev(self._h, d_bases, d_off, n_reads, d_min_pos, d_min_off, n_min, k, x_low,
+                                                 x_high, delta_len, rec_cap, d_rec_read, d_rec_p1, d_rec_p2, d_rec_count,
+                                                 d_rec_bucket, d_sorted_rec, d_bucket_off, d_bucket_dropped, C.byref(n_rec),
+                                                 C.byref(n_b)))
+        return int(n_rec.value), int(n_b.value)
 
     # ------------------------------------------------------------------ (b) alignment
     def sg_align_pairs(self, cat, off, pair_a, pair_b, match=2, mismatch=-2, gap_open=12, gap_ext=1, want_cigar=True,

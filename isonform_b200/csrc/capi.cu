@@ -119,12 +119,7 @@ int isof_destroy(isof_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     flush_timers(ctx);
-    DevBuf *bufs[] = {&ctx->b_codes, &ctx->b_seqflags, &ctx->b_pn, &ctx->b_pm, &ctx->b_paoff, &ctx->b_pboff, &ctx->b_ptrace,
-                      &ctx->b_scan_tmp, &ctx->b_bnd, &ctx->b_trace, &ctx->b_nruns, &ctx->b_counters, &ctx->b_misc,
-                      &ctx->b_runoff, &ctx->b_status, &ctx->b_h_bases, &ctx->b_h_off, &ctx->b_h_pa, &ctx->b_h_pb,
-                      &ctx->b_h_score, &ctx->b_h_endq, &ctx->b_h_endr, &ctx->b_h_cig, &ctx->b_h_cigoff, &ctx->b_h_feat,
-                      &ctx->b_m_hash, &ctx->b_m_tmp, &ctx->b_m_cnt, &ctx->b_m_off};
-    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : ctx->all_bufs()) if (b->p) cudaFree(b->p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -203,6 +198,60 @@ int isof_minimizers_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *re
     if (rc == ISOF_OK) TRY(d2h(ctx, out_pos, ctx->b_h_cig.p, sizeof(int32_t) * (size_t)*n_out));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------ (c)
+int isof_spans_batch_dev(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads, const int32_t *min_pos,
+                         const int64_t *min_off, int64_t n_min, int32_t k, int32_t x_low, int32_t x_high, int32_t delta_len,
+                         int64_t rec_cap, int32_t *rec_read, int32_t *rec_p1, int32_t *rec_p2, int32_t *rec_count,
+                         int32_t *rec_bucket, int32_t *sorted_rec, int32_t *bucket_off, uint8_t *bucket_dropped,
+                         int64_t *n_rec, int64_t *n_buckets)
+{
+    if (!ctx || !n_rec || !n_buckets) return ISOF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return isof_spans_core(ctx, bases, read_off, n_reads, min_pos, min_off, n_min, k, x_low, x_high, delta_len, rec_cap, rec_read,
+                           rec_p1, rec_p2, rec_count, rec_bucket, sorted_rec, bucket_off, bucket_dropped, n_rec, n_buckets);
+}
+
+int isof_spans_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads, const int32_t *min_pos,
+                     const int64_t *min_off, int32_t k, int32_t x_low, int32_t x_high, int32_t delta_len, int64_t rec_cap,
+                     int32_t *rec_read, int32_t *rec_p1, int32_t *rec_p2, int32_t *rec_count, int32_t *rec_bucket,
+                     int32_t *sorted_rec, int32_t *bucket_off, uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets)
+{
+    if (!ctx || !read_off || !min_off || !n_rec || !n_buckets || n_reads < 0) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_bases = read_off[n_reads], M = min_off[n_reads];
+    TRY(h2d(ctx, ctx->b_h_bases, bases, (size_t)n_bases));
+    TRY(h2d(ctx, ctx->b_h_off, read_off, sizeof(int64_t) * (size_t)(n_reads + 1)));
+    TRY(h2d(ctx, ctx->b_sh_minpos, min_pos, sizeof(int32_t) * (size_t)M));
+    TRY(h2d(ctx, ctx->b_sh_minoff, min_off, sizeof(int64_t) * (size_t)(n_reads + 1)));
+    const size_t cap = (size_t)std::max<int64_t>(rec_cap, 1);
+    TRY(dev_reserve(ctx, ctx->b_sh_rread, 4 * cap));
+    TRY(dev_reserve(ctx, ctx->b_sh_rp1, 4 * cap));
+    TRY(dev_reserve(ctx, ctx->b_sh_rp2, 4 * cap));
+    TRY(dev_reserve(ctx, ctx->b_sh_rcount, 4 * cap));
+    TRY(dev_reserve(ctx, ctx->b_sh_rbucket, 4 * cap));
+    TRY(dev_reserve(ctx, ctx->b_sh_sorted, 4 * cap));
+    TRY(dev_reserve(ctx, ctx->b_sh_boff, 4 * (cap + 1)));
+    TRY(dev_reserve(ctx, ctx->b_sh_bdrop, cap));
+    int rc = isof_spans_core(ctx, (const uint8_t *)ctx->b_h_bases.p, (const int64_t *)ctx->b_h_off.p, n_reads,
+                             (const int32_t *)ctx->b_sh_minpos.p, (const int64_t *)ctx->b_sh_minoff.p, M, k, x_low, x_high,
+                             delta_len, rec_cap, (int32_t *)ctx->b_sh_rread.p, (int32_t *)ctx->b_sh_rp1.p,
+                             (int32_t *)ctx->b_sh_rp2.p, (int32_t *)ctx->b_sh_rcount.p, (int32_t *)ctx->b_sh_rbucket.p,
+                             (int32_t *)ctx->b_sh_sorted.p, (int32_t *)ctx->b_sh_boff.p, (uint8_t *)ctx->b_sh_bdrop.p, n_rec,
+                             n_buckets);
+    if (rc != ISOF_OK) return rc;
+    const size_t G = (size_t)*n_rec, B = (size_t)*n_buckets;
+    TRY(d2h(ctx, rec_read, ctx->b_sh_rread.p, 4 * G));
+    TRY(d2h(ctx, rec_p1, ctx->b_sh_rp1.p, 4 * G));
+    TRY(d2h(ctx, rec_p2, ctx->b_sh_rp2.p, 4 * G));
+    TRY(d2h(ctx, rec_count, ctx->b_sh_rcount.p, 4 * G));
+    TRY(d2h(ctx, rec_bucket, ctx->b_sh_rbucket.p, 4 * G));
+    TRY(d2h(ctx, sorted_rec, ctx->b_sh_sorted.p, 4 * G));
+    if (G) TRY(d2h(ctx, bucket_off, ctx->b_sh_boff.p, 4 * (B + 1)));
+    TRY(d2h(ctx, bucket_dropped, ctx->b_sh_bdrop.p, B));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISOF_OK;
 }
 
 // ------------------------------------------------------------------------------------------ (b)

@@ -14,6 +14,7 @@
 //      reference's sequential rule (older equal hash is kept until it leaves the window).
 // A second kernel compacts the per-read results into the caller's (out_pos, out_off) layout.
 #include "common.cuh"
+#include "siphash.cuh"
 #include <cub/device/device_scan.cuh>
 
 namespace {
@@ -23,16 +24,6 @@ constexpr int PER_LANE = CHUNK / 32;
 constexpr int KMAX = 128;           // largest k (bytes per k-mer)
 constexpr int WMAX = 128;           // largest w = w_size - k
 constexpr int WARPS = 4;
-
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
-
-#define SIPROUND                                                                                   \
-    do {                                                                                           \
-        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32);                              \
-        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;                                                   \
-        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;                                                   \
-        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32);                              \
-    } while (0)
 
 // CPython siphash13 with k0=k1=0 over `len` bytes starting at byte offset `a` of the 4-byte aligned
 // shared buffer `cw`.  Result as Py_hash_t (-1 -> -2), hash of the empty slice is 0.

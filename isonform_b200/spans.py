@@ -1,0 +1,204 @@
+"""Host-side mirror of the minimizer-pair database / span-search seams, backed by kernel (c).
+
+    get_minimizer_combinations_database(M, k, x_low, x_high, reads)            main:174-212
+    minimizers_comb_iterator(minimizers, k, x_low, x_high)                     main:215-224
+    find_most_supported_span(r_id, m1, p1, m1_curr_spans, db, all_intervals,
+                             k_size, delta_len)                                main:308-338
+    solve_WIS / get_intervals_to_correct                                       main:227-272
+
+`SpanIndex` is built once per batch (one library call: sort-based group-by + all-pairs span
+comparison on the GPU).  It serves the per-read interval lists in the reference's order, materialises
+instance arrays (``array('I')`` of (r_id, p1, p2) triples) only when asked, and exposes a
+dict-compatible view of the pair database for callers that still index ``db[m1][m2]``.
+"""
+from array import array
+
+import numpy as np
+
+from ._lib import default_context, pack_sequences
+
+
+def minimizers_comb_iterator(minimizers, k, x_low, x_high):
+    """main:215-224 (host form; the GPU emits the same pairs in the same order)."""
+    n = len(minimizers)
+    for i in range(n - 1):
+        m1, p1 = minimizers[i]
+        out = []
+        for j in range(i + 1, n):
+            m2, p2 = minimizers[j]
+            d = p2 - p1
+            if x_low < d <= x_high:
+                out.append((m2, p2))
+            elif d > x_high:
+                break
+        yield (m1, p1), out[::-1]
+
+
+class SpanIndex:
+    def __init__(self, reads, M, k, x_low, x_high, delta_len, ctx=None):
+        """reads: {r_id: (acc, seq, qual)} in batch order; M: {r_id: [(kmer, pos)]} as returned by
+        get_minimizers_and_positions (same key order)."""
+        ctx = ctx or default_context()
+        self.k, self.x_low, self.x_high, self.delta_len = k, x_low, x_high, delta_len
+        self.ids = list(M)
+        self.id_of = np.array(self.ids, dtype=np.int64)
+        self.row_of = {r: i for i, r in enumerate(self.ids)}
+        self.reads = reads
+        seqs = [reads[r][1] for r in self.ids]
+        cat, off = pack_sequences(seqs)
+        counts = [len(M[r]) for r in self.ids]
+        min_off = np.zeros(len(self.ids) + 1, dtype=np.int64)
+        np.cumsum(counts, out=min_off[1:])
+        min_pos = np.fromiter((p for r in self.ids for _, p in M[r]), dtype=np.int32, count=int(min_off[-1]))
+        res = ctx.spans_batch(cat, off, min_pos, min_off, k, x_low, x_high, delta_len)
+        self.__dict__.update(res)
+        self.n_rec = len(self.rec_read)
+        # records are emitted in read order: per-read slices
+        self.read_rec_off = np.searchsorted(self.rec_read, np.arange(len(self.ids) + 1), side="left")
+        self.rec_span = self.rec_p2 - self.rec_p1
+        self._by_anchor = None
+
+    # ------------------------------------------------------------------ instances / intervals
+    def instances(self, g):
+        """The `seqs` array find_most_supported_span builds for record g (main:324-337)."""
+        b = self.rec_bucket[g]
+        members = self.sorted_rec[self.bucket_off[b]:self.bucket_off[b + 1]]
+        keep = (self.rec_read[members] != self.rec_read[g]) & (np.abs(self.rec_span[members] - self.rec_span[g]) < self.delta_len)
+        m = members[keep]
+        out = np.empty((len(m) + 1, 3), dtype=np.uint32)
+        out[0] = (self.id_of[self.rec_read[g]], self.rec_p1[g], self.rec_p2[g])
+        out[1:, 0] = self.id_of[self.rec_read[m]]
+        out[1:, 1] = self.rec_p1[m]
+        out[1:, 2] = self.rec_p2[m]
+        return array("I", out.ravel().tolist())
+
+    def interval_records(self, r_id):
+        """Record indices of read r_id that yield an interval, in the reference's order."""
+        i = self.row_of[r_id]
+        g = np.arange(self.read_rec_off[i], self.read_rec_off[i + 1])
+        return g[self.rec_count[g] > 0]
+
+    def intervals(self, r_id, with_instances=True):
+        """all_intervals of main:417-480 for one read: [(start, stop, count, instances)]."""
+        out = []
+        for g in self.interval_records(r_id):
+            inst = self.instances(g) if with_instances else None
+            out.append((int(self.rec_p1[g]) + self.k, int(self.rec_p2[g]), int(self.rec_count[g]), inst))
+        return out
+
+    def find_most_supported_span(self, r_id, m1, p1, m1_curr_spans, minimizer_combinations_database, all_intervals,
+                                 k_size, delta_len):
+        """Reference signature (main:308); `minimizer_combinations_database` is ignored -- the GPU
+        result already holds every bucket."""
+        if self._by_anchor is None:
+            self._by_anchor = {}
+            for g in range(self.n_rec):
+                self._by_anchor.setdefault((int(self.rec_read[g]), int(self.rec_p1[g])), []).append(g)
+        assert delta_len == self.delta_len and k_size == self.k
+        wanted = {p2 for _, p2 in m1_curr_spans}
+        for g in self._by_anchor.get((self.row_of[r_id], p1), []):
+            if self.rec_count[g] > 0 and int(self.rec_p2[g]) in wanted:
+                all_intervals.append((p1 + k_size, int(self.rec_p2[g]), int(self.rec_count[g]), self.instances(g)))
+
+    # ------------------------------------------------------------------ database view
+    def database(self):
+        """{m1: {m2: array('I')}} with the reference's content and key order (main:174-212)."""
+        db = {}
+        first_seen = np.full(len(self.bucket_off) - 1, -1, dtype=np.int64)
+        # dictionary insertion order = first appearance in emission order
+        order = np.argsort(self.sorted_rec[self.bucket_off[:-1]], kind="stable") if len(first_seen) else []
+        for b in order:
+            lo, hi = self.bucket_off[b], self.bucket_off[b + 1]
+            if hi - lo < 2 or self.bucket_dropped[b]:
+                continue
+            members = self.sorted_rec[lo:hi]
+            g0 = members[0]
+            r0 = self.ids[self.rec_read[g0]]
+            seq = self.reads[r0][1]
+            m1 = seq[self.rec_p1[g0]:self.rec_p1[g0] + self.k]
+            m2 = seq[self.rec_p2[g0]:self.rec_p2[g0] + self.k]
+            flat = np.stack([self.id_of[self.rec_read[members]], self.rec_p1[members], self.rec_p2[members]], axis=1)
+            db.setdefault(m1, {})[m2] = array("I", flat.ravel().tolist())
+        return db
+
+
+def get_minimizer_combinations_database(M, k, x_low, x_high, reads, ctx=None, delta_len=5):
+    """Drop-in for main:174-212: returns the dict view; keep the SpanIndex (attribute `.index`) for
+    find_most_supported_span."""
+    idx = SpanIndex(reads, M, k, x_low, x_high, delta_len, ctx)
+    db = _DB(idx.database())
+    db.index = idx
+    return db
+
+
+class _DB(dict):
+    """dict with defaultdict-like misses (the reference indexes absent keys, main:321)."""
+
+    def __missing__(self, key):
+        return _Inner()
+
+
+class _Inner(dict):
+    def __missing__(self, key):
+        return array("I")
+
+
+# ----------------------------------------------------------------------------------------------
+# weighted interval scheduling (host; float tie-breaks are the reference's, main:227-272)
+# ----------------------------------------------------------------------------------------------
+def solve_WIS(all_intervals_sorted_by_finish):
+    n = len(all_intervals_sorted_by_finish)
+    starts = np.fromiter((iv[0] for iv in all_intervals_sorted_by_finish), dtype=np.int64, count=n)
+    stops = np.fromiter((iv[1] for iv in all_intervals_sorted_by_finish), dtype=np.int64, count=n)
+    ws = np.fromiter((iv[2] for iv in all_intervals_sorted_by_finish), dtype=np.int64, count=n)
+    return _solve_wis_arrays(starts, stops, ws)
+
+
+def _solve_wis_arrays(starts, stops, ws):
+    n = len(starts)
+    valid = np.nonzero(starts < stops)[0]
+    if int(starts.max(initial=0)) > int(stops[-1]):
+        raise IndexError("list index out of range")          # the reference indexes past its coordinate table
+    # p[j] = index of the last valid interval with stop <= start_j (0 when none) -- main:227-239
+    pos = np.searchsorted(stops[valid], starts, side="right") - 1
+    p = np.where(pos >= 0, valid[np.maximum(pos, 0)], 0).tolist()
+    v = ((ws - 1) * (stops - starts + 0.0001)).tolist()
+    opt = [0] * (n + 1)
+    for j in range(1, n + 1):
+        a = v[j - 1] + opt[p[j - 1]]
+        b = opt[j - 1]
+        opt[j] = a if a > b else b          # max(): first argument wins ties, same value either way
+    chosen = []
+    j = n
+    while j > 0:
+        if v[j - 1] + opt[p[j - 1]] > opt[j - 1]:
+            chosen.append(j - 1)
+            j = p[j - 1]
+        else:
+            j -= 1
+    return chosen
+
+
+def batch_intervals_for_graph(index, reads):
+    """The per-read loop of main:417-514 (with --exact): returns
+    (all_intervals_for_graph {graph_id: [(start, stop, count, instances)]}, new_all_reads, skipped r_ids)."""
+    all_intervals_for_graph, new_all_reads, skipped = {}, {}, []
+    graph_id = 1
+    for r_id in sorted(reads):
+        g = index.interval_records(r_id)
+        if len(g) == 0:
+            skipped.append(r_id)
+            continue
+        starts = index.rec_p1[g].astype(np.int64) + index.k
+        stops = index.rec_p2[g].astype(np.int64)
+        order = np.argsort(stops, kind="stable")               # list.sort(key=stop) is stable (main:498)
+        chosen = _solve_wis_arrays(starts[order], stops[order], index.rec_count[g][order].astype(np.int64))[::-1]
+        picks = [(int(starts[order[j]]), int(stops[order[j]]), int(index.rec_count[g[order[j]]]), index.instances(g[order[j]]))
+                 for j in chosen]
+        if picks:
+            all_intervals_for_graph[graph_id] = picks
+            new_all_reads[graph_id] = reads[r_id]
+            graph_id += 1
+        else:
+            skipped.append(r_id)
+    return all_intervals_for_graph, new_all_reads, skipped

@@ -234,3 +234,67 @@ def test_align_score_only_and_capacity_retry(ctx):
     cat, off = hotpath.pack_sequences(seqs)
     small = ctx.sg_align_pairs(cat, off, ia, ib, cigar_cap=3)      # forces ISOF_ERR_CAPACITY + retry
     assert small["cigar"].tolist() == full["cigar"].tolist()
+
+
+# ------------------------------------------------------------------------------- pair database / spans
+def _span_case_check(ctx, reads, k, w, xmin, xmax, dl, expect=None):
+    from array import array
+    from isonform_b200 import hotpath, spans
+    M = hotpath.get_minimizers_and_positions(reads, w, k, "lex", ctx)
+    assert M == oracle.get_minimizers_and_positions(reads, w, k, "lex")
+    idx = spans.SpanIndex(reads, M, k, xmin, xmax, dl, ctx)
+    odb = oracle.get_minimizer_combinations_database(M, k, xmin, xmax, reads)
+    want_db = [[m1, m2, list(odb[m1][m2])] for m1 in odb for m2 in odb[m1] if len(odb[m1][m2])]
+    gdb = idx.database()
+    got_db = [[m1, m2, list(gdb[m1][m2])] for m1 in gdb for m2 in gdb[m1]]
+    assert got_db == want_db
+    if expect is not None:
+        assert got_db == expect["db"]
+    for r_id in sorted(reads):
+        want = oracle.pyside.read_intervals(r_id, M[r_id], odb, k, xmin, xmax, dl)
+        got = idx.intervals(r_id)
+        assert [(a, b, c, list(d)) for a, b, c, d in got] == [(a, b, c, list(d)) for a, b, c, d in want], r_id
+        # the reference-signature seam, anchor by anchor
+        seam = []
+        for (m1, p1), sp in spans.minimizers_comb_iterator(M[r_id], k, xmin, xmax):
+            if sp:
+                idx.find_most_supported_span(r_id, m1, p1, sp, None, seam, k, dl)
+        assert [(a, b, c, list(d)) for a, b, c, d in seam] == [(a, b, c, list(d)) for a, b, c, d in want]
+        if expect is not None:
+            e = expect["per_read"][str(r_id)]
+            assert [[a, b, c, hashlib.sha256(array("I", d).tobytes()).hexdigest()[:12]] for a, b, c, d in got] == e["intervals"]
+    graph_iv, new_reads, skipped = spans.batch_intervals_for_graph(idx, reads)
+    gid = 1
+    for r_id in sorted(reads):
+        want = oracle.pyside.read_intervals(r_id, M[r_id], odb, k, xmin, xmax, dl)
+        picks = None
+        if want:
+            srt = sorted(want, key=lambda x: x[1])
+            picks = [srt[j] for j in oracle.solve_WIS(srt)[::-1]]
+        if picks:
+            assert [(a, b, c, list(d)) for a, b, c, d in graph_iv[gid]] == [(a, b, c, list(d)) for a, b, c, d in picks]
+            assert new_reads[gid] == reads[r_id]
+            if expect is not None:
+                assert [[a, b, c, list(d)] for a, b, c, d in graph_iv[gid]] == expect["per_read"][str(r_id)]["wis"]
+            gid += 1
+        else:
+            assert r_id in skipped
+    assert len(graph_iv) == gid - 1
+
+
+def test_spans_golden(ctx):
+    for case in load_golden("spans.json"):
+        reads = {int(r): ("acc", s, "") for r, s in case["reads"].items()}
+        _span_case_check(ctx, reads, case["k"], case["w"], case["xmin"], case["xmax"], case["delta_len"], expect=case)
+
+
+def test_spans_random_cluster_vs_oracle(ctx):
+    from isonform_b200 import polya, synth
+    rd, _iso, _t = synth.make_cluster(seed=21, gene_len=900, n_isoforms=4, n_reads=60, eps=0.03)
+    reads = {i + 1: (acc, polya.remove_read_polyA_ends(s, 12, 1), "") for i, (acc, s) in enumerate(rd)}
+    reads[61] = ("short", "ACGTACGTAC", "")                  # shorter than one window
+    reads[62] = ("withN", rd[0][1][:200] + "NNNN" + rd[0][1][200:400], "")
+    reads[63] = ("lower", rd[1][1][:300].lower(), "")
+    reads[64] = ("empty", "", "")
+    _span_case_check(ctx, reads, 20, 31, 40, 80, 5)
+    _span_case_check(ctx, reads, 9, 20, 18, 60, 10)

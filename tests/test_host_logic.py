@@ -62,3 +62,18 @@ def test_synth_is_deterministic_and_shaped():
     assert all(set(s) <= set("ACGT") for _, s in r1)
     r3, _, _ = synth.make_config("C1", seed=99)
     assert r3 != r1
+
+
+def test_wis_mirror_matches_oracle_on_golden_intervals():
+    from isonform_b200 import spans
+    for case in load_golden("spans.json"):
+        reads = {int(r): ("acc", s, "") for r, s in case["reads"].items()}
+        M = oracle.get_minimizers_and_positions(reads, case["w"], case["k"], "lex")
+        db = oracle.get_minimizer_combinations_database(M, case["k"], case["xmin"], case["xmax"], reads)
+        for r_id in sorted(reads):
+            iv = oracle.pyside.read_intervals(r_id, M[r_id], db, case["k"], case["xmin"], case["xmax"], case["delta_len"])
+            assert list(spans.minimizers_comb_iterator(M[r_id], case["k"], case["xmin"], case["xmax"])) == \
+                list(oracle.minimizers_comb_iterator(M[r_id], case["k"], case["xmin"], case["xmax"]))
+            if iv:
+                srt = sorted(iv, key=lambda x: x[1])
+                assert spans.solve_WIS(srt) == oracle.solve_WIS(srt)
