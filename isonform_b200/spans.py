@@ -103,22 +103,33 @@ class SpanIndex:
     # ------------------------------------------------------------------ database view
     def database(self):
         """{m1: {m2: array('I')}} with the reference's content and key order (main:174-212)."""
+        nb = len(self.bucket_off) - 1
+        if nb == 0:
+            return {}
+        first_rec = self.sorted_rec[self.bucket_off[:-1]]            # smallest record index of each bucket
+        # The reference's outer dict gets key m1 at the FIRST record with that anchor k-mer, even if that
+        # record's bucket is deleted later; the inner dict gets m2 at the bucket's first record.
+        m1_of = []
+        m1_first = {}
+        for b in range(nb):
+            g0 = first_rec[b]
+            seq = self.reads[self.ids[self.rec_read[g0]]][1]
+            m1 = seq[self.rec_p1[g0]:self.rec_p1[g0] + self.k]
+            m1_of.append(m1)
+            if m1 not in m1_first or g0 < m1_first[m1]:
+                m1_first[m1] = g0
+        order = sorted(range(nb), key=lambda b: (m1_first[m1_of[b]], first_rec[b]))
         db = {}
-        first_seen = np.full(len(self.bucket_off) - 1, -1, dtype=np.int64)
-        # dictionary insertion order = first appearance in emission order
-        order = np.argsort(self.sorted_rec[self.bucket_off[:-1]], kind="stable") if len(first_seen) else []
         for b in order:
             lo, hi = self.bucket_off[b], self.bucket_off[b + 1]
             if hi - lo < 2 or self.bucket_dropped[b]:
                 continue
             members = self.sorted_rec[lo:hi]
             g0 = members[0]
-            r0 = self.ids[self.rec_read[g0]]
-            seq = self.reads[r0][1]
-            m1 = seq[self.rec_p1[g0]:self.rec_p1[g0] + self.k]
+            seq = self.reads[self.ids[self.rec_read[g0]]][1]
             m2 = seq[self.rec_p2[g0]:self.rec_p2[g0] + self.k]
             flat = np.stack([self.id_of[self.rec_read[members]], self.rec_p1[members], self.rec_p2[members]], axis=1)
-            db.setdefault(m1, {})[m2] = array("I", flat.ravel().tolist())
+            db.setdefault(m1_of[b], {})[m2] = array("I", flat.ravel().tolist())
         return db
 
 
