@@ -133,13 +133,50 @@ class SpanIndex:
         return db
 
 
-def get_minimizer_combinations_database(M, k, x_low, x_high, reads, ctx=None, delta_len=5):
-    """Drop-in for main:174-212: returns the dict view; keep the SpanIndex (attribute `.index`) for
-    find_most_supported_span."""
-    idx = SpanIndex(reads, M, k, x_low, x_high, delta_len, ctx)
-    db = _DB(idx.database())
-    db.index = idx
-    return db
+class LazySpanDB:
+    """What the drop-in get_minimizer_combinations_database returns: the reference only ever hands
+    this object back to find_most_supported_span (main:479), which is where delta_len becomes known,
+    so the GPU index is built on first use.  Indexing it like the reference's dict-of-dicts
+    (``db[m1][m2]`` -> array('I')) materialises the view."""
+
+    def __init__(self, M, k, x_low, x_high, reads, ctx=None):
+        self.M, self.k, self.x_low, self.x_high, self.reads, self.ctx = M, k, x_low, x_high, reads, ctx
+        self._index = {}
+        self._view = None
+
+    def index(self, delta_len):
+        if delta_len not in self._index:
+            self._index[delta_len] = SpanIndex(self.reads, self.M, self.k, self.x_low, self.x_high, delta_len, self.ctx)
+        return self._index[delta_len]
+
+    def view(self):
+        if self._view is None:
+            idx = next(iter(self._index.values())) if self._index else self.index(5)
+            self._view = _DB(idx.database())
+        return self._view
+
+    def __getitem__(self, m1):
+        return self.view()[m1]
+
+    def __iter__(self):
+        return iter(self.view())
+
+    def keys(self):
+        return self.view().keys()
+
+    def __len__(self):
+        return len(self.view())
+
+
+def get_minimizer_combinations_database(M, k, x_low, x_high, reads, ctx=None):
+    """Drop-in for main:174-212 (same positional arguments)."""
+    return LazySpanDB(M, k, x_low, x_high, reads, ctx)
+
+
+def find_most_supported_span(r_id, m1, p1, m1_curr_spans, minimizer_combinations_database, all_intervals, k_size, delta_len):
+    """Drop-in for main:308-338 when `minimizer_combinations_database` is a LazySpanDB."""
+    minimizer_combinations_database.index(delta_len).find_most_supported_span(
+        r_id, m1, p1, m1_curr_spans, minimizer_combinations_database, all_intervals, k_size, delta_len)
 
 
 class _DB(dict):

@@ -1,0 +1,95 @@
+"""Test double for isonform_b200._lib.Context backed by the CPU oracle.
+
+TEST INFRASTRUCTURE ONLY: lets the host-side drivers (merge.py, spans.py, patch.py, runner.py) be
+exercised on a machine without a GPU.  The product never imports this (nor the oracle)."""
+import numpy as np
+
+import oracle
+
+
+class FakeContext:
+    def __init__(self):
+        self.calls = {"minimizers": 0, "spans": 0, "align": 0, "pairs": 0}
+
+    # ---- (a)
+    def minimizers_batch(self, cat, off, k, w_size):
+        self.calls["minimizers"] += 1
+        return oracle.minimizers_batch(cat, off, k, w_size, threads=1)
+
+    # ---- (c): same outputs as isof_spans_batch, computed the slow way
+    def spans_batch(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len):
+        self.calls["spans"] += 1
+        cat = np.asarray(cat, dtype=np.uint8)
+        R = len(off) - 1
+        rec = []                                   # (read, p1, p2, key)
+        for r in range(R):
+            seq = bytes(cat[off[r]:off[r + 1]])
+            pos = [int(p) for p in min_pos[min_off[r]:min_off[r + 1]]]
+            for i in range(len(pos) - 1):
+                part = []
+                for j in range(i + 1, len(pos)):
+                    d = pos[j] - pos[i]
+                    if x_low < d <= x_high:
+                        part.append(j)
+                    elif d > x_high:
+                        break
+                for j in reversed(part):
+                    rec.append((r, pos[i], pos[j], (seq[pos[i]:pos[i] + k], seq[pos[j]:pos[j] + k])))
+        G = len(rec)
+        buckets = {}
+        for g, (_r, _p1, _p2, key) in enumerate(rec):
+            buckets.setdefault(key, []).append(g)
+        keys = sorted(buckets, key=lambda kk: kk)          # any deterministic bucket order will do
+        rec_bucket = np.zeros(G, np.int32)
+        sorted_rec, bucket_off, dropped = [], [0], []
+        polya = b"A" * k
+        for b, key in enumerate(keys):
+            for g in buckets[key]:
+                rec_bucket[g] = b
+            sorted_rec += buckets[key]
+            bucket_off.append(len(sorted_rec))
+            dropped.append(1 if (key == (polya, polya) or len(buckets[key]) > 3 * R) else 0)
+        rec_read = np.array([x[0] for x in rec], np.int32)
+        rec_p1 = np.array([x[1] for x in rec], np.int32)
+        rec_p2 = np.array([x[2] for x in rec], np.int32)
+        rec_count = np.zeros(G, np.int32)
+        for g in range(G):
+            mem = buckets[rec[g][3]]
+            if dropped[rec_bucket[g]] or len(mem) < 3:
+                continue
+            span = rec[g][2] - rec[g][1]
+            rec_count[g] = 1 + sum(1 for h in mem if rec[h][0] != rec[g][0] and abs(span - (rec[h][2] - rec[h][1])) < delta_len)
+        return {"rec_read": rec_read, "rec_p1": rec_p1, "rec_p2": rec_p2, "rec_count": rec_count, "rec_bucket": rec_bucket,
+                "sorted_rec": np.array(sorted_rec, np.int32), "bucket_off": np.array(bucket_off, np.int32),
+                "bucket_dropped": np.array(dropped, np.uint8)}
+
+    # ---- (b)
+    def sg_align_pairs(self, cat, off, pair_a, pair_b, match=2, mismatch=-2, gap_open=12, gap_ext=1, want_cigar=True,
+                       features_delta_len=None, cigar_cap=None):
+        self.calls["align"] += 1
+        self.calls["pairs"] += len(pair_a)
+        cat = np.asarray(cat, dtype=np.uint8)
+        P = len(pair_a)
+        score = np.zeros(P, np.int32); eq = np.zeros(P, np.int32); er = np.zeros(P, np.int32)
+        coff = np.zeros(P + 1, np.int64)
+        runs_all, feats = [], (np.zeros((P, 12), np.int32) if features_delta_len is not None else None)
+        for p in range(P):
+            s1 = bytes(cat[off[pair_a[p]]:off[pair_a[p] + 1]]).decode("latin-1")
+            s2 = bytes(cat[off[pair_b[p]]:off[pair_b[p] + 1]]).decode("latin-1")
+            sc, q, r, runs = oracle.sg_align(s1, s2, match, mismatch, gap_open, gap_ext)
+            score[p], eq[p], er[p] = sc, q, r
+            runs_all.append(runs)
+            coff[p + 1] = coff[p] + len(runs)
+            if feats is not None:
+                tup = oracle.cigar_runs_to_tuples(runs)
+                a1, a2 = oracle.cigar_to_seq(tup, s1, s2)
+                alen = sum(l for l, _ in tup)
+                sm = oracle.find_first_significant_match(a1, a2, 30, 0.7)
+                em = oracle.find_first_significant_match(a1[::-1], a2[::-1], 30, 0.7)
+                nm = [l for l, o in tup if o != "="]
+                f = [alen, len(tup), sum(nm), max(nm + [0]), sm, em, 0, 0, 0, 0, 0, 0]
+                if sm >= 0 and em >= 0:
+                    f[6:12] = oracle.isoform_features(tup, features_delta_len, sm, alen - em)[:6]
+                feats[p] = f
+        cig = np.concatenate(runs_all).astype(np.uint32) if (want_cigar and runs_all) else (np.zeros(0, np.uint32) if want_cigar else None)
+        return {"score": score, "end_q": eq, "end_r": er, "cigar_off": coff, "cigar": cig, "features": feats}
