@@ -61,6 +61,10 @@ ISOF_API const char *isof_last_error(const isof_ctx *ctx);
 ISOF_API int isof_set_stream(isof_ctx *ctx, void *cuda_stream);
 /* Upper bound for the alignment trace scratch in bytes (default: 40% of free device memory). */
 ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
+/* The DP kernel has two arithmetic paths with identical results: a packed 16-bit path (two alignments
+ * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any
+ * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
+ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
 
 /* Per-ctx counters, reset by isof_profile_reset.  Kernel times are measured with CUDA events on the
  * ctx stream around each launch when profiling is enabled (isof_profile_enable(ctx,1)); enabling

@@ -144,6 +144,13 @@ int isof_set_trace_budget(isof_ctx *ctx, size_t bytes)
     return ISOF_OK;
 }
 
+int isof_set_packed(isof_ctx *ctx, int on)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->disable_packed = (on == 0);
+    return ISOF_OK;
+}
+
 int isof_profile_enable(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;

@@ -25,6 +25,7 @@ struct isof_ctx {
     char err[512] = {0};
     size_t trace_budget = 0;          // bytes; 0 = decide at first use
     bool profiling = false;
+    bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
     isof_profile prof;
     // pending (start, stop, slot) event pairs when profiling
     struct Timed { cudaEvent_t a, b; int slot; };

@@ -48,6 +48,9 @@ struct AlignParams {
     int64_t bnd_stride;        // int2 elements per warp
     int32_t *score, *endq, *endr, *nruns;
     int c_eo, c_ee, c_fo, c_fe, c_sm, c_sx;
+    // packed 16-bit path (two alignments per warp): 4*score + 2 tag bits per half
+    uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
+    int h_max_min_len, h_max_max_len;      // eligibility: min(n,m) <= h_max_min_len and max(n,m) <= h_max_max_len
 };
 
 __device__ __forceinline__ int base_code(uint8_t c)
@@ -84,7 +87,8 @@ __global__ void encode_kernel(const uint8_t *__restrict__ cat, const int64_t *__
 __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const uint8_t *__restrict__ flags,
                             const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, int64_t P,
                             int32_t *__restrict__ pn, int32_t *__restrict__ pm, uint8_t *__restrict__ pwild,
-                            int64_t *__restrict__ words, unsigned long long *__restrict__ misc)
+                            int64_t *__restrict__ words, unsigned long long *__restrict__ misc, int h_max_min_len,
+                            int h_max_max_len)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0, padded = 0;
@@ -103,7 +107,10 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                 w = (int64_t)ns * (m + 31) * 32 + TRACE_SLACK;
                 cells = (unsigned long long)n * m;
                 padded = (unsigned long long)ns * SROWS * m;
-                pwild[p] = flags[a] | flags[b];
+                // bit0: a wildcard is present (32-bit WILD path); bit1: eligible for the packed 16-bit path
+                const int wild = flags[a] | flags[b];
+                const int elig = !wild && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len;
+                pwild[p] = (uint8_t)(wild | (elig << 1));
                 mm = m;
             }
         }
@@ -250,6 +257,175 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed path: two alignments (A in the low, B in the high 16 bits of every register) per warp.
+// Values are 4*score + tag (2 bits).  E and F are kept re-tagged with their class for the 3-way
+// max (E: 01, F: 10, diagonal: 11, so VIMNMX3.S16x2 resolves DIAG > F > E), and that class tag
+// doubles as the "came from extension" marker of the next cell: E_ext = Eh + 4*(-ext) keeps tag 01,
+// F_ext = Fh + 4*(-ext) - 1 turns 10 into 01, while the opening candidates carry tag 00, so bit 0 of
+// max(open, ext) is the extension flag and extension wins ties.  Every operation is per-half
+// (VIADD.16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2 / LOP3), so the two alignments never interact;
+// they may differ in size (loops run to the larger one, stores and end tracking are per half).
+// Trace words are unpacked per alignment into the same layout the 32-bit path writes.
+// ---------------------------------------------------------------------------------------------
+constexpr int CS16 = 8;                       // base codes at bits 8..9 of each half
+constexpr uint32_t NEG16 = 0x83008300u;       // -32000 in both halves (a clean multiple of 4)
+
+__device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
+
+__device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
+                                          int2 *__restrict__ bnd)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int nA = P.pn[pA], mA = P.pm[pA], nB = P.pn[pB], mB = P.pm[pB];
+    const uint8_t *__restrict__ qA = P.codes + P.seq_off[P.pa[pA]];
+    const uint8_t *__restrict__ rA = P.codes + P.seq_off[P.pb[pA]];
+    const uint8_t *__restrict__ qB = P.codes + P.seq_off[P.pa[pB]];
+    const uint8_t *__restrict__ rB = P.codes + P.seq_off[P.pb[pB]];
+    uint32_t *__restrict__ traceA = P.trace + (P.ptrace[pA] - P.chunk_base);
+    uint32_t *__restrict__ traceB = P.trace + (P.ptrace[pB] - P.chunk_base);
+    const int m = max(mA, mB);
+    const int T = m + 31, TA = mA + 31, TB = mB + 31;
+    const int nsA = (nA + SROWS - 1) / SROWS, nsB = (nB + SROWS - 1) / SROWS, ns = max(nsA, nsB);
+    const int last_laneA = ((nA - 1) % SROWS) / R, last_rA = (nA - 1) % R;
+    const int last_laneB = ((nB - 1) % SROWS) / R, last_rB = (nB - 1) % R;
+    const uint32_t h_eo = P.h_eo, h_ee = P.h_ee, h_fo = P.h_fo, h_fe = P.h_fe, h_sm = P.h_sm, h_sx = P.h_sx;
+    const uint32_t C3 = (3u << CS16) | (3u << (CS16 + 16));
+    int bcolA = INT_MIN, bcolA_i = 0, browA = INT_MIN, browA_j = 0;
+    int bcolB = INT_MIN, bcolB_i = 0, browB = INT_MIN, browB_j = 0;
+
+    for (int s = 0; s < ns; ++s) {
+        const int i0 = s * SROWS + lane * R;
+        uint32_t qc[R], Hl[R], Eh[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t a = (i0 + r < nA) ? (uint32_t)qA[i0 + r] : 0u;
+            const uint32_t b = (i0 + r < nB) ? (uint32_t)qB[i0 + r] : 0u;
+            qc[r] = (a << CS16) | (b << (CS16 + 16));
+            Hl[r] = 0u;
+            Eh[r] = NEG16 | 0x00010001u;
+        }
+        const bool has_prev = s > 0, has_next = s + 1 < ns;
+        const bool liveA = s < nsA, liveB = s < nsB, lastA = s == nsA - 1, lastB = s == nsB - 1;
+        uint32_t diag0 = 0u, Hbot = 0u, Fbot = NEG16 | 0x00020002u;
+        uint32_t rc_next = 0u;
+        if (lane == 0) rc_next = ((uint32_t)rA[0] << CS16) | ((uint32_t)rB[0] << (CS16 + 16));
+        int2 b_next = make_int2(0, (int)(NEG16 | 0x00020002u));
+        if (has_prev && lane == 0) b_next = __ldcg(&bnd[0]);
+        uint32_t *tpA = traceA + (size_t)s * TA * 32 + lane;
+        uint32_t *tpB = traceB + (size_t)s * TB * 32 + lane;
+
+        for (int t = 0; t < T; ++t, tpA += 32, tpB += 32) {
+            const int j = t - lane;
+            const uint32_t rc = rc_next;
+            const int2 bu = b_next;
+            {
+                const int jn = j + 1;
+                if ((unsigned)jn < (unsigned)m) {
+                    const uint32_t a = (jn < mA) ? (uint32_t)rA[jn] : 0u;
+                    const uint32_t b = (jn < mB) ? (uint32_t)rB[jn] : 0u;
+                    rc_next = (a << CS16) | (b << (CS16 + 16));
+                    if (has_prev && lane == 0) b_next = __ldcg(&bnd[jn]);
+                }
+            }
+            uint32_t hu = __shfl_up_sync(FULL, Hbot, 1);
+            uint32_t fu = __shfl_up_sync(FULL, Fbot, 1);
+            if (lane == 0) { hu = (uint32_t)bu.x; fu = (uint32_t)bu.y; }
+            if ((unsigned)j < (unsigned)m) {
+                uint32_t up = hu, fup = fu, diag = diag0;
+                diag0 = hu;
+                uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t left = Hl[r];
+                    const uint32_t Ee = __vadd2(Eh[r], h_ee);
+                    const uint32_t E = __viaddmax_s16x2(left, h_eo, Ee);
+                    const uint32_t Ehn = E | 0x00010001u;
+                    const uint32_t Fe = __vadd2(fup, h_fe);
+                    const uint32_t F = __viaddmax_s16x2(up, h_fo, Fe);
+                    const uint32_t Fh = (F & 0xfffefffeu) | 0x00020002u;
+                    const uint32_t y = qc[r] ^ rc ^ C3;
+                    const uint32_t sc = __viaddmax_s16x2(y, h_sm, h_sx);
+                    const uint32_t Hd = __vadd2(diag, sc);
+                    const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
+                    // nibble [src1 src0 f e] per half
+                    const uint32_t sel1 = (E & 0x00010001u) | ((F << 1) & ~0x00010001u);      // bit0 <- e, bit1 <- f
+                    const uint32_t sel2 = (sel1 & 0x00030003u) | ((H << 2) & ~0x00030003u);   // bits 3:2 <- src
+                    const uint32_t nib = sel2 & 0x000f000fu;
+                    if (r < 4) acc0 += nib << (4 * r); else acc1 += nib << (4 * (r - 4));
+                    const uint32_t Hc = H & 0xfffcfffcu;
+                    diag = left;
+                    Hl[r] = Hc;
+                    Eh[r] = Ehn;
+                    up = Hc;
+                    fup = Fh;
+                }
+                Hbot = up; Fbot = fup;
+                if (liveA && j < mA) *tpA = __byte_perm(acc0, acc1, 0x5410);
+                if (liveB && j < mB) *tpB = __byte_perm(acc0, acc1, 0x7632);
+                if (has_next && lane == 31) bnd[j] = make_int2((int)Hbot, (int)Fbot);
+                if (liveA && j == mA - 1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int v = lo16(Hl[r]);
+                        if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
+                    }
+                }
+                if (liveB && j == mB - 1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int v = hi16(Hl[r]);
+                        if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
+                    }
+                }
+                if (lastA && lane == last_laneA && j < mA) {
+                    uint32_t hv = Hl[0];
+#pragma unroll
+                    for (int r = 1; r < R; ++r) if (r == last_rA) hv = Hl[r];
+                    const int v = lo16(hv);
+                    if (v > browA) { browA = v; browA_j = j; }
+                }
+                if (lastB && lane == last_laneB && j < mB) {
+                    uint32_t hv = Hl[0];
+#pragma unroll
+                    for (int r = 1; r < R; ++r) if (r == last_rB) hv = Hl[r];
+                    const int v = hi16(hv);
+                    if (v > browB) { browB = v; browB_j = j; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    browA = __shfl_sync(FULL, browA, last_laneA); browA_j = __shfl_sync(FULL, browA_j, last_laneA);
+    browB = __shfl_sync(FULL, browB, last_laneB); browB_j = __shfl_sync(FULL, browB_j, last_laneB);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        int ov = __shfl_xor_sync(FULL, bcolA, d), oi = __shfl_xor_sync(FULL, bcolA_i, d);
+        if (ov > bcolA || (ov == bcolA && oi < bcolA_i)) { bcolA = ov; bcolA_i = oi; }
+        ov = __shfl_xor_sync(FULL, bcolB, d); oi = __shfl_xor_sync(FULL, bcolB_i, d);
+        if (ov > bcolB || (ov == bcolB && oi < bcolB_i)) { bcolB = ov; bcolB_i = oi; }
+    }
+    if (lane == 0) {
+        int sc = browA, eq = nA - 1, er = browA_j;
+        if (bcolA > sc) { sc = bcolA; eq = bcolA_i; er = mA - 1; }
+        else if (bcolA == sc && er == mA - 1 && bcolA_i < eq) eq = bcolA_i;
+        P.score[pA] = sc >> 2; P.endq[pA] = eq; P.endr[pA] = er;
+        sc = browB; eq = nB - 1; er = browB_j;
+        if (bcolB > sc) { sc = bcolB; eq = bcolB_i; er = mB - 1; }
+        else if (bcolB == sc && er == mB - 1 && bcolB_i < eq) eq = bcolB_i;
+        P.score[pB] = sc >> 2; P.endq[pB] = eq; P.endr[pB] = er;
+    }
+}
+
+__device__ __forceinline__ void dp_pair32(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd)
+{
+    if (P.pwild[p] & 1) dp_pair<true>(P, p, lane, bnd);
+    else dp_pair<false>(P, p, lane, bnd);
+}
+
+// One task = two consecutive pairs of the chunk.  Both eligible -> one packed pass; otherwise each
+// pair runs through the 32-bit path.
 __global__ void __launch_bounds__(DP_WARPS * 32)
 sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsigned long long *__restrict__ counter)
 {
@@ -259,10 +435,14 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
         unsigned long long tkt = 0;
         if (lane == 0) tkt = atomicAdd(counter, 1ull);
         tkt = __shfl_sync(0xffffffffu, tkt, 0);
-        const int64_t p = start + (int64_t)tkt;
-        if (p >= end) break;
-        if (P.pwild[p]) dp_pair<true>(P, p, lane, bnd);
-        else dp_pair<false>(P, p, lane, bnd);
+        const int64_t pA = start + 2 * (int64_t)tkt;
+        if (pA >= end) break;
+        const int64_t pB = pA + 1;
+        if (pB < end && (P.pwild[pA] & 2) && (P.pwild[pB] & 2)) dp_pair16(P, pA, pB, lane, bnd);
+        else {
+            dp_pair32(P, pA, lane, bnd);
+            if (pB < end) dp_pair32(P, pB, lane, bnd);
+        }
     }
 }
 
@@ -452,6 +632,16 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
 {
     cudaStream_t st = ctx->stream;
     if (h_total_runs) *h_total_runs = 0;
+    // ---- eligibility of the packed 16-bit path (4*score + 2 tag bits must fit a signed half):
+    //   positive side  4*match*min(n,m) + 16 <= 32767
+    //   negative side  4*(2*open + ext*max(n,m) + |mismatch| + |match|) <= 31000   (sentinel is -32000)
+    //   substitution   (1 << CS16) >= 4*(match - mismatch)
+    int h_max_min_len = 0, h_max_max_len = 0;
+    if (!ctx->disable_packed && match > 0 && mismatch <= match && 4 * (match - mismatch) <= (1 << CS16)) {
+        h_max_min_len = (32767 - 16) / (4 * match);
+        const int room = 31000 / 4 - 2 * gap_open - std::abs(mismatch) - std::abs(match);
+        h_max_max_len = room <= 0 ? 0 : (gap_ext > 0 ? room / gap_ext : INT_MAX);
+    }
     if (P < 0 || n_seqs < 0) return isof_fail(ctx, ISOF_ERR_ARG, "negative count");
     if (match - mismatch > 256 || match - mismatch < 0 || gap_open < 0 || gap_ext < 0 ||
         std::abs(match) > 1024 || std::abs(mismatch) > 1024 || gap_open > 4096 || gap_ext > 4096)
@@ -489,7 +679,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     {
         LaunchTimer t(ctx, SLOT_OTHER);
         plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
-                                                                      words, misc);
+                                                                      words, misc, h_max_min_len, h_max_max_len);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     size_t tmp_bytes = 0;
@@ -567,6 +757,15 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.c_fe = -gap_ext * S + 10;
     A.c_sm = match * S + 12 - (3 << CODE_SHIFT);
     A.c_sx = mismatch * S + 12;
+    auto pk = [](int v) { return ((uint32_t)(v & 0xffff)) | ((uint32_t)(v & 0xffff) << 16); };
+    A.h_eo = pk(-4 * gap_open);
+    A.h_ee = pk(-4 * gap_ext);
+    A.h_fo = pk(-4 * gap_open);
+    A.h_fe = pk(-4 * gap_ext - 1);
+    A.h_sm = pk(4 * match + 3 - (3 << CS16));
+    A.h_sx = pk(4 * mismatch + 3);
+    A.h_max_min_len = h_max_min_len;
+    A.h_max_max_len = h_max_max_len;
     int64_t *run_base = (int64_t *)(misc + 4);
     CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
 
@@ -577,7 +776,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         A.chunk_base = start_off[c];
         {
             LaunchTimer t(ctx, SLOT_DP);
-            int blocks = (int)std::min<int64_t>((cnt + DP_WARPS - 1) / DP_WARPS, occ_blocks);
+            const int64_t tasks = (cnt + 1) / 2;
+            int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
             sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, st>>>(A, ps, pe, counters + c);
         }
         {

@@ -7,6 +7,7 @@ from isonform_b200 import _lib, hotpath, synth
 ctx = _lib.Context(0)
 ctx.profile_enable(True)
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+if len(sys.argv) > 2: ctx.set_packed(sys.argv[2] != "0")
 reads, _, _ = synth.make_config("C2", n_reads=n_reads)
 seqs = [s for _, s in reads]
 cat, off = hotpath.pack_sequences(seqs)

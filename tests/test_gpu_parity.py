@@ -298,3 +298,52 @@ def test_spans_random_cluster_vs_oracle(ctx):
     reads[64] = ("empty", "", "")
     _span_case_check(ctx, reads, 20, 31, 40, 80, 5)
     _span_case_check(ctx, reads, 9, 20, 18, 60, 10)
+
+
+# ------------------------------------------------------------------------------- packed vs 32-bit DP paths
+def test_packed_and_32bit_paths_agree_and_match_oracle(ctx):
+    """Tasks pair up consecutive alignments; mix sizes, wildcards (forces the 32-bit path for a task),
+    odd counts and over-long sequences so every dispatch branch of sg_dp_kernel runs."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(53)
+    seqs, pa, pb = [], [], []
+    for i in range(61):                                   # odd number of pairs
+        n = int(rng.integers(1, 700))
+        x = _rand_dna(rng, n)
+        y = synth.mutate(rng, x, 0.06) if i % 3 else _rand_dna(rng, int(rng.integers(1, 700)))
+        if i % 9 == 4:
+            y = y[:len(y) // 2] + "N" + y[len(y) // 2:]    # wildcard -> 32-bit WILD path for this task
+        seqs += [x, y or "C"]; pa.append(2 * i); pb.append(2 * i + 1)
+    big = _rand_dna(rng, 4300)                             # min(n,m) > 4093: not eligible for 16 bit at match=2
+    seqs += [big, synth.mutate(rng, big, 0.03)]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    for params in [(2, -2, 12, 1), (2, -8, 12, 1), (5, -4, 10, 2), (1, -1, 0, 0)]:
+        ctx.set_packed(True)
+        a = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, features_delta_len=5)
+        ctx.set_packed(False)
+        try:
+            b = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, features_delta_len=5)
+        finally:
+            ctx.set_packed(True)
+        for key in ("score", "cigar_off", "cigar", "features"):
+            assert np.array_equal(a[key], b[key]), (params, key)
+        for p in range(0, len(pa), 5):
+            sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params)
+            assert int(a["score"][p]) == sc
+            assert a["cigar"][a["cigar_off"][p]:a["cigar_off"][p + 1]].tolist() == runs.tolist(), (params, p)
+
+
+def test_packed_path_range_limits(ctx):
+    """Sequences right at the 16-bit eligibility limits (4*match*min(n,m)+16 <= 32767) and scores that
+    use the whole range: identical sequences maximise the score, unrelated ones the negative side."""
+    from isonform_b200 import hotpath
+    rng = np.random.default_rng(59)
+    a = _rand_dna(rng, 4093)
+    b = _rand_dna(rng, 4093)
+    seqs = [a, a, a, b, a[:4000], a[50:], "A" * 4093, "C" * 4093]
+    pa, pb = [0, 2, 4, 6], [1, 3, 5, 7]
+    res = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx=ctx)
+    for p in range(4):
+        sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], 2, -2, 12, 1)
+        assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er)
+        assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
+    assert int(res["score"][0]) == 2 * 4093
