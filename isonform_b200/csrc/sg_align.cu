@@ -51,6 +51,8 @@ struct AlignParams {
     // packed 16-bit path (two alignments per warp): 4*score + 2 tag bits per half
     uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
     int h_max_min_len, h_max_max_len;      // eligibility: min(n,m) <= h_max_min_len and max(n,m) <= h_max_max_len
+    uint32_t k_fclean, k_sel1, k_sel3;     // 0xfffefffe, 0x00010001, 0x00030003 (kept in registers on purpose)
+    uint8_t *playout;                      // per pair: columns per step of the path that wrote its trace (1 or PC)
 };
 
 __device__ __forceinline__ int base_code(uint8_t c)
@@ -104,7 +106,7 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
             if (n <= 0 || m <= 0) { atomicOr(&misc[0], 2ull); n = m = 0; }
             else {
                 int ns = (n + SROWS - 1) / SROWS;
-                w = (int64_t)ns * (m + 31) * 32 + TRACE_SLACK;
+                w = (int64_t)ns * (m + 64) * 32 + TRACE_SLACK;        // covers the 1- and 2-column layouts
                 cells = (unsigned long long)n * m;
                 padded = (unsigned long long)ns * SROWS * m;
                 // bit0: a wildcard is present (32-bit WILD path); bit1: eligible for the packed 16-bit path
@@ -162,6 +164,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
     const int last_lane = ((n - 1) % SROWS) / R, last_r = (n - 1) % R;
     const int c_eo = P.c_eo, c_ee = P.c_ee, c_fo = P.c_fo, c_fe = P.c_fe, c_sm = P.c_sm, c_sx = P.c_sx;
     int best_col = INT_MIN, best_col_i = 0, best_row = INT_MIN, best_row_j = 0;
+    if (lane == 0) P.playout[p] = 1;
 
     for (int s = 0; s < nstripes; ++s) {
         const int i0 = s * SROWS + lane * R;
@@ -270,10 +273,15 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
 // ---------------------------------------------------------------------------------------------
 constexpr int CS16 = 8;                       // base codes at bits 8..9 of each half
 constexpr uint32_t NEG16 = 0x83008300u;       // -32000 in both halves (a clean multiple of 4)
+constexpr int PC = 2;                         // columns per step of the packed path (uint2 trace stores)
 
 __device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
 
+// Lane l handles, at step t, the PC consecutive columns starting at jb = PC*(t-l): the per-step
+// overhead (shuffles, prefetch, stores, loop) is paid once per PC*8 cells per alignment.
+// Trace layout of a packed pair: word[((stripe*T + t)*32 + lane)*PC + c], T = ceil(m/PC)+31, column
+// j = PC*(t-lane)+c; P.playout[p] = PC tells the traceback.
 __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
                                           int2 *__restrict__ bnd)
 {
@@ -286,14 +294,17 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     uint32_t *__restrict__ traceA = P.trace + (P.ptrace[pA] - P.chunk_base);
     uint32_t *__restrict__ traceB = P.trace + (P.ptrace[pB] - P.chunk_base);
     const int m = max(mA, mB);
-    const int T = m + 31, TA = mA + 31, TB = mB + 31;
+    const int T = (m + PC - 1) / PC + 31, TA = (mA + PC - 1) / PC + 31, TB = (mB + PC - 1) / PC + 31;
     const int nsA = (nA + SROWS - 1) / SROWS, nsB = (nB + SROWS - 1) / SROWS, ns = max(nsA, nsB);
     const int last_laneA = ((nA - 1) % SROWS) / R, last_rA = (nA - 1) % R;
     const int last_laneB = ((nB - 1) % SROWS) / R, last_rB = (nB - 1) % R;
     const uint32_t h_eo = P.h_eo, h_ee = P.h_ee, h_fo = P.h_fo, h_fe = P.h_fe, h_sm = P.h_sm, h_sx = P.h_sx;
+    // masks live in registers (kernel parameters) so that "(x & mask) | imm" is ONE LOP3
+    const uint32_t k_fclean = P.k_fclean, k_sel1 = P.k_sel1, k_sel3 = P.k_sel3;
     const uint32_t C3 = (3u << CS16) | (3u << (CS16 + 16));
     int bcolA = INT_MIN, bcolA_i = 0, browA = INT_MIN, browA_j = 0;
     int bcolB = INT_MIN, bcolB_i = 0, browB = INT_MIN, browB_j = 0;
+    if (lane == 0) { P.playout[pA] = PC; P.playout[pB] = PC; }
 
     for (int s = 0; s < ns; ++s) {
         const int i0 = s * SROWS + lane * R;
@@ -307,92 +318,117 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             Eh[r] = NEG16 | 0x00010001u;
         }
         const bool has_prev = s > 0, has_next = s + 1 < ns;
-        const bool liveA = s < nsA, liveB = s < nsB, lastA = s == nsA - 1, lastB = s == nsB - 1;
-        uint32_t diag0 = 0u, Hbot = 0u, Fbot = NEG16 | 0x00020002u;
-        uint32_t rc_next = 0u;
-        if (lane == 0) rc_next = ((uint32_t)rA[0] << CS16) | ((uint32_t)rB[0] << (CS16 + 16));
-        int2 b_next = make_int2(0, (int)(NEG16 | 0x00020002u));
-        if (has_prev && lane == 0) b_next = __ldcg(&bnd[0]);
-        uint32_t *tpA = traceA + (size_t)s * TA * 32 + lane;
-        uint32_t *tpB = traceB + (size_t)s * TB * 32 + lane;
+        const bool liveA = s < nsA, liveB = s < nsB;
+        const bool trackA = (s == nsA - 1) && lane == last_laneA, trackB = (s == nsB - 1) && lane == last_laneB;
+        uint32_t diag0 = 0u;
+        uint32_t Hbot[PC], Fbot[PC], rc_next[PC];
+        int2 b_next[PC];
+#pragma unroll
+        for (int c = 0; c < PC; ++c) {
+            Hbot[c] = 0u;
+            Fbot[c] = NEG16 | 0x00020002u;
+            rc_next[c] = 0u;
+            b_next[c] = make_int2(0, (int)(NEG16 | 0x00020002u));
+            if (lane == 0) {
+                const uint32_t a = (c < mA) ? (uint32_t)rA[c] : 0u, b = (c < mB) ? (uint32_t)rB[c] : 0u;
+                rc_next[c] = (a << CS16) | (b << (CS16 + 16));
+                if (has_prev && c < m) b_next[c] = __ldcg(&bnd[c]);
+            }
+        }
+        uint2 *tpA = reinterpret_cast<uint2 *>(traceA) + (size_t)s * TA * 32 + lane;
+        uint2 *tpB = reinterpret_cast<uint2 *>(traceB) + (size_t)s * TB * 32 + lane;
 
         for (int t = 0; t < T; ++t, tpA += 32, tpB += 32) {
-            const int j = t - lane;
-            const uint32_t rc = rc_next;
-            const int2 bu = b_next;
-            {
-                const int jn = j + 1;
+            const int jb = PC * (t - lane);
+            uint32_t rc[PC], hu[PC], fu[PC];
+#pragma unroll
+            for (int c = 0; c < PC; ++c) {
+                rc[c] = rc_next[c];
+                hu[c] = __shfl_up_sync(FULL, Hbot[c], 1);
+                fu[c] = __shfl_up_sync(FULL, Fbot[c], 1);
+                if (lane == 0) { hu[c] = (uint32_t)b_next[c].x; fu[c] = (uint32_t)b_next[c].y; }
+            }
+            {   // prefetch the next block's reference bases / boundary cells
+                const int jn = jb + PC;
                 if ((unsigned)jn < (unsigned)m) {
-                    const uint32_t a = (jn < mA) ? (uint32_t)rA[jn] : 0u;
-                    const uint32_t b = (jn < mB) ? (uint32_t)rB[jn] : 0u;
-                    rc_next = (a << CS16) | (b << (CS16 + 16));
-                    if (has_prev && lane == 0) b_next = __ldcg(&bnd[jn]);
+#pragma unroll
+                    for (int c = 0; c < PC; ++c) {
+                        const uint32_t a = (jn + c < mA) ? (uint32_t)rA[jn + c] : 0u;
+                        const uint32_t b = (jn + c < mB) ? (uint32_t)rB[jn + c] : 0u;
+                        rc_next[c] = (a << CS16) | (b << (CS16 + 16));
+                        if (has_prev && lane == 0 && jn + c < m) b_next[c] = __ldcg(&bnd[jn + c]);
+                    }
                 }
             }
-            uint32_t hu = __shfl_up_sync(FULL, Hbot, 1);
-            uint32_t fu = __shfl_up_sync(FULL, Fbot, 1);
-            if (lane == 0) { hu = (uint32_t)bu.x; fu = (uint32_t)bu.y; }
-            if ((unsigned)j < (unsigned)m) {
-                uint32_t up = hu, fup = fu, diag = diag0;
-                diag0 = hu;
-                uint32_t acc0 = 0u, acc1 = 0u;
+            if ((unsigned)jb < (unsigned)m) {
+                uint32_t wA[PC], wB[PC];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t left = Hl[r];
-                    const uint32_t Ee = __vadd2(Eh[r], h_ee);
-                    const uint32_t E = __viaddmax_s16x2(left, h_eo, Ee);
-                    const uint32_t Ehn = E | 0x00010001u;
-                    const uint32_t Fe = __vadd2(fup, h_fe);
-                    const uint32_t F = __viaddmax_s16x2(up, h_fo, Fe);
-                    const uint32_t Fh = (F & 0xfffefffeu) | 0x00020002u;
-                    const uint32_t y = qc[r] ^ rc ^ C3;
-                    const uint32_t sc = __viaddmax_s16x2(y, h_sm, h_sx);
-                    const uint32_t Hd = __vadd2(diag, sc);
-                    const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
-                    // nibble [src1 src0 f e] per half
-                    const uint32_t sel1 = (E & 0x00010001u) | ((F << 1) & ~0x00010001u);      // bit0 <- e, bit1 <- f
-                    const uint32_t sel2 = (sel1 & 0x00030003u) | ((H << 2) & ~0x00030003u);   // bits 3:2 <- src
-                    const uint32_t nib = sel2 & 0x000f000fu;
-                    if (r < 4) acc0 += nib << (4 * r); else acc1 += nib << (4 * (r - 4));
-                    const uint32_t Hc = H & 0xfffcfffcu;
-                    diag = left;
-                    Hl[r] = Hc;
-                    Eh[r] = Ehn;
-                    up = Hc;
-                    fup = Fh;
-                }
-                Hbot = up; Fbot = fup;
-                if (liveA && j < mA) *tpA = __byte_perm(acc0, acc1, 0x5410);
-                if (liveB && j < mB) *tpB = __byte_perm(acc0, acc1, 0x7632);
-                if (has_next && lane == 31) bnd[j] = make_int2((int)Hbot, (int)Fbot);
-                if (liveA && j == mA - 1) {
+                for (int c = 0; c < PC; ++c) {
+                    uint32_t up = hu[c], fup = fu[c];
+                    uint32_t diag = (c == 0) ? diag0 : hu[c - 1];
+                    uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const int v = lo16(Hl[r]);
-                        if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
+                        const uint32_t left = Hl[r];
+                        const uint32_t Ee = __vadd2(Eh[r], h_ee);
+                        const uint32_t E = __viaddmax_s16x2(left, h_eo, Ee);
+                        const uint32_t Ehn = E | 0x00010001u;
+                        const uint32_t Fe = __vadd2(fup, h_fe);
+                        const uint32_t F = __viaddmax_s16x2(up, h_fo, Fe);
+                        const uint32_t Fh = (F & k_fclean) | 0x00020002u;
+                        const uint32_t y = qc[r] ^ rc[c] ^ C3;
+                        const uint32_t sc = __viaddmax_s16x2(y, h_sm, h_sx);
+                        const uint32_t Hd = __vadd2(diag, sc);
+                        const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
+                        // nibble [src1 src0 f e] per half
+                        const uint32_t sel1 = (E & k_sel1) | ((F << 1) & ~k_sel1);        // bit0 <- e, bit1 <- f
+                        const uint32_t sel2 = (sel1 & k_sel3) | ((H << 2) & ~k_sel3);     // bits 3:2 <- src
+                        const uint32_t nib = sel2 & 0x000f000fu;
+                        if (r < 4) acc0 += nib << (4 * r); else acc1 += nib << (4 * (r - 4));
+                        const uint32_t Hc = H & 0xfffcfffcu;
+                        diag = left;
+                        Hl[r] = Hc;
+                        Eh[r] = Ehn;
+                        up = Hc;
+                        fup = Fh;
+                    }
+                    Hbot[c] = up; Fbot[c] = fup;
+                    wA[c] = __byte_perm(acc0, acc1, 0x5410);
+                    wB[c] = __byte_perm(acc0, acc1, 0x7632);
+                    const int j = jb + c;
+                    if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)up, (int)fup);
+                    if (liveA && j == mA - 1) {             // last column of A: smallest i wins ties
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int v = lo16(Hl[r]);
+                            if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
+                        }
+                    }
+                    if (liveB && j == mB - 1) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int v = hi16(Hl[r]);
+                            if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
+                        }
+                    }
+                    if (trackA && j < mA) {                 // last row of A: smallest j wins ties
+                        uint32_t hv = Hl[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r) if (r == last_rA) hv = Hl[r];
+                        const int v = lo16(hv);
+                        if (v > browA) { browA = v; browA_j = j; }
+                    }
+                    if (trackB && j < mB) {
+                        uint32_t hv = Hl[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r) if (r == last_rB) hv = Hl[r];
+                        const int v = hi16(hv);
+                        if (v > browB) { browB = v; browB_j = j; }
                     }
                 }
-                if (liveB && j == mB - 1) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int v = hi16(Hl[r]);
-                        if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
-                    }
-                }
-                if (lastA && lane == last_laneA && j < mA) {
-                    uint32_t hv = Hl[0];
-#pragma unroll
-                    for (int r = 1; r < R; ++r) if (r == last_rA) hv = Hl[r];
-                    const int v = lo16(hv);
-                    if (v > browA) { browA = v; browA_j = j; }
-                }
-                if (lastB && lane == last_laneB && j < mB) {
-                    uint32_t hv = Hl[0];
-#pragma unroll
-                    for (int r = 1; r < R; ++r) if (r == last_rB) hv = Hl[r];
-                    const int v = hi16(hv);
-                    if (v > browB) { browB = v; browB_j = j; }
-                }
+                diag0 = hu[PC - 1];
+                if (liveA && jb < mA) *tpA = make_uint2(wA[0], wA[1]);
+                if (liveB && jb < mB) *tpB = make_uint2(wB[0], wB[1]);
             }
         }
         __syncwarp();
@@ -460,7 +496,8 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const uint32_t *trace = P.trace + (P.ptrace[p] - P.chunk_base);
     uint32_t *tail = P.trace + (P.ptrace[p + 1] - P.chunk_base);     // runs go to tail[-1], tail[-2], ...
-    const int T = m + 31;
+    const int pc = P.playout[p];                      // columns per step of the writer (1: 32-bit path, 2: packed)
+    const int T = (m + pc - 1) / pc + 31;
     int i = P.endq[p], j = P.endr[p];
     int nr = 0;
     uint32_t cur_op = 0xffu, cur_len = 0;
@@ -481,7 +518,8 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
         if (i < 0) { PUSH(ISOF_CIGAR_D, j + 1); break; }
         if (j < 0) { PUSH(ISOF_CIGAR_I, i + 1); break; }
         const int s = i >> 8, l = (i >> 3) & 31, r = i & 7;
-        const uint32_t word = __ldcg(&trace[((size_t)s * T + (j + l)) * 32 + l]);
+        const int jt = (pc == 1) ? j : (j >> 1), jc = (pc == 1) ? 0 : (j & 1);
+        const uint32_t word = __ldcg(&trace[(((size_t)s * T + (jt + l)) * 32 + l) * pc + jc]);
         const int nib = (word >> (4 * r)) & 15;
         if (where == 3) {
             const int src = nib >> 2;
@@ -700,7 +738,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     const int64_t total_words = (int64_t)pin[4];
     ctx->prof.dp_cells += (int64_t)pin[2];
     ctx->prof.dp_cells_padded += (int64_t)pin[3];
-    ctx->prof.trace_bytes += (total_words - (int64_t)TRACE_SLACK * P) * 4;
+    ctx->prof.trace_bytes += (int64_t)pin[3] / 2;                 // 4 bits per updated cell
     if ((int64_t)max_m * 16 * (std::abs(match) + std::abs(mismatch) + gap_ext) + 16LL * gap_open > (1LL << 28))
         return isof_fail(ctx, ISOF_ERR_RANGE, "sequence too long for the 32-bit tagged score range");
 
@@ -743,7 +781,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
                              (long long)max_chunk_words * 4);
     }
     const int occ_blocks = ctx->sm_count * 4;           // DP_WARPS*32 threads each
-    const int64_t bnd_stride = ((int64_t)max_m + 64) & ~63LL;
+    const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
     TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
 
     AlignParams A;
@@ -764,6 +802,9 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.h_fe = pk(-4 * gap_ext - 1);
     A.h_sm = pk(4 * match + 3 - (3 << CS16));
     A.h_sx = pk(4 * mismatch + 3);
+    A.k_fclean = 0xfffefffeu; A.k_sel1 = 0x00010001u; A.k_sel3 = 0x00030003u;
+    TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P));
+    A.playout = (uint8_t *)ctx->b_layout.p;
     A.h_max_min_len = h_max_min_len;
     A.h_max_max_len = h_max_max_len;
     int64_t *run_base = (int64_t *)(misc + 4);
