@@ -38,7 +38,9 @@ import numpy as np  # noqa: E402
 K_SIZE, W_SIZE = 20, 31
 MATCH, MISMATCH, GAP_OPEN, GAP_EXT = 2, -2, 12, 1
 DELTA_LEN = 5
-OPS_PER_CELL = 13        # ALU-pipe instructions per DP cell in the SASS of sg_dp_kernel
+# ALU-pipe instructions per DP cell in the SASS of sg_dp_kernel: the packed 16-bit
+# path issues 14 per packed row (= 2 cells), the 32-bit path 13 per row (= 1 cell)
+OPS_PER_CELL_PACKED, OPS_PER_CELL_32 = 7.0, 13.0
 
 
 def parse_args():
@@ -334,6 +336,8 @@ def run_b200(args):
         alg_bytes = (0.5 * prof["dp_cells"] + 2.0 * wl["n_bases"] * K) / max(prof["dp_launches"], 1)
         achieved_gbs = alg_bytes / (dp_ms_launch * 1e-3) / 1e9
         cups = prof["dp_cells"] / (prof["dp_ms"] * 1e-3)
+        packed_frac = prof["dp_cells_packed"] / max(prof["dp_cells"], 1)
+        OPS_PER_CELL = packed_frac * OPS_PER_CELL_PACKED + (1.0 - packed_frac) * OPS_PER_CELL_32
         line = {
             "metric": "interval_alignments_per_s", "value": value, "unit": "alignments/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": ms_dev_max / K, "higher_is_better": True,
@@ -359,7 +363,7 @@ def run_b200(args):
             "int_alu": {"cell_updates_per_s": cups, "gcups_kernel": cups / 1e9, "ops_per_cell": OPS_PER_CELL,
                         "achieved_lane_ops_per_s": cups * OPS_PER_CELL, "peak_lane_ops_per_s": int32_peak,
                         "frac": cups * OPS_PER_CELL / int32_peak if int32_peak else None,
-                        "padded_cell_frac": prof["dp_cells_padded"] / max(prof["dp_cells"], 1),
+                        "padded_cell_frac": prof["dp_cells_padded"] / max(prof["dp_cells"], 1), "packed_path_cell_frac": packed_frac,
                         "peak_source": "isof_int32_peak micro-kernel (independent VIADDMNMX chains), measured in this run"},
             "kernel_ms_per_step": {"dp": prof["dp_ms"] / K, "traceback_cigar_features": prof["traceback_ms"] / K,
                                    "minimizers": prof["minimizer_ms"] / K, "plan_encode": prof["other_ms"] / K},

@@ -78,6 +78,7 @@ typedef struct {
     double other_ms;             /* planning / encoding / span kernels                           */
     int64_t dp_cells;            /* sum len(s1)*len(s2) over aligned pairs                       */
     int64_t dp_cells_padded;     /* cells actually updated (stripe padding included)             */
+    int64_t dp_cells_packed;     /* part of dp_cells that went through the packed 16-bit path    */
     int64_t trace_bytes;         /* trace bytes written by the DP kernel                         */
     int64_t h2d_bytes, d2h_bytes;
 } isof_profile;

@@ -132,6 +132,20 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
     if (p == P) words[P] = 0;
 }
 
+// statistics only: cells of the pairs that take the packed path in chunk [start,end)
+__global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pn,
+                                    const int32_t *__restrict__ pm, int64_t start, int64_t end,
+                                    unsigned long long *__restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pA = start + 2 * t, pB = pA + 1;
+    unsigned long long c = 0;
+    if (pB < end && (pwild[pA] & 2) && (pwild[pB] & 2))
+        c = (unsigned long long)pn[pA] * pm[pA] + (unsigned long long)pn[pB] * pm[pB];
+    for (int d = 16; d; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // chunk_start[c] = first pair whose trace offset is >= c*budget   (c = 0..n_chunks)
 __global__ void chunk_bounds_kernel(const int64_t *__restrict__ ptrace, int64_t P, int64_t budget, int n_chunks,
                                     int64_t *__restrict__ chunk_start)
@@ -818,6 +832,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         {
             LaunchTimer t(ctx, SLOT_DP);
             const int64_t tasks = (cnt + 1) / 2;
+            if (ctx->profiling)
+                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, st>>>(pwild, pn, pm, ps, pe, misc + 5);
             int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
             sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, st>>>(A, ps, pe, counters + c);
         }
@@ -856,6 +872,11 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     CUDA_TRY(ctx, cudaMemcpyAsync(pin64, run_base, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (h_total_runs) *h_total_runs = pin64[0];
+    if (ctx->profiling) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(pin64 + 1, misc + 5, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        ctx->prof.dp_cells_packed += pin64[1];
+    }
     if (d_cigar && pin64[0] > cigar_cap)
         return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap,
                          (long long)pin64[0]);
