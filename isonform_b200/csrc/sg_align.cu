@@ -296,6 +296,58 @@ __device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
 // overhead (shuffles, prefetch, stores, loop) is paid once per PC*8 cells per alignment.
 // Trace layout of a packed pair: word[((stripe*T + t)*32 + lane)*PC + c], T = ceil(m/PC)+31, column
 // j = PC*(t-lane)+c; P.playout[p] = PC tells the traceback.
+//
+// The step loop of a stripe is peeled into fill / steady / drain.  In the steady range every lane
+// is inside both alignments with a full look-ahead block, so that loop has no bounds checks, no
+// end-cell bookkeeping and unconditional stores; fill, drain and the last stripes (which track the
+// end cell) go through the general step.
+struct P16Const {
+    uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx, k_fclean, k_sel1, k_sel3;
+};
+
+struct P16State {
+    uint32_t qc[R], Hl[R], Eh[R];
+    uint32_t Hbot[PC], Fbot[PC], rc_next[PC];
+    int2 b_next[PC];
+    uint32_t diag0;
+};
+
+// one column of 8 packed rows; returns the two trace words (A, B)
+__device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const uint32_t rc, uint32_t up, uint32_t fup,
+                                           uint32_t diag, uint32_t &hbot, uint32_t &fbot, uint32_t &wA, uint32_t &wB)
+{
+    const uint32_t C3 = (3u << CS16) | (3u << (CS16 + 16));
+    uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t left = S.Hl[r];
+        const uint32_t Ee = __vadd2(S.Eh[r], K.h_ee);
+        const uint32_t E = __viaddmax_s16x2(left, K.h_eo, Ee);
+        const uint32_t Ehn = E | 0x00010001u;
+        const uint32_t Fe = __vadd2(fup, K.h_fe);
+        const uint32_t F = __viaddmax_s16x2(up, K.h_fo, Fe);
+        const uint32_t Fh = (F & K.k_fclean) | 0x00020002u;
+        const uint32_t y = S.qc[r] ^ rc ^ C3;
+        const uint32_t sc = __viaddmax_s16x2(y, K.h_sm, K.h_sx);
+        const uint32_t Hd = __vadd2(diag, sc);
+        const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
+        // nibble [src1 src0 f e] per half
+        const uint32_t sel1 = (E & K.k_sel1) | ((F << 1) & ~K.k_sel1);        // bit0 <- e, bit1 <- f
+        const uint32_t sel2 = (sel1 & K.k_sel3) | ((H << 2) & ~K.k_sel3);     // bits 3:2 <- src
+        const uint32_t nib = sel2 & 0x000f000fu;
+        if (r < 4) acc0 += nib << (4 * r); else acc1 += nib << (4 * (r - 4));
+        const uint32_t Hc = H & 0xfffcfffcu;
+        diag = left;
+        S.Hl[r] = Hc;
+        S.Eh[r] = Ehn;
+        up = Hc;
+        fup = Fh;
+    }
+    hbot = up; fbot = fup;
+    wA = __byte_perm(acc0, acc1, 0x5410);
+    wB = __byte_perm(acc0, acc1, 0x7632);
+}
+
 __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
                                           int2 *__restrict__ bnd)
 {
@@ -307,70 +359,72 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     const uint8_t *__restrict__ rB = P.codes + P.seq_off[P.pb[pB]];
     uint32_t *__restrict__ traceA = P.trace + (P.ptrace[pA] - P.chunk_base);
     uint32_t *__restrict__ traceB = P.trace + (P.ptrace[pB] - P.chunk_base);
-    const int m = max(mA, mB);
+    const int m = max(mA, mB), mmin = min(mA, mB);
     const int T = (m + PC - 1) / PC + 31, TA = (mA + PC - 1) / PC + 31, TB = (mB + PC - 1) / PC + 31;
     const int nsA = (nA + SROWS - 1) / SROWS, nsB = (nB + SROWS - 1) / SROWS, ns = max(nsA, nsB);
     const int last_laneA = ((nA - 1) % SROWS) / R, last_rA = (nA - 1) % R;
     const int last_laneB = ((nB - 1) % SROWS) / R, last_rB = (nB - 1) % R;
-    const uint32_t h_eo = P.h_eo, h_ee = P.h_ee, h_fo = P.h_fo, h_fe = P.h_fe, h_sm = P.h_sm, h_sx = P.h_sx;
-    // masks live in registers (kernel parameters) so that "(x & mask) | imm" is ONE LOP3
-    const uint32_t k_fclean = P.k_fclean, k_sel1 = P.k_sel1, k_sel3 = P.k_sel3;
-    const uint32_t C3 = (3u << CS16) | (3u << (CS16 + 16));
+    P16Const K;
+    K.h_eo = P.h_eo; K.h_ee = P.h_ee; K.h_fo = P.h_fo; K.h_fe = P.h_fe; K.h_sm = P.h_sm; K.h_sx = P.h_sx;
+    K.k_fclean = P.k_fclean; K.k_sel1 = P.k_sel1; K.k_sel3 = P.k_sel3;   // masks in registers: "(x & mask) | imm" is ONE LOP3
     int bcolA = INT_MIN, bcolA_i = 0, browA = INT_MIN, browA_j = 0;
     int bcolB = INT_MIN, bcolB_i = 0, browB = INT_MIN, browB_j = 0;
     if (lane == 0) { P.playout[pA] = PC; P.playout[pB] = PC; }
+    // steady range of t: lane 31 has started (t >= 31) and lane 0's look-ahead block is inside both
+    // references: PC*t + 2*PC <= mmin
+    const int t_steady_end = (mmin - 2 * PC) / PC + 1;          // exclusive; may be <= 31 (then no steady range)
 
     for (int s = 0; s < ns; ++s) {
         const int i0 = s * SROWS + lane * R;
-        uint32_t qc[R], Hl[R], Eh[R];
+        P16State S;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const uint32_t a = (i0 + r < nA) ? (uint32_t)qA[i0 + r] : 0u;
             const uint32_t b = (i0 + r < nB) ? (uint32_t)qB[i0 + r] : 0u;
-            qc[r] = (a << CS16) | (b << (CS16 + 16));
-            Hl[r] = 0u;
-            Eh[r] = NEG16 | 0x00010001u;
+            S.qc[r] = (a << CS16) | (b << (CS16 + 16));
+            S.Hl[r] = 0u;
+            S.Eh[r] = NEG16 | 0x00010001u;
         }
         const bool has_prev = s > 0, has_next = s + 1 < ns;
         const bool liveA = s < nsA, liveB = s < nsB;
         const bool trackA = (s == nsA - 1) && lane == last_laneA, trackB = (s == nsB - 1) && lane == last_laneB;
-        uint32_t diag0 = 0u;
-        uint32_t Hbot[PC], Fbot[PC], rc_next[PC];
-        int2 b_next[PC];
+        const bool track_stripe = (s == nsA - 1) || (s == nsB - 1);          // warp-uniform
+        S.diag0 = 0u;
 #pragma unroll
         for (int c = 0; c < PC; ++c) {
-            Hbot[c] = 0u;
-            Fbot[c] = NEG16 | 0x00020002u;
-            rc_next[c] = 0u;
-            b_next[c] = make_int2(0, (int)(NEG16 | 0x00020002u));
+            S.Hbot[c] = 0u;
+            S.Fbot[c] = NEG16 | 0x00020002u;
+            S.rc_next[c] = 0u;
+            S.b_next[c] = make_int2(0, (int)(NEG16 | 0x00020002u));
             if (lane == 0) {
                 const uint32_t a = (c < mA) ? (uint32_t)rA[c] : 0u, b = (c < mB) ? (uint32_t)rB[c] : 0u;
-                rc_next[c] = (a << CS16) | (b << (CS16 + 16));
-                if (has_prev && c < m) b_next[c] = __ldcg(&bnd[c]);
+                S.rc_next[c] = (a << CS16) | (b << (CS16 + 16));
+                if (has_prev && c < m) S.b_next[c] = __ldcg(&bnd[c]);
             }
         }
         uint2 *tpA = reinterpret_cast<uint2 *>(traceA) + (size_t)s * TA * 32 + lane;
         uint2 *tpB = reinterpret_cast<uint2 *>(traceB) + (size_t)s * TB * 32 + lane;
 
-        for (int t = 0; t < T; ++t, tpA += 32, tpB += 32) {
+        // ---------------- general step (bounds checks + end-cell bookkeeping) ----------------
+        auto general_step = [&](const int t) {
             const int jb = PC * (t - lane);
             uint32_t rc[PC], hu[PC], fu[PC];
 #pragma unroll
             for (int c = 0; c < PC; ++c) {
-                rc[c] = rc_next[c];
-                hu[c] = __shfl_up_sync(FULL, Hbot[c], 1);
-                fu[c] = __shfl_up_sync(FULL, Fbot[c], 1);
-                if (lane == 0) { hu[c] = (uint32_t)b_next[c].x; fu[c] = (uint32_t)b_next[c].y; }
+                rc[c] = S.rc_next[c];
+                hu[c] = __shfl_up_sync(FULL, S.Hbot[c], 1);
+                fu[c] = __shfl_up_sync(FULL, S.Fbot[c], 1);
+                if (lane == 0) { hu[c] = (uint32_t)S.b_next[c].x; fu[c] = (uint32_t)S.b_next[c].y; }
             }
-            {   // prefetch the next block's reference bases / boundary cells
+            {
                 const int jn = jb + PC;
                 if ((unsigned)jn < (unsigned)m) {
 #pragma unroll
                     for (int c = 0; c < PC; ++c) {
                         const uint32_t a = (jn + c < mA) ? (uint32_t)rA[jn + c] : 0u;
                         const uint32_t b = (jn + c < mB) ? (uint32_t)rB[jn + c] : 0u;
-                        rc_next[c] = (a << CS16) | (b << (CS16 + 16));
-                        if (has_prev && lane == 0 && jn + c < m) b_next[c] = __ldcg(&bnd[jn + c]);
+                        S.rc_next[c] = (a << CS16) | (b << (CS16 + 16));
+                        if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = __ldcg(&bnd[jn + c]);
                     }
                 }
             }
@@ -378,72 +432,85 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
-                    uint32_t up = hu[c], fup = fu[c];
-                    uint32_t diag = (c == 0) ? diag0 : hu[c - 1];
-                    uint32_t acc0 = 0u, acc1 = 0u;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const uint32_t left = Hl[r];
-                        const uint32_t Ee = __vadd2(Eh[r], h_ee);
-                        const uint32_t E = __viaddmax_s16x2(left, h_eo, Ee);
-                        const uint32_t Ehn = E | 0x00010001u;
-                        const uint32_t Fe = __vadd2(fup, h_fe);
-                        const uint32_t F = __viaddmax_s16x2(up, h_fo, Fe);
-                        const uint32_t Fh = (F & k_fclean) | 0x00020002u;
-                        const uint32_t y = qc[r] ^ rc[c] ^ C3;
-                        const uint32_t sc = __viaddmax_s16x2(y, h_sm, h_sx);
-                        const uint32_t Hd = __vadd2(diag, sc);
-                        const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
-                        // nibble [src1 src0 f e] per half
-                        const uint32_t sel1 = (E & k_sel1) | ((F << 1) & ~k_sel1);        // bit0 <- e, bit1 <- f
-                        const uint32_t sel2 = (sel1 & k_sel3) | ((H << 2) & ~k_sel3);     // bits 3:2 <- src
-                        const uint32_t nib = sel2 & 0x000f000fu;
-                        if (r < 4) acc0 += nib << (4 * r); else acc1 += nib << (4 * (r - 4));
-                        const uint32_t Hc = H & 0xfffcfffcu;
-                        diag = left;
-                        Hl[r] = Hc;
-                        Eh[r] = Ehn;
-                        up = Hc;
-                        fup = Fh;
-                    }
-                    Hbot[c] = up; Fbot[c] = fup;
-                    wA[c] = __byte_perm(acc0, acc1, 0x5410);
-                    wB[c] = __byte_perm(acc0, acc1, 0x7632);
+                    p16_column(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
                     const int j = jb + c;
-                    if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)up, (int)fup);
+                    if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
                     if (liveA && j == mA - 1) {             // last column of A: smallest i wins ties
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const int v = lo16(Hl[r]);
+                            const int v = lo16(S.Hl[r]);
                             if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
                         }
                     }
                     if (liveB && j == mB - 1) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const int v = hi16(Hl[r]);
+                            const int v = hi16(S.Hl[r]);
                             if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
                         }
                     }
                     if (trackA && j < mA) {                 // last row of A: smallest j wins ties
-                        uint32_t hv = Hl[0];
+                        uint32_t hv = S.Hl[0];
 #pragma unroll
-                        for (int r = 1; r < R; ++r) if (r == last_rA) hv = Hl[r];
+                        for (int r = 1; r < R; ++r) if (r == last_rA) hv = S.Hl[r];
                         const int v = lo16(hv);
                         if (v > browA) { browA = v; browA_j = j; }
                     }
                     if (trackB && j < mB) {
-                        uint32_t hv = Hl[0];
+                        uint32_t hv = S.Hl[0];
 #pragma unroll
-                        for (int r = 1; r < R; ++r) if (r == last_rB) hv = Hl[r];
+                        for (int r = 1; r < R; ++r) if (r == last_rB) hv = S.Hl[r];
                         const int v = hi16(hv);
                         if (v > browB) { browB = v; browB_j = j; }
                     }
                 }
-                diag0 = hu[PC - 1];
-                if (liveA && jb < mA) *tpA = make_uint2(wA[0], wA[1]);
-                if (liveB && jb < mB) *tpB = make_uint2(wB[0], wB[1]);
+                S.diag0 = hu[PC - 1];
+                if (liveA && jb < mA) tpA[(size_t)t * 32] = make_uint2(wA[0], wA[1]);
+                if (liveB && jb < mB) tpB[(size_t)t * 32] = make_uint2(wB[0], wB[1]);
             }
+        };
+
+        const bool can_steady = liveA && liveB && !track_stripe && t_steady_end > 31;
+        const int t1 = can_steady ? 31 : T, t2 = can_steady ? t_steady_end : T;
+        for (int t = 0; t < t1; ++t) general_step(t);
+        if (can_steady) {
+            // ---------------- steady state: no bounds checks, no bookkeeping ----------------
+            const uint8_t *pa_ = rA + PC * (31 - lane) + PC;       // look-ahead block of step t = 31
+            const uint8_t *pb_ = rB + PC * (31 - lane) + PC;
+            const int2 *pbn = bnd + PC * 31 + PC;                  // lane 0 only
+            int2 *pbs = bnd + PC * (31 - 31);                      // lane 31 only: jb at t = 31
+            uint2 *sA = tpA + (size_t)31 * 32, *sB = tpB + (size_t)31 * 32;
+#pragma unroll 1
+            for (int t = 31; t < t2; ++t) {
+                uint32_t rc[PC], hu[PC], fu[PC];
+#pragma unroll
+                for (int c = 0; c < PC; ++c) {
+                    rc[c] = S.rc_next[c];
+                    hu[c] = __shfl_up_sync(FULL, S.Hbot[c], 1);
+                    fu[c] = __shfl_up_sync(FULL, S.Fbot[c], 1);
+                    if (lane == 0) { hu[c] = (uint32_t)S.b_next[c].x; fu[c] = (uint32_t)S.b_next[c].y; }
+                }
+#pragma unroll
+                for (int c = 0; c < PC; ++c)
+                    S.rc_next[c] = ((uint32_t)pa_[c] << CS16) | ((uint32_t)pb_[c] << (CS16 + 16));
+                if (has_prev && lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < PC; ++c) S.b_next[c] = __ldcg(pbn + c);
+                }
+                uint32_t wA[PC], wB[PC];
+#pragma unroll
+                for (int c = 0; c < PC; ++c)
+                    p16_column(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
+                S.diag0 = hu[PC - 1];
+                *sA = make_uint2(wA[0], wA[1]);
+                *sB = make_uint2(wB[0], wB[1]);
+                if (has_next && lane == 31) {
+#pragma unroll
+                    for (int c = 0; c < PC; ++c) pbs[c] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
+                }
+                pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
+            }
+            for (int t = t2; t < T; ++t) general_step(t);
         }
         __syncwarp();
     }
@@ -476,7 +543,7 @@ __device__ __forceinline__ void dp_pair32(const AlignParams &P, const int64_t p,
 
 // One task = two consecutive pairs of the chunk.  Both eligible -> one packed pass; otherwise each
 // pair runs through the 32-bit path.
-__global__ void __launch_bounds__(DP_WARPS * 32)
+__global__ void __launch_bounds__(DP_WARPS * 32, 2)
 sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsigned long long *__restrict__ counter)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
