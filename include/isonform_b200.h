@@ -65,6 +65,11 @@ ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
  * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any
  * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
 ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
+/* Alignment batches whose trace exceeds the scratch budget are cut into chunks.  on=1 (default):
+ * chunks alternate between two streams with double-buffered scratch, so a chunk's tail (idle SMs while
+ * its last pairs finish) and its traceback overlap the next chunk's DP.  on=0: one stream, one
+ * buffer (per-kernel event timings are then exact; bench.py uses it for the roofline step). */
+ISOF_API int isof_set_overlap(isof_ctx *ctx, int on);
 
 /* Per-ctx counters, reset by isof_profile_reset.  Kernel times are measured with CUDA events on the
  * ctx stream around each launch when profiling is enabled (isof_profile_enable(ctx,1)); enabling

@@ -38,7 +38,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs"]
@@ -64,6 +64,7 @@ def load():
     L.isof_set_stream.argtypes = [vp, vp]
     L.isof_set_trace_budget.argtypes = [vp, C.c_size_t]
     L.isof_set_packed.argtypes = [vp, C.c_int]
+    L.isof_set_overlap.argtypes = [vp, C.c_int]
     L.isof_profile_enable.argtypes = [vp, C.c_int]
     L.isof_profile_reset.argtypes = [vp]
     L.isof_profile_get.argtypes = [vp, C.POINTER(Profile)]
@@ -143,6 +144,10 @@ class Context:
     def set_packed(self, on=True):
         """Enable (default) / disable the packed 16-bit DP path; results are identical either way."""
         self._check(self._L.isof_set_packed(self._h, 1 if on else 0))
+
+    def set_overlap(self, on=True):
+        """Two-stream chunk pipelining (default on); off gives exact per-kernel event timings."""
+        self._check(self._L.isof_set_overlap(self._h, 1 if on else 0))
 
     def profile_enable(self, on=True):
         self._check(self._L.isof_profile_enable(self._h, 1 if on else 0))

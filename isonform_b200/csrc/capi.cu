@@ -107,6 +107,7 @@ int isof_init(int device, isof_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
     ctx->pinned_cap = 4096;
     if (cudaMallocHost(&ctx->pinned, ctx->pinned_cap) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
     *out = ctx;
@@ -122,6 +123,7 @@ int isof_destroy(isof_ctx *ctx)
     for (DevBuf *b : ctx->all_bufs()) if (b->p) cudaFree(b->p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return ISOF_OK;
 }
@@ -148,6 +150,13 @@ int isof_set_packed(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;
     ctx->disable_packed = (on == 0);
+    return ISOF_OK;
+}
+
+int isof_set_overlap(isof_ctx *ctx, int on)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->overlap = (on != 0);
     return ISOF_OK;
 }
 

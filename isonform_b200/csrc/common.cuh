@@ -25,14 +25,16 @@ struct isof_ctx {
     char err[512] = {0};
     size_t trace_budget = 0;          // bytes; 0 = decide at first use
     bool profiling = false;
-    bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
+    bool disable_packed = false;
+    bool overlap = true;              // pipeline trace chunks over two streams (double-buffered scratch)
+    cudaStream_t aux_stream = nullptr;      // force the 32-bit DP path (tests / A-B measurements)
     isof_profile prof;
     // pending (start, stop, slot) event pairs when profiling
     struct Timed { cudaEvent_t a, b; int slot; };
     std::vector<Timed> timed;
     // scratch
     DevBuf b_codes, b_seqflags, b_pn, b_pm, b_paoff, b_pboff, b_ptrace, b_scan_tmp, b_bnd, b_trace, b_nruns,
-        b_counters, b_misc, b_runoff, b_status, b_layout;
+        b_counters, b_misc, b_runoff, b_status, b_layout, b_trace2, b_bnd2, b_runoff2, b_pboff2, b_scan_tmp2;
     DevBuf b_h_bases, b_h_off, b_h_pa, b_h_pb, b_h_score, b_h_endq, b_h_endr, b_h_cig, b_h_cigoff, b_h_feat;
     DevBuf b_m_hash, b_m_tmp, b_m_cnt, b_m_off;
     DevBuf b_s_mread, b_s_mkey, b_s_mpolya, b_s_mcnt, b_s_moff, b_s_key1, b_s_key2, b_s_keyt, b_s_keyo, b_s_idx0, b_s_idx1,
@@ -41,7 +43,7 @@ struct isof_ctx {
     std::vector<DevBuf *> all_bufs()
     {
         return {&b_codes, &b_seqflags, &b_pn, &b_pm, &b_paoff, &b_pboff, &b_ptrace, &b_scan_tmp, &b_bnd, &b_trace, &b_nruns,
-                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
+                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_trace2, &b_bnd2, &b_runoff2, &b_pboff2, &b_scan_tmp2, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
                 &b_h_endr, &b_h_cig, &b_h_cigoff, &b_h_feat, &b_m_hash, &b_m_tmp, &b_m_cnt, &b_m_off, &b_s_mread, &b_s_mkey,
                 &b_s_mpolya, &b_s_mcnt, &b_s_moff, &b_s_key1, &b_s_key2, &b_s_keyt, &b_s_keyo, &b_s_idx0, &b_s_idx1, &b_s_idx2,
                 &b_s_forb, &b_s_head, &b_s_bid, &b_s_sorttmp, &b_sh_minpos, &b_sh_minoff, &b_sh_rread, &b_sh_rp1, &b_sh_rp2,
@@ -102,20 +104,21 @@ struct LaunchTimer {
     isof_ctx *ctx;
     int slot;
     cudaEvent_t a = nullptr, b = nullptr;
-    LaunchTimer(isof_ctx *c, int s) : ctx(c), slot(s)
+    cudaStream_t st;
+    LaunchTimer(isof_ctx *c, int s, cudaStream_t stream = nullptr) : ctx(c), slot(s), st(stream ? stream : c->stream)
     {
         ctx->prof.launches++;
         if (slot == SLOT_DP) ctx->prof.dp_launches++;
         if (ctx->profiling) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, st);
         }
     }
     ~LaunchTimer()
     {
         if (ctx->profiling) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, st);
             ctx->timed.push_back({a, b, slot});
         }
     }

@@ -831,6 +831,9 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         if (ctx->trace_budget < (64u << 20)) ctx->trace_budget = 64u << 20;
     }
     int64_t budget_words = (int64_t)(ctx->trace_budget / 4);
+    // pipelined mode: two half-size buffers, chunks alternate between two streams
+    const bool want_overlap = ctx->overlap && total_words > budget_words / 2;
+    if (want_overlap) budget_words /= 2;
     if (budget_words > total_words) budget_words = total_words;
     if (budget_words < 1) budget_words = 1;
     const int n_chunks = (int)(total_words / budget_words) + 1;
@@ -855,15 +858,24 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     int64_t max_chunk_words = 0;
     for (int c = 0; c < n_chunks; ++c) max_chunk_words = std::max(max_chunk_words, start_off[c + 1] - start_off[c]);
-    if ((size_t)max_chunk_words * 4 > ctx->b_trace.cap) {
-        int rc = dev_reserve(ctx, ctx->b_trace, (size_t)max_chunk_words * 4);
-        if (rc != ISOF_OK)
-            return isof_fail(ctx, ISOF_ERR_NOMEM, "trace scratch of %lld bytes does not fit (largest pair/chunk)",
-                             (long long)max_chunk_words * 4);
+    const bool pipelined = want_overlap && n_chunks > 1;
+    for (DevBuf *tb : {&ctx->b_trace, &ctx->b_trace2}) {
+        if (tb == &ctx->b_trace2 && !pipelined) break;
+        if ((size_t)max_chunk_words * 4 > tb->cap) {
+            int rc = dev_reserve(ctx, *tb, (size_t)max_chunk_words * 4);
+            if (rc != ISOF_OK)
+                return isof_fail(ctx, ISOF_ERR_NOMEM, "trace scratch of %lld bytes does not fit (largest pair/chunk)",
+                                 (long long)max_chunk_words * 4);
+        }
     }
-    const int occ_blocks = ctx->sm_count * 4;           // DP_WARPS*32 threads each
+    const int occ_blocks = ctx->sm_count * 2;           // resident CTAs (128 registers x 256 threads: 2 per SM)
     const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
     TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
+    if (pipelined) {
+        TRY(dev_reserve(ctx, ctx->b_bnd2, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
+        TRY(dev_reserve(ctx, ctx->b_runoff2, sizeof(int64_t) * (size_t)(P + 1)));
+        TRY(dev_reserve(ctx, ctx->b_pboff2, sizeof(int64_t) * (size_t)(P + 1)));
+    }
 
     AlignParams A;
     A.cat = d_cat; A.codes = codes; A.seq_off = d_off; A.pa = d_pa; A.pb = d_pb; A.pn = pn; A.pm = pm; A.pwild = pwild;
@@ -891,49 +903,86 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     int64_t *run_base = (int64_t *)(misc + 4);
     CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
 
+    // ---- chunk pipeline.  Serial mode: everything on `st`.  Pipelined mode: chunk c runs on stream c%2 with
+    // its own trace / boundary / scan scratch; the only cross-chunk dependency is the running CIGAR offset
+    // (cigar_copy of chunk c needs advance_base of chunk c-1), carried by one event per chunk.
+    cudaStream_t lanes[2] = {st, pipelined ? ctx->aux_stream : st};
+    std::vector<cudaEvent_t> done((size_t)n_chunks, nullptr);
+    cudaEvent_t fork = nullptr;
+    if (pipelined) {
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventRecord(fork, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(lanes[1], fork, 0));
+    }
+    int prev = -1, live = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t ps = chunk_start[c], pe = chunk_start[c + 1];
         if (pe <= ps) continue;
         const int64_t cnt = pe - ps;
+        const int w = pipelined ? (live & 1) : 0;
+        ++live;
+        cudaStream_t cs = lanes[w];
         A.chunk_base = start_off[c];
+        A.trace = (uint32_t *)(w ? ctx->b_trace2.p : ctx->b_trace.p);
+        A.bnd = (int2 *)(w ? ctx->b_bnd2.p : ctx->b_bnd.p);
+        int64_t *c_runoff = w ? (int64_t *)ctx->b_runoff2.p : runoff;
+        int64_t *c_nruns64 = w ? (int64_t *)ctx->b_pboff2.p : nruns64;
+        DevBuf &c_scan = w ? ctx->b_scan_tmp2 : ctx->b_scan_tmp;
         {
-            LaunchTimer t(ctx, SLOT_DP);
+            LaunchTimer t(ctx, SLOT_DP, cs);
             const int64_t tasks = (cnt + 1) / 2;
             if (ctx->profiling)
-                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, st>>>(pwild, pn, pm, ps, pe, misc + 5);
+                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, ps, pe, misc + 5);
             int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
-            sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, st>>>(A, ps, pe, counters + c);
+            sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, cs>>>(A, ps, pe, counters + c);
         }
         {
-            LaunchTimer t(ctx, SLOT_TB);
-            sg_traceback_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, st>>>(A, ps, pe);
+            LaunchTimer t(ctx, SLOT_TB, cs);
+            sg_traceback_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, cs>>>(A, ps, pe);
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (d_features) {
-            LaunchTimer t(ctx, SLOT_TB);
-            sg_features_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, st>>>(A, ps, pe, delta_len, d_features);
+            LaunchTimer t(ctx, SLOT_TB, cs);
+            sg_features_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, cs>>>(A, ps, pe, delta_len, d_features);
         }
         {
-            LaunchTimer t(ctx, SLOT_TB);
-            nruns_to_i64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(nruns, ps, cnt, nruns64);
+            LaunchTimer t(ctx, SLOT_TB, cs);
+            nruns_to_i64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(nruns, ps, cnt, c_nruns64);
         }
         size_t tb2 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb2, nruns64, runoff, cnt, st);
-        TRY(dev_reserve(ctx, ctx->b_scan_tmp, tb2));
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, c_nruns64, c_runoff, cnt, cs);
+        TRY(dev_reserve(ctx, c_scan, tb2));
         {
-            LaunchTimer t(ctx, SLOT_TB);
-            CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tb2, nruns64, runoff, cnt, st));
+            LaunchTimer t(ctx, SLOT_TB, cs);
+            CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(c_scan.p, tb2, c_nruns64, c_runoff, cnt, cs));
         }
+        if (pipelined && prev >= 0) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, done[prev], 0));
         {
-            LaunchTimer t(ctx, SLOT_TB);
-            cigar_copy_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, st>>>(A, ps, pe, runoff, run_base, d_cigar,
+            LaunchTimer t(ctx, SLOT_TB, cs);
+            cigar_copy_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, cs>>>(A, ps, pe, c_runoff, run_base, d_cigar,
                                                                                  cigar_cap, d_cigar_off);
         }
         {
-            LaunchTimer t(ctx, SLOT_TB);
-            advance_base_kernel<<<1, 1, 0, st>>>(run_base, runoff, nruns, ps, pe, d_cigar_off, P);
+            LaunchTimer t(ctx, SLOT_TB, cs);
+            advance_base_kernel<<<1, 1, 0, cs>>>(run_base, c_runoff, nruns, ps, pe, d_cigar_off, P);
         }
         CUDA_TRY(ctx, cudaGetLastError());
+        if (pipelined) {
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventRecord(done[c], cs));
+        }
+        prev = c;
+    }
+    if (pipelined) {
+        if (prev >= 0) CUDA_TRY(ctx, cudaStreamWaitEvent(st, done[prev], 0));      // join: the chain orders all chunks
+        // the aux stream may still hold the (ordered-before) second-to-last chunk: join it explicitly
+        cudaEvent_t tail = nullptr;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&tail, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventRecord(tail, lanes[1]));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, tail, 0));
+        cudaEventDestroy(tail);
+        cudaEventDestroy(fork);
+        for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
     }
     int64_t *pin64 = (int64_t *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(pin64, run_base, 8, cudaMemcpyDeviceToHost, st));

@@ -347,3 +347,28 @@ def test_packed_path_range_limits(ctx):
         assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er)
         assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
     assert int(res["score"][0]) == 2 * 4093
+
+
+def test_pipelined_and_serial_chunking_agree(ctx):
+    """Many small chunks: the two-stream pipeline (default) and the serial path give identical output,
+    including the CIGAR offsets that are chained across chunks."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(61)
+    base = _rand_dna(rng, 500)
+    seqs = [synth.mutate(rng, base, 0.05) for _ in range(24)]
+    ia, ib = np.triu_indices(len(seqs), 1)
+    ctx.set_trace_budget(3 << 20)
+    try:
+        ctx.set_overlap(True)
+        a = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+        ctx.set_overlap(False)
+        b = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+    finally:
+        ctx.set_overlap(True)
+        ctx.set_trace_budget(0)
+    for key in ("score", "end_q", "end_r", "cigar_off", "cigar", "features"):
+        if a[key] is not None:
+            assert np.array_equal(a[key], b[key]), key
+    for p in range(0, len(ia), 11):
+        sc, eq, er, runs = oracle.sg_align(seqs[ia[p]], seqs[ib[p]], 2, -2, 12, 1)
+        assert a["cigar"][a["cigar_off"][p]:a["cigar_off"][p + 1]].tolist() == runs.tolist()
