@@ -5,7 +5,8 @@
 
 A *step* is one pass of the hot path over one synthetic isONclust batch (BASELINE.json configs[1]:
 1000 ONT-like reads of a 10-isoform 3 kb gene at 5 % error, SURVEY.md section 8d "C2"):
-  (a) minimizer extraction over the batch (k=20, w=31), and
+  (a) minimizer extraction over the batch (k=20, w=31),
+  (c) the minimizer-pair database + span search (xmin=40, xmax=80, delta_len=5), and
   (b) the all-pairs semi-global affine alignment (2,-2,12,1) of the batch's isoform consensuses with
       traceback, CIGAR and the integer merge-decision features -- the `merge_consensuses` loop of
       the reference (IsoformGeneration.py:473-501), where at 5 % error every read is its own group
@@ -36,6 +37,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 K_SIZE, W_SIZE = 20, 31
+X_MIN, X_MAX = 40, 80            # main:623-625 raises xmin to 2k; xmax default 80
 MATCH, MISMATCH, GAP_OPEN, GAP_EXT = 2, -2, 12, 1
 DELTA_LEN = 5
 # ALU-pipe instructions per DP cell in the SASS of sg_dp_kernel: the packed 16-bit
@@ -225,12 +227,23 @@ def run_b200(args):
     d_feat = torch.empty((P, _lib.N_FEATURES), dtype=torch.int32, device=dev)
     d_mpos = torch.empty(wl["n_bases"] + R, dtype=torch.int32, device=dev)
     d_moff = torch.empty(R + 1, dtype=torch.int64, device=dev)
+    rec_cap = 8 * (wl["n_bases"] // 5) + 1024                 # ~0.15 minimizers/base, ~6 partners each
+    d_rec = [torch.empty(rec_cap, dtype=torch.int32, device=dev) for _ in range(6)]
+    d_boff = torch.empty(rec_cap + 1, dtype=torch.int32, device=dev)
+    d_bdrop = torch.empty(rec_cap, dtype=torch.uint8, device=dev)
     cig_cap = [max(64 * P, 1 << 20)]
     d_cig = [torch.empty(cig_cap[0], dtype=torch.int32, device=dev)]
+
+    stats = {}
 
     def step_dev():
         n_min = ctx.minimizers_batch_dev(d_cat.data_ptr(), d_off.data_ptr(), R, wl["n_bases"], K_SIZE, W_SIZE,
                                          d_mpos.data_ptr(), d_mpos.numel(), d_moff.data_ptr())
+        n_rec, _n_b = ctx.spans_batch_dev(d_cat.data_ptr(), d_off.data_ptr(), R, d_mpos.data_ptr(), d_moff.data_ptr(), n_min,
+                                          K_SIZE, X_MIN, X_MAX, DELTA_LEN, rec_cap, d_rec[0].data_ptr(), d_rec[1].data_ptr(),
+                                          d_rec[2].data_ptr(), d_rec[3].data_ptr(), d_rec[4].data_ptr(), d_rec[5].data_ptr(),
+                                          d_boff.data_ptr(), d_bdrop.data_ptr())
+        stats["n_rec"] = n_rec
         while True:
             try:
                 runs = ctx.sg_align_pairs_dev(d_cat.data_ptr(), d_off.data_ptr(), R, wl["n_bases"], d_ia.data_ptr(),
@@ -301,10 +314,18 @@ def run_b200(args):
     h_moff = torch.empty(R + 1, dtype=torch.int64).pin_memory()
     L = ctx._L
     n_out = C.c_int64(0)
+    h_rec = [torch.empty(rec_cap, dtype=torch.int32).pin_memory() for _ in range(6)]
+    h_boff = torch.empty(rec_cap + 1, dtype=torch.int32).pin_memory()
+    h_bdrop = torch.empty(rec_cap, dtype=torch.uint8).pin_memory()
+    n_rec_h, n_b_h = C.c_int64(0), C.c_int64(0)
 
     def step_e2e():
         ctx._check(L.isof_minimizers_batch(ctx._h, h_cat.data_ptr(), h_off.data_ptr(), R, K_SIZE, W_SIZE, h_mpos.data_ptr(),
                                            h_mpos.numel(), h_moff.data_ptr(), C.byref(n_out)))
+        ctx._check(L.isof_spans_batch(ctx._h, h_cat.data_ptr(), h_off.data_ptr(), R, h_mpos.data_ptr(), h_moff.data_ptr(), K_SIZE,
+                                      X_MIN, X_MAX, DELTA_LEN, rec_cap, h_rec[0].data_ptr(), h_rec[1].data_ptr(),
+                                      h_rec[2].data_ptr(), h_rec[3].data_ptr(), h_rec[4].data_ptr(), h_rec[5].data_ptr(),
+                                      h_boff.data_ptr(), h_bdrop.data_ptr(), C.byref(n_rec_h), C.byref(n_b_h)))
         ctx._check(L.isof_sg_features_pairs(ctx._h, h_cat.data_ptr(), h_off.data_ptr(), R, h_ia.data_ptr(), h_ib.data_ptr(), P,
                                             MATCH, MISMATCH, GAP_OPEN, GAP_EXT, DELTA_LEN, h_score.data_ptr(),
                                             h_feat.data_ptr(), h_cig.data_ptr(), h_cig.numel(), h_coff.data_ptr()))
@@ -357,13 +378,14 @@ def run_b200(args):
             "steps": K, "warmup": args.warmup, "ms_per_step": ms_dev_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": wl["name"], "n_reads": R, "pairs_per_batch": P, "mean_read_len": wl["n_bases"] / R,
-                       "k": K_SIZE, "w": W_SIZE, "scores": [MATCH, MISMATCH, GAP_OPEN, GAP_EXT], "delta_len": DELTA_LEN,
+                       "k": K_SIZE, "w": W_SIZE, "xmin": X_MIN, "xmax": X_MAX, "scores": [MATCH, MISMATCH, GAP_OPEN, GAP_EXT],
+                       "delta_len": DELTA_LEN,
                        "parallelism": "1 cluster per GPU, no data-path collective",
                        "l2": "per-step trace working set %.0f GB >> 126 MB L2; no explicit flush" % (
                            prof["trace_bytes"] / PROF_STEPS / 1e9)},
             "gcups": cells_all * K / (ms_dev_max * 1e-3) / 1e9,
             "reads_per_s": reads_all * K / (ms_dev_max * 1e-3),
-            "minimizers_per_step": int(n_min), "cigar_runs_per_step": int(n_runs), "merges_per_step": int(merges),
+            "minimizers_per_step": int(n_min), "minimizer_pairs_per_step": int(stats.get("n_rec", 0)), "cigar_runs_per_step": int(n_runs), "merges_per_step": int(merges),
             "e2e": {"value": e2e_value, "unit": "alignments/s",
                     "h2d_bytes_per_step": int(prof_e2e["h2d_bytes"] // K), "d2h_bytes_per_step": int(prof_e2e["d2h_bytes"] // K),
                     "ms_per_step": ms_e2e_max / K, "gcups": cells_all * K / (ms_e2e_max * 1e-3) / 1e9},
@@ -381,7 +403,7 @@ def run_b200(args):
                         "padded_cell_frac": prof["dp_cells_padded"] / max(prof["dp_cells"], 1), "packed_path_cell_frac": packed_frac,
                         "peak_source": "isof_int32_peak micro-kernel (independent VIADDMNMX chains), measured in this run"},
             "kernel_ms_per_step": {"dp": prof["dp_ms"] / PROF_STEPS, "traceback_cigar_features": prof["traceback_ms"] / PROF_STEPS,
-                                   "minimizers": prof["minimizer_ms"] / PROF_STEPS, "plan_encode": prof["other_ms"] / PROF_STEPS,
+                                   "minimizers": prof["minimizer_ms"] / PROF_STEPS, "plan_encode_spans": prof["other_ms"] / PROF_STEPS,
                                    "note": "serialised roofline step; in the timed (pipelined) steps traceback overlaps DP"},
             "clocks": clk,
         }
