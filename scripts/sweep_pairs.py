@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""BASELINE config 5: interval-pair alignment sweep 50 bp - 5 kb (pairs (x, mutate(x, eps))).
+
+    python scripts/sweep_pairs.py [--out profiles/rNN_sweep.json] [--cpu]
+
+Reports pairs/s and GCUPS through the host-buffer C ABI (isof_sg_align_pairs incl. H2D/D2H) per
+(length, eps, score set).  With --cpu the oracle port (all host cores) runs on a bounded sample."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from isonform_b200 import _lib, hotpath, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--lengths", default="50,100,200,500,1000,2000,5000")
+    args = ap.parse_args()
+    ctx = _lib.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    rows = []
+    rng = np.random.default_rng(5)
+    for L in [int(x) for x in args.lengths.split(",")]:
+        n_pairs = int(max(2000, min(200000, 4e9 / (L * L))))
+        for eps in (0.01, 0.05, 0.15):
+            nb = min(n_pairs, 2000)
+            base = [synth.random_dna(rng, L) for _ in range(nb)]
+            muts = [synth.mutate(rng, x, eps) or "A" for x in base]
+            seqs = base + muts                  # pair p = (orig[p % nb], mutated copy of it)
+            pa = (np.arange(n_pairs) % nb).astype(np.int32)
+            pb = (nb + (np.arange(n_pairs) % nb)).astype(np.int32)
+            cat, off = hotpath.pack_sequences(seqs)
+            lens = np.diff(off)
+            cells = float((lens[pa].astype(np.int64) * lens[pb]).sum())
+            for name, sc in (("bubble", (2, -8, 12, 1)), ("isoform", (2, -2, 12, 1))):
+                ctx.sg_align_pairs(cat, off, pa[:1000], pb[:1000], *sc)            # warm-up
+                t0 = time.perf_counter()
+                res = ctx.sg_align_pairs(cat, off, pa, pb, *sc)
+                dt = time.perf_counter() - t0
+                row = {"len": L, "eps": eps, "scores": name, "pairs": n_pairs, "pairs_per_s": n_pairs / dt,
+                       "gcups": cells / dt / 1e9, "cigar_runs": int(len(res["cigar"]))}
+                if args.cpu:
+                    import oracle
+                    ns = int(max(16, min(n_pairs, 2e9 / (L * L))))
+                    t0 = time.perf_counter()
+                    oracle.sg_align_pairs(cat, off, pa[:ns], pb[:ns], *sc, threads=os.cpu_count())
+                    dtc = time.perf_counter() - t0
+                    row["cpu_pairs_per_s"] = ns / dtc
+                    row["cpu_cores"] = oracle.num_threads()
+                    row["speedup"] = row["pairs_per_s"] / row["cpu_pairs_per_s"]
+                rows.append(row)
+                print(json.dumps(row), flush=True)
+    if args.out:
+        json.dump({"config": "C5 pair sweep, host-buffer C ABI incl. copies", "rows": rows}, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

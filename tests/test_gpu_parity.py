@@ -372,3 +372,108 @@ def test_pipelined_and_serial_chunking_agree(ctx):
     for p in range(0, len(ia), 11):
         sc, eq, er, runs = oracle.sg_align(seqs[ia[p]], seqs[ib[p]], 2, -2, 12, 1)
         assert a["cigar"][a["cigar_off"][p]:a["cigar_off"][p + 1]].tolist() == runs.tolist()
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def _rescore(s1, s2, runs, match, mismatch, gap_open, gap_ext):
+    """(score with interior gaps charged and end gaps free, query consumed, ref consumed)."""
+    ops = [(int(r) >> 4, int(r) & 15) for r in runs]
+    i = j = sc = 0
+    for k_, (ln, op) in enumerate(ops):
+        edge = k_ == 0 or k_ == len(ops) - 1
+        if op in (7, 8):
+            a = np.frombuffer(s1[i:i + ln].encode(), np.uint8)
+            b = np.frombuffer(s2[j:j + ln].encode(), np.uint8)
+            assert bool((a == b).all()) == (op == 7) or ln == 0
+            sc += int((a == b).sum()) * match + int((a != b).sum()) * mismatch
+            i += ln; j += ln
+        elif op == 1:
+            i += ln; sc -= 0 if edge else gap_open + (ln - 1) * gap_ext
+        else:
+            j += ln; sc -= 0 if edge else gap_open + (ln - 1) * gap_ext
+    return sc, i, j
+
+
+def test_c2_size_all_pairs_properties_and_oracle_sample(ctx):
+    """BASELINE config-2 read lengths (2.7 kb, 5 % error), all pairs of 110 reads (5 995 alignments, 4.5e10
+    cells): size-independent properties on every pair, bit-exact oracle comparison on a sample, and the
+    packed and 32-bit paths against each other on a slice."""
+    from isonform_b200 import hotpath, synth, polya
+    reads, _iso, _t = synth.make_config("C2", n_reads=110)
+    seqs = sorted((polya.remove_read_polyA_ends(s, 12, 1) for _, s in reads), key=len)
+    ia, ib = np.triu_indices(len(seqs), 1)
+    res = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+    off = res["cigar_off"]
+    assert off[0] == 0 and (np.diff(off) > 0).all() and off[-1] == len(res["cigar"])
+    lens = np.array([len(s) for s in seqs])
+    runs_len = res["cigar"] >> 4
+    ops = res["cigar"] & 15
+    assert set(np.unique(ops).tolist()) <= {1, 2, 7, 8}
+    # per pair: columns consumed == sequence lengths (vectorised over all 5 995 cigars)
+    seg = np.repeat(np.arange(len(ia)), np.diff(off))
+    q_used = np.bincount(seg, weights=runs_len * np.isin(ops, (1, 7, 8)), minlength=len(ia)).astype(np.int64)
+    r_used = np.bincount(seg, weights=runs_len * np.isin(ops, (2, 7, 8)), minlength=len(ia)).astype(np.int64)
+    assert np.array_equal(q_used, lens[ia]) and np.array_equal(r_used, lens[ib])
+    assert np.array_equal(res["features"][:, 0], np.bincount(seg, weights=runs_len, minlength=len(ia)).astype(np.int64))
+    assert np.array_equal(res["features"][:, 1], np.diff(off))
+    # no two adjacent runs share an op (run-length encoding is canonical)
+    same = (ops[1:] == ops[:-1]) & (seg[1:] == seg[:-1])
+    assert not same.any()
+    # scores: re-scoring the cigar never undercuts the reported score; identical reads score 2*len
+    rng = np.random.default_rng(7)
+    sample = rng.choice(len(ia), size=36, replace=False)
+    for p in sample:
+        runs = res["cigar"][off[p]:off[p + 1]]
+        sc, qi, rj = _rescore(seqs[ia[p]], seqs[ib[p]], runs, 2, -2, 12, 1)
+        assert sc >= int(res["score"][p])
+        osc, oeq, oer, oruns = oracle.sg_align(seqs[ia[p]], seqs[ib[p]], 2, -2, 12, 1)
+        assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (osc, oeq, oer)
+        assert runs.tolist() == oruns.tolist()
+    merge = hotpath._merge_from_features(res["features"], 0.15, 5, 30, 50)
+    for p in sample[:12]:
+        assert bool(merge[p]) == oracle.align_to_merge(seqs[ia[p]], seqs[ib[p]], 0.15, 5, 30, 50)
+    # packed vs 32-bit on a slice
+    sl = slice(0, 400)
+    ctx.set_packed(False)
+    try:
+        ref32 = hotpath.align_pairs(seqs, ia[sl], ib[sl], 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+    finally:
+        ctx.set_packed(True)
+    assert np.array_equal(ref32["score"], res["score"][sl]) and np.array_equal(ref32["features"], res["features"][sl])
+    assert np.array_equal(ref32["cigar"], res["cigar"][:off[400]])
+    # self alignment is the identity
+    self_res = hotpath.align_pairs(seqs[:8], np.arange(8), np.arange(8), 2, -2, 12, 1, ctx=ctx)
+    assert self_res["score"].tolist() == [2 * len(s) for s in seqs[:8]]
+    assert [int(r) for r in self_res["cigar"]] == [(len(s) << 4) | 7 for s in seqs[:8]]
+
+
+def test_c2_size_minimizers_and_spans_properties(ctx):
+    """Full C2 batch (1000 reads): minimizer/pair invariants that hold at any size, plus an oracle check on
+    a sample of reads."""
+    from isonform_b200 import hotpath, polya, spans, synth
+    reads_l, _iso, _t = synth.make_config("C2")
+    reads = {i + 1: (acc, polya.remove_read_polyA_ends(s, 12, 1), "") for i, (acc, s) in enumerate(reads_l)}
+    k, w = 20, 31
+    M = hotpath.get_minimizers_and_positions(reads, w, k, "lex", ctx)
+    for r in (1, 17, 333, 1000):
+        assert M[r] == oracle.get_kmer_minimizers(reads[r][1], k, w)
+    for r in list(reads)[::37]:
+        pos = np.array([p for _, p in M[r]])
+        assert (np.diff(pos) > 0).all() and pos[0] <= w - k and pos[-1] < len(reads[r][1]) - k
+        assert (np.diff(pos) <= w - k + 1).all()          # every window holds a minimizer
+    idx = spans.SpanIndex(reads, M, k, 40, 80, 5, ctx)
+    d = idx.rec_p2 - idx.rec_p1
+    assert ((d > 40) & (d <= 80)).all()
+    assert (np.diff(idx.rec_read) >= 0).all()             # emission order: read by read
+    sizes = np.diff(idx.bucket_off)
+    assert sizes.sum() == idx.n_rec and (sizes > 0).all()
+    assert np.array_equal(np.sort(idx.sorted_rec), np.arange(idx.n_rec))
+    bsz = sizes[idx.rec_bucket]
+    assert ((idx.rec_count > 0) == ((bsz >= 3) & (idx.bucket_dropped[idx.rec_bucket] == 0))).all()
+    assert (idx.rec_count <= bsz).all()
+    # oracle comparison for three reads (the reference loop over the same database)
+    odb = oracle.get_minimizer_combinations_database(M, k, 40, 80, reads)
+    for r in (2, 500, 999):
+        want = oracle.pyside.read_intervals(r, M[r], odb, k, 40, 80, 5)
+        got = idx.intervals(r)
+        assert [(a, b, c, list(x)) for a, b, c, x in got] == [(a, b, c, list(x)) for a, b, c, x in want]
