@@ -142,7 +142,7 @@ def cpu_step(wl, sample_pairs, threads):
     sel = np.linspace(0, wl["n_pairs"] - 1, num=sample_pairs).astype(np.int64)
     t0 = time.perf_counter()
     oracle.sg_align_pairs(wl["cat"], wl["off"], wl["ia"][sel], wl["ib"][sel], MATCH, MISMATCH, GAP_OPEN, GAP_EXT,
-                          threads=threads, want_cigar=True)
+                          threads=threads, want_cigar=True, simd=True)
     t_al = time.perf_counter() - t0
     lens = np.diff(wl["off"])
     cells = int((lens[wl["ia"][sel]].astype(np.int64) * lens[wl["ib"][sel]]).sum())
@@ -182,7 +182,7 @@ def run_reference(args):
             "gcups": cells * args.steps / t / 1e9,
             "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": oracle.num_threads(), "kind": "port",
                              "sample": "%d of %d pairs per step (evenly spaced) + minimizers of all %d reads; "
-                                       "oracle/isof_oracle.c scalar Gotoh+trace, OpenMP over pairs"
+                                       "oracle/isof_oracle.c Gotoh+trace+cigar, 16 pairs per thread in int16 SIMD lanes (AVX2 where available), OpenMP"
                                        % (sample, wl["n_pairs"], wl["n_reads"])},
             "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -415,7 +415,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": sample / (t_min + t_al), "unit": "alignments/s", "cores": oracle.num_threads(),
                                     "kind": "port", "gcups": c / t_al / 1e9, "minimizer_mbases_per_s": wl["n_bases"] / t_min / 1e6,
                                     "sample": "%d of %d pairs (evenly spaced) + minimizers of all %d reads; "
-                                              "oracle/isof_oracle.c scalar Gotoh+trace, OpenMP over pairs"
+                                              "oracle/isof_oracle.c Gotoh+trace+cigar, 16 pairs per thread in int16 SIMD lanes (AVX2 where available), OpenMP"
                                               % (sample, P, R)}
         print(json.dumps(line))
     if world > 1:

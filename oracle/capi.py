@@ -51,6 +51,8 @@ def lib():
                                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                  C.c_int]
+        L.isof_oracle_sg_align_pairs_simd.restype = C.c_int64
+        L.isof_oracle_sg_align_pairs_simd.argtypes = L.isof_oracle_sg_align_pairs.argtypes
         L.isof_oracle_num_threads.restype = C.c_int32
         del u8p
         _lib = L
@@ -106,7 +108,9 @@ def sg_align(s1, s2, match=2, mismatch=-2, gap_open=12, gap_ext=1, tiebreak=None
     return sc.value, eq.value, er.value, runs[:nr.value].copy()
 
 
-def sg_align_pairs(cat, off, ia, ib, match, mismatch, gap_open, gap_ext, threads=0, want_cigar=True):
+def sg_align_pairs(cat, off, ia, ib, match, mismatch, gap_open, gap_ext, threads=0, want_cigar=True, simd=False):
+    """Batch alignment on the CPU.  simd=False: the scalar checker, one pair per thread.  simd=True: 16 pairs
+    per thread in int16 lanes (the CPU baseline of bench.py); bit-identical results."""
     cat = np.ascontiguousarray(cat, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.int64)
     ia = np.ascontiguousarray(ia, dtype=np.int32)
@@ -117,7 +121,8 @@ def sg_align_pairs(cat, off, ia, ib, match, mismatch, gap_open, gap_ext, threads
     score = np.empty(P, np.int32); eq = np.empty(P, np.int32); er = np.empty(P, np.int32)
     cig = np.empty(max(cap, 1), np.uint32)
     coff = np.empty(P + 1, np.int64)
-    tot = lib().isof_oracle_sg_align_pairs(cat.ctypes.data, off.ctypes.data, ia.ctypes.data, ib.ctypes.data,
+    fn = lib().isof_oracle_sg_align_pairs_simd if simd else lib().isof_oracle_sg_align_pairs
+    tot = fn(cat.ctypes.data, off.ctypes.data, ia.ctypes.data, ib.ctypes.data,
                                            P, match, mismatch, gap_open, gap_ext, score.ctypes.data,
                                            eq.ctypes.data, er.ctypes.data,
                                            cig.ctypes.data if want_cigar else None, coff.ctypes.data, cap,

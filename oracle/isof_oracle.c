@@ -401,3 +401,227 @@ ISOF_API int32_t isof_oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Inter-pair SIMD batch aligner (CPU baseline of bench.py).                                   */
+/*                                                                                            */
+/* Same recurrences, tie-breaks and cigar walk as isof_oracle_sg_align_tb with the default    */
+/* table, but 16 pairs advance in lock step in int16 lanes (the innermost loop runs over the   */
+/* lanes and is auto-vectorised: AVX2 where the CPU has it, via target_clones).  This is the   */
+/* shape of a production CPU aligner (libparasail is SIMD too); the scalar function above      */
+/* stays the checker and tests/test_oracle_golden.py holds the two bit-identical.              */
+/* Falls back to the scalar routine for pairs outside the int16 range.                         */
+/* ------------------------------------------------------------------------------------------ */
+#define VL 16
+#define NEG16V (-16000)
+
+typedef struct {
+    int32_t n[VL], m[VL];
+    const uint8_t *s1[VL], *s2[VL];
+    int64_t pair[VL];
+    int lanes;
+} group_t;
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define ISOF_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define ISOF_CLONES
+#endif
+
+ISOF_CLONES
+static void group_fill(int N, int M, const int16_t *restrict q1 /* N x VL */, const int16_t *restrict c2 /* M x VL */,
+                       int16_t *restrict H /* (M+1) x VL */, int16_t *restrict F /* M x VL */, uint8_t *restrict trace,
+                       int16_t match, int16_t mismatch, int16_t open, int16_t ext, const int32_t *restrict nn,
+                       const int32_t *restrict mm, int32_t *restrict best_col, int32_t *restrict best_col_i,
+                       int32_t *restrict best_row, int32_t *restrict best_row_j)
+{
+    for (int j = 0; j <= M; ++j) for (int v = 0; v < VL; ++v) H[(size_t)j * VL + v] = 0;
+    for (int j = 0; j < M; ++j) for (int v = 0; v < VL; ++v) F[(size_t)j * VL + v] = NEG16V;
+    for (int i = 0; i < N; ++i) {
+        int16_t Hdiag[VL], Hleft[VL], Eleft[VL];
+        const int16_t *restrict qc = q1 + (size_t)i * VL;
+        for (int v = 0; v < VL; ++v) { Hdiag[v] = 0; Hleft[v] = 0; Eleft[v] = NEG16V; }
+        uint8_t *restrict trow = trace + (size_t)i * M * VL;
+        for (int j = 0; j < M; ++j) {
+            int16_t *restrict Hup = H + (size_t)(j + 1) * VL;
+            int16_t *restrict Fp = F + (size_t)j * VL;
+            const int16_t *restrict rc = c2 + (size_t)j * VL;
+            uint8_t *restrict t = trow + (size_t)j * VL;
+#pragma omp simd
+            for (int v = 0; v < VL; ++v) {
+                const int16_t eo = (int16_t)(Hleft[v] - open), ee = (int16_t)(Eleft[v] - ext);
+                const int16_t E = eo > ee ? eo : ee;
+                const uint8_t fe = eo > ee ? 0 : T_E_EXT;
+                const int16_t fo = (int16_t)(Hup[v] - open), fx = (int16_t)(Fp[v] - ext);
+                const int16_t Fv = fo > fx ? fo : fx;
+                const uint8_t ff = fo > fx ? 0 : T_F_EXT;
+                const int16_t wild = (int16_t)((qc[v] > 3) | (rc[v] > 3));
+                const int16_t sm = qc[v] == rc[v] ? match : mismatch;
+                const int16_t s = wild ? 0 : sm;
+                const int16_t Hd = (int16_t)(Hdiag[v] + s);
+                int16_t Hv = Hd > E ? Hd : E;
+                Hv = Hv > Fv ? Hv : Fv;
+                const uint8_t src = (Hv == Hd) ? (T_SRC_DIAG << 2) : ((Hv == Fv) ? (T_SRC_F << 2) : (T_SRC_E << 2));
+                t[v] = (uint8_t)(src | ff | fe);
+                Hdiag[v] = Hup[v];
+                Hup[v] = Hv;
+                Fp[v] = Fv;
+                Hleft[v] = Hv;
+                Eleft[v] = E;
+            }
+        }
+        for (int v = 0; v < VL; ++v) {
+            if (i < nn[v]) {                                   /* last column of lane v */
+                const int32_t hv = H[(size_t)mm[v] * VL + v];
+                if (hv > best_col[v]) { best_col[v] = hv; best_col_i[v] = i; }
+            }
+            if (i == nn[v] - 1) {                              /* last row of lane v */
+                for (int j = 0; j < mm[v]; ++j) {
+                    const int32_t hv = H[(size_t)(j + 1) * VL + v];
+                    if (hv > best_row[v]) { best_row[v] = hv; best_row_j[v] = j; }
+                }
+            }
+        }
+    }
+}
+
+static int simd_ok(int32_t n, int32_t m, int32_t match, int32_t mismatch, int32_t open, int32_t ext)
+{
+    int64_t mn = n < m ? n : m, mx = n > m ? n : m;
+    int64_t am = match < 0 ? -match : match, ax = mismatch < 0 ? -mismatch : mismatch;
+    if (am * mn > 30000) return 0;
+    if (2 * (int64_t)open + (int64_t)ext * mx + ax + am > 15000) return 0;
+    return n > 0 && m > 0;
+}
+
+ISOF_API int64_t isof_oracle_sg_align_pairs_simd(const uint8_t *cat, const int64_t *off, const int32_t *ia,
+                                                 const int32_t *ib, int64_t P, int32_t match, int32_t mismatch,
+                                                 int32_t open, int32_t ext, int32_t *score, int32_t *end_q,
+                                                 int32_t *end_r, uint32_t *cigar, int64_t *cigar_off,
+                                                 int64_t cigar_cap, int threads)
+{
+    uint32_t **runs = (uint32_t **)calloc((size_t)P, sizeof(uint32_t *));
+    int32_t *nr = (int32_t *)calloc((size_t)P, sizeof(int32_t));
+    int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)(P > 0 ? P : 1));
+    int err = 0;
+    /* SIMD-eligible pairs first, sorted by (n, m) so that lanes of a group have similar shapes */
+    int64_t ne = 0;
+    for (int64_t p = 0; p < P; ++p) {
+        int32_t n = (int32_t)(off[ia[p] + 1] - off[ia[p]]), m = (int32_t)(off[ib[p] + 1] - off[ib[p]]);
+        if (simd_ok(n, m, match, mismatch, open, ext)) order[ne++] = p;
+    }
+    /* insertion into buckets would be overkill: a simple shell sort on n*65536+m */
+    for (int64_t gap = ne / 2; gap > 0; gap /= 2)
+        for (int64_t a = gap; a < ne; ++a) {
+            int64_t t = order[a], b = a;
+            int64_t kt = ((off[ia[t] + 1] - off[ia[t]]) << 20) + (off[ib[t] + 1] - off[ib[t]]);
+            while (b >= gap) {
+                int64_t u = order[b - gap];
+                int64_t ku = ((off[ia[u] + 1] - off[ia[u]]) << 20) + (off[ib[u] + 1] - off[ib[u]]);
+                if (ku <= kt) break;
+                order[b] = u; b -= gap;
+            }
+            order[b] = t;
+        }
+    const int64_t ngroups = (ne + VL - 1) / VL;
+    (void)threads;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int64_t g = 0; g < ngroups; ++g) {
+        int32_t nn[VL], mm[VL];
+        int64_t pp[VL];
+        int lanes = 0, N = 0, M = 0;
+        for (int v = 0; v < VL; ++v) {
+            int64_t idx = g * VL + v;
+            if (idx < ne) {
+                int64_t p = order[idx];
+                pp[v] = p; nn[v] = (int32_t)(off[ia[p] + 1] - off[ia[p]]); mm[v] = (int32_t)(off[ib[p] + 1] - off[ib[p]]);
+                if (nn[v] > N) N = nn[v];
+                if (mm[v] > M) M = mm[v];
+                ++lanes;
+            } else { pp[v] = -1; nn[v] = 0; mm[v] = 0; }
+        }
+        int16_t *q1 = (int16_t *)malloc(sizeof(int16_t) * (size_t)N * VL);
+        int16_t *c2 = (int16_t *)malloc(sizeof(int16_t) * (size_t)M * VL);
+        int16_t *H = (int16_t *)malloc(sizeof(int16_t) * (size_t)(M + 1) * VL);
+        int16_t *F = (int16_t *)malloc(sizeof(int16_t) * (size_t)M * VL);
+        uint8_t *trace = (uint8_t *)malloc((size_t)N * (size_t)M * VL);
+        if (!q1 || !c2 || !H || !F || !trace) { err = 1; free(q1); free(c2); free(H); free(F); free(trace); continue; }
+        for (int v = 0; v < VL; ++v) {
+            const uint8_t *a = pp[v] >= 0 ? cat + off[ia[pp[v]]] : NULL;
+            const uint8_t *b = pp[v] >= 0 ? cat + off[ib[pp[v]]] : NULL;
+            for (int i = 0; i < N; ++i) q1[(size_t)i * VL + v] = (int16_t)(i < nn[v] ? base_code(a[i]) : 6);
+            for (int j = 0; j < M; ++j) c2[(size_t)j * VL + v] = (int16_t)(j < mm[v] ? base_code(b[j]) : 7);
+        }
+        int32_t bc[VL], bci[VL], br[VL], brj[VL];
+        for (int v = 0; v < VL; ++v) { bc[v] = br[v] = -(1 << 30); bci[v] = brj[v] = 0; }
+        group_fill(N, M, q1, c2, H, F, trace, (int16_t)match, (int16_t)mismatch, (int16_t)open, (int16_t)ext, nn, mm, bc, bci,
+                   br, brj);
+        for (int v = 0; v < VL; ++v) {
+            if (pp[v] < 0) continue;
+            const int64_t p = pp[v];
+            const int32_t n = nn[v], m = mm[v];
+            const uint8_t *s1 = cat + off[ia[p]], *s2 = cat + off[ib[p]];
+            int32_t sc = br[v], eq = n - 1, er = brj[v];
+            if (bc[v] > sc) { sc = bc[v]; eq = bci[v]; er = m - 1; }
+            else if (bc[v] == sc && er == m - 1 && bci[v] < eq) eq = bci[v];
+            score[p] = sc; end_q[p] = eq; end_r[p] = er;
+            uint32_t *rev = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + m + 2));
+            int32_t cnt = 0;
+            uint32_t cur_op = 0xffffffffu, cur_len = 0;
+#define PUSH2(op, len)                                                                             \
+    do {                                                                                           \
+        if ((len) > 0) {                                                                           \
+            if (cur_op == (uint32_t)(op)) cur_len += (uint32_t)(len);                              \
+            else { if (cur_len) rev[cnt++] = (cur_len << 4) | cur_op; cur_op = (op); cur_len = (len); } \
+        }                                                                                          \
+    } while (0)
+            int32_t i = eq, j = er;
+            if (eq + 1 == n) PUSH2(OP_D, m - 1 - j); else PUSH2(OP_I, n - 1 - i);
+            int where = T_SRC_DIAG;
+            while (i >= 0 || j >= 0) {
+                if (i < 0) { PUSH2(OP_D, j + 1); break; }
+                if (j < 0) { PUSH2(OP_I, i + 1); break; }
+                const uint8_t t = trace[((size_t)i * M + (size_t)j) * VL + v];
+                if (where == T_SRC_DIAG) {
+                    int src = t >> 2;
+                    if (src == T_SRC_DIAG) { PUSH2(upc(s1[i]) == upc(s2[j]) ? OP_EQ : OP_X, 1); --i; --j; }
+                    else where = src;
+                } else if (where == T_SRC_E) { PUSH2(OP_D, 1); --j; where = (t & T_E_EXT) ? T_SRC_E : T_SRC_DIAG; }
+                else { PUSH2(OP_I, 1); --i; where = (t & T_F_EXT) ? T_SRC_F : T_SRC_DIAG; }
+            }
+            if (cur_len) rev[cnt++] = (cur_len << 4) | cur_op;
+#undef PUSH2
+            runs[p] = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(cnt > 0 ? cnt : 1));
+            for (int q = 0; q < cnt; ++q) runs[p][q] = rev[cnt - 1 - q];
+            nr[p] = cnt;
+            free(rev);
+        }
+        free(q1); free(c2); free(H); free(F); free(trace);
+    }
+    /* everything the int16 lanes cannot hold goes through the scalar routine */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int64_t p = 0; p < P; ++p) {
+        if (runs[p]) continue;
+        int32_t n = (int32_t)(off[ia[p] + 1] - off[ia[p]]), m = (int32_t)(off[ib[p] + 1] - off[ib[p]]);
+        int32_t cap = n + m + 2;
+        runs[p] = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(cap > 0 ? cap : 1));
+        int32_t rc = isof_oracle_sg_align(cat + off[ia[p]], n, cat + off[ib[p]], m, match, mismatch, open, ext, &score[p],
+                                          &end_q[p], &end_r[p], runs[p], cap, &nr[p]);
+        if (rc < 0) err = 1;
+    }
+    int64_t tot = 0;
+    for (int64_t p = 0; p < P; ++p) {
+        cigar_off[p] = tot;
+        if (!err && cigar && tot + nr[p] <= cigar_cap) memcpy(cigar + tot, runs[p], sizeof(uint32_t) * (size_t)nr[p]);
+        tot += nr[p];
+        free(runs[p]);
+    }
+    cigar_off[P] = tot;
+    free(runs); free(nr); free(order);
+    return err ? -1 : tot;
+}

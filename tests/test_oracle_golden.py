@@ -221,3 +221,29 @@ def test_tiebreak_table_is_live():
         assert a[0] == b[0]
         changed += int(a[1:3] != b[1:3])
     assert changed > 0
+
+
+def test_simd_batch_aligner_is_bit_identical_to_the_scalar_checker():
+    """The inter-pair SIMD CPU aligner (bench.py's CPU baseline) against the scalar restatement: ragged
+    groups, wildcards, tie-heavy alphabets, a pair outside the int16 range (scalar fallback)."""
+    rng = np.random.default_rng(12)
+    seqs = []
+    for i in range(90):
+        alpha = ["ACGT", "AC", "ACGTN", "A", "ACGTacgt"][i % 5]
+        seqs.append("".join(alpha[int(x)] for x in rng.integers(0, len(alpha), size=int(rng.integers(1, 330)))))
+    big = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=16500))
+    seqs += [big, big[:16400] + "ACGT"]
+    cat = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.int64)
+    ia = rng.integers(0, 90, size=75).astype(np.int32)
+    ib = rng.integers(0, 90, size=75).astype(np.int32)
+    for params in [(2, -2, 12, 1), (2, -8, 12, 1), (1, -1, 1, 1), (2, -2, 0, 0)]:
+        a = oracle.sg_align_pairs(cat, off, ia, ib, *params, threads=2, simd=False)
+        b = oracle.sg_align_pairs(cat, off, ia, ib, *params, threads=2, simd=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), params
+    ia2 = np.array([90, 3], dtype=np.int32); ib2 = np.array([91, 4], dtype=np.int32)     # 16.5 kb: int16 cannot hold it
+    a = oracle.sg_align_pairs(cat, off, ia2, ib2, 2, -2, 12, 1, simd=False)
+    b = oracle.sg_align_pairs(cat, off, ia2, ib2, 2, -2, 12, 1, simd=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
