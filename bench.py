@@ -151,10 +151,12 @@ def cpu_step(wl, sample_pairs, threads):
 
 def pick_cpu_sample(wl, threads, target_s=12.0):
     """Size the pair sample so that one CPU step takes about target_s seconds."""
-    probe = max(threads, 8)
+    unit = 16 * threads                       # the SIMD port aligns 16 pairs per thread at a time
+    probe = min(unit, wl["n_pairs"])
     _tm, t_al, _ = cpu_step(wl, probe, threads)
     per_pair = max(t_al / probe, 1e-6)
-    return int(max(probe, min(wl["n_pairs"], target_s / per_pair)))
+    want = int(max(probe, min(wl["n_pairs"], target_s / per_pair)))
+    return min(wl["n_pairs"], max(unit, (want // unit) * unit))
 
 
 def run_reference(args):
