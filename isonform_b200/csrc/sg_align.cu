@@ -2,20 +2,23 @@
 // CIGAR-compatible with the parasail.sg_trace_scan_16/_32 call behind
 // consensus.parasail_alignment (reference modules/consensus.py:55-67).
 //
-// DP kernel (sg_dp_kernel): one warp per pair, anti-diagonal wavefront.  The query (rows) is cut
-// into stripes of 256 rows; lane l owns 8 consecutive rows and, at step t, the column j = t - l.
-// Per step a lane receives H/F of the row above from lane l-1 (one shuffle each), keeps H(i,j-1),
-// E(i,j-1) of its rows in registers and emits one 32-bit trace word (8 rows x 4 bits).
-// Scores are held as 16*score + tag: the low 4 bits carry the provenance of a value so that the
-// DPX max instructions (VIADDMNMX / VIMNMX3) resolve every tie exactly like the restated library
-// (DIAG > F > E; gap extension wins a tie against gap opening) and the trace nibble falls out of
-// the winning operands' tags without a single compare instruction:
+// DP kernel (sg_dp_kernel): persistent warps pull tasks (two consecutive pairs) from an atomic counter.
+// Anti-diagonal wavefront per warp: the query (rows) is cut into stripes of 256 rows; lane l owns 8
+// consecutive rows and, at step t, the two columns 2(t-l), 2(t-l)+1.  Per step a lane receives H/F of the
+// row above from lane l-1 (shuffles), keeps H(i,j-1), E(i,j-1) of its rows in registers and emits one
+// 32-bit trace word (8 rows x 4 bits) per column and alignment.
+// Scores are held as scale*score + tag: the low bits carry the provenance of a value so that the DPX max
+// instructions (VIADDMNMX / VIMNMX3) resolve every tie exactly like the restated library (DIAG > F > E;
+// gap extension wins a tie against gap opening) and the trace nibble falls out of the winning operands'
+// tags without a single compare instruction.  32-bit path (16*score + 4 tag bits):
 //     E candidates:  open -> ..0100   extend -> ..0101      (bit0 = E came from extension)
 //     F candidates:  open -> ..1000   extend -> ..1010      (bit1 = F came from extension)
 //     diagonal:                ..1100
 //     nibble = [src1 src0 f_ext e_ext],  src: 3 diag, 2 F (consumes query, 'I'), 1 E (consumes ref, 'D')
-// Trace layout per pair: word[(stripe*(m+31) + t)*32 + lane]  -> every step is one coalesced 128 B
-// store.  The bottom row of a stripe (H,F per column) goes through a per-warp global line buffer.
+// The packed path (two alignments per warp in 16-bit halves, 4*score + 2 tag bits) is described at
+// dp_pair16.  Trace layout per pair: word[((stripe*T + t)*32 + lane)*2 + col], T = ceil(m/2)+31 -> every
+// step is one coalesced 256 B store.  The bottom row of a stripe (H,F per column) goes through a per-warp
+// global line buffer.
 //
 // Traceback kernel: one thread per pair walks the trace from the end cell and writes the CIGAR
 // runs backwards into the tail of the pair's own trace region, so the runs end up in alignment
@@ -165,93 +168,166 @@ __global__ void chunk_bounds_kernel(const int64_t *__restrict__ ptrace, int64_t 
 // ---------------------------------------------------------------------------------------------
 // DP
 // ---------------------------------------------------------------------------------------------
+// 32-bit path: one alignment per warp, 16*score + 4-bit tag, two columns per step, the step loop peeled
+// into fill / steady / drain exactly like the packed path below (which documents the scheme).
+struct P32State {
+    int qc[R], Hl[R], El[R];
+    int Hbot[2], Fbot[2], rc_next[2];
+    int2 b_next[2];
+    int diag0;
+};
+
+template <bool WILD>
+__device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, const int rc, int up, int fup, int diag,
+                                           int &hbot, int &fbot, uint32_t &word)
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int left = S.Hl[r];
+        const int Ee = S.El[r] + P.c_ee;
+        const int E = __viaddmax_s32(left, P.c_eo, Ee);
+        const int Fe = fup + P.c_fe;
+        const int F = __viaddmax_s32(up, P.c_fo, Fe);
+        const int y = S.qc[r] ^ rc ^ (3 << CODE_SHIFT);
+        int sc = __viaddmax_s32(y, P.c_sm, P.c_sx);
+        if (WILD) { if ((S.qc[r] | rc) & (4 << CODE_SHIFT)) sc = 12; }
+        const int Hd = diag + sc;
+        const int H = __vimax3_s32(Hd, F, E);
+        uint32_t nib = ((uint32_t)H & ~1u) | ((uint32_t)E & 1u);
+        nib = (nib & ~2u) | ((uint32_t)F & 2u);
+        acc |= (nib & 15u) << (4 * r);
+        const int Hc = H & ~15;
+        diag = left;
+        S.Hl[r] = Hc;
+        S.El[r] = E & ~15;
+        up = Hc;
+        fup = F & ~15;
+    }
+    hbot = up; fbot = fup;
+    word = acc;
+}
+
 template <bool WILD>
 __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd)
 {
+    constexpr int C2 = 2;                         // columns per step
     const unsigned FULL = 0xffffffffu;
     const int n = P.pn[p], m = P.pm[p];
     const uint8_t *__restrict__ q = P.codes + P.seq_off[P.pa[p]];
     const uint8_t *__restrict__ rf = P.codes + P.seq_off[P.pb[p]];
     uint32_t *__restrict__ trace = P.trace + (P.ptrace[p] - P.chunk_base);
-    const int T = m + 31;
+    const int T = (m + C2 - 1) / C2 + 31;
     const int nstripes = (n + SROWS - 1) / SROWS;
     const int last_lane = ((n - 1) % SROWS) / R, last_r = (n - 1) % R;
-    const int c_eo = P.c_eo, c_ee = P.c_ee, c_fo = P.c_fo, c_fe = P.c_fe, c_sm = P.c_sm, c_sx = P.c_sx;
     int best_col = INT_MIN, best_col_i = 0, best_row = INT_MIN, best_row_j = 0;
-    if (lane == 0) P.playout[p] = 1;
+    if (lane == 0) P.playout[p] = C2;
+    const int t_steady_end = (m - 2 * C2) / C2 + 1;
 
     for (int s = 0; s < nstripes; ++s) {
         const int i0 = s * SROWS + lane * R;
-        int qc[R], Hl[R], El[R];
+        P32State S;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            qc[r] = (i0 + r < n) ? ((int)q[i0 + r] << CODE_SHIFT) : 0;
-            Hl[r] = 0;           // H(i,-1) = 0: free leading gap
-            El[r] = NEGV;
+            S.qc[r] = (i0 + r < n) ? ((int)q[i0 + r] << CODE_SHIFT) : 0;
+            S.Hl[r] = 0;           // H(i,-1) = 0: free leading gap
+            S.El[r] = NEGV;
         }
         const bool has_prev = s > 0, has_next = s + 1 < nstripes, is_last = !has_next;
-        int diag0 = 0;           // H(i0-1, j-1); H(.,-1) = 0
-        int Hbot = 0, Fbot = NEGV;
-        int rc_next = (lane == 0) ? ((int)rf[0] << CODE_SHIFT) : 0;
-        int2 b_next = make_int2(0, NEGV);
-        if (has_prev && lane == 0) b_next = __ldcg(&bnd[0]);
-        uint32_t *tp = trace + (size_t)s * T * 32 + lane;
+        const bool track = is_last && lane == last_lane;
+        S.diag0 = 0;
+#pragma unroll
+        for (int c = 0; c < C2; ++c) {
+            S.Hbot[c] = 0; S.Fbot[c] = NEGV; S.rc_next[c] = 0;
+            S.b_next[c] = make_int2(0, NEGV);
+            if (lane == 0) {
+                S.rc_next[c] = (c < m) ? ((int)rf[c] << CODE_SHIFT) : 0;
+                if (has_prev && c < m) S.b_next[c] = __ldcg(&bnd[c]);
+            }
+        }
+        uint2 *tp = reinterpret_cast<uint2 *>(trace) + (size_t)s * T * 32 + lane;
 
-        for (int t = 0; t < T; ++t, tp += 32) {
-            const int j = t - lane;
-            const int rc = rc_next;
-            const int2 bu = b_next;
-            {   // prefetch the next column's reference base / boundary cell
-                const int jn = j + 1;
+        auto general_step = [&](const int t) {
+            const int jb = C2 * (t - lane);
+            int rc[C2], hu[C2], fu[C2];
+#pragma unroll
+            for (int c = 0; c < C2; ++c) {
+                rc[c] = S.rc_next[c];
+                hu[c] = __shfl_up_sync(FULL, S.Hbot[c], 1);
+                fu[c] = __shfl_up_sync(FULL, S.Fbot[c], 1);
+                if (lane == 0) { hu[c] = S.b_next[c].x; fu[c] = S.b_next[c].y; }
+            }
+            {
+                const int jn = jb + C2;
                 if ((unsigned)jn < (unsigned)m) {
-                    rc_next = (int)rf[jn] << CODE_SHIFT;
-                    if (has_prev && lane == 0) b_next = __ldcg(&bnd[jn]);
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) {
+                        S.rc_next[c] = (jn + c < m) ? ((int)rf[jn + c] << CODE_SHIFT) : 0;
+                        if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = __ldcg(&bnd[jn + c]);
+                    }
                 }
             }
-            int hu = __shfl_up_sync(FULL, Hbot, 1);
-            int fu = __shfl_up_sync(FULL, Fbot, 1);
-            if (lane == 0) { hu = bu.x; fu = bu.y; }
-            if ((unsigned)j < (unsigned)m) {
-                int up = hu, fup = fu, diag = diag0;
-                diag0 = hu;
-                uint32_t acc = 0;
+            if ((unsigned)jb < (unsigned)m) {
+                uint32_t w[C2];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int left = Hl[r];
-                    const int Ee = El[r] + c_ee;
-                    const int E = __viaddmax_s32(left, c_eo, Ee);
-                    const int Fe = fup + c_fe;
-                    const int F = __viaddmax_s32(up, c_fo, Fe);
-                    const int y = qc[r] ^ rc ^ (3 << CODE_SHIFT);
-                    int sc = __viaddmax_s32(y, c_sm, c_sx);
-                    if (WILD) { if ((qc[r] | rc) & (4 << CODE_SHIFT)) sc = 12; }
-                    const int Hd = diag + sc;
-                    const int H = __vimax3_s32(Hd, F, E);
-                    uint32_t nib = ((uint32_t)H & ~1u) | ((uint32_t)E & 1u);
-                    nib = (nib & ~2u) | ((uint32_t)F & 2u);
-                    acc |= (nib & 15u) << (4 * r);
-                    const int Hc = H & ~15;
-                    diag = left;
-                    Hl[r] = Hc;
-                    El[r] = E & ~15;
-                    up = Hc;
-                    fup = F & ~15;
-                }
-                Hbot = up; Fbot = fup;
-                *tp = acc;
-                if (has_next && lane == 31) bnd[j] = make_int2(Hbot, Fbot);
-                if (j == m - 1) {                      // last column: smallest i wins ties
+                for (int c = 0; c < C2; ++c) {
+                    p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c]);
+                    const int j = jb + c;
+                    if (has_next && lane == 31 && j < m) bnd[j] = make_int2(S.Hbot[c], S.Fbot[c]);
+                    if (j == m - 1) {                      // last column: smallest i wins ties
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (i0 + r < n && Hl[r] > best_col) { best_col = Hl[r]; best_col_i = i0 + r; }
-                }
-                if (is_last && lane == last_lane) {    // last row: smallest j wins ties
-                    int hv = Hl[0];
+                        for (int r = 0; r < R; ++r)
+                            if (i0 + r < n && S.Hl[r] > best_col) { best_col = S.Hl[r]; best_col_i = i0 + r; }
+                    }
+                    if (track && j < m) {                  // last row: smallest j wins ties
+                        int hv = S.Hl[0];
 #pragma unroll
-                    for (int r = 1; r < R; ++r) if (r == last_r) hv = Hl[r];
-                    if (hv > best_row) { best_row = hv; best_row_j = j; }
+                        for (int r = 1; r < R; ++r) if (r == last_r) hv = S.Hl[r];
+                        if (hv > best_row) { best_row = hv; best_row_j = j; }
+                    }
                 }
+                S.diag0 = hu[C2 - 1];
+                tp[(size_t)t * 32] = make_uint2(w[0], w[1]);
             }
+        };
+
+        const bool can_steady = !is_last && t_steady_end > 31;
+        const int t1 = can_steady ? 31 : T, t2 = can_steady ? t_steady_end : T;
+        for (int t = 0; t < t1; ++t) general_step(t);
+        if (can_steady) {
+            const uint8_t *pr = rf + C2 * (31 - lane) + C2;
+            const int2 *pbn = bnd + C2 * 31 + C2;
+            int2 *pbs = bnd;
+            uint2 *sp = tp + (size_t)31 * 32;
+#pragma unroll 1
+            for (int t = 31; t < t2; ++t) {
+                int rc[C2], hu[C2], fu[C2];
+#pragma unroll
+                for (int c = 0; c < C2; ++c) {
+                    rc[c] = S.rc_next[c];
+                    hu[c] = __shfl_up_sync(FULL, S.Hbot[c], 1);
+                    fu[c] = __shfl_up_sync(FULL, S.Fbot[c], 1);
+                    if (lane == 0) { hu[c] = S.b_next[c].x; fu[c] = S.b_next[c].y; }
+                }
+#pragma unroll
+                for (int c = 0; c < C2; ++c) S.rc_next[c] = (int)pr[c] << CODE_SHIFT;
+                if (has_prev && lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) S.b_next[c] = __ldcg(pbn + c);
+                }
+                uint32_t w[C2];
+#pragma unroll
+                for (int c = 0; c < C2; ++c)
+                    p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c]);
+                S.diag0 = hu[C2 - 1];
+                *sp = make_uint2(w[0], w[1]);
+                if (has_next && lane == 31) {
+#pragma unroll
+                    for (int c = 0; c < C2; ++c) pbs[c] = make_int2(S.Hbot[c], S.Fbot[c]);
+                }
+                pr += C2; pbn += C2; pbs += C2; sp += 32;
+            }
+            for (int t = t2; t < T; ++t) general_step(t);
         }
         __syncwarp();
     }
