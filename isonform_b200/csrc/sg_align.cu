@@ -912,26 +912,29 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     if (want_overlap) budget_words /= 2;
     if (budget_words > total_words) budget_words = total_words;
     if (budget_words < 1) budget_words = 1;
-    const int n_chunks = (int)(total_words / budget_words) + 1;
+    const bool single = total_words <= budget_words;          // everything fits one chunk: no device round trips
+    const int n_chunks = single ? 1 : (int)(total_words / budget_words) + 1;
     TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2));
     int64_t *chunk_start_d = (int64_t *)ctx->b_counters.p;
     unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);
     CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2), st));
-    {
-        LaunchTimer t(ctx, SLOT_OTHER);
-        chunk_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(ptrace, P, budget_words, n_chunks, chunk_start_d);
+    std::vector<int64_t> chunk_start((size_t)n_chunks + 1), start_off((size_t)n_chunks + 1);
+    if (single) {
+        chunk_start[0] = 0; chunk_start[1] = P;
+        start_off[0] = 0; start_off[1] = total_words;
+    } else {
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            chunk_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(ptrace, P, budget_words, n_chunks, chunk_start_d);
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(chunk_start.data(), chunk_start_d, sizeof(int64_t) * (size_t)(n_chunks + 1),
+                                      cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        // the largest chunk decides the scratch size: offsets of chunk starts are needed on the host
+        for (int c = 0; c <= n_chunks; ++c)
+            CUDA_TRY(ctx, cudaMemcpyAsync(&start_off[c], ptrace + chunk_start[c], 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
-    std::vector<int64_t> chunk_start((size_t)n_chunks + 1), chunk_base((size_t)n_chunks + 1);
-    CUDA_TRY(ctx, cudaMemcpyAsync(chunk_start.data(), chunk_start_d, sizeof(int64_t) * (size_t)(n_chunks + 1),
-                                  cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    // the largest chunk decides the scratch size: offsets of chunk starts are needed on the host
-    std::vector<int64_t> start_off((size_t)n_chunks + 1);
-    for (int c = 0; c <= n_chunks; ++c) {
-        // ptrace[chunk_start[c]] -- fetch individually (n_chunks is small)
-        CUDA_TRY(ctx, cudaMemcpyAsync(&start_off[c], ptrace + chunk_start[c], 8, cudaMemcpyDeviceToHost, st));
-    }
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     int64_t max_chunk_words = 0;
     for (int c = 0; c < n_chunks; ++c) max_chunk_words = std::max(max_chunk_words, start_off[c + 1] - start_off[c]);
     const bool pipelined = want_overlap && n_chunks > 1;
