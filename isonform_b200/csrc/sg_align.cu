@@ -291,7 +291,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
             }
         };
 
-        const bool can_steady = !is_last && t_steady_end > 31;
+        const bool can_steady = t_steady_end > 31;
         const int t1 = can_steady ? 31 : T, t2 = can_steady ? t_steady_end : T;
         for (int t = 0; t < t1; ++t) general_step(t);
         if (can_steady) {
@@ -299,8 +299,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
             const int2 *pbn = bnd + C2 * 31 + C2;
             int2 *pbs = bnd;
             uint2 *sp = tp + (size_t)31 * 32;
-#pragma unroll 1
-            for (int t = 31; t < t2; ++t) {
+            auto steady_step = [&](const int t, const bool with_track) {
                 int rc[C2], hu[C2], fu[C2];
 #pragma unroll
                 for (int c = 0; c < C2; ++c) {
@@ -317,8 +316,15 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                 }
                 uint32_t w[C2];
 #pragma unroll
-                for (int c = 0; c < C2; ++c)
+                for (int c = 0; c < C2; ++c) {
                     p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c]);
+                    if (with_track && track) {             // last row: smallest j wins ties
+                        int hv = S.Hl[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r) if (r == last_r) hv = S.Hl[r];
+                        if (hv > best_row) { best_row = hv; best_row_j = C2 * (t - lane) + c; }
+                    }
+                }
                 S.diag0 = hu[C2 - 1];
                 *sp = make_uint2(w[0], w[1]);
                 if (has_next && lane == 31) {
@@ -326,6 +332,13 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                     for (int c = 0; c < C2; ++c) pbs[c] = make_int2(S.Hbot[c], S.Fbot[c]);
                 }
                 pr += C2; pbn += C2; pbs += C2; sp += 32;
+            };
+            if (!is_last) {
+#pragma unroll 1
+                for (int t = 31; t < t2; ++t) steady_step(t, false);
+            } else {
+#pragma unroll 1
+                for (int t = 31; t < t2; ++t) steady_step(t, true);
             }
             for (int t = t2; t < T; ++t) general_step(t);
         }
@@ -546,18 +559,18 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             }
         };
 
-        const bool can_steady = liveA && liveB && !track_stripe && t_steady_end > 31;
+        const bool can_steady = liveA && liveB && t_steady_end > 31;
         const int t1 = can_steady ? 31 : T, t2 = can_steady ? t_steady_end : T;
         for (int t = 0; t < t1; ++t) general_step(t);
         if (can_steady) {
-            // ---------------- steady state: no bounds checks, no bookkeeping ----------------
+            // ---------------- steady state: no bounds checks; end-cell bookkeeping only in the last stripes,
+            // and there only the running maximum of the last row (the last column is reached in the drain)
             const uint8_t *pa_ = rA + PC * (31 - lane) + PC;       // look-ahead block of step t = 31
             const uint8_t *pb_ = rB + PC * (31 - lane) + PC;
             const int2 *pbn = bnd + PC * 31 + PC;                  // lane 0 only
             int2 *pbs = bnd + PC * (31 - 31);                      // lane 31 only: jb at t = 31
             uint2 *sA = tpA + (size_t)31 * 32, *sB = tpB + (size_t)31 * 32;
-#pragma unroll 1
-            for (int t = 31; t < t2; ++t) {
+            auto steady_step = [&](const int t, const bool with_track) {
                 uint32_t rc[PC], hu[PC], fu[PC];
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
@@ -575,8 +588,26 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 }
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
-                for (int c = 0; c < PC; ++c)
+                for (int c = 0; c < PC; ++c) {
                     p16_column(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
+                    if (with_track) {
+                        const int j = PC * (t - lane) + c;
+                        if (trackA) {
+                            uint32_t hv = S.Hl[0];
+#pragma unroll
+                            for (int r = 1; r < R; ++r) if (r == last_rA) hv = S.Hl[r];
+                            const int v = lo16(hv);
+                            if (v > browA) { browA = v; browA_j = j; }
+                        }
+                        if (trackB) {
+                            uint32_t hv = S.Hl[0];
+#pragma unroll
+                            for (int r = 1; r < R; ++r) if (r == last_rB) hv = S.Hl[r];
+                            const int v = hi16(hv);
+                            if (v > browB) { browB = v; browB_j = j; }
+                        }
+                    }
+                }
                 S.diag0 = hu[PC - 1];
                 *sA = make_uint2(wA[0], wA[1]);
                 *sB = make_uint2(wB[0], wB[1]);
@@ -585,6 +616,13 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     for (int c = 0; c < PC; ++c) pbs[c] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
                 }
                 pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
+            };
+            if (!track_stripe) {
+#pragma unroll 1
+                for (int t = 31; t < t2; ++t) steady_step(t, false);
+            } else {
+#pragma unroll 1
+                for (int t = 31; t < t2; ++t) steady_step(t, true);
             }
             for (int t = t2; t < T; ++t) general_step(t);
         }
