@@ -107,7 +107,8 @@ int isof_init(int device, isof_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
-    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
+    for (auto &as : ctx->aux_stream)
+        if (cudaStreamCreateWithFlags(&as, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
     ctx->pinned_cap = 4096;
     if (cudaMallocHost(&ctx->pinned, ctx->pinned_cap) != cudaSuccess) { delete ctx; return ISOF_ERR_CUDA; }
     *out = ctx;
@@ -123,7 +124,7 @@ int isof_destroy(isof_ctx *ctx)
     for (DevBuf *b : ctx->all_bufs()) if (b->p) cudaFree(b->p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    for (auto &as : ctx->aux_stream) if (as) cudaStreamDestroy(as);
     delete ctx;
     return ISOF_OK;
 }

@@ -714,6 +714,15 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
         if (j < 0) { PUSH(ISOF_CIGAR_I, i + 1); break; }
         const int s = i >> 8, l = (i >> 3) & 31, r = i & 7;
         const int jt = (pc == 1) ? j : (j >> 1), jc = (pc == 1) ? 0 : (j & 1);
+        {   // the path mostly follows the diagonal: pull the line it will need 16 steps from now into L2
+            const int ip = i - 16, jp = j - 16;
+            if (ip >= 0 && jp >= 0) {
+                const int sp_ = ip >> 8, lp = (ip >> 3) & 31;
+                const int jtp = (pc == 1) ? jp : (jp >> 1);
+                const uint32_t *pf = &trace[(((size_t)sp_ * T + (jtp + lp)) * 32 + lp) * pc];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
+        }
         const uint32_t word = __ldcg(&trace[(((size_t)s * T + (jt + l)) * 32 + l) * pc + jc]);
         const int nib = (word >> (4 * r)) & 15;
         if (where == 3) {
@@ -945,9 +954,10 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         if (ctx->trace_budget < (64u << 20)) ctx->trace_budget = 64u << 20;
     }
     int64_t budget_words = (int64_t)(ctx->trace_budget / 4);
-    // pipelined mode: two half-size buffers, chunks alternate between two streams
-    const bool want_overlap = ctx->overlap && total_words > budget_words / 2;
-    if (want_overlap) budget_words /= 2;
+    // pipelined mode: NLANES smaller buffers, chunk c runs on stream c % NLANES
+    constexpr int NL = isof_ctx::NLANES;
+    const bool want_overlap = ctx->overlap && total_words > budget_words / NL;
+    if (want_overlap) budget_words /= NL;
     if (budget_words > total_words) budget_words = total_words;
     if (budget_words < 1) budget_words = 1;
     const bool single = total_words <= budget_words;          // everything fits one chunk: no device round trips
@@ -976,8 +986,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     int64_t max_chunk_words = 0;
     for (int c = 0; c < n_chunks; ++c) max_chunk_words = std::max(max_chunk_words, start_off[c + 1] - start_off[c]);
     const bool pipelined = want_overlap && n_chunks > 1;
-    for (DevBuf *tb : {&ctx->b_trace, &ctx->b_trace2}) {
-        if (tb == &ctx->b_trace2 && !pipelined) break;
+    for (int w = 0; w < (pipelined ? NL : 1); ++w) {
+        DevBuf *tb = w ? &ctx->b_trace_x[w - 1] : &ctx->b_trace;
         if ((size_t)max_chunk_words * 4 > tb->cap) {
             int rc = dev_reserve(ctx, *tb, (size_t)max_chunk_words * 4);
             if (rc != ISOF_OK)
@@ -989,9 +999,11 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
     TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
     if (pipelined) {
-        TRY(dev_reserve(ctx, ctx->b_bnd2, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
-        TRY(dev_reserve(ctx, ctx->b_runoff2, sizeof(int64_t) * (size_t)(P + 1)));
-        TRY(dev_reserve(ctx, ctx->b_pboff2, sizeof(int64_t) * (size_t)(P + 1)));
+        for (int w = 0; w < NL - 1; ++w) {
+            TRY(dev_reserve(ctx, ctx->b_bnd_x[w], sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
+            TRY(dev_reserve(ctx, ctx->b_runoff_x[w], sizeof(int64_t) * (size_t)(P + 1)));
+            TRY(dev_reserve(ctx, ctx->b_pboff_x[w], sizeof(int64_t) * (size_t)(P + 1)));
+        }
     }
 
     AlignParams A;
@@ -1023,28 +1035,30 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     // ---- chunk pipeline.  Serial mode: everything on `st`.  Pipelined mode: chunk c runs on stream c%2 with
     // its own trace / boundary / scan scratch; the only cross-chunk dependency is the running CIGAR offset
     // (cigar_copy of chunk c needs advance_base of chunk c-1), carried by one event per chunk.
-    cudaStream_t lanes[2] = {st, pipelined ? ctx->aux_stream : st};
+    cudaStream_t lanes[NL];
+    lanes[0] = st;
+    for (int w = 1; w < NL; ++w) lanes[w] = pipelined ? ctx->aux_stream[w - 1] : st;
     std::vector<cudaEvent_t> done((size_t)n_chunks, nullptr);
     cudaEvent_t fork = nullptr;
     if (pipelined) {
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventRecord(fork, st));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(lanes[1], fork, 0));
+        for (int w = 1; w < NL; ++w) CUDA_TRY(ctx, cudaStreamWaitEvent(lanes[w], fork, 0));
     }
     int prev = -1, live = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t ps = chunk_start[c], pe = chunk_start[c + 1];
         if (pe <= ps) continue;
         const int64_t cnt = pe - ps;
-        const int w = pipelined ? (live & 1) : 0;
+        const int w = pipelined ? (live % NL) : 0;
         ++live;
         cudaStream_t cs = lanes[w];
         A.chunk_base = start_off[c];
-        A.trace = (uint32_t *)(w ? ctx->b_trace2.p : ctx->b_trace.p);
-        A.bnd = (int2 *)(w ? ctx->b_bnd2.p : ctx->b_bnd.p);
-        int64_t *c_runoff = w ? (int64_t *)ctx->b_runoff2.p : runoff;
-        int64_t *c_nruns64 = w ? (int64_t *)ctx->b_pboff2.p : nruns64;
-        DevBuf &c_scan = w ? ctx->b_scan_tmp2 : ctx->b_scan_tmp;
+        A.trace = (uint32_t *)(w ? ctx->b_trace_x[w - 1].p : ctx->b_trace.p);
+        A.bnd = (int2 *)(w ? ctx->b_bnd_x[w - 1].p : ctx->b_bnd.p);
+        int64_t *c_runoff = w ? (int64_t *)ctx->b_runoff_x[w - 1].p : runoff;
+        int64_t *c_nruns64 = w ? (int64_t *)ctx->b_pboff_x[w - 1].p : nruns64;
+        DevBuf &c_scan = w ? ctx->b_scan_tmp_x[w - 1] : ctx->b_scan_tmp;
         {
             LaunchTimer t(ctx, SLOT_DP, cs);
             const int64_t tasks = (cnt + 1) / 2;
@@ -1092,12 +1106,14 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     }
     if (pipelined) {
         if (prev >= 0) CUDA_TRY(ctx, cudaStreamWaitEvent(st, done[prev], 0));      // join: the chain orders all chunks
-        // the aux stream may still hold the (ordered-before) second-to-last chunk: join it explicitly
-        cudaEvent_t tail = nullptr;
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&tail, cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaEventRecord(tail, lanes[1]));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(st, tail, 0));
-        cudaEventDestroy(tail);
+        // the aux streams may still hold (ordered-before) earlier chunks: join them explicitly
+        for (int w = 1; w < NL; ++w) {
+            cudaEvent_t tail = nullptr;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&tail, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventRecord(tail, lanes[w]));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, tail, 0));
+            cudaEventDestroy(tail);
+        }
         cudaEventDestroy(fork);
         for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
     }
