@@ -67,7 +67,10 @@ def make_workload(args, rank):
     n_reads = args.reads
     if n_reads is None and args.workload == "C4":
         n_reads = 1000                      # one 1000-read batch of the 2000-read cluster
-    reads, _iso, _truth = synth.make_config(args.workload, seed=base_seed + 1000 * rank, n_reads=n_reads)
+    # rank 0 gets the canonical cluster; other ranks get clusters of the same gene family with re-drawn reads
+    # (same size statistics, so that "weak scaling" compares like with like)
+    reads, _iso, _truth = synth.make_config(args.workload, seed=base_seed, n_reads=n_reads,
+                                            read_seed=None if rank == 0 else rank)
     seqs = [remove_read_polyA_ends(s, 12, 1) for _, s in reads]       # main:351
     seqs_sorted = sorted(seqs, key=len)                                # merge_consensuses sorts by length (:471)
     cat, off = pack_sequences(seqs_sorted)

@@ -71,11 +71,15 @@ def mutate(rng, seq, eps):
     return bytes(out).decode()
 
 
-def make_cluster(seed, gene_len, n_isoforms, n_reads, eps, polya=True):
-    """Returns (reads: list[(acc, seq)], isoforms: list[str], truth: list[int])."""
+def make_cluster(seed, gene_len, n_isoforms, n_reads, eps, polya=True, read_seed=None):
+    """Returns (reads: list[(acc, seq)], isoforms: list[str], truth: list[int]).
+    `seed` fixes the gene and its isoforms; `read_seed` (default: continue the same stream) re-draws only
+    the reads, giving statistically identical clusters of the same gene (used for weak scaling)."""
     rng = np.random.default_rng(seed)
     exons = make_gene(rng, gene_len)
     isoforms = make_isoforms(rng, exons, n_isoforms)
+    if read_seed is not None:
+        rng = np.random.default_rng([seed, read_seed])
     truth = rng.integers(0, len(isoforms), size=n_reads)
     reads = []
     for r in range(n_reads):
@@ -94,13 +98,13 @@ CONFIGS = {
 }
 
 
-def make_config(name, seed=None, n_reads=None):
+def make_config(name, seed=None, n_reads=None, read_seed=None):
     cfg = dict(CONFIGS[name])
     if seed is not None:
         cfg["seed"] = seed
     if n_reads is not None:
         cfg["n_reads"] = n_reads
-    return make_cluster(cfg["seed"], cfg["gene_len"], cfg["n_isoforms"], cfg["n_reads"], cfg["eps"])
+    return make_cluster(cfg["seed"], cfg["gene_len"], cfg["n_isoforms"], cfg["n_reads"], cfg["eps"], read_seed=read_seed)
 
 
 def write_fastq(path, reads):
