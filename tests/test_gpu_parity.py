@@ -481,3 +481,27 @@ def test_c2_size_minimizers_and_spans_properties(ctx):
         want = oracle.pyside.read_intervals(r, M[r], odb, k, 40, 80, 5)
         got = idx.intervals(r)
         assert [(a, b, c, list(x)) for a, b, c, x in got] == [(a, b, c, list(x)) for a, b, c, x in want]
+
+
+def test_c4_size_long_reads_vs_oracle(ctx):
+    """BASELINE config-4 read lengths (10 kb, 5 % error): beyond the 16-bit range, so the 32-bit path with
+    40-stripe traces; all pairs of 6 reads bit-exact against the oracle, plus minimizers/spans of the reads."""
+    from isonform_b200 import hotpath, polya, spans, synth
+    reads_l, _iso, _t = synth.make_config("C4", n_reads=6)
+    seqs = [polya.remove_read_polyA_ends(s, 12, 1) for _, s in reads_l]
+    assert min(len(s) for s in seqs) > 6000
+    ia, ib = np.triu_indices(len(seqs), 1)
+    res = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+    cat = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.int64)
+    osc, _oeq, _oer, ocig, ooff = oracle.sg_align_pairs(cat, off, ia.astype(np.int32), ib.astype(np.int32), 2, -2, 12, 1, threads=0)
+    assert res["score"].tolist() == osc.tolist()
+    assert res["cigar_off"].tolist() == ooff.tolist() and np.array_equal(res["cigar"], ocig)
+    reads = {i + 1: ("r%d" % i, s, "") for i, s in enumerate(seqs)}
+    M = hotpath.get_minimizers_and_positions(reads, 31, 20, "lex", ctx)
+    assert M == oracle.get_minimizers_and_positions(reads, 31, 20, "lex")
+    idx = spans.SpanIndex(reads, M, 20, 40, 80, 5, ctx)
+    odb = oracle.get_minimizer_combinations_database(M, 20, 40, 80, reads)
+    for r in reads:
+        want = oracle.pyside.read_intervals(r, M[r], odb, 20, 40, 80, 5)
+        assert [(a, b, c, list(x)) for a, b, c, x in idx.intervals(r)] == [(a, b, c, list(x)) for a, b, c, x in want]
