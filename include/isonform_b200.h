@@ -143,6 +143,16 @@ ISOF_API int isof_spans_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t
                               int32_t delta_len, int64_t rec_cap, int32_t *rec_read, int32_t *rec_p1, int32_t *rec_p2,
                               int32_t *rec_count, int32_t *rec_bucket, int32_t *sorted_rec, int32_t *bucket_off,
                               uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets);
+/* Super-batched form for the in-process runner: the reads of n_batches independent batches back to back
+ * (batch b owns reads batch_read_off[b] .. batch_read_off[b+1]-1).  Buckets never mix batches and the
+ * over-abundance rule (main:206) uses the read count of the bucket's own batch; records of a batch are
+ * contiguous (reads are), and so are its buckets.  One launch sequence instead of one per batch. */
+ISOF_API int isof_spans_multi(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                              const int32_t *batch_read_off, int32_t n_batches, const int32_t *min_pos,
+                              const int64_t *min_off, int32_t k, int32_t x_low, int32_t x_high, int32_t delta_len,
+                              int64_t rec_cap, int32_t *rec_read, int32_t *rec_p1, int32_t *rec_p2, int32_t *rec_count,
+                              int32_t *rec_bucket, int32_t *sorted_rec, int32_t *bucket_off, uint8_t *bucket_dropped,
+                              int64_t *n_rec, int64_t *n_buckets);
 /* Device-pointer variant (n_rec / n_buckets are HOST pointers; two scalar read-backs). */
 ISOF_API int isof_spans_batch_dev(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
                                   const int32_t *min_pos, const int64_t *min_off, int64_t n_min, int32_t k, int32_t x_low,

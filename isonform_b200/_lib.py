@@ -40,7 +40,7 @@ class Profile(C.Structure):
 
 EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
-           "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
+           "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs"]
 
 _lib = None
@@ -72,6 +72,8 @@ def load():
     L.isof_minimizers_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_minimizers_batch_dev.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_spans_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   C.POINTER(i64), C.POINTER(i64)]
+    L.isof_spans_multi.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp,
                                    C.POINTER(i64), C.POINTER(i64)]
     L.isof_spans_batch_dev.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp,
                                        C.POINTER(i64), C.POINTER(i64)]
@@ -193,8 +195,9 @@ class Context:
         return int(n_out.value)
 
     # ------------------------------------------------------------------ (c) pair database + span search
-    def spans_batch(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len):
-        """dict of numpy arrays, see isof_spans_batch in include/isonform_b200.h."""
+    def spans_batch(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len, batch_read_off=None):
+        """dict of numpy arrays, see isof_spans_batch / isof_spans_multi in include/isonform_b200.h.
+        batch_read_off (int32[n_batches+1]) turns the call into the super-batched form."""
         cat = np.ascontiguousarray(cat, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.int64)
         min_pos = np.ascontiguousarray(min_pos, dtype=np.int32)
@@ -207,7 +210,12 @@ class Context:
                                                             "sorted_rec")}
             boff = np.zeros(cap + 1, np.int32)
             bdrop = np.zeros(cap, np.uint8)
-            rc = self._L.isof_spans_batch(self._h, cat.ctypes.data, off.ctypes.data, R, min_pos.ctypes.data,
+            if batch_read_off is not None:
+                bro = np.ascontiguousarray(batch_read_off, dtype=np.int32)
+                bro_ptr, nbt = bro.ctypes.data, len(bro) - 1
+            else:
+                bro_ptr, nbt = None, 1
+            rc = self._L.isof_spans_multi(self._h, cat.ctypes.data, off.ctypes.data, R, bro_ptr, nbt, min_pos.ctypes.data,
                                           min_off.ctypes.data, k, x_low, x_high, delta_len, cap, a["rec_read"].ctypes.data,
                                           a["rec_p1"].ctypes.data, a["rec_p2"].ctypes.data, a["rec_count"].ctypes.data,
                                           a["rec_bucket"].ctypes.data, a["sorted_rec"].ctypes.data, boff.ctypes.data,

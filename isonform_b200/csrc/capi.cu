@@ -235,6 +235,17 @@ int isof_spans_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_of
                      int32_t *rec_read, int32_t *rec_p1, int32_t *rec_p2, int32_t *rec_count, int32_t *rec_bucket,
                      int32_t *sorted_rec, int32_t *bucket_off, uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets)
 {
+    return isof_spans_multi(ctx, bases, read_off, n_reads, nullptr, 1, min_pos, min_off, k, x_low, x_high, delta_len, rec_cap,
+                            rec_read, rec_p1, rec_p2, rec_count, rec_bucket, sorted_rec, bucket_off, bucket_dropped, n_rec,
+                            n_buckets);
+}
+
+int isof_spans_multi(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_off, int32_t n_reads,
+                     const int32_t *batch_read_off, int32_t n_batches, const int32_t *min_pos, const int64_t *min_off, int32_t k,
+                     int32_t x_low, int32_t x_high, int32_t delta_len, int64_t rec_cap, int32_t *rec_read, int32_t *rec_p1,
+                     int32_t *rec_p2, int32_t *rec_count, int32_t *rec_bucket, int32_t *sorted_rec, int32_t *bucket_off,
+                     uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets)
+{
     if (!ctx || !read_off || !min_off || !n_rec || !n_buckets || n_reads < 0) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int64_t n_bases = read_off[n_reads], M = min_off[n_reads];
@@ -242,6 +253,13 @@ int isof_spans_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_of
     TRY(h2d(ctx, ctx->b_h_off, read_off, sizeof(int64_t) * (size_t)(n_reads + 1)));
     TRY(h2d(ctx, ctx->b_sh_minpos, min_pos, sizeof(int32_t) * (size_t)M));
     TRY(h2d(ctx, ctx->b_sh_minoff, min_off, sizeof(int64_t) * (size_t)(n_reads + 1)));
+    const int32_t *d_batch_off = nullptr;
+    if (batch_read_off && n_batches > 1) {
+        if (batch_read_off[0] != 0 || batch_read_off[n_batches] != n_reads)
+            return isof_fail(ctx, ISOF_ERR_ARG, "batch_read_off must cover reads 0..n_reads");
+        TRY(h2d(ctx, ctx->b_sh_batchoff, batch_read_off, sizeof(int32_t) * (size_t)(n_batches + 1)));
+        d_batch_off = (const int32_t *)ctx->b_sh_batchoff.p;
+    }
     const size_t cap = (size_t)std::max<int64_t>(rec_cap, 1);
     TRY(dev_reserve(ctx, ctx->b_sh_rread, 4 * cap));
     TRY(dev_reserve(ctx, ctx->b_sh_rp1, 4 * cap));
@@ -256,7 +274,7 @@ int isof_spans_batch(isof_ctx *ctx, const uint8_t *bases, const int64_t *read_of
                              delta_len, rec_cap, (int32_t *)ctx->b_sh_rread.p, (int32_t *)ctx->b_sh_rp1.p,
                              (int32_t *)ctx->b_sh_rp2.p, (int32_t *)ctx->b_sh_rcount.p, (int32_t *)ctx->b_sh_rbucket.p,
                              (int32_t *)ctx->b_sh_sorted.p, (int32_t *)ctx->b_sh_boff.p, (uint8_t *)ctx->b_sh_bdrop.p, n_rec,
-                             n_buckets);
+                             n_buckets, d_batch_off, n_batches);
     if (rc != ISOF_OK) return rc;
     const size_t G = (size_t)*n_rec, B = (size_t)*n_buckets;
     TRY(d2h(ctx, rec_read, ctx->b_sh_rread.p, 4 * G));

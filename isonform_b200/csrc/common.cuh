@@ -40,7 +40,7 @@ struct isof_ctx {
     DevBuf b_h_bases, b_h_off, b_h_pa, b_h_pb, b_h_score, b_h_endq, b_h_endr, b_h_cig, b_h_cigoff, b_h_feat;
     DevBuf b_m_hash, b_m_tmp, b_m_cnt, b_m_off;
     DevBuf b_s_mread, b_s_mkey, b_s_mpolya, b_s_mcnt, b_s_moff, b_s_key1, b_s_key2, b_s_keyt, b_s_keyo, b_s_idx0, b_s_idx1,
-        b_s_idx2, b_s_forb, b_s_head, b_s_bid, b_s_sorttmp;
+        b_s_idx2, b_s_forb, b_s_head, b_s_bid, b_s_sorttmp, b_s_rbatch, b_sh_batchoff;
     DevBuf b_sh_minpos, b_sh_minoff, b_sh_rread, b_sh_rp1, b_sh_rp2, b_sh_rcount, b_sh_rbucket, b_sh_sorted, b_sh_boff, b_sh_bdrop;
     std::vector<DevBuf *> all_bufs()
     {
@@ -48,7 +48,7 @@ struct isof_ctx {
                 &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_trace_x[0], &b_trace_x[1], &b_bnd_x[0], &b_bnd_x[1], &b_runoff_x[0], &b_runoff_x[1], &b_pboff_x[0], &b_pboff_x[1], &b_scan_tmp_x[0], &b_scan_tmp_x[1], &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
                 &b_h_endr, &b_h_cig, &b_h_cigoff, &b_h_feat, &b_m_hash, &b_m_tmp, &b_m_cnt, &b_m_off, &b_s_mread, &b_s_mkey,
                 &b_s_mpolya, &b_s_mcnt, &b_s_moff, &b_s_key1, &b_s_key2, &b_s_keyt, &b_s_keyo, &b_s_idx0, &b_s_idx1, &b_s_idx2,
-                &b_s_forb, &b_s_head, &b_s_bid, &b_s_sorttmp, &b_sh_minpos, &b_sh_minoff, &b_sh_rread, &b_sh_rp1, &b_sh_rp2,
+                &b_s_forb, &b_s_head, &b_s_bid, &b_s_sorttmp, &b_s_rbatch, &b_sh_batchoff, &b_sh_minpos, &b_sh_minoff, &b_sh_rread, &b_sh_rp1, &b_sh_rp2,
                 &b_sh_rcount, &b_sh_rbucket, &b_sh_sorted, &b_sh_boff, &b_sh_bdrop};
     }
     void *pinned = nullptr;           // small pinned staging for scalar read-backs
@@ -134,7 +134,7 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
                     const int64_t *d_min_off, int64_t M, int32_t k, int32_t x_low, int32_t x_high, int32_t delta_len,
                     int64_t rec_cap, int32_t *d_rec_read, int32_t *d_rec_p1, int32_t *d_rec_p2, int32_t *d_rec_count,
                     int32_t *d_rec_bucket, int32_t *d_sorted_rec, int32_t *d_bucket_off, uint8_t *d_bucket_dropped,
-                    int64_t *h_n_rec, int64_t *h_n_buckets);
+                    int64_t *h_n_rec, int64_t *h_n_buckets, const int32_t *d_batch_read_off = nullptr, int32_t n_batches = 1);
 int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off, int32_t n_seqs, int64_t n_bases,
                        const int32_t *d_pa, const int32_t *d_pb, int64_t P, int32_t match, int32_t mismatch,
                        int32_t gap_open, int32_t gap_ext, int32_t *d_score, int32_t *d_endq, int32_t *d_endr,

@@ -88,7 +88,8 @@ __global__ void span_emit_kernel(const int32_t *__restrict__ min_pos, const int6
                                  const uint8_t *__restrict__ mpolya, const int64_t *__restrict__ moff_rec,
                                  uint64_t *__restrict__ key1, uint64_t *__restrict__ key2, int32_t *__restrict__ rread,
                                  int32_t *__restrict__ rp1, int32_t *__restrict__ rp2, uint8_t *__restrict__ rforb,
-                                 uint32_t *__restrict__ iota)
+                                 uint32_t *__restrict__ iota, const int32_t *__restrict__ batch_read_off, int n_batches,
+                                 uint32_t *__restrict__ rbatch)
 {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= M) return;
@@ -106,6 +107,12 @@ __global__ void span_emit_kernel(const int32_t *__restrict__ min_pos, const int6
     int64_t g = moff_rec[x];
     const uint64_t k1 = mkey[x];
     const uint8_t pa = mpolya[x];
+    uint32_t bt = 0;
+    if (batch_read_off) {                       // largest b with batch_read_off[b] <= r
+        int lo = 0, hi = n_batches;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (batch_read_off[mid] <= r) lo = mid; else hi = mid; }
+        bt = (uint32_t)lo;
+    }
     for (int64_t y = last; y >= first; --y, ++g) {          // farthest partner first
         key1[g] = k1;
         key2[g] = mkey[y];
@@ -114,6 +121,7 @@ __global__ void span_emit_kernel(const int32_t *__restrict__ min_pos, const int6
         rp2[g] = min_pos[y];
         rforb[g] = pa & mpolya[y];
         iota[g] = (uint32_t)g;
+        if (rbatch) rbatch[g] = bt;
     }
 }
 
@@ -125,14 +133,25 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
 }
 
 // head[s] = 1 where a new bucket starts in sorted order
-__global__ void span_head_kernel(const uint64_t *__restrict__ key1_sorted, const uint64_t *__restrict__ key2,
-                                 const uint32_t *__restrict__ perm, int64_t G, int32_t *__restrict__ head)
+__global__ void span_head_kernel(const uint64_t *__restrict__ key1, const uint64_t *__restrict__ key2,
+                                 const uint32_t *__restrict__ rbatch, const uint32_t *__restrict__ perm, int64_t G,
+                                 int32_t *__restrict__ head)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= G) return;
     int h = 1;
-    if (s > 0) h = (key1_sorted[s] != key1_sorted[s - 1]) || (key2[perm[s]] != key2[perm[s - 1]]);
+    if (s > 0) {
+        const uint32_t a = perm[s], b = perm[s - 1];
+        h = (key1[a] != key1[b]) || (key2[a] != key2[b]) || (rbatch && rbatch[a] != rbatch[b]);
+    }
     head[s] = h;
+}
+
+__global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, int64_t G,
+                                  uint32_t *__restrict__ dst)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < G) dst[s] = src[idx[s]];
 }
 
 // bid_incl = inclusive sum of head; bucket b = bid_incl-1
@@ -151,12 +170,15 @@ __global__ void span_bucket_kernel(const int32_t *__restrict__ head, const int32
 }
 
 __global__ void span_drop_kernel(const int32_t *__restrict__ bucket_off, int32_t B, const int32_t *__restrict__ sorted_rec,
-                                 const uint8_t *__restrict__ rforb, int R, uint8_t *__restrict__ dropped)
+                                 const uint8_t *__restrict__ rforb, int R, const int32_t *__restrict__ batch_read_off,
+                                 const uint32_t *__restrict__ rbatch, uint8_t *__restrict__ dropped)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int st = bucket_off[b], sz = bucket_off[b + 1] - st;
-    dropped[b] = (rforb[sorted_rec[st]] || sz > 3 * R) ? 1 : 0;
+    int reads_in_batch = R;                      // main:206 uses len(reads) of the batch the bucket belongs to
+    if (batch_read_off) { const uint32_t bt = rbatch[sorted_rec[st]]; reads_in_batch = batch_read_off[bt + 1] - batch_read_off[bt]; }
+    dropped[b] = (rforb[sorted_rec[st]] || sz > 3 * reads_in_batch) ? 1 : 0;
 }
 
 // find_most_supported_span: per record, 1 + number of other-read records of the bucket within delta_len
@@ -189,9 +211,10 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
                     const int64_t *d_min_off, int64_t M, int32_t k, int32_t x_low, int32_t x_high, int32_t delta_len,
                     int64_t rec_cap, int32_t *d_rec_read, int32_t *d_rec_p1, int32_t *d_rec_p2, int32_t *d_rec_count,
                     int32_t *d_rec_bucket, int32_t *d_sorted_rec, int32_t *d_bucket_off, uint8_t *d_bucket_dropped,
-                    int64_t *h_n_rec, int64_t *h_n_buckets)
+                    int64_t *h_n_rec, int64_t *h_n_buckets, const int32_t *d_batch_read_off, int32_t n_batches)
 {
     cudaStream_t st = ctx->stream;
+    if (n_batches <= 1) d_batch_read_off = nullptr;
     *h_n_rec = 0;
     *h_n_buckets = 0;
     if (R < 0 || M < 0 || k <= 0) return isof_fail(ctx, ISOF_ERR_ARG, "bad span arguments");
@@ -236,6 +259,12 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
     TRY(dev_reserve(ctx, ctx->b_s_idx2, sizeof(uint32_t) * (size_t)G));
     TRY(dev_reserve(ctx, ctx->b_s_forb, (size_t)G));
     TRY(dev_reserve(ctx, ctx->b_s_head, sizeof(int32_t) * (size_t)G));
+    uint32_t *rbatch = nullptr, *rbatch_t = nullptr;
+    if (d_batch_read_off) {
+        TRY(dev_reserve(ctx, ctx->b_s_rbatch, sizeof(uint32_t) * (size_t)G * 2));
+        rbatch = (uint32_t *)ctx->b_s_rbatch.p;
+        rbatch_t = rbatch + G;
+    }
     TRY(dev_reserve(ctx, ctx->b_s_bid, sizeof(int32_t) * (size_t)G));
     uint64_t *key1 = (uint64_t *)ctx->b_s_key1.p, *key2 = (uint64_t *)ctx->b_s_key2.p;
     uint64_t *keyt = (uint64_t *)ctx->b_s_keyt.p, *keyo = (uint64_t *)ctx->b_s_keyo.p;
@@ -246,7 +275,8 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
     {
         LaunchTimer t(ctx, SLOT_OTHER);
         span_emit_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_min_pos, d_min_off, M, x_low, x_high, mread, mkey, mpolya,
-                                                                      moff, key1, key2, d_rec_read, d_rec_p1, d_rec_p2, rforb, idx0);
+                                                                      moff, key1, key2, d_rec_read, d_rec_p1, d_rec_p2, rforb, idx0,
+                                                                      d_batch_read_off, n_batches, rbatch);
     }
     // ---- stable LSD sort: by key2, then by key1
     const int bits = (k <= 31) ? std::min(64, 2 * k) : 64;          // packed keys use 2k bits; hashed keys set bit 63
@@ -267,10 +297,28 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
         LaunchTimer t(ctx, SLOT_OTHER);
         CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_s_sorttmp.p, ts, keyt, keyo, idx1, idx2, (int)G, 0, end_bit, st));
     }
+    if (rbatch) {
+        // third (most significant) pass: the batch a record belongs to, so that buckets never mix batches
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            gather_u32_kernel<<<gb, 256, 0, st>>>(rbatch, idx2, G, rbatch_t);
+        }
+        int nbits = 1;
+        while ((1 << nbits) < n_batches) ++nbits;
+        size_t t4 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t4, rbatch_t, (uint32_t *)keyo, idx2, idx1, (int)G, 0, nbits, st);
+        TRY(dev_reserve(ctx, ctx->b_s_sorttmp, std::max(ts, t4)));
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_s_sorttmp.p, t4, rbatch_t, (uint32_t *)keyo, idx2, idx1, (int)G, 0,
+                                                          nbits, st));
+        }
+        std::swap(idx1, idx2);                  // idx2 again holds the final permutation
+    }
     // ---- buckets
     {
         LaunchTimer t(ctx, SLOT_OTHER);
-        span_head_kernel<<<gb, 256, 0, st>>>(keyo, key2, idx2, G, head);
+        span_head_kernel<<<gb, 256, 0, st>>>(key1, key2, rbatch, idx2, G, head);
     }
     size_t t3 = 0;
     cub::DeviceScan::InclusiveSum(nullptr, t3, head, bid, (int)G, st);
@@ -290,7 +338,8 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
     *h_n_buckets = B;
     {
         LaunchTimer t(ctx, SLOT_OTHER);
-        span_drop_kernel<<<(B + 255) / 256, 256, 0, st>>>(d_bucket_off, B, d_sorted_rec, rforb, R, d_bucket_dropped);
+        span_drop_kernel<<<(B + 255) / 256, 256, 0, st>>>(d_bucket_off, B, d_sorted_rec, rforb, R, d_batch_read_off, rbatch,
+                                                          d_bucket_dropped);
     }
     {
         LaunchTimer t(ctx, SLOT_OTHER);

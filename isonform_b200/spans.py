@@ -35,23 +35,24 @@ def minimizers_comb_iterator(minimizers, k, x_low, x_high):
 
 
 class SpanIndex:
-    def __init__(self, reads, M, k, x_low, x_high, delta_len, ctx=None):
+    def __init__(self, reads, M, k, x_low, x_high, delta_len, ctx=None, _arrays=None):
         """reads: {r_id: (acc, seq, qual)} in batch order; M: {r_id: [(kmer, pos)]} as returned by
         get_minimizers_and_positions (same key order)."""
-        ctx = ctx or default_context()
         self.k, self.x_low, self.x_high, self.delta_len = k, x_low, x_high, delta_len
         self.ids = list(M)
         self.id_of = np.array(self.ids, dtype=np.int64)
         self.row_of = {r: i for i, r in enumerate(self.ids)}
         self.reads = reads
-        seqs = [reads[r][1] for r in self.ids]
-        cat, off = pack_sequences(seqs)
-        counts = [len(M[r]) for r in self.ids]
-        min_off = np.zeros(len(self.ids) + 1, dtype=np.int64)
-        np.cumsum(counts, out=min_off[1:])
-        min_pos = np.fromiter((p for r in self.ids for _, p in M[r]), dtype=np.int32, count=int(min_off[-1]))
-        res = ctx.spans_batch(cat, off, min_pos, min_off, k, x_low, x_high, delta_len)
-        self.__dict__.update(res)
+        if _arrays is None:
+            ctx = ctx or default_context()
+            seqs = [reads[r][1] for r in self.ids]
+            cat, off = pack_sequences(seqs)
+            counts = [len(M[r]) for r in self.ids]
+            min_off = np.zeros(len(self.ids) + 1, dtype=np.int64)
+            np.cumsum(counts, out=min_off[1:])
+            min_pos = np.fromiter((p for r in self.ids for _, p in M[r]), dtype=np.int32, count=int(min_off[-1]))
+            _arrays = ctx.spans_batch(cat, off, min_pos, min_off, k, x_low, x_high, delta_len)
+        self.__dict__.update(_arrays)
         self.n_rec = len(self.rec_read)
         # records are emitted in read order: per-read slices
         self.read_rec_off = np.searchsorted(self.rec_read, np.arange(len(self.ids) + 1), side="left")
@@ -131,6 +132,47 @@ class SpanIndex:
             flat = np.stack([self.id_of[self.rec_read[members]], self.rec_p1[members], self.rec_p2[members]], axis=1)
             db.setdefault(m1_of[b], {})[m2] = array("I", flat.ravel().tolist())
         return db
+
+
+def span_indexes_multi(batches, Ms, k, x_low, x_high, delta_len, ctx=None):
+    """Super-batched form: one library call (isof_spans_multi) for many independent batches.
+    batches: list of {r_id: (acc, seq, qual)}; Ms: the matching minimizer dicts.  Returns one SpanIndex per
+    batch, identical to building them one by one."""
+    ctx = ctx or default_context()
+    seqs, min_pos_parts, counts, batch_read_off = [], [], [], [0]
+    for reads, M in zip(batches, Ms):
+        for r in M:
+            seqs.append(reads[r][1])
+            counts.append(len(M[r]))
+            min_pos_parts.extend(p for _, p in M[r])
+        batch_read_off.append(len(seqs))
+    cat, off = pack_sequences(seqs)
+    min_off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(counts, out=min_off[1:])
+    min_pos = np.asarray(min_pos_parts, dtype=np.int32)
+    res = ctx.spans_batch(cat, off, min_pos, min_off, k, x_low, x_high, delta_len,
+                          batch_read_off=np.asarray(batch_read_off, dtype=np.int32) if len(batches) > 1 else None)
+    out = []
+    rec_lo_all = np.searchsorted(res["rec_read"], batch_read_off, side="left")
+    # buckets are grouped by batch (most significant sort key): bucket b belongs to the batch of its first record
+    first_rec = res["sorted_rec"][res["bucket_off"][:-1]] if len(res["bucket_off"]) > 1 else np.zeros(0, np.int32)
+    bucket_batch = np.searchsorted(np.asarray(batch_read_off), res["rec_read"][first_rec], side="right") - 1
+    for b, (reads, M) in enumerate(zip(batches, Ms)):
+        lo, hi = int(rec_lo_all[b]), int(rec_lo_all[b + 1])
+        bsel = np.nonzero(bucket_batch == b)[0]
+        if len(bsel):
+            b_lo, b_hi = int(bsel[0]), int(bsel[-1]) + 1
+            assert np.array_equal(bsel, np.arange(b_lo, b_hi))
+            s_lo, s_hi = int(res["bucket_off"][b_lo]), int(res["bucket_off"][b_hi])
+        else:
+            b_lo = b_hi = 0
+            s_lo = s_hi = 0
+        arrays = {"rec_read": res["rec_read"][lo:hi] - batch_read_off[b], "rec_p1": res["rec_p1"][lo:hi],
+                  "rec_p2": res["rec_p2"][lo:hi], "rec_count": res["rec_count"][lo:hi],
+                  "rec_bucket": res["rec_bucket"][lo:hi] - b_lo, "sorted_rec": res["sorted_rec"][s_lo:s_hi] - lo,
+                  "bucket_off": res["bucket_off"][b_lo:b_hi + 1] - s_lo, "bucket_dropped": res["bucket_dropped"][b_lo:b_hi]}
+        out.append(SpanIndex(reads, M, k, x_low, x_high, delta_len, _arrays=arrays))
+    return out
 
 
 class LazySpanDB:

@@ -17,8 +17,29 @@ class FakeContext:
         return oracle.minimizers_batch(cat, off, k, w_size, threads=1)
 
     # ---- (c): same outputs as isof_spans_batch, computed the slow way
-    def spans_batch(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len):
+    def spans_batch(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len, batch_read_off=None):
         self.calls["spans"] += 1
+        if batch_read_off is not None and len(batch_read_off) > 2:
+            # super-batched form: per batch, then concatenated with global record / bucket numbering
+            parts, rec_base, sort_base = [], 0, 0
+            off = np.asarray(off); min_off = np.asarray(min_off)
+            for b in range(len(batch_read_off) - 1):
+                r0, r1 = int(batch_read_off[b]), int(batch_read_off[b + 1])
+                sub = self._spans_one(cat[off[r0]:off[r1]], off[r0:r1 + 1] - off[r0], min_pos[min_off[r0]:min_off[r1]],
+                                      min_off[r0:r1 + 1] - min_off[r0], k, x_low, x_high, delta_len)
+                sub["rec_read"] = sub["rec_read"] + r0
+                sub["rec_bucket"] = sub["rec_bucket"] + sum(len(p["bucket_dropped"]) for p in parts)
+                sub["sorted_rec"] = sub["sorted_rec"] + rec_base
+                sub["bucket_off"] = sub["bucket_off"] + sort_base
+                rec_base += len(sub["rec_read"]); sort_base += len(sub["sorted_rec"])
+                parts.append(sub)
+            out = {key: np.concatenate([p[key] for p in parts]) for key in ("rec_read", "rec_p1", "rec_p2", "rec_count",
+                                                                          "rec_bucket", "sorted_rec", "bucket_dropped")}
+            out["bucket_off"] = np.concatenate([p["bucket_off"][:-1] for p in parts] + [np.array([sort_base], np.int32)]).astype(np.int32)
+            return out
+        return self._spans_one(cat, off, min_pos, min_off, k, x_low, x_high, delta_len)
+
+    def _spans_one(self, cat, off, min_pos, min_off, k, x_low, x_high, delta_len):
         cat = np.asarray(cat, dtype=np.uint8)
         R = len(off) - 1
         rec = []                                   # (read, p1, p2, key)

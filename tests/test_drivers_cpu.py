@@ -285,3 +285,24 @@ def test_patch_install_rebinds_reference_seams_and_reference_merge_agrees(tmp_pa
                [[m1, m2, list(db_ref[m1][m2])] for m1 in db_ref for m2 in db_ref[m1] if len(db_ref[m1][m2])]
     finally:
         IG.run_spoa, consensus.parasail_alignment, IG.align_to_merge, IG.merge_consensuses, BMP.actual_merging_process = saved
+
+
+def test_super_batched_front_half_equals_per_batch():
+    """runner.batches_front_half: one minimizer call + one span call for several clusters, same result as
+    batch by batch (incl. an empty batch and a batch whose reads yield no interval)."""
+    batches = []
+    for seed, n in ((41, 14), (42, 9), (43, 11)):
+        rd, _iso, _t = synth.make_cluster(seed=seed, gene_len=600, n_isoforms=2, n_reads=n, eps=0.02)
+        batches.append(runner.read_batch([(acc, s, "") for acc, s in rd]))
+    batches.insert(1, runner.read_batch([("lonely", synth.random_dna(np.random.default_rng(3), 300), "")]))
+    ctx = FakeContext()
+    multi = runner.batches_front_half(batches, 20, 31, 40, 80, 5, ctx)
+    assert ctx.calls["minimizers"] == 1 and ctx.calls["spans"] == 1
+    for reads, (giv, new_reads, skipped, idx) in zip(batches, multi):
+        giv1, new1, skip1, idx1 = runner.batch_front_half(reads, 20, 31, 40, 80, 5, FakeContext())
+        assert skipped == skip1 and new_reads == new1
+        assert {g: [(a, b, c, list(d)) for a, b, c, d in v] for g, v in giv.items()} == \
+               {g: [(a, b, c, list(d)) for a, b, c, d in v] for g, v in giv1.items()}
+        gdb, gdb1 = idx.database(), idx1.database()
+        assert [[m1, m2, list(gdb[m1][m2])] for m1 in gdb for m2 in gdb[m1]] == \
+               [[m1, m2, list(gdb1[m1][m2])] for m1 in gdb1 for m2 in gdb1[m1]]

@@ -505,3 +505,23 @@ def test_c4_size_long_reads_vs_oracle(ctx):
     for r in reads:
         want = oracle.pyside.read_intervals(r, M[r], odb, 20, 40, 80, 5)
         assert [(a, b, c, list(x)) for a, b, c, x in idx.intervals(r)] == [(a, b, c, list(x)) for a, b, c, x in want]
+
+
+def test_super_batched_front_half_on_gpu(ctx):
+    """isof_spans_multi: several clusters in one launch sequence == cluster by cluster == oracle."""
+    from isonform_b200 import runner, synth
+    batches = []
+    for seed, n in ((51, 40), (52, 25), (53, 33), (54, 1)):
+        rd, _iso, _t = synth.make_cluster(seed=seed, gene_len=800, n_isoforms=3, n_reads=n, eps=0.02)
+        batches.append(runner.read_batch([(acc, s, "") for acc, s in rd]))
+    multi = runner.batches_front_half(batches, 20, 31, 40, 80, 5, ctx)
+    for reads, (giv, new_reads, skipped, idx) in zip(batches, multi):
+        giv1, new1, skip1, idx1 = runner.batch_front_half(reads, 20, 31, 40, 80, 5, ctx)
+        assert skipped == skip1 and new_reads == new1
+        assert {g: [(a, b, c, list(d)) for a, b, c, d in v] for g, v in giv.items()} == \
+               {g: [(a, b, c, list(d)) for a, b, c, d in v] for g, v in giv1.items()}
+        M = oracle.get_minimizers_and_positions(reads, 31, 20)
+        odb = oracle.get_minimizer_combinations_database(M, 20, 40, 80, reads)
+        for r in list(reads)[::5]:
+            want = oracle.pyside.read_intervals(r, M[r], odb, 20, 40, 80, 5)
+            assert [(a, b, c, list(x)) for a, b, c, x in idx.intervals(r)] == [(a, b, c, list(x)) for a, b, c, x in want]
