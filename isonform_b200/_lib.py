@@ -14,10 +14,6 @@ SO_PATH = os.path.join(HERE, "libisonform_b200.so")
 
 N_FEATURES = 12
 OPS = {0: "M", 1: "I", 2: "D", 7: "=", 8: "X"}
-_OP_CHARS = np.full(16, ord("?"), dtype=np.uint8)
-for _k, _v in OPS.items():
-    _OP_CHARS[_k] = ord(_v)
-
 ISOF_OK, ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_NOMEM, ERR_RANGE = 0, -1, -2, -3, -4, -5
 
 

@@ -898,17 +898,17 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     TRY(dev_reserve(ctx, ctx->b_pn, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_pm, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_status, (size_t)P));
-    TRY(dev_reserve(ctx, ctx->b_paoff, sizeof(int64_t) * (size_t)(P + 1)));      // trace words per pair
+    TRY(dev_reserve(ctx, ctx->b_words, sizeof(int64_t) * (size_t)(P + 1)));      // trace words per pair
     TRY(dev_reserve(ctx, ctx->b_ptrace, sizeof(int64_t) * (size_t)(P + 1)));     // exclusive scan
     TRY(dev_reserve(ctx, ctx->b_nruns, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_runoff, sizeof(int64_t) * (size_t)(P + 1)));
-    TRY(dev_reserve(ctx, ctx->b_pboff, sizeof(int64_t) * (size_t)(P + 1)));      // nruns as int64
+    TRY(dev_reserve(ctx, ctx->b_nruns64, sizeof(int64_t) * (size_t)(P + 1)));      // nruns as int64
     TRY(dev_reserve(ctx, ctx->b_misc, 64));
     uint8_t *codes = (uint8_t *)ctx->b_codes.p, *flags = (uint8_t *)ctx->b_seqflags.p;
     int32_t *pn = (int32_t *)ctx->b_pn.p, *pm = (int32_t *)ctx->b_pm.p, *nruns = (int32_t *)ctx->b_nruns.p;
     uint8_t *pwild = (uint8_t *)ctx->b_status.p;
-    int64_t *words = (int64_t *)ctx->b_paoff.p, *ptrace = (int64_t *)ctx->b_ptrace.p;
-    int64_t *runoff = (int64_t *)ctx->b_runoff.p, *nruns64 = (int64_t *)ctx->b_pboff.p;
+    int64_t *words = (int64_t *)ctx->b_words.p, *ptrace = (int64_t *)ctx->b_ptrace.p;
+    int64_t *runoff = (int64_t *)ctx->b_runoff.p, *nruns64 = (int64_t *)ctx->b_nruns64.p;
     unsigned long long *misc = (unsigned long long *)ctx->b_misc.p;   // [0] err [1] max m [2] cells [3] padded [4] run_base
     CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 64, st));
     CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
@@ -1002,7 +1002,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         for (int w = 0; w < NL - 1; ++w) {
             TRY(dev_reserve(ctx, ctx->b_bnd_x[w], sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
             TRY(dev_reserve(ctx, ctx->b_runoff_x[w], sizeof(int64_t) * (size_t)(P + 1)));
-            TRY(dev_reserve(ctx, ctx->b_pboff_x[w], sizeof(int64_t) * (size_t)(P + 1)));
+            TRY(dev_reserve(ctx, ctx->b_nruns64_x[w], sizeof(int64_t) * (size_t)(P + 1)));
         }
     }
 
@@ -1057,7 +1057,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         A.trace = (uint32_t *)(w ? ctx->b_trace_x[w - 1].p : ctx->b_trace.p);
         A.bnd = (int2 *)(w ? ctx->b_bnd_x[w - 1].p : ctx->b_bnd.p);
         int64_t *c_runoff = w ? (int64_t *)ctx->b_runoff_x[w - 1].p : runoff;
-        int64_t *c_nruns64 = w ? (int64_t *)ctx->b_pboff_x[w - 1].p : nruns64;
+        int64_t *c_nruns64 = w ? (int64_t *)ctx->b_nruns64_x[w - 1].p : nruns64;
         DevBuf &c_scan = w ? ctx->b_scan_tmp_x[w - 1] : ctx->b_scan_tmp;
         {
             LaunchTimer t(ctx, SLOT_DP, cs);

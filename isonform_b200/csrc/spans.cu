@@ -279,9 +279,7 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
                                                                       d_batch_read_off, n_batches, rbatch);
     }
     // ---- stable LSD sort: by key2, then by key1
-    const int bits = (k <= 31) ? std::min(64, 2 * k) : 64;          // packed keys use 2k bits; hashed keys set bit 63
-    const int end_bit = (k <= 31) ? 64 : 64;
-    (void)bits;
+    const int end_bit = 64;          // packed keys use 2k bits, but a hashed (fallback) key sets bit 63
     size_t ts = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, ts, key2, keyo, idx0, idx1, (int)G, 0, end_bit, st);
     TRY(dev_reserve(ctx, ctx->b_s_sorttmp, ts));

@@ -18,8 +18,7 @@ import sys
 
 import numpy as np
 
-from . import _lib
-from ._lib import default_context, pack_sequences, runs_to_string, runs_to_tuples
+from ._lib import default_context, pack_sequences, runs_to_string, runs_to_tuples  # noqa: F401 (re-exported)
 
 _CIGAR_SPLIT = re.compile(r"[=DXSMI]+")
 
@@ -82,10 +81,7 @@ def align_pairs(seqs, pair_a, pair_b, match_score=2, mismatch_penalty=-2, openin
                 want_cigar=True, features_delta_len=None):
     """Batched parasail_alignment over index pairs into `seqs` (one library call)."""
     ctx = ctx or default_context()
-    for s in seqs:
-        if len(s) == 0:
-            pass            # only an error if a pair actually references it (checked on the device)
-    cat, off = pack_sequences(seqs)
+    cat, off = pack_sequences(seqs)         # an empty sequence is an error only if a pair references it (device check)
     return ctx.sg_align_pairs(cat, off, pair_a, pair_b, match_score, mismatch_penalty, opening_penalty, gap_ext,
                               want_cigar=want_cigar, features_delta_len=features_delta_len)
 
