@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include <cub/device/device_scan.cuh>
 #include <climits>
+#include <type_traits>
 
 namespace {
 
@@ -56,6 +57,7 @@ struct AlignParams {
     int h_max_min_len, h_max_max_len;      // eligibility: min(n,m) <= h_max_min_len and max(n,m) <= h_max_max_len
     uint32_t k_fclean, k_sel1, k_sel3;     // 0xfffefffe, 0x00010001, 0x00030003 (kept in registers on purpose)
     uint8_t *playout;                      // per pair: columns per step of the path that wrote its trace (1 or PC)
+    uint8_t *plastrr;                      // per pair: rows per lane used in the pair's LAST stripe (2,4,6,8)
 };
 
 __device__ __forceinline__ int base_code(uint8_t c)
@@ -111,10 +113,13 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                 int ns = (n + SROWS - 1) / SROWS;
                 w = (int64_t)ns * (m + 64) * 32 + TRACE_SLACK;        // covers the 1- and 2-column layouts
                 cells = (unsigned long long)n * m;
-                padded = (unsigned long long)ns * SROWS * m;
                 // bit0: a wildcard is present (32-bit WILD path); bit1: eligible for the packed 16-bit path
                 const int wild = flags[a] | flags[b];
                 const int elig = !wild && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len;
+                // rows actually updated: full stripes + the compacted last stripe (2/4/6/8 rows per lane)
+                const int need = n - (ns - 1) * SROWS;
+                const int rr = need > 192 ? 8 : need > 128 ? 6 : need > 64 ? 4 : 2;
+                padded = (unsigned long long)((ns - 1) * SROWS + (elig ? rr * 32 : SROWS)) * m;
                 pwild[p] = (uint8_t)(wild | (elig << 1));
                 mm = m;
             }
@@ -221,7 +226,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
     const int nstripes = (n + SROWS - 1) / SROWS;
     const int last_lane = ((n - 1) % SROWS) / R, last_r = (n - 1) % R;
     int best_col = INT_MIN, best_col_i = 0, best_row = INT_MIN, best_row_j = 0;
-    if (lane == 0) P.playout[p] = C2;
+    if (lane == 0) { P.playout[p] = C2; P.plastrr[p] = R; }
     const int t_steady_end = (m - 2 * C2) / C2 + 1;
 
     for (int s = 0; s < nstripes; ++s) {
@@ -401,14 +406,15 @@ struct P16State {
     uint32_t diag0;
 };
 
-// one column of 8 packed rows; returns the two trace words (A, B)
+// one column of RR packed rows per lane; returns the two trace words (A, B)
+template <int RR>
 __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const uint32_t rc, uint32_t up, uint32_t fup,
                                            uint32_t diag, uint32_t &hbot, uint32_t &fbot, uint32_t &wA, uint32_t &wB)
 {
     const uint32_t C3 = (3u << CS16) | (3u << (CS16 + 16));
     uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < RR; ++r) {
         const uint32_t left = S.Hl[r];
         const uint32_t Ee = __vadd2(S.Eh[r], K.h_ee);
         const uint32_t E = __viaddmax_s16x2(left, K.h_eo, Ee);
@@ -451,8 +457,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     const int m = max(mA, mB), mmin = min(mA, mB);
     const int T = (m + PC - 1) / PC + 31, TA = (mA + PC - 1) / PC + 31, TB = (mB + PC - 1) / PC + 31;
     const int nsA = (nA + SROWS - 1) / SROWS, nsB = (nB + SROWS - 1) / SROWS, ns = max(nsA, nsB);
-    const int last_laneA = ((nA - 1) % SROWS) / R, last_rA = (nA - 1) % R;
-    const int last_laneB = ((nB - 1) % SROWS) / R, last_rB = (nB - 1) % R;
+    int last_laneA = 0, last_rA = 0, last_laneB = 0, last_rB = 0;       // set in the alignment's last stripe
     P16Const K;
     K.h_eo = P.h_eo; K.h_ee = P.h_ee; K.h_fo = P.h_fo; K.h_fe = P.h_fe; K.h_sm = P.h_sm; K.h_sx = P.h_sx;
     K.k_fclean = P.k_fclean; K.k_sel1 = P.k_sel1; K.k_sel3 = P.k_sel3;   // masks in registers: "(x & mask) | imm" is ONE LOP3
@@ -463,11 +468,16 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     // references: PC*t + 2*PC <= mmin
     const int t_steady_end = (mmin - 2 * PC) / PC + 1;          // exclusive; may be <= 31 (then no steady range)
 
-    for (int s = 0; s < ns; ++s) {
-        const int i0 = s * SROWS + lane * R;
+    // The last stripe of the task is compacted: with `need` rows left, every lane takes RR = 2, 4, 6 or 8
+    // rows (the smallest that covers them), so no lane idles on padding rows.  Earlier stripes are full.
+    auto run_stripe = [&](auto rr_tag, const int s) {
+        constexpr int RR = decltype(rr_tag)::value;
+        const int i0 = s * SROWS + lane * RR;
+        if (s == nsA - 1) { last_laneA = ((nA - 1) - s * SROWS) / RR; last_rA = ((nA - 1) - s * SROWS) % RR; if (lane == 0) P.plastrr[pA] = RR; }
+        if (s == nsB - 1) { last_laneB = ((nB - 1) - s * SROWS) / RR; last_rB = ((nB - 1) - s * SROWS) % RR; if (lane == 0) P.plastrr[pB] = RR; }
         P16State S;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < RR; ++r) {
             const uint32_t a = (i0 + r < nA) ? (uint32_t)qA[i0 + r] : 0u;
             const uint32_t b = (i0 + r < nB) ? (uint32_t)qB[i0 + r] : 0u;
             S.qc[r] = (a << CS16) | (b << (CS16 + 16));
@@ -521,19 +531,19 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
-                    p16_column(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
+                    p16_column<RR>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
                     const int j = jb + c;
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
                     if (liveA && j == mA - 1) {             // last column of A: smallest i wins ties
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
+                        for (int r = 0; r < RR; ++r) {
                             const int v = lo16(S.Hl[r]);
                             if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
                         }
                     }
                     if (liveB && j == mB - 1) {
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
+                        for (int r = 0; r < RR; ++r) {
                             const int v = hi16(S.Hl[r]);
                             if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
                         }
@@ -541,14 +551,14 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     if (trackA && j < mA) {                 // last row of A: smallest j wins ties
                         uint32_t hv = S.Hl[0];
 #pragma unroll
-                        for (int r = 1; r < R; ++r) if (r == last_rA) hv = S.Hl[r];
+                        for (int r = 1; r < RR; ++r) if (r == last_rA) hv = S.Hl[r];
                         const int v = lo16(hv);
                         if (v > browA) { browA = v; browA_j = j; }
                     }
                     if (trackB && j < mB) {
                         uint32_t hv = S.Hl[0];
 #pragma unroll
-                        for (int r = 1; r < R; ++r) if (r == last_rB) hv = S.Hl[r];
+                        for (int r = 1; r < RR; ++r) if (r == last_rB) hv = S.Hl[r];
                         const int v = hi16(hv);
                         if (v > browB) { browB = v; browB_j = j; }
                     }
@@ -589,20 +599,20 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
-                    p16_column(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
+                    p16_column<RR>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
                     if (with_track) {
                         const int j = PC * (t - lane) + c;
                         if (trackA) {
                             uint32_t hv = S.Hl[0];
 #pragma unroll
-                            for (int r = 1; r < R; ++r) if (r == last_rA) hv = S.Hl[r];
+                            for (int r = 1; r < RR; ++r) if (r == last_rA) hv = S.Hl[r];
                             const int v = lo16(hv);
                             if (v > browA) { browA = v; browA_j = j; }
                         }
                         if (trackB) {
                             uint32_t hv = S.Hl[0];
 #pragma unroll
-                            for (int r = 1; r < R; ++r) if (r == last_rB) hv = S.Hl[r];
+                            for (int r = 1; r < RR; ++r) if (r == last_rB) hv = S.Hl[r];
                             const int v = hi16(hv);
                             if (v > browB) { browB = v; browB_j = j; }
                         }
@@ -627,6 +637,13 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             for (int t = t2; t < T; ++t) general_step(t);
         }
         __syncwarp();
+    };
+    for (int s = 0; s < ns; ++s) {
+        const int need = max(min(nA - s * SROWS, SROWS), min(nB - s * SROWS, SROWS));
+        if (need > 192) run_stripe(std::integral_constant<int, 8>{}, s);
+        else if (need > 128) run_stripe(std::integral_constant<int, 6>{}, s);
+        else if (need > 64) run_stripe(std::integral_constant<int, 4>{}, s);
+        else run_stripe(std::integral_constant<int, 2>{}, s);
     }
     browA = __shfl_sync(FULL, browA, last_laneA); browA_j = __shfl_sync(FULL, browA_j, last_laneA);
     browB = __shfl_sync(FULL, browB, last_laneB); browB_j = __shfl_sync(FULL, browB_j, last_laneB);
@@ -691,8 +708,9 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const uint32_t *trace = P.trace + (P.ptrace[p] - P.chunk_base);
     uint32_t *tail = P.trace + (P.ptrace[p + 1] - P.chunk_base);     // runs go to tail[-1], tail[-2], ...
-    const int pc = P.playout[p];                      // columns per step of the writer (1: 32-bit path, 2: packed)
+    const int pc = P.playout[p];                      // columns per step of the writer
     const int T = (m + pc - 1) / pc + 31;
+    const int last_s = (n - 1) >> 8, rr_last = P.plastrr[p];   // rows per lane in the (possibly compacted) last stripe
     int i = P.endq[p], j = P.endr[p];
     int nr = 0;
     uint32_t cur_op = 0xffu, cur_len = 0;
@@ -712,12 +730,15 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     while (i >= 0 || j >= 0) {
         if (i < 0) { PUSH(ISOF_CIGAR_D, j + 1); break; }
         if (j < 0) { PUSH(ISOF_CIGAR_I, i + 1); break; }
-        const int s = i >> 8, l = (i >> 3) & 31, r = i & 7;
+        const int s = i >> 8;
+        int l = (i >> 3) & 31, r = i & 7;
+        if (s == last_s && rr_last != 8) { l = (i & 255) / rr_last; r = (i & 255) % rr_last; }
         const int jt = (pc == 1) ? j : (j >> 1), jc = (pc == 1) ? 0 : (j & 1);
         {   // the path mostly follows the diagonal: pull the line it will need 16 steps from now into L2
             const int ip = i - 16, jp = j - 16;
             if (ip >= 0 && jp >= 0) {
-                const int sp_ = ip >> 8, lp = (ip >> 3) & 31;
+                const int sp_ = ip >> 8;
+                const int lp = (sp_ == last_s && rr_last != 8) ? (ip & 255) / rr_last : (ip >> 3) & 31;
                 const int jtp = (pc == 1) ? jp : (jp >> 1);
                 const uint32_t *pf = &trace[(((size_t)sp_ * T + (jtp + lp)) * 32 + lp) * pc];
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
@@ -1025,8 +1046,9 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.h_sm = pk(4 * match + 3 - (3 << CS16));
     A.h_sx = pk(4 * mismatch + 3);
     A.k_fclean = 0xfffefffeu; A.k_sel1 = 0x00010001u; A.k_sel3 = 0x00030003u;
-    TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P * 2));
     A.playout = (uint8_t *)ctx->b_layout.p;
+    A.plastrr = A.playout + P;
     A.h_max_min_len = h_max_min_len;
     A.h_max_max_len = h_max_max_len;
     int64_t *run_base = (int64_t *)(misc + 4);
