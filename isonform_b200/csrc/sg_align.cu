@@ -505,7 +505,8 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
         uint2 *tpB = reinterpret_cast<uint2 *>(traceB) + (size_t)s * TB * 32 + lane;
 
         // ---------------- general step (bounds checks + end-cell bookkeeping) ----------------
-        auto general_step = [&](const int t) {
+        auto general_step = [&](const int t, auto track_tag) {
+            constexpr bool TR = decltype(track_tag)::value;      // false: no end-cell bookkeeping (fill steps of inner stripes)
             const int jb = PC * (t - lane);
             uint32_t rc[PC], hu[PC], fu[PC];
 #pragma unroll
@@ -534,28 +535,28 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     p16_column<RR>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
                     const int j = jb + c;
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
-                    if (liveA && j == mA - 1) {             // last column of A: smallest i wins ties
+                    if (TR && liveA && j == mA - 1) {       // last column of A: smallest i wins ties
 #pragma unroll
                         for (int r = 0; r < RR; ++r) {
                             const int v = lo16(S.Hl[r]);
                             if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
                         }
                     }
-                    if (liveB && j == mB - 1) {
+                    if (TR && liveB && j == mB - 1) {
 #pragma unroll
                         for (int r = 0; r < RR; ++r) {
                             const int v = hi16(S.Hl[r]);
                             if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
                         }
                     }
-                    if (trackA && j < mA) {                 // last row of A: smallest j wins ties
+                    if (TR && trackA && j < mA) {           // last row of A: smallest j wins ties
                         uint32_t hv = S.Hl[0];
 #pragma unroll
                         for (int r = 1; r < RR; ++r) if (r == last_rA) hv = S.Hl[r];
                         const int v = lo16(hv);
                         if (v > browA) { browA = v; browA_j = j; }
                     }
-                    if (trackB && j < mB) {
+                    if (TR && trackB && j < mB) {
                         uint32_t hv = S.Hl[0];
 #pragma unroll
                         for (int r = 1; r < RR; ++r) if (r == last_rB) hv = S.Hl[r];
@@ -571,7 +572,9 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 
         const bool can_steady = liveA && liveB && t_steady_end > 31;
         const int t1 = can_steady ? 31 : T, t2 = can_steady ? t_steady_end : T;
-        for (int t = 0; t < t1; ++t) general_step(t);
+        // fill steps of an inner stripe cannot reach a last column when the shorter reference has > 64 columns
+        if (can_steady && !track_stripe && mmin > 2 * 31 + 2) { for (int t = 0; t < t1; ++t) general_step(t, std::false_type{}); }
+        else { for (int t = 0; t < t1; ++t) general_step(t, std::true_type{}); }
         if (can_steady) {
             // ---------------- steady state: no bounds checks; end-cell bookkeeping only in the last stripes,
             // and there only the running maximum of the last row (the last column is reached in the drain)
@@ -634,7 +637,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 #pragma unroll 1
                 for (int t = 31; t < t2; ++t) steady_step(t, true);
             }
-            for (int t = t2; t < T; ++t) general_step(t);
+            for (int t = t2; t < T; ++t) general_step(t, std::true_type{});
         }
         __syncwarp();
     };
