@@ -70,6 +70,13 @@ ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
  * its last pairs finish) and its traceback overlap the next chunk's DP.  on=0: one stream, one
  * buffer (per-kernel event timings are then exact; bench.py uses it for the roofline step). */
 ISOF_API int isof_set_overlap(isof_ctx *ctx, int on);
+/* Debug build only (libisonform_b200_dbg.so, -DISOF_CHECK): every kernel carries device-side bounds
+ * assertions (trace / boundary / sequence / output indices, CIGAR-tail vs unread-trace overlap) that record a
+ * bit per violated class instead of trapping.  Returns and clears the mask; bit 31 is set iff the assertions
+ * are compiled in (the release library always reports 0). */
+ISOF_API int isof_debug_violations(isof_ctx *ctx, unsigned int *mask);
+/* Launches a kernel whose only assertion is false (class 30): proves the reporting path end to end. */
+ISOF_API int isof_debug_selftest(isof_ctx *ctx);
 
 /* Per-ctx counters, reset by isof_profile_reset.  Kernel times are measured with CUDA events on the
  * ctx stream around each launch when profiling is enabled (isof_profile_enable(ctx,1)); enabling

@@ -11,6 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libisonform_b200.so")
+SO_PATH_DEBUG = os.path.join(HERE, "libisonform_b200_dbg.so")     # same sources with -DISOF_CHECK
 
 N_FEATURES = 12
 OPS = {0: "M", 1: "I", 2: "D", 7: "=", 8: "X"}
@@ -34,23 +35,28 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_debug_violations", "isof_debug_selftest",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs"]
 
 _lib = None
+_lib_debug = None
 
 
-def load():
-    """Load the shared library (no CUDA call yet).  Raises if it has not been built."""
-    global _lib
-    if _lib is not None:
+def load(debug=False):
+    """Load the shared library (no CUDA call yet).  Raises if it has not been built.
+    debug=True loads the assertion-carrying build (tests only)."""
+    global _lib, _lib_debug
+    if debug and _lib_debug is not None:
+        return _lib_debug
+    if not debug and _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
-        raise ImportError("libisonform_b200.so is not built: run `python -m isonform_b200.build` "
-                          "(needs nvcc; there is no CPU fallback)")
-    L = C.CDLL(SO_PATH)
+    path = SO_PATH_DEBUG if debug else SO_PATH
+    if not os.path.exists(path):
+        raise ImportError("%s is not built: run `python -m isonform_b200.build` "
+                          "(needs nvcc; there is no CPU fallback)" % os.path.basename(path))
+    L = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.isof_version.restype = C.c_int
     L.isof_init.argtypes = [C.c_int, C.POINTER(vp)]
@@ -61,6 +67,8 @@ def load():
     L.isof_set_trace_budget.argtypes = [vp, C.c_size_t]
     L.isof_set_packed.argtypes = [vp, C.c_int]
     L.isof_set_overlap.argtypes = [vp, C.c_int]
+    L.isof_debug_violations.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.isof_debug_selftest.argtypes = [vp]
     L.isof_profile_enable.argtypes = [vp, C.c_int]
     L.isof_profile_reset.argtypes = [vp]
     L.isof_profile_get.argtypes = [vp, C.POINTER(Profile)]
@@ -82,7 +90,10 @@ def load():
         getattr(L, name)
         if name not in ("isof_last_error",):
             getattr(L, name).restype = C.c_int
-    _lib = L
+    if debug:
+        _lib_debug = L
+    else:
+        _lib = L
     return L
 
 
@@ -107,8 +118,8 @@ def runs_to_tuples(runs):
 class Context:
     """One GPU context.  Not thread-safe; calls are stream-ordered."""
 
-    def __init__(self, device=0):
-        self._L = load()
+    def __init__(self, device=0, debug=False):
+        self._L = load(debug)
         h = C.c_void_p()
         rc = self._L.isof_init(int(device), C.byref(h))
         if rc != ISOF_OK:
@@ -142,6 +153,15 @@ class Context:
     def set_packed(self, on=True):
         """Enable (default) / disable the packed 16-bit DP path; results are identical either way."""
         self._check(self._L.isof_set_packed(self._h, 1 if on else 0))
+
+    def debug_violations(self):
+        """(mask, compiled_in): violated assertion classes since the last call; see isof_debug_violations."""
+        m = C.c_uint(0)
+        self._check(self._L.isof_debug_violations(self._h, C.byref(m)))
+        return int(m.value) & 0x7fffffff, bool(m.value & 0x80000000)
+
+    def debug_selftest(self):
+        self._check(self._L.isof_debug_selftest(self._h))
 
     def set_overlap(self, on=True):
         """Two-stream chunk pipelining (default on); off gives exact per-kernel event timings."""

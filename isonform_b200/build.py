@@ -12,6 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libisonform_b200.so")
+SO_DEBUG = os.path.join(HERE, "libisonform_b200_dbg.so")          # -DISOF_CHECK: device-side bounds assertions
 SOURCES = ["capi.cu", "minimizers.cu", "sg_align.cu", "spans.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -31,15 +32,22 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    deps = _deps()
-    if not force and not _stale(SO, deps):
+def build(force=False, verbose=False, debug=None):
+    """debug=None builds both libraries, False/True only the release / assertion build."""
+    if debug is None:
+        build(force, verbose, False)
+        build(force, False, True)
         return SO
+    deps = _deps()
+    target = SO_DEBUG if debug else SO
+    if not force and not _stale(target, deps):
+        return target
     objs = []
+    extra = ["-DISOF_CHECK"] if debug else []
 
     def compile_one(src):
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", ".dbg.o" if debug else ".o"))
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -49,11 +57,11 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", SO] + objs + ["-Xlinker", "--exclude-libs=ALL", "-lcudart_static"]
+    cmd = [NVCC, "-shared", "-o", target] + objs + ["-Xlinker", "--exclude-libs=ALL", "-lcudart_static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return SO
+    return target
 
 
 if __name__ == "__main__":

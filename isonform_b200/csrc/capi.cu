@@ -154,6 +154,29 @@ int isof_set_packed(isof_ctx *ctx, int on)
     return ISOF_OK;
 }
 
+namespace { __global__ void selftest_kernel() { ISOF_ASSERT(threadIdx.x > 1000u, 30); } }
+
+int isof_debug_selftest(isof_ctx *ctx)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    selftest_kernel<<<1, 32, 0, ctx->stream>>>();
+    CUDA_TRY(ctx, cudaGetLastError());
+    return ISOF_OK;
+}
+
+int isof_debug_violations(isof_ctx *ctx, unsigned int *mask)
+{
+    if (!ctx || !mask) return ISOF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    *mask = isof_viol_align() | isof_viol_minimizers() | isof_viol_spans() | isof_read_violations_tu();
+#ifdef ISOF_CHECK
+    *mask |= 0x80000000u;             // this library was built with the assertions compiled in
+#endif
+    return ISOF_OK;
+}
+
 int isof_set_overlap(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;

@@ -57,6 +57,33 @@ struct isof_ctx {
 
 enum { SLOT_DP = 0, SLOT_TB = 1, SLOT_MIN = 2, SLOT_OTHER = 3 };
 
+// Device-side bounds assertions (compute-sanitizer is not available on the target pool).  The debug
+// build (-DISOF_CHECK, libisonform_b200_dbg.so) records violated checks as bits of a device word that
+// isof_debug_violations() reads back; nothing traps, so a bad index cannot wedge the GPU.  Compiled out
+// of the release library.
+enum {
+    CHK_TRACE_STORE = 0, CHK_BND = 1, CHK_SEQ_LOAD = 2, CHK_TRACE_LOAD = 3, CHK_TAIL_OVERLAP = 4, CHK_MIN_SMEM = 5,
+    CHK_MIN_OUT = 6, CHK_SPAN_REC = 7, CHK_CIGAR_COPY = 8
+};
+#ifdef __CUDACC__
+static __device__ unsigned int g_isof_violations;     // one copy per translation unit (no -rdc); see isof_viol_*()
+static inline unsigned isof_read_violations_tu()
+{
+    unsigned v = 0, z = 0;
+    cudaMemcpyFromSymbol(&v, g_isof_violations, sizeof(v));
+    cudaMemcpyToSymbol(g_isof_violations, &z, sizeof(z));
+    return v;
+}
+#ifdef ISOF_CHECK
+#define ISOF_ASSERT(cond, code)                                                                    \
+    do {                                                                                           \
+        if (!(cond)) atomicOr(&g_isof_violations, 1u << (code));                                   \
+    } while (0)
+#else
+#define ISOF_ASSERT(cond, code) ((void)0)
+#endif
+#endif
+
 static inline int isof_fail(isof_ctx *ctx, int code, const char *fmt, ...)
 {
     if (ctx) {
@@ -125,6 +152,10 @@ struct LaunchTimer {
         }
     }
 };
+
+unsigned isof_viol_align();
+unsigned isof_viol_minimizers();
+unsigned isof_viol_spans();
 
 // internal entry points implemented in the .cu files
 int isof_minimizers_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_off, int32_t R, int64_t n_bases,

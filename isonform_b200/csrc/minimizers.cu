@@ -106,6 +106,7 @@ minimizer_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ 
                     int len = min(k, n - i);
                     h = py_siphash13(cw, q, len);
                 }
+                ISOF_ASSERT(w + q < CHUNK + WMAX, CHK_MIN_SMEM);
                 hs[w + q] = h;
             }
             __syncwarp();
@@ -162,7 +163,10 @@ minimizer_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ 
                 int excl = incl - my_n;
 #pragma unroll
                 for (int u = 0; u < PER_LANE; ++u)
-                    if ((em_mask >> u) & 1u) out[emitted + excl + __popc(em_mask & ((1u << u) - 1u))] = la[u];
+                    if ((em_mask >> u) & 1u) {
+                        ISOF_ASSERT(emitted + excl + __popc(em_mask & ((1u << u) - 1u)) <= n, CHK_MIN_OUT);
+                        out[emitted + excl + __popc(em_mask & ((1u << u) - 1u))] = la[u];
+                    }
                 emitted += __shfl_sync(0xffffffffu, incl, 31);
                 // carried state = last selectable position's arg-min
                 unsigned have = __ballot_sync(0xffffffffu, last_la >= 0 || la[0] >= 0);
@@ -190,6 +194,7 @@ minimizer_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ 
                                 if (h < mn) { mn = h; arg = i - x; }
                             }
                             pos = arg;
+                            ISOF_ASSERT(emitted <= n, CHK_MIN_OUT);
                             out[emitted++] = pos;
                         } else if (hs[w + q] < hs[w + (pos - c0)]) {
                             pos = i;
@@ -243,6 +248,8 @@ __global__ void cnt_to_i64_kernel(const int32_t *cnt, int64_t *out, int R)
 }
 
 }  // namespace
+
+unsigned isof_viol_minimizers() { return isof_read_violations_tu(); }
 
 int isof_minimizers_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_off, int32_t R, int64_t n_bases,
                          int32_t k, int32_t w_size, int32_t *d_out_pos, int64_t out_cap, int64_t *d_out_off,

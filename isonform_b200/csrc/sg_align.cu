@@ -58,6 +58,7 @@ struct AlignParams {
     uint32_t k_fclean, k_sel1, k_sel3;     // 0xfffefffe, 0x00010001, 0x00030003 (kept in registers on purpose)
     uint8_t *playout;                      // per pair: columns per step of the path that wrote its trace (1 or PC)
     uint8_t *plastrr;                      // per pair: rows per lane used in the pair's LAST stripe (2,4,6,8)
+    int64_t chunk_words;                   // words of this chunk's trace scratch (debug assertions)
 };
 
 __device__ __forceinline__ int base_code(uint8_t c)
@@ -278,6 +279,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                 for (int c = 0; c < C2; ++c) {
                     p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c]);
                     const int j = jb + c;
+                    ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2(S.Hbot[c], S.Fbot[c]);
                     if (j == m - 1) {                      // last column: smallest i wins ties
 #pragma unroll
@@ -292,6 +294,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                     }
                 }
                 S.diag0 = hu[C2 - 1];
+                ISOF_ASSERT((uint32_t *)(tp + (size_t)t * 32 + 1) <= P.trace + (P.ptrace[p + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
                 tp[(size_t)t * 32] = make_uint2(w[0], w[1]);
             }
         };
@@ -314,7 +317,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                     if (lane == 0) { hu[c] = S.b_next[c].x; fu[c] = S.b_next[c].y; }
                 }
 #pragma unroll
-                for (int c = 0; c < C2; ++c) S.rc_next[c] = (int)pr[c] << CODE_SHIFT;
+                for (int c = 0; c < C2; ++c) { ISOF_ASSERT(pr + c < rf + m, CHK_SEQ_LOAD); S.rc_next[c] = (int)pr[c] << CODE_SHIFT; }
                 if (has_prev && lane == 0) {
 #pragma unroll
                     for (int c = 0; c < C2; ++c) S.b_next[c] = __ldcg(pbn + c);
@@ -331,10 +334,11 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                     }
                 }
                 S.diag0 = hu[C2 - 1];
+                ISOF_ASSERT((uint32_t *)(sp + 1) <= P.trace + (P.ptrace[p + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
                 *sp = make_uint2(w[0], w[1]);
                 if (has_next && lane == 31) {
 #pragma unroll
-                    for (int c = 0; c < C2; ++c) pbs[c] = make_int2(S.Hbot[c], S.Fbot[c]);
+                    for (int c = 0; c < C2; ++c) { ISOF_ASSERT(pbs + c < bnd + P.bnd_stride, CHK_BND); pbs[c] = make_int2(S.Hbot[c], S.Fbot[c]); }
                 }
                 pr += C2; pbn += C2; pbs += C2; sp += 32;
             };
@@ -534,6 +538,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 for (int c = 0; c < PC; ++c) {
                     p16_column<RR>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
                     const int j = jb + c;
+                    ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
                     if (TR && liveA && j == mA - 1) {       // last column of A: smallest i wins ties
 #pragma unroll
@@ -565,8 +570,14 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     }
                 }
                 S.diag0 = hu[PC - 1];
-                if (liveA && jb < mA) tpA[(size_t)t * 32] = make_uint2(wA[0], wA[1]);
-                if (liveB && jb < mB) tpB[(size_t)t * 32] = make_uint2(wB[0], wB[1]);
+                if (liveA && jb < mA) {
+                    ISOF_ASSERT((uint32_t *)(tpA + (size_t)t * 32 + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                    tpA[(size_t)t * 32] = make_uint2(wA[0], wA[1]);
+                }
+                if (liveB && jb < mB) {
+                    ISOF_ASSERT((uint32_t *)(tpB + (size_t)t * 32 + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                    tpB[(size_t)t * 32] = make_uint2(wB[0], wB[1]);
+                }
             }
         };
 
@@ -594,7 +605,10 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 }
 #pragma unroll
                 for (int c = 0; c < PC; ++c)
+                {
+                    ISOF_ASSERT(pa_ + c < rA + mA && pb_ + c < rB + mB && pa_ >= rA && pb_ >= rB, CHK_SEQ_LOAD);
                     S.rc_next[c] = ((uint32_t)pa_[c] << CS16) | ((uint32_t)pb_[c] << (CS16 + 16));
+                }
                 if (has_prev && lane == 0) {
 #pragma unroll
                     for (int c = 0; c < PC; ++c) S.b_next[c] = __ldcg(pbn + c);
@@ -622,11 +636,14 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     }
                 }
                 S.diag0 = hu[PC - 1];
+                ISOF_ASSERT((uint32_t *)(sA + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                ISOF_ASSERT((uint32_t *)(sB + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                ISOF_ASSERT((uint32_t *)sA >= traceA && (uint32_t *)sB >= traceB, CHK_TRACE_STORE);
                 *sA = make_uint2(wA[0], wA[1]);
                 *sB = make_uint2(wB[0], wB[1]);
                 if (has_next && lane == 31) {
 #pragma unroll
-                    for (int c = 0; c < PC; ++c) pbs[c] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
+                    for (int c = 0; c < PC; ++c) { ISOF_ASSERT(pbs + c < bnd + P.bnd_stride, CHK_BND); pbs[c] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]); }
                 }
                 pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
             };
@@ -717,12 +734,14 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     int i = P.endq[p], j = P.endr[p];
     int nr = 0;
     uint32_t cur_op = 0xffu, cur_len = 0;
+    const uint32_t *last_read = trace - 1;            // highest trace word still to be read (debug assertion)
+    (void)last_read;
 #define PUSH(op, len)                                                                              \
     do {                                                                                           \
         if ((len) > 0) {                                                                           \
             if (cur_op == (uint32_t)(op)) cur_len += (uint32_t)(len);                              \
             else {                                                                                 \
-                if (cur_len) { ++nr; tail[-nr] = (cur_len << 4) | cur_op; }                        \
+                if (cur_len) { ++nr; ISOF_ASSERT(tail - nr > last_read, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; } \
                 cur_op = (op); cur_len = (len);                                                    \
             }                                                                                      \
         }                                                                                          \
@@ -747,7 +766,10 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
             }
         }
-        const uint32_t word = __ldcg(&trace[(((size_t)s * T + (jt + l)) * 32 + l) * pc + jc]);
+        const uint32_t *wp = &trace[(((size_t)s * T + (jt + l)) * 32 + l) * pc + jc];
+        ISOF_ASSERT(wp >= trace && wp < tail - TRACE_SLACK && wp < tail - nr, CHK_TRACE_LOAD);
+        last_read = wp;
+        const uint32_t word = __ldcg(wp);
         const int nib = (word >> (4 * r)) & 15;
         if (where == 3) {
             const int src = nib >> 2;
@@ -765,7 +787,7 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
             where = (nib & 2) ? 2 : 3;
         }
     }
-    if (cur_len) { ++nr; tail[-nr] = (cur_len << 4) | cur_op; }
+    if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; }
 #undef PUSH
     P.nruns[p] = nr;
 }
@@ -784,6 +806,7 @@ __global__ void cigar_copy_kernel(const AlignParams P, const int64_t start, cons
     if (lane == 0 && cigar_off) cigar_off[p] = dst;
     if (!cigar) return;
     const uint32_t *src = P.trace + (P.ptrace[p + 1] - P.chunk_base) - nr;
+    ISOF_ASSERT(src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
     for (int x = lane; x < nr; x += 32)
         if (dst + x < cigar_cap) cigar[dst + x] = src[x];
 }
@@ -886,6 +909,8 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
 }
 
 }  // namespace
+
+unsigned isof_viol_align() { return isof_read_violations_tu(); }
 
 // ---------------------------------------------------------------------------------------------
 // host-side orchestration (all pointers are device pointers)
@@ -1054,6 +1079,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.plastrr = A.playout + P;
     A.h_max_min_len = h_max_min_len;
     A.h_max_max_len = h_max_max_len;
+    A.chunk_words = 0;
     int64_t *run_base = (int64_t *)(misc + 4);
     CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
 

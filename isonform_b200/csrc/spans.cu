@@ -114,6 +114,7 @@ __global__ void span_emit_kernel(const int32_t *__restrict__ min_pos, const int6
         bt = (uint32_t)lo;
     }
     for (int64_t y = last; y >= first; --y, ++g) {          // farthest partner first
+        ISOF_ASSERT(g < moff_rec[x + 1], CHK_SPAN_REC);
         key1[g] = k1;
         key2[g] = mkey[y];
         rread[g] = r;
@@ -205,6 +206,8 @@ __global__ void span_count_kernel(const int32_t *__restrict__ rread, const int32
 }
 
 }  // namespace
+
+unsigned isof_viol_spans() { return isof_read_violations_tu(); }
 
 // All pointers device pointers.  h_n_rec / h_n_buckets are host pointers.
 int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read_off, int32_t R, const int32_t *d_min_pos,

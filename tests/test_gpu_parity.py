@@ -525,3 +525,63 @@ def test_super_batched_front_half_on_gpu(ctx):
         for r in list(reads)[::5]:
             want = oracle.pyside.read_intervals(r, M[r], odb, 20, 40, 80, 5)
             assert [(a, b, c, list(x)) for a, b, c, x in idx.intervals(r)] == [(a, b, c, list(x)) for a, b, c, x in want]
+
+
+# ------------------------------------------------------------------------------- bounds assertions (debug build)
+def test_debug_build_bounds_assertions_stay_silent():
+    """compute-sanitizer is not available on the target pool, so the library has a second build with
+    device-side bounds assertions (trace / boundary / sequence / output indices, CIGAR tail vs unread trace).
+    Run a spread of shapes through it -- packed and 32-bit paths, tiny and multi-stripe pairs, many chunks
+    through the three-stream pipeline, ragged minimizer batches, spans -- and require an empty violation mask
+    (and the usual bit-exactness)."""
+    from isonform_b200 import _lib, hotpath, spans, synth
+    dctx = _lib.Context(0, debug=True)
+    try:
+        assert dctx.debug_violations() == (0, True)
+        dctx.debug_selftest()                                  # the reporting path itself works ...
+        assert dctx.debug_violations() == (1 << 30, True)
+        assert dctx.debug_violations() == (0, True)            # ... and reading clears it
+        rng = np.random.default_rng(71)
+        # alignment shapes
+        seqs, pa, pb = [], [], []
+        for (n, m) in [(1, 1), (2, 70), (70, 2), (63, 65), (64, 64), (65, 63), (129, 200), (192, 193), (255, 257), (256, 256),
+                       (257, 255), (300, 1), (511, 700), (700, 511), (1025, 130), (130, 1025), (2047, 2049)]:
+            x = _rand_dna(rng, max(n, m))
+            y = synth.mutate(rng, x, 0.06) + _rand_dna(rng, m)
+            seqs += [x[:n], y[:m]]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+        seqs += ["ACGTN" * 30, "ACGT" * 40]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)      # wildcard -> 32-bit
+        big = _rand_dna(rng, 4500)
+        seqs += [big, synth.mutate(rng, big, 0.04)]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)   # > 16-bit range
+        for packed in (True, False):
+            dctx.set_packed(packed)
+            for params in [(2, -2, 12, 1), (2, -8, 12, 1), (1, -1, 1, 1)]:
+                res = hotpath.align_pairs(seqs, pa, pb, *params, ctx=dctx, features_delta_len=5)
+                for p in range(0, len(pa), 3):
+                    sc, _q, _r, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params)
+                    assert int(res["score"][p]) == sc
+                    assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
+        dctx.set_packed(True)
+        assert dctx.debug_violations()[0] == 0
+        # all pairs through many small chunks (pipeline of three streams)
+        base = _rand_dna(rng, 900)
+        pool = [synth.mutate(rng, base, 0.05) for _ in range(20)]
+        ia, ib = np.triu_indices(len(pool), 1)
+        dctx.set_trace_budget(6 << 20)
+        a = hotpath.align_pairs(pool, ia, ib, 2, -2, 12, 1, ctx=dctx, features_delta_len=5)
+        dctx.set_trace_budget(0)
+        b = hotpath.align_pairs(pool, ia, ib, 2, -2, 12, 1, ctx=dctx, features_delta_len=5)
+        assert np.array_equal(a["cigar"], b["cigar"]) and np.array_equal(a["features"], b["features"])
+        assert dctx.debug_violations()[0] == 0
+        # minimizers + spans
+        reads = {i + 1: ("r", _rand_dna(rng, int(rng.integers(0, 900)), "ACGT" if i % 4 else "AC"), "") for i in range(80)}
+        M = hotpath.get_minimizers_and_positions(reads, 31, 20, "lex", dctx)
+        assert M == oracle.get_minimizers_and_positions(reads, 31, 20, "lex")
+        spans.SpanIndex(reads, M, 20, 40, 80, 5, dctx)
+        assert dctx.debug_violations()[0] == 0
+    finally:
+        dctx.close()
+
+
+def test_release_build_has_no_assertions(ctx):
+    ctx.debug_selftest()
+    assert ctx.debug_violations() == (0, False)
