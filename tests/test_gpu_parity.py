@@ -585,3 +585,26 @@ def test_debug_build_bounds_assertions_stay_silent():
 def test_release_build_has_no_assertions(ctx):
     ctx.debug_selftest()
     assert ctx.debug_violations() == (0, False)
+
+
+def test_bubble_decisions_batch_vs_oracle(ctx):
+    """align_bubble_nodes' gates + alignment + parse_cigar_diversity for a batch of bubble-like consensus
+    pairs (SimplifyGraph.py:630-664), against the oracle pair by pair."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(83)
+    seqs, pa, pb = [], [], []
+    for i in range(400):
+        ln = int(rng.integers(1, 260)) if i % 9 else int(rng.integers(1, 12))
+        x = _rand_dna(rng, ln)
+        y = synth.mutate(rng, x, [0.0, 0.02, 0.08, 0.2][i % 4])
+        if i % 6 == 0 and len(y) > 30:
+            c = len(y) // 2; y = y[:c] + y[c + int(rng.integers(1, 14)):]
+        if i % 10 == 3:
+            y = y + _rand_dna(rng, int(rng.integers(1, 80)))
+        seqs += [x, y or "G"]; pa.append(2 * i); pb.append(2 * i + 1)
+    for dl in (5, 10):
+        pop, aligned = hotpath.bubble_decisions(seqs, pa, pb, dl, ctx)
+        for p in range(len(pa)):
+            want = oracle.align_bubble_decision(seqs[pa[p]], seqs[pb[p]], dl)
+            assert (bool(pop[p]), bool(aligned[p])) == want, (p, dl, len(seqs[pa[p]]), len(seqs[pb[p]]))
+        assert aligned.any() and (~aligned).any() and pop.any() and (~pop).any()
