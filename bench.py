@@ -410,6 +410,12 @@ def run_b200(args):
                         "frac": cups * OPS_PER_CELL / int32_peak if int32_peak else None,
                         "padded_cell_frac": prof["dp_cells_padded"] / max(prof["dp_cells"], 1), "packed_path_cell_frac": packed_frac,
                         "peak_source": "isof_int32_peak micro-kernel (independent VIADDMNMX chains), measured in this run"},
+            "minimizer_kernel": {"mbases_per_s": wl["n_bases"] * PROF_STEPS / max(prof["minimizer_ms"], 1e-9) / 1e3,
+                                 "minimizers_per_s": n_min * PROF_STEPS / max(prof["minimizer_ms"], 1e-9) * 1e3,
+                                 "int32_ops_per_base": 180, "int32_frac": (wl["n_bases"] * PROF_STEPS * 180.0 /
+                                                                           max(prof["minimizer_ms"] * 1e-3, 1e-12)) / int32_peak,
+                                 "note": "all four launches of isof_minimizers_batch_dev (hash+select, count scan, compaction); "
+                                         "launch-latency bound at one 1000-read batch"},
             "kernel_ms_per_step": {"dp": prof["dp_ms"] / PROF_STEPS, "traceback_cigar_features": prof["traceback_ms"] / PROF_STEPS,
                                    "minimizers": prof["minimizer_ms"] / PROF_STEPS, "plan_encode_spans": prof["other_ms"] / PROF_STEPS,
                                    "note": "serialised roofline step; in the timed (pipelined) steps traceback overlaps DP"},
