@@ -91,6 +91,7 @@ typedef struct {
     int64_t dp_cells;            /* sum len(s1)*len(s2) over aligned pairs                       */
     int64_t dp_cells_padded;     /* cells actually updated (stripe padding included)             */
     int64_t dp_cells_packed;     /* part of dp_cells that went through the packed 16-bit path    */
+    int64_t dp_cells_profile;    /* part of dp_cells_packed that used the shared-memory query profile */
     int64_t trace_bytes;         /* trace bytes written by the DP kernel                         */
     int64_t h2d_bytes, d2h_bytes;
 } isof_profile;

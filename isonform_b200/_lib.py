@@ -27,7 +27,7 @@ class IsofError(RuntimeError):
 class Profile(C.Structure):
     _fields_ = [("launches", C.c_int64), ("dp_launches", C.c_int64), ("dp_ms", C.c_double),
                 ("traceback_ms", C.c_double), ("minimizer_ms", C.c_double), ("other_ms", C.c_double),
-                ("dp_cells", C.c_int64), ("dp_cells_padded", C.c_int64), ("dp_cells_packed", C.c_int64),
+                ("dp_cells", C.c_int64), ("dp_cells_padded", C.c_int64), ("dp_cells_packed", C.c_int64), ("dp_cells_profile", C.c_int64),
                 ("trace_bytes", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 

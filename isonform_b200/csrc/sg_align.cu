@@ -143,16 +143,18 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
 
 // statistics only: cells of the pairs that take the packed path in chunk [start,end)
 __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pn,
-                                    const int32_t *__restrict__ pm, int64_t start, int64_t end,
-                                    unsigned long long *__restrict__ out)
+                                    const int32_t *__restrict__ pm, const int32_t *__restrict__ pb, int64_t start,
+                                    int64_t end, unsigned long long *__restrict__ out)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t pA = start + 2 * t, pB = pA + 1;
-    unsigned long long c = 0;
-    if (pB < end && (pwild[pA] & 2) && (pwild[pB] & 2))
+    unsigned long long c = 0, cp = 0;               // packed path / of those, the query-profile variant
+    if (pB < end && (pwild[pA] & 2) && (pwild[pB] & 2)) {
         c = (unsigned long long)pn[pA] * pm[pA] + (unsigned long long)pn[pB] * pm[pB];
-    for (int d = 16; d; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+        if (pb[pA] == pb[pB]) cp = c;
+    }
+    for (int d = 16; d; d >>= 1) { c += __shfl_down_sync(0xffffffffu, c, d); cp += __shfl_down_sync(0xffffffffu, cp, d); }
+    if ((threadIdx.x & 31) == 0 && c) { atomicAdd(out, c); if (cp) atomicAdd(out + 1, cp); }
 }
 
 // chunk_start[c] = first pair whose trace offset is >= c*budget   (c = 0..n_chunks)
@@ -410,12 +412,25 @@ struct P16State {
     uint32_t diag0;
 };
 
-// one column of RR packed rows per lane; returns the two trace words (A, B)
-template <int RR>
+// one column of RR packed rows per lane; returns the two trace words (A, B).
+// PROF: both alignments share the reference, so the substitution scores of this lane's rows against the
+// column's base come from the lane's query profile in shared memory (two LDS.128 on the otherwise idle
+// LSU pipe) instead of one LOP3 + one VIADDMNMX per row; `rc` is then the plain base code 0..3.
+template <int RR, bool PROF>
 __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const uint32_t rc, uint32_t up, uint32_t fup,
-                                           uint32_t diag, uint32_t &hbot, uint32_t &fbot, uint32_t &wA, uint32_t &wB)
+                                           uint32_t diag, uint32_t &hbot, uint32_t &fbot, uint32_t &wA, uint32_t &wB,
+                                           const uint4 *__restrict__ prof)
 {
     const uint32_t C3 = (3u << CS16) | (3u << (CS16 + 16));
+    uint32_t scv[8];
+    if (PROF) {
+        const uint4 v0 = prof[rc * 64];                  // [code][half 0][lane]
+        scv[0] = v0.x; scv[1] = v0.y; scv[2] = v0.z; scv[3] = v0.w;
+        if (RR > 4) {
+            const uint4 v1 = prof[rc * 64 + 32];         // [code][half 1][lane]
+            scv[4] = v1.x; scv[5] = v1.y; scv[6] = v1.z; scv[7] = v1.w;
+        }
+    }
     uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
@@ -426,8 +441,12 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
         const uint32_t Fe = __vadd2(fup, K.h_fe);
         const uint32_t F = __viaddmax_s16x2(up, K.h_fo, Fe);
         const uint32_t Fh = (F & K.k_fclean) | 0x00020002u;
-        const uint32_t y = S.qc[r] ^ rc ^ C3;
-        const uint32_t sc = __viaddmax_s16x2(y, K.h_sm, K.h_sx);
+        uint32_t sc;
+        if (PROF) sc = scv[r];
+        else {
+            const uint32_t y = S.qc[r] ^ rc ^ C3;
+            sc = __viaddmax_s16x2(y, K.h_sm, K.h_sx);
+        }
         const uint32_t Hd = __vadd2(diag, sc);
         const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
         // nibble [src1 src0 f e] per half
@@ -448,7 +467,7 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
 }
 
 __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
-                                          int2 *__restrict__ bnd)
+                                          int2 *__restrict__ bnd, uint4 *__restrict__ prof_warp)
 {
     const unsigned FULL = 0xffffffffu;
     const int nA = P.pn[pA], mA = P.pm[pA], nB = P.pn[pB], mB = P.pm[pB];
@@ -474,8 +493,14 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 
     // The last stripe of the task is compacted: with `need` rows left, every lane takes RR = 2, 4, 6 or 8
     // rows (the smallest that covers them), so no lane idles on padding rows.  Earlier stripes are full.
-    auto run_stripe = [&](auto rr_tag, const int s) {
+    // same reference in both halves (the all-pairs drivers order pairs column-major to make this the rule)
+    const bool same_ref = (rA == rB);
+    uint4 *prof = prof_warp + lane;                   // [code 4][half 2][lane 32] uint4 = 4 packed scores
+    const uint32_t sc_mis = K.h_sx & 0xffffu;                                  // 4*mismatch + 3
+    const uint32_t sc_mat = (K.h_sm + (3u << CS16)) & 0xffffu;                 // 4*match + 3
+    auto run_stripe = [&](auto rr_tag, auto prof_tag, const int s) {
         constexpr int RR = decltype(rr_tag)::value;
+        constexpr bool PROF = decltype(prof_tag)::value;
         const int i0 = s * SROWS + lane * RR;
         if (s == nsA - 1) { last_laneA = ((nA - 1) - s * SROWS) / RR; last_rA = ((nA - 1) - s * SROWS) % RR; if (lane == 0) P.plastrr[pA] = RR; }
         if (s == nsB - 1) { last_laneB = ((nB - 1) - s * SROWS) / RR; last_rB = ((nB - 1) - s * SROWS) % RR; if (lane == 0) P.plastrr[pB] = RR; }
@@ -487,6 +512,23 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             S.qc[r] = (a << CS16) | (b << (CS16 + 16));
             S.Hl[r] = 0u;
             S.Eh[r] = NEG16 | 0x00010001u;
+        }
+        if (PROF) {
+            // query profile of this lane's rows: packed (A | B << 16) substitution scores per base code
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t qa = (r < RR) ? ((S.qc[r < RR ? r : 0] >> CS16) & 7u) : 4u;
+                    const uint32_t qb = (r < RR) ? ((S.qc[r < RR ? r : 0] >> (CS16 + 16)) & 7u) : 4u;
+                    v[r] = ((qa == (uint32_t)c) ? sc_mat : sc_mis) | (((qb == (uint32_t)c) ? sc_mat : sc_mis) << 16);
+                }
+                prof[c * 64] = make_uint4(v[0], v[1], v[2], v[3]);
+                prof[c * 64 + 32] = make_uint4(v[4], v[5], v[6], v[7]);
+            }
+            __syncwarp();
         }
         const bool has_prev = s > 0, has_next = s + 1 < ns;
         const bool liveA = s < nsA, liveB = s < nsB;
@@ -501,7 +543,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             S.b_next[c] = make_int2(0, (int)(NEG16 | 0x00020002u));
             if (lane == 0) {
                 const uint32_t a = (c < mA) ? (uint32_t)rA[c] : 0u, b = (c < mB) ? (uint32_t)rB[c] : 0u;
-                S.rc_next[c] = (a << CS16) | (b << (CS16 + 16));
+                S.rc_next[c] = PROF ? a : ((a << CS16) | (b << (CS16 + 16)));
                 if (has_prev && c < m) S.b_next[c] = __ldcg(&bnd[c]);
             }
         }
@@ -527,7 +569,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     for (int c = 0; c < PC; ++c) {
                         const uint32_t a = (jn + c < mA) ? (uint32_t)rA[jn + c] : 0u;
                         const uint32_t b = (jn + c < mB) ? (uint32_t)rB[jn + c] : 0u;
-                        S.rc_next[c] = (a << CS16) | (b << (CS16 + 16));
+                        S.rc_next[c] = PROF ? a : ((a << CS16) | (b << (CS16 + 16)));
                         if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = __ldcg(&bnd[jn + c]);
                     }
                 }
@@ -536,7 +578,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
-                    p16_column<RR>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
+                    p16_column<RR, PROF>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c], prof);
                     const int j = jb + c;
                     ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
@@ -607,7 +649,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 for (int c = 0; c < PC; ++c)
                 {
                     ISOF_ASSERT(pa_ + c < rA + mA && pb_ + c < rB + mB && pa_ >= rA && pb_ >= rB, CHK_SEQ_LOAD);
-                    S.rc_next[c] = ((uint32_t)pa_[c] << CS16) | ((uint32_t)pb_[c] << (CS16 + 16));
+                    S.rc_next[c] = PROF ? (uint32_t)pa_[c] : (((uint32_t)pa_[c] << CS16) | ((uint32_t)pb_[c] << (CS16 + 16)));
                 }
                 if (has_prev && lane == 0) {
 #pragma unroll
@@ -616,7 +658,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
-                    p16_column<RR>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c]);
+                    p16_column<RR, PROF>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c], prof);
                     if (with_track) {
                         const int j = PC * (t - lane) + c;
                         if (trackA) {
@@ -660,10 +702,17 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     };
     for (int s = 0; s < ns; ++s) {
         const int need = max(min(nA - s * SROWS, SROWS), min(nB - s * SROWS, SROWS));
-        if (need > 192) run_stripe(std::integral_constant<int, 8>{}, s);
-        else if (need > 128) run_stripe(std::integral_constant<int, 6>{}, s);
-        else if (need > 64) run_stripe(std::integral_constant<int, 4>{}, s);
-        else run_stripe(std::integral_constant<int, 2>{}, s);
+        if (same_ref) {
+            if (need > 192) run_stripe(std::integral_constant<int, 8>{}, std::true_type{}, s);
+            else if (need > 128) run_stripe(std::integral_constant<int, 6>{}, std::true_type{}, s);
+            else if (need > 64) run_stripe(std::integral_constant<int, 4>{}, std::true_type{}, s);
+            else run_stripe(std::integral_constant<int, 2>{}, std::true_type{}, s);
+        } else {
+            if (need > 192) run_stripe(std::integral_constant<int, 8>{}, std::false_type{}, s);
+            else if (need > 128) run_stripe(std::integral_constant<int, 6>{}, std::false_type{}, s);
+            else if (need > 64) run_stripe(std::integral_constant<int, 4>{}, std::false_type{}, s);
+            else run_stripe(std::integral_constant<int, 2>{}, std::false_type{}, s);
+        }
     }
     browA = __shfl_sync(FULL, browA, last_laneA); browA_j = __shfl_sync(FULL, browA_j, last_laneA);
     browB = __shfl_sync(FULL, browB, last_laneB); browB_j = __shfl_sync(FULL, browB_j, last_laneB);
@@ -697,6 +746,7 @@ __device__ __forceinline__ void dp_pair32(const AlignParams &P, const int64_t p,
 __global__ void __launch_bounds__(DP_WARPS * 32, 2)
 sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsigned long long *__restrict__ counter)
 {
+    __shared__ uint4 s_prof[DP_WARPS][4 * 2 * 32];      // per warp: query profile [code][row half][lane], 4 KB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int2 *bnd = P.bnd + (size_t)(blockIdx.x * DP_WARPS + warp) * P.bnd_stride;
     for (;;) {
@@ -706,7 +756,7 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
         const int64_t pA = start + 2 * (int64_t)tkt;
         if (pA >= end) break;
         const int64_t pB = pA + 1;
-        if (pB < end && (P.pwild[pA] & 2) && (P.pwild[pB] & 2)) dp_pair16(P, pA, pB, lane, bnd);
+        if (pB < end && (P.pwild[pA] & 2) && (P.pwild[pB] & 2)) dp_pair16(P, pA, pB, lane, bnd, s_prof[warp]);
         else {
             dp_pair32(P, pA, lane, bnd);
             if (pB < end) dp_pair32(P, pB, lane, bnd);
@@ -1114,7 +1164,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             LaunchTimer t(ctx, SLOT_DP, cs);
             const int64_t tasks = (cnt + 1) / 2;
             if (ctx->profiling)
-                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, ps, pe, misc + 5);
+                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, ps, pe, misc + 5);
             int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
             sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, cs>>>(A, ps, pe, counters + c);
         }
@@ -1173,9 +1223,10 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (h_total_runs) *h_total_runs = pin64[0];
     if (ctx->profiling) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(pin64 + 1, misc + 5, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(pin64 + 1, misc + 5, 16, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         ctx->prof.dp_cells_packed += pin64[1];
+        ctx->prof.dp_cells_profile += pin64[2];
     }
     if (d_cigar && pin64[0] > cigar_cap)
         return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap,

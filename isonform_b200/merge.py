@@ -127,23 +127,27 @@ def _row_decisions(pool, rows, n, seq1_override, delta, delta_len, d3, d5, ctx):
             seqs.append(seq1_override[i])
         else:
             left[i] = i
-    pa, pb, owner = [], [], []
-    for i in rows:
-        li = left[i]
-        l1 = len(seqs[li])
-        for j in range(i + 1, n):
-            if len(seqs[j]) < l1:
+    # pairs are issued grouped by the right-hand string j (column-major over the block), so that consecutive
+    # alignments share their reference sequence -- the DP kernel then reads substitution scores from a
+    # per-lane query profile instead of recomputing them (csrc/sg_align.cu, PROF path)
+    pa, pb, cell = [], [], []
+    lens = [len(x) for x in seqs]
+    for j in range(min(rows) + 1 if rows else n, n):
+        for i in rows:
+            if i >= j:
+                break
+            li = left[i]
+            if lens[j] < lens[li]:
                 pa.append(j); pb.append(li)
             else:
                 pa.append(li); pb.append(j)
-        owner.append((i, len(pa)))
+            cell.append((i, j))
+    out = {i: np.zeros(n - 1 - i, dtype=bool) for i in rows}
     if not pa:
-        return {i: np.zeros(0, dtype=bool) for i in rows}
+        return out
     dec = hotpath.align_to_merge_pairs(seqs, pa, pb, delta, delta_len, d3, d5, ctx)
-    out, lo = {}, 0
-    for i, hi in owner:
-        out[i] = dec[lo:hi]
-        lo = hi
+    for (i, j), d in zip(cell, dec):
+        out[i][j - i - 1] = d
     return out
 
 

@@ -562,10 +562,10 @@ def test_debug_build_bounds_assertions_stay_silent():
                     assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
         dctx.set_packed(True)
         assert dctx.debug_violations()[0] == 0
-        # all pairs through many small chunks (pipeline of three streams)
+        # all pairs through many small chunks (pipeline of three streams); grouped by reference -> profile path
         base = _rand_dna(rng, 900)
         pool = [synth.mutate(rng, base, 0.05) for _ in range(20)]
-        ia, ib = np.triu_indices(len(pool), 1)
+        ib, ia = np.tril_indices(len(pool), -1)
         dctx.set_trace_budget(6 << 20)
         a = hotpath.align_pairs(pool, ia, ib, 2, -2, 12, 1, ctx=dctx, features_delta_len=5)
         dctx.set_trace_budget(0)
@@ -608,3 +608,39 @@ def test_bubble_decisions_batch_vs_oracle(ctx):
             want = oracle.align_bubble_decision(seqs[pa[p]], seqs[pb[p]], dl)
             assert (bool(pop[p]), bool(aligned[p])) == want, (p, dl, len(seqs[pa[p]]), len(seqs[pb[p]]))
         assert aligned.any() and (~aligned).any() and pop.any() and (~pop).any()
+
+
+def test_profile_path_same_reference_tasks(ctx):
+    """Tasks whose two alignments share the reference take the shared-memory query-profile variant of the
+    packed path.  Group all pairs of a pool by reference (column-major), compare with the oracle and with the
+    same pairs issued in an order where no task shares a reference (plain packed path) and on the 32-bit path."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(97)
+    base = _rand_dna(rng, 700)
+    pool = [synth.mutate(rng, base, 0.06)[int(rng.integers(0, 40)):] for _ in range(26)]
+    pool += [_rand_dna(rng, int(rng.integers(1, 300))) for _ in range(6)]         # short / unrelated, odd stripe shapes
+    pool.sort(key=len)
+    ib, ia = np.tril_indices(len(pool), -1)                                       # grouped by reference ib
+    for params in [(2, -2, 12, 1), (2, -8, 12, 1), (3, -1, 4, 2)]:
+        grouped = hotpath.align_pairs(pool, ia, ib, *params, ctx=ctx, features_delta_len=5)
+        perm = rng.permutation(len(ia))                                           # breaks the grouping
+        shuffled = hotpath.align_pairs(pool, ia[perm], ib[perm], *params, ctx=ctx, features_delta_len=5)
+        inv = np.argsort(perm)
+        assert np.array_equal(grouped["score"], shuffled["score"][inv])
+        assert np.array_equal(grouped["features"], shuffled["features"][inv])
+        ctx.set_packed(False)
+        try:
+            ref32 = hotpath.align_pairs(pool, ia, ib, *params, ctx=ctx, features_delta_len=5)
+        finally:
+            ctx.set_packed(True)
+        for key in ("score", "cigar_off", "cigar", "features"):
+            assert np.array_equal(grouped[key], ref32[key]), (params, key)
+        for p in range(0, len(ia), 9):
+            sc, _q, _r, runs = oracle.sg_align(pool[ia[p]], pool[ib[p]], *params)
+            assert int(grouped["score"][p]) == sc
+            assert grouped["cigar"][grouped["cigar_off"][p]:grouped["cigar_off"][p + 1]].tolist() == runs.tolist(), (params, p)
+    # identical query AND reference in both halves, and self-alignment
+    same = hotpath.align_pairs(pool, [3, 3, 5, 5, 7], [9, 9, 9, 9, 7], 2, -2, 12, 1, ctx=ctx)
+    sc, _q, _r, runs = oracle.sg_align(pool[3], pool[9], 2, -2, 12, 1)
+    assert same["score"][:2].tolist() == [sc, sc]
+    assert same["cigar"][same["cigar_off"][1]:same["cigar_off"][2]].tolist() == runs.tolist()
