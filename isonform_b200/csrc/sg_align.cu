@@ -24,6 +24,7 @@
 // runs backwards into the tail of the pair's own trace region, so the runs end up in alignment
 // order and a coalesced copy moves them to the caller's buffer.
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <climits>
 #include <type_traits>
@@ -59,6 +60,8 @@ struct AlignParams {
     uint8_t *playout;                      // per pair: columns per step of the path that wrote its trace (1 or PC)
     uint8_t *plastrr;                      // per pair: rows per lane used in the pair's LAST stripe (2,4,6,8)
     int64_t chunk_words;                   // words of this chunk's trace scratch (debug assertions)
+    const int32_t *order;                  // per chunk: pair ids sorted by (packed-eligible first, reference index);
+                                           // task t = (order[start+2t], order[start+2t+1]) -> partners share the reference
 };
 
 __device__ __forceinline__ int base_code(uint8_t c)
@@ -141,15 +144,29 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
     if (p == P) words[P] = 0;
 }
 
+// sort key of a pair inside its chunk: packed-eligible pairs first, then by reference index, so that the two
+// alignments of a task share their reference whenever the batch allows it (query-profile path)
+__global__ void task_key_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pb, int64_t start,
+                                int64_t cnt, uint32_t *__restrict__ key, int32_t *__restrict__ val)
+{
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= cnt) return;
+    const int64_t p = start + x;
+    key[x] = ((pwild[p] & 2) ? 0u : 0x80000000u) | ((uint32_t)pb[p] & 0x7fffffffu);
+    val[x] = (int32_t)p;
+}
+
 // statistics only: cells of the pairs that take the packed path in chunk [start,end)
 __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pn,
-                                    const int32_t *__restrict__ pm, const int32_t *__restrict__ pb, int64_t start,
-                                    int64_t end, unsigned long long *__restrict__ out)
+                                    const int32_t *__restrict__ pm, const int32_t *__restrict__ pb,
+                                    const int32_t *__restrict__ order, int64_t start, int64_t end,
+                                    unsigned long long *__restrict__ out)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t pA = start + 2 * t, pB = pA + 1;
+    const int64_t xA = start + 2 * t, xB = xA + 1;
     unsigned long long c = 0, cp = 0;               // packed path / of those, the query-profile variant
-    if (pB < end && (pwild[pA] & 2) && (pwild[pB] & 2)) {
+    const int64_t pA = xA < end ? order[xA] : 0, pB = xB < end ? order[xB] : 0;
+    if (xB < end && (pwild[pA] & 2) && (pwild[pB] & 2)) {
         c = (unsigned long long)pn[pA] * pm[pA] + (unsigned long long)pn[pB] * pm[pB];
         if (pb[pA] == pb[pB]) cp = c;
     }
@@ -753,13 +770,14 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
         unsigned long long tkt = 0;
         if (lane == 0) tkt = atomicAdd(counter, 1ull);
         tkt = __shfl_sync(0xffffffffu, tkt, 0);
-        const int64_t pA = start + 2 * (int64_t)tkt;
-        if (pA >= end) break;
-        const int64_t pB = pA + 1;
-        if (pB < end && (P.pwild[pA] & 2) && (P.pwild[pB] & 2)) dp_pair16(P, pA, pB, lane, bnd, s_prof[warp]);
+        const int64_t xA = start + 2 * (int64_t)tkt;
+        if (xA >= end) break;
+        const bool two = xA + 1 < end;
+        const int64_t pA = P.order[xA], pB = two ? P.order[xA + 1] : pA;
+        if (two && (P.pwild[pA] & 2) && (P.pwild[pB] & 2)) dp_pair16(P, pA, pB, lane, bnd, s_prof[warp]);
         else {
             dp_pair32(P, pA, lane, bnd);
-            if (pB < end) dp_pair32(P, pB, lane, bnd);
+            if (two) dp_pair32(P, pB, lane, bnd);
         }
     }
 }
@@ -1124,6 +1142,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.h_sm = pk(4 * match + 3 - (3 << CS16));
     A.h_sx = pk(4 * mismatch + 3);
     A.k_fclean = 0xfffefffeu; A.k_sel1 = 0x00010001u; A.k_sel3 = 0x00030003u;
+    TRY(dev_reserve(ctx, ctx->b_order, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P * 2));
     A.playout = (uint8_t *)ctx->b_layout.p;
     A.plastrr = A.playout + P;
@@ -1133,6 +1152,21 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     int64_t *run_base = (int64_t *)(misc + 4);
     CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
 
+    // ---- reserve every per-lane scratch for the largest chunk up front: a reallocation inside the loop would
+    // free memory that an earlier chunk of the same lane may still be using and stall the pipeline
+    {
+        int64_t max_cnt = 1;
+        for (int c = 0; c < n_chunks; ++c) max_cnt = std::max(max_cnt, chunk_start[c + 1] - chunk_start[c]);
+        size_t t_sort = 0, t_scan = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (uint32_t *)nullptr, (uint32_t *)nullptr, (int32_t *)nullptr,
+                                        (int32_t *)nullptr, (int)max_cnt, 0, 32, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, t_scan, (int64_t *)nullptr, (int64_t *)nullptr, max_cnt, st);
+        for (int w = 0; w < (pipelined ? NL : 1); ++w) {
+            TRY(dev_reserve(ctx, w ? ctx->b_taskkey_x[w - 1] : ctx->b_taskkey,
+                            (sizeof(uint32_t) * 2 + sizeof(int32_t)) * (size_t)max_cnt + 64));
+            TRY(dev_reserve(ctx, w ? ctx->b_scan_tmp_x[w - 1] : ctx->b_scan_tmp, std::max(t_sort, t_scan) + 256));
+        }
+    }
     // ---- chunk pipeline.  Serial mode: everything on `st`.  Pipelined mode: chunk c runs on stream c%2 with
     // its own trace / boundary / scan scratch; the only cross-chunk dependency is the running CIGAR offset
     // (cigar_copy of chunk c needs advance_base of chunk c-1), carried by one event per chunk.
@@ -1160,11 +1194,25 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         int64_t *c_runoff = w ? (int64_t *)ctx->b_runoff_x[w - 1].p : runoff;
         int64_t *c_nruns64 = w ? (int64_t *)ctx->b_nruns64_x[w - 1].p : nruns64;
         DevBuf &c_scan = w ? ctx->b_scan_tmp_x[w - 1] : ctx->b_scan_tmp;
+        {   // task order of the chunk: stable radix sort of the pair ids by (eligibility, reference)
+            DevBuf &kb = w ? ctx->b_taskkey_x[w - 1] : ctx->b_taskkey;
+            TRY(dev_reserve(ctx, kb, (sizeof(uint32_t) * 2 + sizeof(int32_t)) * (size_t)cnt + 64));
+            uint32_t *key_in = (uint32_t *)kb.p, *key_out = key_in + cnt;
+            int32_t *val_in = (int32_t *)(key_out + cnt);
+            int32_t *order = (int32_t *)ctx->b_order.p;
+            LaunchTimer t(ctx, SLOT_OTHER, cs);
+            task_key_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(pwild, d_pb, ps, cnt, key_in, val_in);
+            size_t tso = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tso, key_in, key_out, val_in, order + ps, (int)cnt, 0, 32, cs);
+            TRY(dev_reserve(ctx, c_scan, tso));
+            CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(c_scan.p, tso, key_in, key_out, val_in, order + ps, (int)cnt, 0, 32, cs));
+            A.order = order;
+        }
         {
             LaunchTimer t(ctx, SLOT_DP, cs);
             const int64_t tasks = (cnt + 1) / 2;
             if (ctx->profiling)
-                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, ps, pe, misc + 5);
+                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, A.order, ps, pe, misc + 5);
             int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
             sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, cs>>>(A, ps, pe, counters + c);
         }
