@@ -274,10 +274,11 @@ class Context:
             if want_cigar and P:
                 lens = np.diff(off)
                 ns = max(len(lens), 1)
-                # a typical alignment of similar sequences has far fewer runs than n+m; start small
-                # (out-of-range indices are reported by the library, not here)
+                # an alignment has at most n+m+1 runs; reads at 5 % error produce about (n+m)/12.  Start at a
+                # fifth of the worst case (a too small buffer costs a second full run: ISOF_ERR_CAPACITY);
+                # out-of-range indices are reported by the library, not here
                 worst = int((lens[np.clip(pa, 0, ns - 1)] + lens[np.clip(pb, 0, ns - 1)] + 2).sum()) if len(lens) else 1
-                cap = int(min(worst, max(64 * P, 1 << 16)))
+                cap = int(min(worst, worst // 5 + 64 * P + (1 << 16)))
             else:
                 cap = 0
         else:
