@@ -61,7 +61,9 @@ struct AlignParams {
     uint8_t *plastrr;                      // per pair: rows per lane used in the pair's LAST stripe (2,4,6,8)
     int64_t chunk_words;                   // words of this chunk's trace scratch (debug assertions)
     const int32_t *order;                  // per chunk: pair ids sorted by (packed-eligible first, reference index);
-                                           // task t = (order[start+2t], order[start+2t+1]) -> partners share the reference
+                                           // packed task t = (order[start+2t], order[start+2t+1]) -> partners share the
+                                           // reference; the pairs behind the eligible ones are single 32-bit tasks
+    const unsigned long long *n_elig;      // per chunk: number of packed-eligible pairs (device scalar)
 };
 
 __device__ __forceinline__ int base_code(uint8_t c)
@@ -147,26 +149,32 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
 // sort key of a pair inside its chunk: packed-eligible pairs first, then by reference index, so that the two
 // alignments of a task share their reference whenever the batch allows it (query-profile path)
 __global__ void task_key_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pb, int64_t start,
-                                int64_t cnt, uint32_t *__restrict__ key, int32_t *__restrict__ val)
+                                int64_t cnt, uint32_t *__restrict__ key, int32_t *__restrict__ val,
+                                unsigned long long *__restrict__ n_elig)
 {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= cnt) return;
-    const int64_t p = start + x;
-    key[x] = ((pwild[p] & 2) ? 0u : 0x80000000u) | ((uint32_t)pb[p] & 0x7fffffffu);
-    val[x] = (int32_t)p;
+    int el = 0;
+    if (x < cnt) {
+        const int64_t p = start + x;
+        el = (pwild[p] & 2) ? 1 : 0;
+        key[x] = (el ? 0u : 0x80000000u) | ((uint32_t)pb[p] & 0x7fffffffu);
+        val[x] = (int32_t)p;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, el);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_elig, (unsigned long long)__popc(m));
 }
 
 // statistics only: cells of the pairs that take the packed path in chunk [start,end)
 __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pn,
                                     const int32_t *__restrict__ pm, const int32_t *__restrict__ pb,
-                                    const int32_t *__restrict__ order, int64_t start, int64_t end,
-                                    unsigned long long *__restrict__ out)
+                                    const int32_t *__restrict__ order, const unsigned long long *__restrict__ n_elig,
+                                    int64_t start, int64_t end, unsigned long long *__restrict__ out)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t xA = start + 2 * t, xB = xA + 1;
     unsigned long long c = 0, cp = 0;               // packed path / of those, the query-profile variant
     const int64_t pA = xA < end ? order[xA] : 0, pB = xB < end ? order[xB] : 0;
-    if (xB < end && (pwild[pA] & 2) && (pwild[pB] & 2)) {
+    if (xB < end && t < (int64_t)(*n_elig) / 2) {
         c = (unsigned long long)pn[pA] * pm[pA] + (unsigned long long)pn[pB] * pm[pB];
         if (pb[pA] == pb[pB]) cp = c;
     }
@@ -204,8 +212,16 @@ struct P32State {
 
 template <bool WILD>
 __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, const int rc, int up, int fup, int diag,
-                                           int &hbot, int &fbot, uint32_t &word)
+                                           int &hbot, int &fbot, uint32_t &word, const uint4 *__restrict__ prof)
 {
+    // !WILD: the substitution scores of this lane's 8 rows against the column's base come from the lane's
+    // query profile in shared memory (rc is then the plain base code 0..3); WILD keeps the arithmetic form.
+    int scv[8];
+    if (!WILD) {
+        const uint4 v0 = prof[rc * 64], v1 = prof[rc * 64 + 32];
+        scv[0] = (int)v0.x; scv[1] = (int)v0.y; scv[2] = (int)v0.z; scv[3] = (int)v0.w;
+        scv[4] = (int)v1.x; scv[5] = (int)v1.y; scv[6] = (int)v1.z; scv[7] = (int)v1.w;
+    }
     uint32_t acc = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -214,9 +230,13 @@ __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, co
         const int E = __viaddmax_s32(left, P.c_eo, Ee);
         const int Fe = fup + P.c_fe;
         const int F = __viaddmax_s32(up, P.c_fo, Fe);
-        const int y = S.qc[r] ^ rc ^ (3 << CODE_SHIFT);
-        int sc = __viaddmax_s32(y, P.c_sm, P.c_sx);
-        if (WILD) { if ((S.qc[r] | rc) & (4 << CODE_SHIFT)) sc = 12; }
+        int sc;
+        if (!WILD) sc = scv[r];
+        else {
+            const int y = S.qc[r] ^ rc ^ (3 << CODE_SHIFT);
+            sc = __viaddmax_s32(y, P.c_sm, P.c_sx);
+            if ((S.qc[r] | rc) & (4 << CODE_SHIFT)) sc = 12;
+        }
         const int Hd = diag + sc;
         const int H = __vimax3_s32(Hd, F, E);
         uint32_t nib = ((uint32_t)H & ~1u) | ((uint32_t)E & 1u);
@@ -234,8 +254,11 @@ __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, co
 }
 
 template <bool WILD>
-__device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd)
+__device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd,
+                                        uint4 *__restrict__ prof_warp)
 {
+    uint4 *prof = prof_warp + lane;
+    constexpr int RSH = WILD ? CODE_SHIFT : 0;    // reference bases: shifted codes (arithmetic form) or plain codes (profile)
     constexpr int C2 = 2;                         // columns per step
     const unsigned FULL = 0xffffffffu;
     const int n = P.pn[p], m = P.pm[p];
@@ -258,6 +281,19 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
             S.Hl[r] = 0;           // H(i,-1) = 0: free leading gap
             S.El[r] = NEGV;
         }
+        if (!WILD) {
+            const int sc_mat = P.c_sm + (3 << CODE_SHIFT), sc_mis = P.c_sx;       // 16*match+12, 16*mismatch+12
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = (uint32_t)(((S.qc[r] >> CODE_SHIFT) == c) ? sc_mat : sc_mis);
+                prof[c * 64] = make_uint4(v[0], v[1], v[2], v[3]);
+                prof[c * 64 + 32] = make_uint4(v[4], v[5], v[6], v[7]);
+            }
+            __syncwarp();
+        }
         const bool has_prev = s > 0, has_next = s + 1 < nstripes, is_last = !has_next;
         const bool track = is_last && lane == last_lane;
         S.diag0 = 0;
@@ -266,7 +302,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
             S.Hbot[c] = 0; S.Fbot[c] = NEGV; S.rc_next[c] = 0;
             S.b_next[c] = make_int2(0, NEGV);
             if (lane == 0) {
-                S.rc_next[c] = (c < m) ? ((int)rf[c] << CODE_SHIFT) : 0;
+                S.rc_next[c] = (c < m) ? ((int)rf[c] << RSH) : 0;
                 if (has_prev && c < m) S.b_next[c] = __ldcg(&bnd[c]);
             }
         }
@@ -287,7 +323,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                 if ((unsigned)jn < (unsigned)m) {
 #pragma unroll
                     for (int c = 0; c < C2; ++c) {
-                        S.rc_next[c] = (jn + c < m) ? ((int)rf[jn + c] << CODE_SHIFT) : 0;
+                        S.rc_next[c] = (jn + c < m) ? ((int)rf[jn + c] << RSH) : 0;
                         if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = __ldcg(&bnd[jn + c]);
                     }
                 }
@@ -296,7 +332,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                 uint32_t w[C2];
 #pragma unroll
                 for (int c = 0; c < C2; ++c) {
-                    p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c]);
+                    p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c], prof);
                     const int j = jb + c;
                     ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2(S.Hbot[c], S.Fbot[c]);
@@ -336,7 +372,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                     if (lane == 0) { hu[c] = S.b_next[c].x; fu[c] = S.b_next[c].y; }
                 }
 #pragma unroll
-                for (int c = 0; c < C2; ++c) { ISOF_ASSERT(pr + c < rf + m, CHK_SEQ_LOAD); S.rc_next[c] = (int)pr[c] << CODE_SHIFT; }
+                for (int c = 0; c < C2; ++c) { ISOF_ASSERT(pr + c < rf + m, CHK_SEQ_LOAD); S.rc_next[c] = (int)pr[c] << RSH; }
                 if (has_prev && lane == 0) {
 #pragma unroll
                     for (int c = 0; c < C2; ++c) S.b_next[c] = __ldcg(pbn + c);
@@ -344,7 +380,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                 uint32_t w[C2];
 #pragma unroll
                 for (int c = 0; c < C2; ++c) {
-                    p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c]);
+                    p32_column<WILD>(S, P, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], w[c], prof);
                     if (with_track && track) {             // last row: smallest j wins ties
                         int hv = S.Hl[0];
 #pragma unroll
@@ -752,10 +788,11 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     }
 }
 
-__device__ __forceinline__ void dp_pair32(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd)
+__device__ __forceinline__ void dp_pair32(const AlignParams &P, const int64_t p, const int lane, int2 *__restrict__ bnd,
+                                          uint4 *__restrict__ prof_warp)
 {
-    if (P.pwild[p] & 1) dp_pair<true>(P, p, lane, bnd);
-    else dp_pair<false>(P, p, lane, bnd);
+    if (P.pwild[p] & 1) dp_pair<true>(P, p, lane, bnd, prof_warp);
+    else dp_pair<false>(P, p, lane, bnd, prof_warp);
 }
 
 // One task = two consecutive pairs of the chunk.  Both eligible -> one packed pass; otherwise each
@@ -770,14 +807,15 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
         unsigned long long tkt = 0;
         if (lane == 0) tkt = atomicAdd(counter, 1ull);
         tkt = __shfl_sync(0xffffffffu, tkt, 0);
-        const int64_t xA = start + 2 * (int64_t)tkt;
-        if (xA >= end) break;
-        const bool two = xA + 1 < end;
-        const int64_t pA = P.order[xA], pB = two ? P.order[xA + 1] : pA;
-        if (two && (P.pwild[pA] & 2) && (P.pwild[pB] & 2)) dp_pair16(P, pA, pB, lane, bnd, s_prof[warp]);
-        else {
-            dp_pair32(P, pA, lane, bnd);
-            if (two) dp_pair32(P, pB, lane, bnd);
+        // tickets [0, n_pk): packed tasks over the eligible pairs; the rest: one 32-bit pair per ticket
+        const int64_t n_pk = (int64_t)(*P.n_elig) / 2;
+        if ((int64_t)tkt < n_pk) {
+            const int64_t xA = start + 2 * (int64_t)tkt;
+            dp_pair16(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
+        } else {
+            const int64_t x = start + 2 * n_pk + ((int64_t)tkt - n_pk);
+            if (x >= end) break;
+            dp_pair32(P, P.order[x], lane, bnd, s_prof[warp]);
         }
     }
 }
@@ -1079,10 +1117,11 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     if (budget_words < 1) budget_words = 1;
     const bool single = total_words <= budget_words;          // everything fits one chunk: no device round trips
     const int n_chunks = single ? 1 : (int)(total_words / budget_words) + 1;
-    TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2));
+    TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 3));
     int64_t *chunk_start_d = (int64_t *)ctx->b_counters.p;
-    unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);
-    CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2), st));
+    unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);      // task tickets per chunk
+    unsigned long long *elig_counts = counters + n_chunks + 2;                                  // eligible pairs per chunk
+    CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2, st));
     std::vector<int64_t> chunk_start((size_t)n_chunks + 1), start_off((size_t)n_chunks + 1);
     if (single) {
         chunk_start[0] = 0; chunk_start[1] = P;
@@ -1201,18 +1240,19 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             int32_t *val_in = (int32_t *)(key_out + cnt);
             int32_t *order = (int32_t *)ctx->b_order.p;
             LaunchTimer t(ctx, SLOT_OTHER, cs);
-            task_key_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(pwild, d_pb, ps, cnt, key_in, val_in);
+            task_key_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(pwild, d_pb, ps, cnt, key_in, val_in, elig_counts + c);
             size_t tso = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tso, key_in, key_out, val_in, order + ps, (int)cnt, 0, 32, cs);
             TRY(dev_reserve(ctx, c_scan, tso));
             CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(c_scan.p, tso, key_in, key_out, val_in, order + ps, (int)cnt, 0, 32, cs));
             A.order = order;
+            A.n_elig = elig_counts + c;
         }
         {
             LaunchTimer t(ctx, SLOT_DP, cs);
-            const int64_t tasks = (cnt + 1) / 2;
+            const int64_t tasks = cnt;               // upper bound on tickets (all pairs single); CTAs are persistent anyway
             if (ctx->profiling)
-                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, A.order, ps, pe, misc + 5);
+                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, A.order, A.n_elig, ps, pe, misc + 5);
             int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
             sg_dp_kernel<<<blocks, DP_WARPS * 32, 0, cs>>>(A, ps, pe, counters + c);
         }
