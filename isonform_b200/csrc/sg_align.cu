@@ -56,7 +56,6 @@ struct AlignParams {
     // packed 16-bit path (two alignments per warp): 4*score + 2 tag bits per half
     uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
     int h_max_min_len, h_max_max_len;      // eligibility: min(n,m) <= h_max_min_len and max(n,m) <= h_max_max_len
-    uint32_t k_fclean, k_sel1, k_sel3;     // 0xfffefffe, 0x00010001, 0x00030003 (kept in registers on purpose)
     uint8_t *playout;                      // per pair: columns per step of the path that wrote its trace (1 or PC)
     uint8_t *plastrr;                      // per pair: rows per lane used in the pair's LAST stripe (2,4,6,8)
     int64_t chunk_words;                   // words of this chunk's trace scratch (debug assertions)
@@ -441,6 +440,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
 constexpr int CS16 = 8;                       // base codes at bits 8..9 of each half
 constexpr uint32_t NEG16 = 0x83008300u;       // -32000 in both halves (a clean multiple of 4)
 constexpr int PC = 2;                         // columns per step of the packed path (uint2 trace stores)
+constexpr int TRACE_FMT_SPLIT = 16;           // playout flag: trace word = [src x8 (hi16) | fe x8 (lo16)], 2 bits per row
 
 __device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
@@ -454,8 +454,16 @@ __device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
 // is inside both alignments with a full look-ahead block, so that loop has no bounds checks, no
 // end-cell bookkeeping and unconditional stores; fill, drain and the last stripes (which track the
 // end cell) go through the general step.
+// d = a * M + c on the FMA pipe (IMAD); inline PTX so the multiply is not strength-reduced to ALU-pipe shifts
+__device__ __forceinline__ uint32_t mad_u32(const uint32_t a, const uint32_t mult, const uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(mult), "r"(c));
+    return d;
+}
+
 struct P16Const {
-    uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx, k_fclean, k_sel1, k_sel3;
+    uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
 };
 
 struct P16State {
@@ -484,30 +492,32 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
             scv[4] = v1.x; scv[5] = v1.y; scv[6] = v1.z; scv[7] = v1.w;
         }
     }
-    uint32_t acc0 = 0u, acc1 = 0u;
+    // Trace bits are gathered with integer multiply-adds (FMA pipe), not shifts and masks (ALU pipe, the
+    // bound): per half, acc_ef collects [f e] of row r at bits 2r+1:2r and acc_h the source tag of H.
+    // H - (H & ~3) is the tag, so acc_h = sum_r (H_r - Hc_r) * 4^r needs no mask of its own.
+    uint32_t acc_ef = 0u, acc_h = 0u;
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
         const uint32_t left = S.Hl[r];
-        const uint32_t Ee = __vadd2(S.Eh[r], K.h_ee);
-        const uint32_t E = __viaddmax_s16x2(left, K.h_eo, Ee);
+        const uint32_t Ee = __vadd2(S.Eh[r], K.h_ee);               // tag 01 (extension)
+        const uint32_t E = __viaddmax_s16x2(left, K.h_eo, Ee);      // open: tag 00; bit 0 = extended, ties extend
         const uint32_t Ehn = E | 0x00010001u;
-        const uint32_t Fe = __vadd2(fup, K.h_fe);
-        const uint32_t F = __viaddmax_s16x2(up, K.h_fo, Fe);
-        const uint32_t Fh = (F & K.k_fclean) | 0x00020002u;
+        const uint32_t Fe = __vadd2(fup, K.h_fe);                   // tag 10 (extension)
+        const uint32_t F = __viaddmax_s16x2(up, K.h_fo, Fe);        // open: tag 00; bit 1 = extended, ties extend
+        const uint32_t Fh = F | 0x00020002u;
         uint32_t sc;
         if (PROF) sc = scv[r];
         else {
             const uint32_t y = S.qc[r] ^ rc ^ C3;
             sc = __viaddmax_s16x2(y, K.h_sm, K.h_sx);
         }
-        const uint32_t Hd = __vadd2(diag, sc);
-        const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);
-        // nibble [src1 src0 f e] per half
-        const uint32_t sel1 = (E & K.k_sel1) | ((F << 1) & ~K.k_sel1);        // bit0 <- e, bit1 <- f
-        const uint32_t sel2 = (sel1 & K.k_sel3) | ((H << 2) & ~K.k_sel3);     // bits 3:2 <- src
-        const uint32_t nib = sel2 & 0x000f000fu;
-        if (r < 4) acc0 += nib << (4 * r); else acc1 += nib << (4 * (r - 4));
+        const uint32_t Hd = __vadd2(diag, sc);                      // tag 11
+        const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);             // ties: diagonal > F > E
         const uint32_t Hc = H & 0xfffcfffcu;
+        const uint32_t ef = (E | F) & 0x00030003u;
+        acc_ef = mad_u32(ef, 1u << (2 * r), acc_ef);
+        acc_h = mad_u32(H, 1u << (2 * r), acc_h);
+        acc_h = mad_u32(Hc, 0u - (1u << (2 * r)), acc_h);
         diag = left;
         S.Hl[r] = Hc;
         S.Eh[r] = Ehn;
@@ -515,8 +525,8 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
         fup = Fh;
     }
     hbot = up; fbot = fup;
-    wA = __byte_perm(acc0, acc1, 0x5410);
-    wB = __byte_perm(acc0, acc1, 0x7632);
+    wA = __byte_perm(acc_ef, acc_h, 0x5410);         // A: [src x8 | fe x8]
+    wB = __byte_perm(acc_ef, acc_h, 0x7632);
 }
 
 __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
@@ -536,10 +546,9 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     int last_laneA = 0, last_rA = 0, last_laneB = 0, last_rB = 0;       // set in the alignment's last stripe
     P16Const K;
     K.h_eo = P.h_eo; K.h_ee = P.h_ee; K.h_fo = P.h_fo; K.h_fe = P.h_fe; K.h_sm = P.h_sm; K.h_sx = P.h_sx;
-    K.k_fclean = P.k_fclean; K.k_sel1 = P.k_sel1; K.k_sel3 = P.k_sel3;   // masks in registers: "(x & mask) | imm" is ONE LOP3
     int bcolA = INT_MIN, bcolA_i = 0, browA = INT_MIN, browA_j = 0;
     int bcolB = INT_MIN, bcolB_i = 0, browB = INT_MIN, browB_j = 0;
-    if (lane == 0) { P.playout[pA] = PC; P.playout[pB] = PC; }
+    if (lane == 0) { P.playout[pA] = PC | TRACE_FMT_SPLIT; P.playout[pB] = PC | TRACE_FMT_SPLIT; }
     // steady range of t: lane 31 has started (t >= 31) and lane 0's look-ahead block is inside both
     // references: PC*t + 2*PC <= mmin
     const int t_steady_end = (mmin - 2 * PC) / PC + 1;          // exclusive; may be <= 31 (then no steady range)
@@ -834,7 +843,9 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const uint32_t *trace = P.trace + (P.ptrace[p] - P.chunk_base);
     uint32_t *tail = P.trace + (P.ptrace[p + 1] - P.chunk_base);     // runs go to tail[-1], tail[-2], ...
-    const int pc = P.playout[p];                      // columns per step of the writer
+    const int lay = P.playout[p];
+    const int pc = lay & 15;                          // columns per step of the writer
+    const bool split = (lay & 16) != 0;               // packed path: [src x8 | fe x8] 2-bit fields; 32-bit path: nibbles
     const int T = (m + pc - 1) / pc + 31;
     const int last_s = (n - 1) >> 8, rr_last = P.plastrr[p];   // rows per lane in the (possibly compacted) last stripe
     int i = P.endq[p], j = P.endr[p];
@@ -876,7 +887,7 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
         ISOF_ASSERT(wp >= trace && wp < tail - TRACE_SLACK && wp < tail - nr, CHK_TRACE_LOAD);
         last_read = wp;
         const uint32_t word = __ldcg(wp);
-        const int nib = (word >> (4 * r)) & 15;
+        const int nib = split ? ((((word >> (16 + 2 * r)) & 3) << 2) | ((word >> (2 * r)) & 3)) : ((word >> (4 * r)) & 15);
         if (where == 3) {
             const int src = nib >> 2;
             if (src == 3) {
@@ -1177,10 +1188,9 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.h_eo = pk(-4 * gap_open);
     A.h_ee = pk(-4 * gap_ext);
     A.h_fo = pk(-4 * gap_open);
-    A.h_fe = pk(-4 * gap_ext - 1);
+    A.h_fe = pk(-4 * gap_ext);
     A.h_sm = pk(4 * match + 3 - (3 << CS16));
     A.h_sx = pk(4 * mismatch + 3);
-    A.k_fclean = 0xfffefffeu; A.k_sel1 = 0x00010001u; A.k_sel3 = 0x00030003u;
     TRY(dev_reserve(ctx, ctx->b_order, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P * 2));
     A.playout = (uint8_t *)ctx->b_layout.p;
