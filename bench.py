@@ -42,9 +42,9 @@ MATCH, MISMATCH, GAP_OPEN, GAP_EXT = 2, -2, 12, 1
 DELTA_LEN = 5
 # ALU-pipe instructions per DP cell in the SASS of sg_dp_kernel: the packed 16-bit
 # path issues 12 per packed row (= 2 cells), 10 when the substitution scores come from the shared-memory
-# query profile (tasks whose two alignments share the reference); the 32-bit path 11 per row (= 1 cell; 13 with
+# query profile (tasks whose two alignments share the reference); the 32-bit path 10 per row (= 1 cell; 12 with
 # wildcards).  Trace-bit gathering runs as IMADs on the FMA pipe and is not counted here.
-OPS_PER_CELL_PACKED, OPS_PER_CELL_PROFILE, OPS_PER_CELL_32 = 6.0, 5.0, 11.0
+OPS_PER_CELL_PACKED, OPS_PER_CELL_PROFILE, OPS_PER_CELL_32 = 6.0, 5.0, 10.0
 
 
 def parse_args():

@@ -202,6 +202,14 @@ __global__ void chunk_bounds_kernel(const int64_t *__restrict__ ptrace, int64_t 
 // ---------------------------------------------------------------------------------------------
 // 32-bit path: one alignment per warp, 16*score + 4-bit tag, two columns per step, the step loop peeled
 // into fill / steady / drain exactly like the packed path below (which documents the scheme).
+// d = a * M + c on the FMA pipe (IMAD); inline PTX so the multiply is not strength-reduced to ALU-pipe shifts
+__device__ __forceinline__ uint32_t mad_u32(const uint32_t a, const uint32_t mult, const uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(mult), "r"(c));
+    return d;
+}
+
 struct P32State {
     int qc[R], Hl[R], El[R];
     int Hbot[2], Fbot[2], rc_next[2];
@@ -221,7 +229,10 @@ __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, co
         scv[0] = (int)v0.x; scv[1] = (int)v0.y; scv[2] = (int)v0.z; scv[3] = (int)v0.w;
         scv[4] = (int)v1.x; scv[5] = (int)v1.y; scv[6] = (int)v1.z; scv[7] = (int)v1.w;
     }
-    uint32_t acc = 0;
+    // Trace nibble of row r = [src1 src0 f e]: src is bits 3:2 of H's tag (H - Hc is that tag), e is bit 0 of E,
+    // f is bit 1 of F (E's tag is 4|e, F's 8|2f, so (E | F) & 3 is [f e]).  Both are gathered with IMADs on the
+    // FMA pipe; one LOP3 per column merges them.
+    uint32_t acc_ef = 0u, acc_h = 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int left = S.Hl[r];
@@ -238,10 +249,11 @@ __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, co
         }
         const int Hd = diag + sc;
         const int H = __vimax3_s32(Hd, F, E);
-        uint32_t nib = ((uint32_t)H & ~1u) | ((uint32_t)E & 1u);
-        nib = (nib & ~2u) | ((uint32_t)F & 2u);
-        acc |= (nib & 15u) << (4 * r);
         const int Hc = H & ~15;
+        const uint32_t ef = ((uint32_t)E | (uint32_t)F) & 3u;
+        acc_ef = mad_u32(ef, 1u << (4 * r), acc_ef);
+        acc_h = mad_u32((uint32_t)H, 1u << (4 * r), acc_h);
+        acc_h = mad_u32((uint32_t)Hc, 0u - (1u << (4 * r)), acc_h);
         diag = left;
         S.Hl[r] = Hc;
         S.El[r] = E & ~15;
@@ -249,7 +261,7 @@ __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, co
         fup = F & ~15;
     }
     hbot = up; fbot = fup;
-    word = acc;
+    word = (acc_h & 0xccccccccu) | acc_ef;
 }
 
 template <bool WILD>
@@ -454,14 +466,6 @@ __device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
 // is inside both alignments with a full look-ahead block, so that loop has no bounds checks, no
 // end-cell bookkeeping and unconditional stores; fill, drain and the last stripes (which track the
 // end cell) go through the general step.
-// d = a * M + c on the FMA pipe (IMAD); inline PTX so the multiply is not strength-reduced to ALU-pipe shifts
-__device__ __forceinline__ uint32_t mad_u32(const uint32_t a, const uint32_t mult, const uint32_t c)
-{
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(mult), "r"(c));
-    return d;
-}
-
 struct P16Const {
     uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
 };

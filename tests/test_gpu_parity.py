@@ -644,3 +644,38 @@ def test_profile_path_same_reference_tasks(ctx):
     sc, _q, _r, runs = oracle.sg_align(pool[3], pool[9], 2, -2, 12, 1)
     assert same["score"][:2].tolist() == [sc, sc]
     assert same["cigar"][same["cigar_off"][1]:same["cigar_off"][2]].tolist() == runs.tolist()
+
+
+def test_packed_profile_range_extremes_debug_build():
+    """Shared-reference tasks (query-profile variant of the packed path) at the edges of the 16-bit range:
+    longest eligible references, all-match and all-mismatch content, queries of very different lengths sharing
+    a task (one half runs on padding rows for many stripes).  Debug build: the bounds assertions must stay
+    silent; results must equal the oracle's."""
+    from isonform_b200 import _lib, hotpath, synth
+    rng = np.random.default_rng(131)
+    dctx = _lib.Context(0, debug=True)
+    try:
+        for params, lmax in [((2, -2, 12, 1), 7722), ((2, -8, 12, 1), 7716)]:
+            ref_long = _rand_dna(rng, lmax)
+            ref_mid = _rand_dna(rng, 4093)
+            refs = [ref_long, "C" * lmax, ref_mid, "G" * 4093]
+            queries = ["A", "AC", _rand_dna(rng, 100), ref_long[3000:3255], ref_long[100:356], "A" * 257, ref_mid[:511],
+                       synth.mutate(rng, ref_mid[200:900], 0.05), "A" * 4093, ref_mid, synth.mutate(rng, ref_mid, 0.03)[:4093],
+                       "G" * 4093, "T" * 4000, ref_long[:4093], _rand_dna(rng, 3)]
+            seqs = queries + refs
+            pa, pb = [], []
+            for r in range(len(refs)):                      # grouped by reference, lengths interleaved long/short
+                order = list(range(len(queries)))
+                rng.shuffle(order)
+                pa += order; pb += [len(queries) + r] * len(order)
+            dctx.profile_enable(True); dctx.profile_reset()
+            res = hotpath.align_pairs(seqs, pa, pb, *params, ctx=dctx)
+            prof = dctx.profile()
+            assert prof["dp_cells_profile"] > 0 and prof["dp_cells_packed"] >= prof["dp_cells_profile"], prof
+            for p in range(len(pa)):
+                sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params)
+                assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er), (params, p)
+                assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist(), (params, p)
+            assert dctx.debug_violations()[0] == 0
+    finally:
+        dctx.close()
