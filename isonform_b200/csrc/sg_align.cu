@@ -247,8 +247,8 @@ __device__ __forceinline__ void p32_column(P32State &S, const AlignParams &P, co
             sc = __viaddmax_s32(y, P.c_sm, P.c_sx);
             if ((S.qc[r] | rc) & (4 << CODE_SHIFT)) sc = 12;
         }
-        const int Hd = diag + sc;
-        const int H = __vimax3_s32(Hd, F, E);
+        const int D = __viaddmax_s32(diag, sc, E);        // off the row-to-row chain (previous column only)
+        const int H = max(D, F);
         const int Hc = H & ~15;
         const uint32_t ef = ((uint32_t)E | (uint32_t)F) & 3u;
         acc_ef = mad_u32(ef, 1u << (4 * r), acc_ef);
@@ -515,8 +515,10 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
             const uint32_t y = S.qc[r] ^ rc ^ C3;
             sc = __viaddmax_s16x2(y, K.h_sm, K.h_sx);
         }
-        const uint32_t Hd = __vadd2(diag, sc);                      // tag 11
-        const uint32_t H = __vimax3_s16x2(Hd, Fh, Ehn);             // ties: diagonal > F > E
+        // max(diag + sc, E) first: it depends on the previous column only, so the row-to-row chain through F is
+        // F -> Fh -> H -> Hc (4 dependent ops) instead of 5
+        const uint32_t D = __viaddmax_s16x2(diag, sc, Ehn);         // diagonal: tag 11
+        const uint32_t H = __vmaxs2(D, Fh);                         // ties: diagonal > F > E
         const uint32_t Hc = H & 0xfffcfffcu;
         const uint32_t ef = (E | F) & 0x00030003u;
         acc_ef = mad_u32(ef, 1u << (2 * r), acc_ef);
@@ -756,7 +758,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
             };
             if (!track_stripe) {
-#pragma unroll 1
+#pragma unroll 2
                 for (int t = 31; t < t2; ++t) steady_step(t, false);
             } else {
 #pragma unroll 1
