@@ -53,6 +53,11 @@ def lib():
                                                  C.c_int]
         L.isof_oracle_sg_align_pairs_simd.restype = C.c_int64
         L.isof_oracle_sg_align_pairs_simd.argtypes = L.isof_oracle_sg_align_pairs.argtypes
+        L.isof_oracle_edit_distance.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+        L.isof_oracle_edit_distance.restype = C.c_int32
+        L.isof_oracle_edit_distance_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                      C.c_void_p, C.c_int]
+        L.isof_oracle_edit_distance_pairs.restype = C.c_int64
         L.isof_oracle_num_threads.restype = C.c_int32
         del u8p
         _lib = L
@@ -130,6 +135,24 @@ def sg_align_pairs(cat, off, ia, ib, match, mismatch, gap_open, gap_ext, threads
     if tot < 0:
         raise RuntimeError("oracle sg_align_pairs failed")
     return score, eq, er, (cig[:tot].copy() if want_cigar else None), coff
+
+
+def edit_distance(s1, s2):
+    """Global unit-cost edit distance (Myers/Hyyro bit-vector); config 5's "edlib CPU" stand-in."""
+    a, b = _b(s1), _b(s2)
+    return int(lib().isof_oracle_edit_distance(a, len(a), b, len(b)))
+
+
+def edit_distance_pairs(cat, off, ia, ib, threads=0):
+    cat = np.ascontiguousarray(cat, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ia = np.ascontiguousarray(ia, dtype=np.int32)
+    ib = np.ascontiguousarray(ib, dtype=np.int32)
+    dist = np.empty(len(ia), np.int32)
+    if lib().isof_oracle_edit_distance_pairs(cat.ctypes.data, off.ctypes.data, ia.ctypes.data, ib.ctypes.data, len(ia),
+                                             dist.ctypes.data, threads) < 0:
+        raise RuntimeError("oracle edit_distance_pairs failed")
+    return dist
 
 
 def num_threads():

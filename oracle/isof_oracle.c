@@ -625,3 +625,78 @@ ISOF_API int64_t isof_oracle_sg_align_pairs_simd(const uint8_t *cat, const int64
     free(runs); free(nr); free(order);
     return err ? -1 : tot;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Global (Needleman-Wunsch, unit cost) edit distance by Myers' bit-vector algorithm in Hyyro's
+ * block form -- the "edlib CPU" column of BASELINE config 5.  edlib is listed by the reference's
+ * setup.py:81 but has ZERO call sites, so there is nothing to be exact against; this is
+ * a restatement of the published algorithm (G. Myers, JACM 46(3) 1999; H. Hyyro, Nordic J.
+ * Computing 10(1) 2003), checked in tests/ against a plain O(nm) DP.  It is a timing baseline
+ * only: nothing in the product computes edit distances.
+ *
+ * The query is cut into blocks of 64 rows; per text character each block is advanced with the
+ * horizontal delta (-1, 0, +1) of the block above as carry-in.  Row 0 of the DP (global mode)
+ * grows by 1 per column, so the first block's carry-in is always +1.
+ * ------------------------------------------------------------------------------------------- */
+static inline int myers_block(uint64_t *pv_io, uint64_t *mv_io, uint64_t eq, int hin)
+{
+    uint64_t pv = *pv_io, mv = *mv_io;
+    const uint64_t hneg = (uint64_t)(hin < 0);
+    const uint64_t xv = eq | mv;
+    eq |= hneg;
+    const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
+    uint64_t ph = mv | ~(xh | pv);
+    uint64_t mh = pv & xh;
+    int hout = 0;
+    if (ph >> 63) hout = 1;
+    else if (mh >> 63) hout = -1;
+    ph = (ph << 1) | (uint64_t)(hin > 0);
+    mh = (mh << 1) | hneg;
+    *pv_io = mh | ~(xv | ph);
+    *mv_io = ph & xv;
+    return hout;
+}
+
+ISOF_API int32_t isof_oracle_edit_distance(const uint8_t *q, int32_t n, const uint8_t *t, int32_t m)
+{
+    if (n == 0) return m;
+    if (m == 0) return n;
+    const int nb = (n + 63) / 64;
+    uint64_t *peq = (uint64_t *)calloc((size_t)nb * 256, sizeof(uint64_t));   /* [block][char] */
+    uint64_t *pv = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)nb);
+    uint64_t *mv = (uint64_t *)calloc((size_t)nb, sizeof(uint64_t));
+    if (!peq || !pv || !mv) { free(peq); free(pv); free(mv); return -1; }
+    for (int32_t i = 0; i < n; ++i) peq[(size_t)(i >> 6) * 256 + q[i]] |= 1ull << (i & 63);
+    for (int b = 0; b < nb; ++b) pv[b] = ~0ull;
+    int64_t bottom = (int64_t)nb * 64;           /* D(64*nb, 0): rows below n are padding, never read upward */
+    for (int32_t j = 0; j < m; ++j) {
+        int h = 1;
+        const uint64_t *pe = peq + t[j];
+        for (int b = 0; b < nb; ++b) h = myers_block(&pv[b], &mv[b], pe[(size_t)b * 256], h);
+        bottom += h;
+    }
+    /* walk the last column up from row 64*nb to row n with the vertical deltas of the last block */
+    for (int r = 63; r >= ((n - 1) & 63) + 1; --r) {
+        if ((pv[nb - 1] >> r) & 1) --bottom;
+        else if ((mv[nb - 1] >> r) & 1) ++bottom;
+    }
+    free(peq); free(pv); free(mv);
+    return (int32_t)bottom;
+}
+
+ISOF_API int64_t isof_oracle_edit_distance_pairs(const uint8_t *cat, const int64_t *off, const int32_t *ia,
+                                                 const int32_t *ib, int64_t P, int32_t *dist, int threads)
+{
+    int err = 0;
+    (void)threads;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (int64_t p = 0; p < P; ++p) {
+        dist[p] = isof_oracle_edit_distance(cat + off[ia[p]], (int32_t)(off[ia[p] + 1] - off[ia[p]]),
+                                            cat + off[ib[p]], (int32_t)(off[ib[p] + 1] - off[ib[p]]));
+        if (dist[p] < 0) err = 1;
+    }
+    return err ? -1 : P;
+}
