@@ -403,7 +403,7 @@ def run_b200(args):
             "gpu_launches": int(launches_timed),
             "roofline": {"kernel": "sg_dp_kernel", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None,
-                         "traffic_note": "ncu --set full (profiles/r01_ncu_v4_summary.txt, 4950-pair launch): dram write 20.38 GB + "
+                         "traffic_note": "ncu --set full (profiles/r01_ncu_v6_summary.txt, 4950-pair launch): dram write 20.38 GB + "
                                          "read 0.66 GB = 1.10x the algorithmic trace bytes of that launch (stripe/row padding), "
                                          "no re-reads",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
