@@ -365,6 +365,33 @@ def run_b200(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     pairs_all, cells_all, reads_all = float(tot[0]), float(tot[1]), float(tot[2])
 
+    # ---- kernel (a) at super-batch scale (the C3 regime: many clusters' reads in one call); rank 0, untimed extra
+    min_super = None
+    if rank == 0:
+        reps = max(1, min(32, int(2.0e8 // max(wl["n_bases"], 1))))
+        offs = [wl["off"][:-1] + i * wl["n_bases"] for i in range(reps)] + [np.array([reps * wl["n_bases"]], np.int64)]
+        d_cat_s = d_cat.repeat(reps)
+        d_off_s = torch.from_numpy(np.concatenate(offs).astype(np.int64)).to(dev)
+        cap_s = reps * wl["n_bases"] // 4 + 1024
+        d_pos_s = torch.empty(cap_s, dtype=torch.int32, device=dev)
+        d_poff_s = torch.empty(reps * R + 1, dtype=torch.int64, device=dev)
+        ctx.profile_enable(False)
+        for _ in range(2):
+            n_s = ctx.minimizers_batch_dev(d_cat_s.data_ptr(), d_off_s.data_ptr(), reps * R, reps * wl["n_bases"], K_SIZE, W_SIZE,
+                                           d_pos_s.data_ptr(), cap_s, d_poff_s.data_ptr())
+        torch.cuda.synchronize()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record(stream)
+        for _ in range(5):
+            ctx.minimizers_batch_dev(d_cat_s.data_ptr(), d_off_s.data_ptr(), reps * R, reps * wl["n_bases"], K_SIZE, W_SIZE,
+                                     d_pos_s.data_ptr(), cap_s, d_poff_s.data_ptr())
+        es1.record(stream)
+        torch.cuda.synchronize()
+        ms_s = es0.elapsed_time(es1) / 5
+        min_super = {"n_reads": reps * R, "mbases": reps * wl["n_bases"] / 1e6, "minimizers": int(n_s), "ms_per_call": ms_s,
+                     "mbases_per_s": reps * wl["n_bases"] / ms_s / 1e3}
+        del d_cat_s, d_off_s, d_pos_s, d_poff_s
+
     if rank == 0:
         K = args.steps
         value = pairs_all * K / (ms_dev_max * 1e-3)
@@ -421,7 +448,9 @@ def run_b200(args):
                                  "int32_ops_per_base": 180, "int32_frac": (wl["n_bases"] * PROF_STEPS * 180.0 /
                                                                            max(prof["minimizer_ms"] * 1e-3, 1e-12)) / int32_peak,
                                  "note": "all four launches of isof_minimizers_batch_dev (hash+select, count scan, compaction); "
-                                         "launch-latency bound at one 1000-read batch"},
+                                         "launch-latency bound at one 1000-read batch; super_batch = the same call over "
+                                         "many batches' reads at once (C3 regime), CUDA events, int32_frac at 180 ops/base",
+                                 "super_batch": dict(min_super, int32_frac=min_super["mbases_per_s"] * 1e6 * 180.0 / int32_peak) if min_super and int32_peak else min_super},
             "kernel_ms_per_step": {"dp": prof["dp_ms"] / PROF_STEPS, "traceback_cigar_features": prof["traceback_ms"] / PROF_STEPS,
                                    "minimizers": prof["minimizer_ms"] / PROF_STEPS, "plan_encode_spans": prof["other_ms"] / PROF_STEPS,
                                    "note": "serialised roofline step; in the timed (pipelined) steps traceback overlaps DP"},

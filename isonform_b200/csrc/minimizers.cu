@@ -6,11 +6,12 @@
 //   2. every lane hashes CHUNK/32 k-mers with SipHash-1-3 (zero key, the CPython `hash(str)` the
 //      reference orders k-mers by, main:85,94); hashes go to a shared ring that also keeps the
 //      w previous hashes;
-//   3. selection: every lane computes, for 8 consecutive positions, the window minimum, its LAST
-//      arg-min and whether the minimum occurs more than once in the window.  If no window of the
+//   3. selection: every lane computes, for the 8 positions q = u*32 + lane (interleaved, so the hash
+//      ring is read without bank conflicts), the window minimum, its LAST arg-min and whether the
+//      minimum occurs more than once in the window.  If no window of the
 //      chunk has a duplicated minimum the reference's state machine is history-free
 //      ("emit when the last arg-min changes", DESIGN.md section minimizers) and the chunk is
-//      emitted in parallel through a warp prefix sum; otherwise lane 0 replays the chunk with the
+//      emitted in parallel (one ballot per group of 32 positions orders the output); otherwise lane 0 replays the chunk with the
 //      reference's sequential rule (older equal hash is kept until it leaves the window).
 // A second kernel compacts the per-read results into the caller's (out_pos, out_off) layout.
 #include "common.cuh"
@@ -110,13 +111,13 @@ minimizer_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ 
                 hs[w + q] = h;
             }
             __syncwarp();
-            // ---- 3. selection
-            const int q0 = lane * PER_LANE;
+            // ---- 3. selection: lane l takes positions q = u*32 + l, so consecutive lanes read consecutive
+            // hashes (no shared-memory bank conflicts) and a ballot per u orders the emitted positions
             int la[PER_LANE];                     // last arg-min of window(i); -1 when i not selectable
             bool tie = false;
 #pragma unroll
             for (int u = 0; u < PER_LANE; ++u) {
-                int q = q0 + u, i = c0 + q;
+                int q = u * 32 + lane, i = c0 + q;
                 la[u] = -1;
                 if (i >= w && i <= i_last) {
                     int64_t mn = hs[w + q];
@@ -132,53 +133,38 @@ minimizer_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ 
             }
             const bool need_seq = __any_sync(0xffffffffu, tie);
             if (!need_seq) {
-                // previous position's state: lane 0 uses the carried `pos`, others the neighbour's la
-                int last_la = la[PER_LANE - 1];
-                int prev = __shfl_up_sync(0xffffffffu, last_la, 1);
-                unsigned em_mask = 0;                 // bit u: position q0+u emits la[u]
 #pragma unroll
                 for (int u = 0; u < PER_LANE; ++u) {
-                    int i = c0 + q0 + u;
+                    const int q = u * 32 + lane, i = c0 + q;
+                    // last arg-min of the previous position: lane-1 of this u, or lane 31 of u-1
+                    int pl = __shfl_up_sync(0xffffffffu, la[u], 1);
+                    if (u > 0) {
+                        const int t = __shfl_sync(0xffffffffu, la[u - 1], 31);
+                        if (lane == 0) pl = t;
+                    }
+                    bool em = false;
                     if (la[u] >= 0) {
-                        bool em;
                         if (i == w) em = true;                                  // initial minimizer
-                        else if (lane == 0 && u == 0) {
-                            // exact sequential rule against the carried state (main:100-108)
-                            em = (pos == i - w - 1) || (hs[w + q0] < hs[w + (pos - c0)]);
-                        } else {
-                            int pl = (u == 0) ? prev : la[u - 1];
-                            em = (la[u] != pl);
-                        }
-                        if (em) em_mask |= 1u << u;
+                        else if (q == 0)                                        // exact sequential rule against the carried state (main:100-108)
+                            em = (pos == i - w - 1) || (hs[w] < hs[w + (pos - c0)]);
+                        else em = (la[u] != pl);
                     }
-                }
-                const int my_n = __popc(em_mask);
-                // warp exclusive scan of my_n
-                int incl = my_n;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                int excl = incl - my_n;
-#pragma unroll
-                for (int u = 0; u < PER_LANE; ++u)
-                    if ((em_mask >> u) & 1u) {
-                        ISOF_ASSERT(emitted + excl + __popc(em_mask & ((1u << u) - 1u)) <= n, CHK_MIN_OUT);
-                        out[emitted + excl + __popc(em_mask & ((1u << u) - 1u))] = la[u];
+                    const unsigned m = __ballot_sync(0xffffffffu, em);
+                    if (em) {
+                        const int slot = emitted + __popc(m & ((1u << lane) - 1u));
+                        ISOF_ASSERT(slot <= n, CHK_MIN_OUT);
+                        out[slot] = la[u];
                     }
-                emitted += __shfl_sync(0xffffffffu, incl, 31);
-                // carried state = last selectable position's arg-min
-                unsigned have = __ballot_sync(0xffffffffu, last_la >= 0 || la[0] >= 0);
-                if (have) {
-                    // last selectable i in this chunk
-                    int i_end = min(c0 + CHUNK - 1, i_last);
-                    int ql = i_end - c0;
-                    int owner = ql / PER_LANE;
+                    emitted += __popc(m);
+                }
+                // carried state = last arg-min of the chunk's last selectable position
+                const int i_end = min(c0 + CHUNK - 1, i_last);
+                if (i_end >= w) {
+                    const int ql = i_end - c0, ul = ql >> 5;
                     int v = la[0];
 #pragma unroll
-                    for (int u = 1; u < PER_LANE; ++u) if (u <= ql - q0) v = la[u];
-                    pos = __shfl_sync(0xffffffffu, v, owner);
+                    for (int u = 1; u < PER_LANE; ++u) if (u == ul) v = la[u];
+                    pos = __shfl_sync(0xffffffffu, v, ql & 31);
                 }
             } else {
                 if (lane == 0) {
