@@ -45,6 +45,9 @@ DELTA_LEN = 5
 # query profile (tasks whose two alignments share the reference); the 32-bit path 10 per row (= 1 cell; 12 with
 # wildcards).  Trace-bit gathering runs as IMADs on the FMA pipe and is not counted here.
 OPS_PER_CELL_PACKED, OPS_PER_CELL_PROFILE, OPS_PER_CELL_32 = 6.0, 5.0, 10.0
+# DRAM bytes per DP cell of sg_dp_kernel measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch
+# over its cell count; profiles/r01_ncu_v6_summary.txt)
+NCU_DRAM_BYTES_PER_CELL = 0.5605
 
 
 def parse_args():
@@ -429,10 +432,13 @@ def run_b200(args):
                     "ms_per_step": ms_e2e_max / K, "gcups": cells_all * K / (ms_e2e_max * 1e-3) / 1e9},
             "gpu_launches": int(launches_timed),
             "roofline": {"kernel": "sg_dp_kernel", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": None,
-                         "traffic_note": "ncu --set full (profiles/r01_ncu_v6_summary.txt, 4950-pair launch): dram write 20.38 GB + "
-                                         "read 0.66 GB = 1.10x the algorithmic trace bytes of that launch (stripe/row padding), "
-                                         "no re-reads",
+                         "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": NCU_DRAM_BYTES_PER_CELL * prof["dp_cells"] / max(prof["dp_launches"], 1),
+                         "traffic_note": "bytes per launch, scaled by cells from the ncu --set full capture of a 4950-pair launch "
+                                         "of the same reads (profiles/r01_ncu_v6_summary.txt: dram write 20.379 GB + read 0.664 GB "
+                                         "over 37.54 G cells = 0.5605 B/cell = 1.12x the 0.5 B/cell of trace: stripe/row padding, "
+                                         "no re-reads); a bench-sized launch writes ~70 GB of trace, too large for ncu's "
+                                         "save/restore replay",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "launch_ms": dp_ms_launch, "launches": int(prof["dp_launches"]),
                          "note": "integer DP: the kernel is INT32-ALU bound, see int_alu; algorithmic bytes = "
