@@ -617,10 +617,14 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
         }
         uint2 *tpA = reinterpret_cast<uint2 *>(traceA) + (size_t)s * TA * 32 + lane;
         uint2 *tpB = reinterpret_cast<uint2 *>(traceB) + (size_t)s * TB * 32 + lane;
+        uint32_t snap[RR];                           // H of the last column (A low half, B high half), set in the drain
+#pragma unroll
+        for (int r = 0; r < RR; ++r) snap[r] = 0x80008000u;
 
         // ---------------- general step (bounds checks + end-cell bookkeeping) ----------------
-        auto general_step = [&](const int t, auto track_tag) {
-            constexpr bool TR = decltype(track_tag)::value;      // false: no end-cell bookkeeping (fill steps of inner stripes)
+        auto general_step = [&](const int t, auto track_tag, auto row_tag) {
+            constexpr bool TR = decltype(track_tag)::value;      // false: the step cannot reach a last column (fill steps before a steady range)
+            constexpr bool TROW = decltype(row_tag)::value;      // false: not a last stripe, no last-row bookkeeping
             const int jb = PC * (t - lane);
             uint32_t rc[PC], hu[PC], fu[PC];
 #pragma unroll
@@ -650,28 +654,24 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     const int j = jb + c;
                     ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
                     if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
-                    if (TR && liveA && j == mA - 1) {       // last column of A: smallest i wins ties
+                    // last column of A / B: every lane passes it exactly once per stripe; keep the column (one LOP3 per
+                    // row) and fold it into the running maximum after the stripe's loop
+                    if (TR && j == mA - 1) {
 #pragma unroll
-                        for (int r = 0; r < RR; ++r) {
-                            const int v = lo16(S.Hl[r]);
-                            if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
-                        }
+                        for (int r = 0; r < RR; ++r) snap[r] = (snap[r] & 0xffff0000u) | (S.Hl[r] & 0x0000ffffu);
                     }
-                    if (TR && liveB && j == mB - 1) {
+                    if (TR && j == mB - 1) {
 #pragma unroll
-                        for (int r = 0; r < RR; ++r) {
-                            const int v = hi16(S.Hl[r]);
-                            if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
-                        }
+                        for (int r = 0; r < RR; ++r) snap[r] = (snap[r] & 0x0000ffffu) | (S.Hl[r] & 0xffff0000u);
                     }
-                    if (TR && trackA && j < mA) {           // last row of A: smallest j wins ties
+                    if (TROW && trackA && j < mA) {         // last row of A: smallest j wins ties
                         uint32_t hv = S.Hl[0];
 #pragma unroll
                         for (int r = 1; r < RR; ++r) if (r == last_rA) hv = S.Hl[r];
                         const int v = lo16(hv);
                         if (v > browA) { browA = v; browA_j = j; }
                     }
-                    if (TR && trackB && j < mB) {
+                    if (TROW && trackB && j < mB) {
                         uint32_t hv = S.Hl[0];
 #pragma unroll
                         for (int r = 1; r < RR; ++r) if (r == last_rB) hv = S.Hl[r];
@@ -693,9 +693,11 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 
         const bool can_steady = liveA && liveB && t_steady_end > 31;
         const int t1 = can_steady ? 31 : T, t2 = can_steady ? t_steady_end : T;
-        // fill steps of an inner stripe cannot reach a last column when the shorter reference has > 64 columns
-        if (can_steady && !track_stripe && mmin > 2 * 31 + 2) { for (int t = 0; t < t1; ++t) general_step(t, std::false_type{}); }
-        else { for (int t = 0; t < t1; ++t) general_step(t, std::true_type{}); }
+        // a steady range exists only when the shorter reference has >= 66 columns; the 31 fill steps before it
+        // stay below column 62 and cannot reach a last column
+        if (can_steady && !track_stripe) { for (int t = 0; t < t1; ++t) general_step(t, std::false_type{}, std::false_type{}); }
+        else if (can_steady) { for (int t = 0; t < t1; ++t) general_step(t, std::false_type{}, std::true_type{}); }
+        else { for (int t = 0; t < t1; ++t) general_step(t, std::true_type{}, std::true_type{}); }
         if (can_steady) {
             // ---------------- steady state: no bounds checks; end-cell bookkeeping only in the last stripes,
             // and there only the running maximum of the last row (the last column is reached in the drain)
@@ -764,7 +766,23 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 #pragma unroll 1
                 for (int t = 31; t < t2; ++t) steady_step(t, true);
             }
-            for (int t = t2; t < T; ++t) general_step(t, std::true_type{});
+            if (track_stripe) { for (int t = t2; t < T; ++t) general_step(t, std::true_type{}, std::true_type{}); }
+            else { for (int t = t2; t < T; ++t) general_step(t, std::true_type{}, std::false_type{}); }
+        }
+        // end cell, last column: smallest i wins ties (rows ascend within a lane and from stripe to stripe)
+        if (liveA) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const int v = lo16(snap[r]);
+                if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
+            }
+        }
+        if (liveB) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const int v = hi16(snap[r]);
+                if (i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
+            }
         }
         __syncwarp();
     };
