@@ -37,7 +37,10 @@ constexpr int TAG_BITS = 4;
 constexpr int NEGV = -(1 << 29);     // "minus infinity", a clean multiple of 16
 constexpr int CODE_SHIFT = 12;       // base codes live at bits 12..14 of a register
 constexpr int TRACE_SLACK = 64;      // spare words at the end of every trace region
-constexpr int DP_WARPS = 8;          // warps per CTA of the DP kernel
+constexpr int DP_WARPS = 1;          // warps per CTA of the DP kernel: single-warp CTAs leave the SM one by one, so the
+                                     // next chunk's CTAs fill every freed slot at once (8-warp CTAs held their registers
+                                     // until the slowest of 8 tasks ended: -3.5 % on C2)
+constexpr int DP_CTAS_PER_SM = 16;   // 128 registers x 32 threads x 16 = the whole register file
 
 struct AlignParams {
     const uint8_t *cat;        // ASCII pool
@@ -830,7 +833,7 @@ __device__ __forceinline__ void dp_pair32(const AlignParams &P, const int64_t p,
 
 // One task = two consecutive pairs of the chunk.  Both eligible -> one packed pass; otherwise each
 // pair runs through the 32-bit path.
-__global__ void __launch_bounds__(DP_WARPS * 32, 2)
+__global__ void __launch_bounds__(DP_WARPS * 32, DP_CTAS_PER_SM)
 sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsigned long long *__restrict__ counter)
 {
     __shared__ uint4 s_prof[DP_WARPS][4 * 2 * 32];      // per warp: query profile [code][row half][lane], 4 KB
@@ -1186,7 +1189,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
                                  (long long)max_chunk_words * 4);
         }
     }
-    const int occ_blocks = ctx->sm_count * 2;           // resident CTAs (128 registers x 256 threads: 2 per SM)
+    const int occ_blocks = ctx->sm_count * DP_CTAS_PER_SM;   // resident CTAs (persistent: one launch fills the GPU once)
     const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
     TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)occ_blocks * DP_WARPS));
     if (pipelined) {
