@@ -24,11 +24,11 @@ struct isof_ctx {
     cudaStream_t stream = nullptr;
     char err[512] = {0};
     size_t trace_budget = 0;          // bytes; 0 = decide at first use
-    bool profiling = false;
-    bool disable_packed = false;
-    bool overlap = true;              // pipeline trace chunks over two streams (double-buffered scratch)
-    static constexpr int NLANES = 3;   // pipeline depth: chunk c runs on stream c%NLANES with its own scratch
-    cudaStream_t aux_stream[NLANES - 1] = {nullptr, nullptr};      // force the 32-bit DP path (tests / A-B measurements)
+    bool profiling = false;           // bracket every launch with CUDA events (isof_profile_*)
+    bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
+    bool overlap = true;              // pipeline trace chunks over NLANES streams, each with its own scratch
+    static constexpr int NLANES = 3;  // pipeline depth: chunk c runs on stream c % NLANES
+    cudaStream_t aux_stream[NLANES - 1] = {nullptr, nullptr};
     isof_profile prof;
     // pending (start, stop, slot) event pairs when profiling
     struct Timed { cudaEvent_t a, b; int slot; };
