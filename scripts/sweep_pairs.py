@@ -46,6 +46,15 @@ def main():
                 dt = time.perf_counter() - t0
                 row = {"len": L, "eps": eps, "scores": name, "pairs": n_pairs, "pairs_per_s": n_pairs / dt,
                        "gcups": cells / dt / 1e9, "cigar_runs": int(len(res["cigar"]))}
+                # device time of the same call (all kernels, CUDA events): what is left when the pageable-memory
+                # numpy wrapper (allocation, H2D/D2H of unpinned buffers) is taken out
+                ctx.profile_enable(True); ctx.profile_reset()
+                ctx.sg_align_pairs(cat, off, pa, pb, *sc)
+                pr = ctx.profile(); ctx.profile_enable(False)
+                dev_ms = pr["dp_ms"] + pr["traceback_ms"] + pr["other_ms"]
+                row["device_ms"] = dev_ms
+                row["device_pairs_per_s"] = n_pairs / (dev_ms * 1e-3)
+                row["device_gcups"] = cells / (dev_ms * 1e-3) / 1e9
                 if args.cpu:
                     import oracle
                     ns = int(max(16 * (os.cpu_count() or 1), min(n_pairs, 1e10 / (L * L))))
