@@ -24,6 +24,15 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--lengths", default="50,100,200,500,1000,2000,5000")
     args = ap.parse_args()
+    # under torchrun (WORLD_SIZE > 1): weak scaling, every rank aligns its own copy of the pair list on its own GPU,
+    # no data-path collective; pairs/s = world * pairs / max-over-ranks time
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     ctx = _lib.Context(int(os.environ.get("LOCAL_RANK", "0")))
     rows = []
     rng = np.random.default_rng(5)
@@ -41,20 +50,30 @@ def main():
             cells = float((lens[pa].astype(np.int64) * lens[pb]).sum())
             for name, sc in (("bubble", (2, -8, 12, 1)), ("isoform", (2, -2, 12, 1))):
                 ctx.sg_align_pairs(cat, off, pa[:1000], pb[:1000], *sc)            # warm-up
+                if dist is not None:
+                    dist.barrier()
                 t0 = time.perf_counter()
                 res = ctx.sg_align_pairs(cat, off, pa, pb, *sc)
                 dt = time.perf_counter() - t0
-                row = {"len": L, "eps": eps, "scores": name, "pairs": n_pairs, "pairs_per_s": n_pairs / dt,
-                       "gcups": cells / dt / 1e9, "cigar_runs": int(len(res["cigar"]))}
+                if dist is not None:
+                    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                    dt = float(tmax[0])
+                row = {"len": L, "eps": eps, "scores": name, "n_gpus": world, "pairs": n_pairs * world,
+                       "pairs_per_s": world * n_pairs / dt, "gcups": world * cells / dt / 1e9, "cigar_runs": int(len(res["cigar"]))}
                 # device time of the same call (all kernels, CUDA events): what is left when the pageable-memory
                 # numpy wrapper (allocation, H2D/D2H of unpinned buffers) is taken out
                 ctx.profile_enable(True); ctx.profile_reset()
                 ctx.sg_align_pairs(cat, off, pa, pb, *sc)
                 pr = ctx.profile(); ctx.profile_enable(False)
                 dev_ms = pr["dp_ms"] + pr["traceback_ms"] + pr["other_ms"]
+                if dist is not None:
+                    tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                    dev_ms = float(tmax[0])
                 row["device_ms"] = dev_ms
-                row["device_pairs_per_s"] = n_pairs / (dev_ms * 1e-3)
-                row["device_gcups"] = cells / (dev_ms * 1e-3) / 1e9
+                row["device_pairs_per_s"] = world * n_pairs / (dev_ms * 1e-3)
+                row["device_gcups"] = world * cells / (dev_ms * 1e-3) / 1e9
                 if args.cpu:
                     import oracle
                     ns = int(max(16 * (os.cpu_count() or 1), min(n_pairs, 1e10 / (L * L))))
@@ -71,8 +90,11 @@ def main():
                     oracle.edit_distance_pairs(cat, off, pa[:nm], pb[:nm], threads=os.cpu_count())
                     row["myers_cpu_pairs_per_s"] = nm / (time.perf_counter() - t0)
                 rows.append(row)
-                print(json.dumps(row), flush=True)
-    if args.out:
+                if rank == 0:
+                    print(json.dumps(row), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    if args.out and rank == 0:
         json.dump({"config": "C5 pair sweep: wall clock of the numpy host API (isof_sg_align_pairs incl. H2D/D2H and buffer allocation); CPU = oracle SIMD port (same affine alignment with traceback), all host cores; myers_cpu = unit-cost edit distance only (Myers/Hyyro restatement standing in for edlib, which has no call site in the reference)", "rows": rows}, open(args.out, "w"), indent=1)
 
 
