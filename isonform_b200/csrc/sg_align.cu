@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/block/block_scan.cuh>
 #include <climits>
 #include <type_traits>
 
@@ -182,6 +183,96 @@ __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int
     }
     for (int d = 16; d; d >>= 1) { c += __shfl_down_sync(0xffffffffu, c, d); cp += __shfl_down_sync(0xffffffffu, cp, d); }
     if ((threadIdx.x & 31) == 0 && c) { atomicAdd(out, c); if (cp) atomicAdd(out + 1, cp); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small batches (P <= SMALL_P pairs over <= SMALL_BASES bases; the per-pair seams of the reference issue their
+// alignments one at a time): the whole set-up -- base codes, plan, trace offsets, task order -- is ONE
+// single-block kernel, and the CIGAR scan/copy after the traceback another, instead of ~14 launches.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_P = 1024;
+constexpr int64_t SMALL_BASES = 1 << 20;
+
+__global__ void __launch_bounds__(1024)
+small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ off, int n_seqs,
+                  const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, int P, uint8_t *__restrict__ codes,
+                  uint8_t *__restrict__ flags, int32_t *__restrict__ pn, int32_t *__restrict__ pm,
+                  uint8_t *__restrict__ pwild, int64_t *__restrict__ ptrace, unsigned long long *__restrict__ misc,
+                  int h_max_min_len, int h_max_max_len, int32_t *__restrict__ order,
+                  unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ ticket)
+{
+    typedef cub::BlockScan<long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ uint32_t s_key[SMALL_P];
+    __shared__ unsigned long long s_stat[4];             // err, max m, cells, padded
+    __shared__ int s_nelig;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 4) s_stat[tid] = 0ull;
+    if (tid == 0) s_nelig = 0;
+    // base codes + per-sequence wildcard flag (warp per sequence)
+    for (int q = warp; q < n_seqs; q += 32) {
+        const int64_t b = off[q], e = off[q + 1];
+        int wild = 0;
+        for (int64_t x = b + lane; x < e; x += 32) {
+            const int c = base_code(cat[x]);
+            codes[x] = (uint8_t)c;
+            wild |= (c == 4);
+        }
+        wild = __any_sync(0xffffffffu, wild);
+        if (lane == 0) flags[q] = (uint8_t)wild;
+    }
+    __syncthreads();
+    // plan (same rules as plan_kernel)
+    long long w = 0;
+    uint32_t key = 0xffffffffu;
+    if (tid < P) {
+        const int a = pa[tid], b = pb[tid];
+        int n = 0, m = 0;
+        w = TRACE_SLACK;
+        uint8_t pw = 0;
+        if (a < 0 || a >= n_seqs || b < 0 || b >= n_seqs) atomicOr(&s_stat[0], 1ull);
+        else {
+            n = (int)(off[a + 1] - off[a]);
+            m = (int)(off[b + 1] - off[b]);
+            if (n <= 0 || m <= 0) { atomicOr(&s_stat[0], 2ull); n = m = 0; }
+            else {
+                const int ns = (n + SROWS - 1) / SROWS;
+                w = (long long)ns * (m + 64) * 32 + TRACE_SLACK;
+                const int wild = flags[a] | flags[b];
+                const int elig = !wild && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len;
+                const int need = n - (ns - 1) * SROWS;
+                const int rr = need > 192 ? 8 : need > 128 ? 6 : need > 64 ? 4 : 2;
+                atomicAdd(&s_stat[2], (unsigned long long)n * m);
+                atomicAdd(&s_stat[3], (unsigned long long)((ns - 1) * SROWS + (elig ? rr * 32 : SROWS)) * m);
+                atomicMax(&s_stat[1], (unsigned long long)m);
+                pw = (uint8_t)(wild | (elig << 1));
+                if (elig) atomicAdd(&s_nelig, 1);
+                key = (elig ? 0u : 0x80000000u) | ((uint32_t)b & 0x7fffffffu);
+            }
+        }
+        pn[tid] = n; pm[tid] = m; pwild[tid] = pw;
+    }
+    s_key[tid] = key;
+    long long excl = 0, total = 0;
+    Scan(scan_tmp).ExclusiveSum(w, excl, total);         // includes a __syncthreads: s_key is complete afterwards
+    if (tid < P) ptrace[tid] = excl;
+    if (tid == 0) ptrace[P] = total;
+    __syncthreads();
+    // task order: stable sort by (eligible first, reference index) as a rank computation
+    if (tid < P) {
+        int rank = 0;
+        for (int q = 0; q < P; ++q) {
+            const uint32_t kq = s_key[q];
+            rank += (kq < key) || (kq == key && q < tid);
+        }
+        order[rank] = tid;
+    }
+    if (tid == 0) {
+        misc[0] = s_stat[0]; misc[1] = s_stat[1]; misc[2] = s_stat[2]; misc[3] = s_stat[3];
+        misc[4] = 0ull; misc[5] = 0ull; misc[6] = 0ull;
+        *n_elig = (unsigned long long)s_nelig;
+        *ticket = 0ull;
+    }
 }
 
 // chunk_start[c] = first pair whose trace offset is >= c*budget   (c = 0..n_chunks)
@@ -936,6 +1027,34 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     P.nruns[p] = nr;
 }
 
+// after the traceback of a small batch: CIGAR offsets (block scan of the run counts), coalesced copy of the runs,
+// running total -- the job of nruns_to_i64 + DeviceScan + cigar_copy_kernel + advance_base_kernel
+__global__ void __launch_bounds__(1024)
+small_finish_kernel(const AlignParams P, const int n_pairs, long long *__restrict__ run_base, uint32_t *__restrict__ cigar,
+                    long long cigar_cap, long long *__restrict__ cigar_off)
+{
+    typedef cub::BlockScan<long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ long long s_off[SMALL_P + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long nr = (tid < n_pairs) ? (long long)P.nruns[tid] : 0, excl = 0, total = 0;
+    Scan(scan_tmp).ExclusiveSum(nr, excl, total);
+    s_off[tid] = excl;
+    if (tid == 0) s_off[n_pairs] = total;
+    __syncthreads();
+    if (cigar_off && tid <= n_pairs) cigar_off[tid] = s_off[tid];
+    if (tid == 0) *run_base = total;
+    if (!cigar) return;
+    for (int p = warp; p < n_pairs; p += 32) {
+        const int n = P.nruns[p];
+        const long long dst = s_off[p];
+        const uint32_t *src = P.trace + (P.ptrace[p + 1] - P.chunk_base) - n;
+        ISOF_ASSERT(src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
+        for (int x = lane; x < n; x += 32)
+            if (dst + x < cigar_cap) cigar[dst + x] = src[x];
+    }
+}
+
 // local exclusive offsets (within the chunk) come from cub; *run_base is the running total
 __global__ void cigar_copy_kernel(const AlignParams P, const int64_t start, const int64_t end,
                                   const int64_t *__restrict__ local_off, const int64_t *__restrict__ run_base,
@@ -1103,27 +1222,39 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     int64_t *words = (int64_t *)ctx->b_words.p, *ptrace = (int64_t *)ctx->b_ptrace.p;
     int64_t *runoff = (int64_t *)ctx->b_runoff.p, *nruns64 = (int64_t *)ctx->b_nruns64.p;
     unsigned long long *misc = (unsigned long long *)ctx->b_misc.p;   // [0] err [1] max m [2] cells [3] padded [4] run_base
-    CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 64, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
-
-    {
+    // small batches: one fused set-up kernel (codes, plan, trace offsets, task order) and one fused CIGAR
+    // scan/copy kernel; the layout of b_counters below is the single-chunk one
+    const bool small = P <= SMALL_P && n_bases <= SMALL_BASES;
+    TRY(dev_reserve(ctx, ctx->b_order, sizeof(int32_t) * (size_t)P));
+    if (small) {
+        TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * 3 * 3));
+        unsigned long long *cnt0 = (unsigned long long *)ctx->b_counters.p + 3;          // counters[0] of a 1-chunk layout
         LaunchTimer t(ctx, SLOT_OTHER);
-        int blocks = std::min((n_seqs * 32 + 255) / 256, ctx->sm_count * 8);
-        encode_kernel<<<std::max(blocks, 1), 256, 0, st>>>(d_cat, d_off, n_seqs, codes, flags);
-    }
-    {
-        LaunchTimer t(ctx, SLOT_OTHER);
-        plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
-                                                                      words, misc, h_max_min_len, h_max_max_len);
+        small_plan_kernel<<<1, 1024, 0, st>>>(d_cat, d_off, n_seqs, d_pa, d_pb, (int)P, codes, flags, pn, pm, pwild, ptrace,
+                                              misc, h_max_min_len, h_max_max_len, (int32_t *)ctx->b_order.p, cnt0 + 3, cnt0);
+    } else {
+        CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 64, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            int blocks = std::min((n_seqs * 32 + 255) / 256, ctx->sm_count * 8);
+            encode_kernel<<<std::max(blocks, 1), 256, 0, st>>>(d_cat, d_off, n_seqs, codes, flags);
+        }
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
+                                                                          words, misc, h_max_min_len, h_max_max_len);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, words, ptrace, P + 1, st);
+        TRY(dev_reserve(ctx, ctx->b_scan_tmp, tmp_bytes));
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, words, ptrace, P + 1, st));
+        }
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, words, ptrace, P + 1, st);
-    TRY(dev_reserve(ctx, ctx->b_scan_tmp, tmp_bytes));
-    {
-        LaunchTimer t(ctx, SLOT_OTHER);
-        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, words, ptrace, P + 1, st));
-    }
     // ---- read back the plan summary
     unsigned long long *pin = (unsigned long long *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(pin, misc, 32, cudaMemcpyDeviceToHost, st));
@@ -1159,7 +1290,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     int64_t *chunk_start_d = (int64_t *)ctx->b_counters.p;
     unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);      // task tickets per chunk
     unsigned long long *elig_counts = counters + n_chunks + 2;                                  // eligible pairs per chunk
-    CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2, st));
+    const bool fused_small = small && single;          // tickets, eligible count and task order came from small_plan_kernel
+    if (!fused_small) CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2, st));
     std::vector<int64_t> chunk_start((size_t)n_chunks + 1), start_off((size_t)n_chunks + 1);
     if (single) {
         chunk_start[0] = 0; chunk_start[1] = P;
@@ -1218,7 +1350,6 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.h_fe = pk(-4 * gap_ext);
     A.h_sm = pk(4 * match + 3 - (3 << CS16));
     A.h_sx = pk(4 * mismatch + 3);
-    TRY(dev_reserve(ctx, ctx->b_order, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P * 2));
     A.playout = (uint8_t *)ctx->b_layout.p;
     A.plastrr = A.playout + P;
@@ -1270,7 +1401,10 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         int64_t *c_runoff = w ? (int64_t *)ctx->b_runoff_x[w - 1].p : runoff;
         int64_t *c_nruns64 = w ? (int64_t *)ctx->b_nruns64_x[w - 1].p : nruns64;
         DevBuf &c_scan = w ? ctx->b_scan_tmp_x[w - 1] : ctx->b_scan_tmp;
-        {   // task order of the chunk: stable radix sort of the pair ids by (eligibility, reference)
+        if (fused_small) {
+            A.order = (int32_t *)ctx->b_order.p;
+            A.n_elig = elig_counts + c;
+        } else {   // task order of the chunk: stable radix sort of the pair ids by (eligibility, reference)
             DevBuf &kb = w ? ctx->b_taskkey_x[w - 1] : ctx->b_taskkey;
             TRY(dev_reserve(ctx, kb, (sizeof(uint32_t) * 2 + sizeof(int32_t)) * (size_t)cnt + 64));
             uint32_t *key_in = (uint32_t *)kb.p, *key_out = key_in + cnt;
@@ -1302,26 +1436,32 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             LaunchTimer t(ctx, SLOT_TB, cs);
             sg_features_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, cs>>>(A, ps, pe, delta_len, d_features);
         }
-        {
+        if (fused_small) {
             LaunchTimer t(ctx, SLOT_TB, cs);
-            nruns_to_i64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(nruns, ps, cnt, c_nruns64);
-        }
-        size_t tb2 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb2, c_nruns64, c_runoff, cnt, cs);
-        TRY(dev_reserve(ctx, c_scan, tb2));
-        {
-            LaunchTimer t(ctx, SLOT_TB, cs);
-            CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(c_scan.p, tb2, c_nruns64, c_runoff, cnt, cs));
-        }
-        if (pipelined && prev >= 0) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, done[prev], 0));
-        {
-            LaunchTimer t(ctx, SLOT_TB, cs);
-            cigar_copy_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, cs>>>(A, ps, pe, c_runoff, run_base, d_cigar,
-                                                                                 cigar_cap, d_cigar_off);
-        }
-        {
-            LaunchTimer t(ctx, SLOT_TB, cs);
-            advance_base_kernel<<<1, 1, 0, cs>>>(run_base, c_runoff, nruns, ps, pe, d_cigar_off, P);
+            small_finish_kernel<<<1, 1024, 0, cs>>>(A, (int)P, (long long *)run_base, d_cigar, (long long)cigar_cap,
+                                                    (long long *)d_cigar_off);
+        } else {
+            {
+                LaunchTimer t(ctx, SLOT_TB, cs);
+                nruns_to_i64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(nruns, ps, cnt, c_nruns64);
+            }
+            size_t tb2 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb2, c_nruns64, c_runoff, cnt, cs);
+            TRY(dev_reserve(ctx, c_scan, tb2));
+            {
+                LaunchTimer t(ctx, SLOT_TB, cs);
+                CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(c_scan.p, tb2, c_nruns64, c_runoff, cnt, cs));
+            }
+            if (pipelined && prev >= 0) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, done[prev], 0));
+            {
+                LaunchTimer t(ctx, SLOT_TB, cs);
+                cigar_copy_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, cs>>>(A, ps, pe, c_runoff, run_base, d_cigar,
+                                                                                     cigar_cap, d_cigar_off);
+            }
+            {
+                LaunchTimer t(ctx, SLOT_TB, cs);
+                advance_base_kernel<<<1, 1, 0, cs>>>(run_base, c_runoff, nruns, ps, pe, d_cigar_off, P);
+            }
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (pipelined) {
