@@ -571,6 +571,24 @@ struct P16State {
     uint32_t diag0;
 };
 
+// Hl[idx] for a run-time idx < RR without dynamic register indexing: a binary tree of selects on the bits of idx
+// (7 SEL for RR = 8; the compare-and-select chain it replaces was 7 ISETP + 7 SEL)
+template <int RR>
+__device__ __forceinline__ uint32_t pick_row(const uint32_t (&h)[R], const int idx)
+{
+    const bool b0 = idx & 1, b1 = idx & 2, b2 = idx & 4;
+    const uint32_t x0 = b0 ? h[1] : h[0];
+    if (RR == 2) return x0;
+    const uint32_t x1 = b0 ? h[3] : h[2];
+    const uint32_t y0 = b1 ? x1 : x0;
+    if (RR == 4) return y0;
+    const uint32_t x2 = b0 ? h[5] : h[4];
+    if (RR == 6) return b2 ? x2 : y0;
+    const uint32_t x3 = b0 ? h[7] : h[6];
+    const uint32_t y1 = b1 ? x3 : x2;
+    return b2 ? y1 : y0;
+}
+
 // one column of RR packed rows per lane; returns the two trace words (A, B).
 // PROF: both alignments share the reference, so the substitution scores of this lane's rows against the
 // column's base come from the lane's query profile in shared memory (two LDS.128 on the otherwise idle
@@ -759,16 +777,12 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                         for (int r = 0; r < RR; ++r) snap[r] = (snap[r] & 0x0000ffffu) | (S.Hl[r] & 0xffff0000u);
                     }
                     if (TROW && trackA && j < mA) {         // last row of A: smallest j wins ties
-                        uint32_t hv = S.Hl[0];
-#pragma unroll
-                        for (int r = 1; r < RR; ++r) if (r == last_rA) hv = S.Hl[r];
+                        const uint32_t hv = pick_row<RR>(S.Hl, last_rA);
                         const int v = lo16(hv);
                         if (v > browA) { browA = v; browA_j = j; }
                     }
                     if (TROW && trackB && j < mB) {
-                        uint32_t hv = S.Hl[0];
-#pragma unroll
-                        for (int r = 1; r < RR; ++r) if (r == last_rB) hv = S.Hl[r];
+                        const uint32_t hv = pick_row<RR>(S.Hl, last_rB);
                         const int v = hi16(hv);
                         if (v > browB) { browB = v; browB_j = j; }
                     }
@@ -826,16 +840,12 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     if (with_track) {
                         const int j = PC * (t - lane) + c;
                         if (trackA) {
-                            uint32_t hv = S.Hl[0];
-#pragma unroll
-                            for (int r = 1; r < RR; ++r) if (r == last_rA) hv = S.Hl[r];
+                            const uint32_t hv = pick_row<RR>(S.Hl, last_rA);
                             const int v = lo16(hv);
                             if (v > browA) { browA = v; browA_j = j; }
                         }
                         if (trackB) {
-                            uint32_t hv = S.Hl[0];
-#pragma unroll
-                            for (int r = 1; r < RR; ++r) if (r == last_rB) hv = S.Hl[r];
+                            const uint32_t hv = pick_row<RR>(S.Hl, last_rB);
                             const int v = hi16(hv);
                             if (v > browB) { browB = v; browB_j = j; }
                         }
