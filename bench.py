@@ -282,7 +282,7 @@ def run_b200(args):
         n_min, n_runs = step_dev()
     int32_peak = ctx.int32_peak()
 
-    # ---- timed: device-resident (production configuration: two-stream chunk pipeline, no per-launch events)
+    # ---- timed: device-resident (production configuration: three-stream chunk pipeline, no per-launch events)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

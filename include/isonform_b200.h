@@ -66,8 +66,8 @@ ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
  * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
 ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
 /* Alignment batches whose trace exceeds the scratch budget are cut into chunks.  on=1 (default):
- * chunks alternate between two streams with double-buffered scratch, so a chunk's tail (idle SMs while
- * its last pairs finish) and its traceback overlap the next chunk's DP.  on=0: one stream, one
+ * chunks rotate over three streams, each with its own scratch, so a chunk's tail (idle SMs while
+ * its last pairs finish) and its traceback overlap the next chunks' DP.  on=0: one stream, one
  * buffer (per-kernel event timings are then exact; bench.py uses it for the roofline step). */
 ISOF_API int isof_set_overlap(isof_ctx *ctx, int on);
 /* Debug build only (libisonform_b200_dbg.so, -DISOF_CHECK): every kernel carries device-side bounds

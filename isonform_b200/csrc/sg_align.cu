@@ -1384,7 +1384,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             TRY(dev_reserve(ctx, w ? ctx->b_scan_tmp_x[w - 1] : ctx->b_scan_tmp, std::max(t_sort, t_scan) + 256));
         }
     }
-    // ---- chunk pipeline.  Serial mode: everything on `st`.  Pipelined mode: chunk c runs on stream c%2 with
+    // ---- chunk pipeline.  Serial mode: everything on `st`.  Pipelined mode: chunk c runs on stream c % NLANES with
     // its own trace / boundary / scan scratch; the only cross-chunk dependency is the running CIGAR offset
     // (cigar_copy of chunk c needs advance_base of chunk c-1), carried by one event per chunk.
     cudaStream_t lanes[NL];
