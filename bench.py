@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--cpu-sample-pairs", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace-budget-gb", type=float, default=None,
+                    help="alignment trace scratch in GB (default: the library's 40-55 %% of free HBM); long-read batches "
+                         "(C4) need more of it to keep every warp slot busy")
     return ap.parse_args()
 
 
@@ -225,6 +228,8 @@ def run_b200(args):
     ctx = _lib.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    if args.trace_budget_gb:
+        ctx.set_trace_budget(int(args.trace_budget_gb * (1 << 30)))
     P, R = wl["n_pairs"], wl["n_reads"]
 
     # ---- device-resident inputs / outputs (torch owns the memory, the library gets raw pointers)

@@ -59,7 +59,7 @@ ISOF_API const char *isof_last_error(const isof_ctx *ctx);
 /* Use an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream, so that
  * the caller's CUDA events bracket the library's kernels.  NULL restores the ctx-owned stream. */
 ISOF_API int isof_set_stream(isof_ctx *ctx, void *cuda_stream);
-/* Upper bound for the alignment trace scratch in bytes (default: 40% of free device memory). */
+/* Upper bound for the alignment trace scratch in bytes (default: 40% of the device memory free at first use, up to 55% for batches of very long pairs). */
 ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
 /* The DP kernel has two arithmetic paths with identical results: a packed 16-bit path (two alignments
  * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any

@@ -23,7 +23,8 @@ struct isof_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     char err[512] = {0};
-    size_t trace_budget = 0;          // bytes; 0 = decide at first use
+    size_t trace_budget = 0;          // bytes set by isof_set_trace_budget; 0 = automatic (40-55 % of free memory)
+    size_t trace_free_at_first_use = 0;
     bool profiling = false;           // bracket every launch with CUDA events (isof_profile_*)
     bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
     bool overlap = true;              // pipeline trace chunks over NLANES streams, each with its own scratch

@@ -663,7 +663,8 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     const int nsA = (nA + SROWS - 1) / SROWS, nsB = (nB + SROWS - 1) / SROWS, ns = max(nsA, nsB);
     int last_laneA = 0, last_rA = 0, last_laneB = 0, last_rB = 0;       // set in the alignment's last stripe
     P16Const K;
-    K.h_eo = P.h_eo; K.h_ee = P.h_ee; K.h_fo = P.h_fo; K.h_fe = P.h_fe; K.h_sm = P.h_sm; K.h_sx = P.h_sx;
+    // the F constants equal the E constants (same penalties, tags come from the stored values): one register each
+    K.h_eo = P.h_eo; K.h_ee = P.h_ee; K.h_fo = K.h_eo; K.h_fe = K.h_ee; K.h_sm = P.h_sm; K.h_sx = P.h_sx;
     int bcolA = INT_MIN, bcolA_i = 0, browA = INT_MIN, browA_j = 0;
     int bcolB = INT_MIN, bcolB_i = 0, browB = INT_MIN, browB_j = 0;
     if (lane == 0) { P.playout[pA] = PC | TRACE_FMT_SPLIT; P.playout[pB] = PC | TRACE_FMT_SPLIT; }
@@ -1280,14 +1281,23 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     if ((int64_t)max_m * 16 * (std::abs(match) + std::abs(mismatch) + gap_ext) + 16LL * gap_open > (1LL << 28))
         return isof_fail(ctx, ISOF_ERR_RANGE, "sequence too long for the 32-bit tagged score range");
 
-    // ---- trace budget / chunks
-    if (ctx->trace_budget == 0) {
+    // ---- trace budget / chunks.  Default: 40 % of the device memory that was free at first use; raised up to
+    // 55 % when the pairs are so long (10 kb reads: 36 MB of trace each) that a smaller buffer could not hold
+    // enough pairs to occupy every resident warp in each of the NLANES chunks in flight.
+    if (ctx->trace_free_at_first_use == 0) {
         size_t fr = 0, tot = 0;
         CUDA_TRY(ctx, cudaMemGetInfo(&fr, &tot));
-        ctx->trace_budget = (size_t)(0.40 * (double)(fr + ctx->b_trace.cap));
-        if (ctx->trace_budget < (64u << 20)) ctx->trace_budget = 64u << 20;
+        ctx->trace_free_at_first_use = fr + ctx->b_trace.cap;
     }
-    int64_t budget_words = (int64_t)(ctx->trace_budget / 4);
+    size_t budget_bytes = ctx->trace_budget;
+    if (budget_bytes == 0) {
+        const double fr = (double)ctx->trace_free_at_first_use;
+        const double want = 4.0 * (double)total_words / (double)P * (double)(ctx->sm_count * DP_CTAS_PER_SM * DP_WARPS) * 1.25 *
+                            (double)isof_ctx::NLANES;
+        budget_bytes = (size_t)std::min(0.55 * fr, std::max(0.40 * fr, want));
+        if (budget_bytes < (64u << 20)) budget_bytes = 64u << 20;
+    }
+    int64_t budget_words = (int64_t)(budget_bytes / 4);
     // pipelined mode: NLANES smaller buffers, chunk c runs on stream c % NLANES
     constexpr int NL = isof_ctx::NLANES;
     const bool want_overlap = ctx->overlap && total_words > budget_words / NL;
