@@ -180,7 +180,17 @@ int isof_debug_violations(isof_ctx *ctx, unsigned int *mask)
 int isof_set_overlap(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;
-    ctx->overlap = (on != 0);
+    const bool want = (on != 0);
+    if (want != ctx->overlap) {
+        // the two modes size their trace scratch differently (one buffer of the whole budget vs NLANES buffers of a
+        // share each): drop the buffers so that the next call re-reserves them and the total stays within the budget
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx, cudaDeviceSynchronize());
+        DevBuf *bufs[] = {&ctx->b_trace, &ctx->b_trace_x[0], &ctx->b_trace_x[1]};
+        for (DevBuf *b : bufs)
+            if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    }
+    ctx->overlap = want;
     return ISOF_OK;
 }
 

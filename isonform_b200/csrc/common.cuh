@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/isonform_b200.h"
@@ -109,7 +110,7 @@ static inline int dev_reserve(isof_ctx *ctx, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return ISOF_OK;
     if (b.p) { CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
-    size_t want = bytes + bytes / 8 + 256;
+    size_t want = bytes + std::min<size_t>(bytes / 8, (size_t)64 << 20) + 256;      // growth slack, capped: trace buffers are tens of GB
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
