@@ -679,3 +679,29 @@ def test_packed_profile_range_extremes_debug_build():
             assert dctx.debug_violations()[0] == 0
     finally:
         dctx.close()
+
+
+def test_small_batch_path_matches_regular_path(ctx):
+    """Calls with <= 1024 pairs over <= 1 MiB of bases use the fused set-up / CIGAR-finish kernels; one pair more
+    sends the same pairs through the regular plan (encode, plan, scan, radix-sorted task order).  Results must be
+    identical, including for out-of-order references, wildcards and pairs that fall to the 32-bit path."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(211)
+    base = _rand_dna(rng, 400)
+    seqs = [synth.mutate(rng, base, 0.08)[int(rng.integers(0, 30)):int(rng.integers(200, 400))] or "A" for _ in range(60)]
+    seqs += [_rand_dna(rng, int(rng.integers(1, 90))) for _ in range(20)]
+    seqs += ["ACGTNNACGT" * 7, "acgtacgtac" * 9, _rand_dna(rng, 4500)]          # wildcard, lower case, > 16-bit range
+    n = len(seqs)
+    pa = rng.integers(0, n, 1025).astype(np.int32)
+    pb = rng.integers(0, n, 1025).astype(np.int32)
+    for params in [(2, -2, 12, 1), (2, -8, 12, 1)]:
+        big = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, features_delta_len=5)             # regular path
+        small = hotpath.align_pairs(seqs, pa[:1024], pb[:1024], *params, ctx=ctx, features_delta_len=5)   # fused path
+        assert np.array_equal(small["score"], big["score"][:1024])
+        assert np.array_equal(small["features"], big["features"][:1024])
+        assert np.array_equal(small["cigar_off"], big["cigar_off"][:1025])
+        assert np.array_equal(small["cigar"], big["cigar"][:big["cigar_off"][1024]])
+        one = hotpath.align_pairs(seqs, pa[7:8], pb[7:8], *params, ctx=ctx)
+        sc, eq, er, runs = oracle.sg_align(seqs[pa[7]], seqs[pb[7]], *params)
+        assert (int(one["score"][0]), int(one["end_q"][0]), int(one["end_r"][0])) == (sc, eq, er)
+        assert one["cigar"].tolist() == runs.tolist()
