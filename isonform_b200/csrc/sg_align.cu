@@ -503,7 +503,7 @@ __device__ __forceinline__ void dp_pair(const AlignParams &P, const int64_t p, c
                 pr += C2; pbn += C2; pbs += C2; sp += 32;
             };
             if (!is_last) {
-#pragma unroll 1
+#pragma unroll 2
                 for (int t = 31; t < t2; ++t) steady_step(t, false);
             } else {
 #pragma unroll 1
@@ -868,7 +868,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 #pragma unroll 2
                 for (int t = 31; t < t2; ++t) steady_step(t, false);
             } else {
-#pragma unroll 1
+#pragma unroll 2
                 for (int t = 31; t < t2; ++t) steady_step(t, true);
             }
             if (track_stripe) { for (int t = t2; t < T; ++t) general_step(t, std::true_type{}, std::true_type{}); }
