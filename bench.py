@@ -46,7 +46,7 @@ DELTA_LEN = 5
 # wildcards).  Trace-bit gathering runs as IMADs on the FMA pipe and is not counted here.
 OPS_PER_CELL_PACKED, OPS_PER_CELL_PROFILE, OPS_PER_CELL_32 = 6.0, 5.0, 10.0
 # DRAM bytes per DP cell of sg_dp_kernel measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch
-# over its cell count; profiles/r01_ncu_v8_summary.txt)
+# over its cell count; profiles/r01_ncu_v10_summary.txt)
 NCU_DRAM_BYTES_PER_CELL = 0.5605
 
 
@@ -440,7 +440,7 @@ def run_b200(args):
                          "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": NCU_DRAM_BYTES_PER_CELL * prof["dp_cells"] / max(prof["dp_launches"], 1),
                          "traffic_note": "bytes per launch, scaled by cells from the ncu --set full capture of a 4950-pair launch "
-                                         "of the same reads (profiles/r01_ncu_v8_summary.txt: dram write 20.379 GB + read 0.664 GB "
+                                         "of the same reads (profiles/r01_ncu_v10_summary.txt: dram write 20.379 GB + read 0.664 GB "
                                          "over 37.54 G cells = 0.5605 B/cell = 1.12x the 0.5 B/cell of trace: stripe/row padding, "
                                          "no re-reads); a bench-sized launch writes ~70 GB of trace, too large for ncu's "
                                          "save/restore replay",
