@@ -71,7 +71,12 @@ class SpanIndex:
         out[1:, 0] = self.id_of[self.rec_read[m]]
         out[1:, 1] = self.rec_p1[m]
         out[1:, 2] = self.rec_p2[m]
-        return array("I", out.ravel().tolist())
+        res = array("I")
+        if res.itemsize == 4:
+            res.frombytes(out.tobytes())                 # same values, without the per-element Python ints
+        else:                                            # pragma: no cover  (platforms where C unsigned int is not 32 bit)
+            res.extend(out.ravel().tolist())
+        return res
 
     def interval_records(self, r_id):
         """Record indices of read r_id that yield an interval, in the reference's order."""
