@@ -20,6 +20,7 @@ from ._lib import default_context
 # pairs per speculative launch: large enough to fill the GPU (148 SMs x 16 warps), small enough
 # that an early `break` wastes little
 _MIN_PAIRS_PER_CALL = 8192
+_MAX_PAIRS_PER_CALL = 1 << 19
 
 
 class AlignmentMemo:
@@ -116,38 +117,39 @@ def _pool(pairs):
 # C1: merge_consensuses  (IsoformGeneration.py:464-507)
 # ----------------------------------------------------------------------------------------------
 def _row_decisions(pool, rows, n, seq1_override, delta, delta_len, d3, d5, ctx):
-    """Decisions for rows `rows` (list of i) against every j > i.  The left string of row i is
+    """Decisions for rows `rows` (ascending list of i) against every j > i.  The left string of row i is
     seq1_override.get(i) or pool[i]; the right string is always the original pool[j]
     (IsoformGeneration.py:476-491: shorter string first, equal lengths keep (seq1, seq2))."""
+    out = {i: np.zeros(n - 1 - i, dtype=bool) for i in rows}
+    if not rows or min(rows) + 1 >= n:
+        return out
     seqs = list(pool)
-    left = {}
+    left = np.arange(n, dtype=np.int64)                    # index of row i's left string in `seqs`
     for i in rows:
         if i in seq1_override:
             left[i] = len(seqs)
             seqs.append(seq1_override[i])
-        else:
-            left[i] = i
-    # pairs are issued grouped by the right-hand string j (column-major over the block), so that consecutive
-    # alignments share their reference sequence -- the DP kernel then reads substitution scores from a
+    lens = np.fromiter((len(x) for x in seqs), dtype=np.int64, count=len(seqs))
+    # pairs are issued grouped by the right-hand string j (column-major over the block: j outer, i inner), so that
+    # consecutive alignments share their reference sequence -- the DP kernel then reads substitution scores from a
     # per-lane query profile instead of recomputing them (csrc/sg_align.cu, PROF path)
-    pa, pb, cell = [], [], []
-    lens = [len(x) for x in seqs]
-    for j in range(min(rows) + 1 if rows else n, n):
-        for i in rows:
-            if i >= j:
-                break
-            li = left[i]
-            if lens[j] < lens[li]:
-                pa.append(j); pb.append(li)
-            else:
-                pa.append(li); pb.append(j)
-            cell.append((i, j))
-    out = {i: np.zeros(n - 1 - i, dtype=bool) for i in rows}
-    if not pa:
-        return out
-    dec = hotpath.align_to_merge_pairs(seqs, pa, pb, delta, delta_len, d3, d5, ctx)
-    for (i, j), d in zip(cell, dec):
-        out[i][j - i - 1] = d
+    r = np.asarray(rows, dtype=np.int64)
+    js = np.arange(int(r[0]) + 1, n, dtype=np.int64)
+    I, J = np.meshgrid(r, js, indexing="xy")               # shape (len(js), len(rows))
+    keep = I < J
+    i_flat, j_flat = I[keep], J[keep]
+    li = left[i_flat]
+    swap = lens[j_flat] < lens[li]
+    pa = np.where(swap, j_flat, li)
+    pb = np.where(swap, li, j_flat)
+    dec = np.asarray(hotpath.align_to_merge_pairs(seqs, pa, pb, delta, delta_len, d3, d5, ctx), dtype=bool)
+    order = np.argsort(i_flat, kind="stable")              # back to row-major: row i, then j ascending
+    dec = dec[order]
+    pos = 0
+    for i in rows:                                          # rows ascending == order of i_flat[order]
+        cnt = n - 1 - i
+        out[i] = dec[pos:pos + cnt].copy()
+        pos += cnt
     return out
 
 
@@ -170,14 +172,16 @@ def merge_consensuses(curr_best_seqs, work_dir, delta, delta_len, reads, max_seq
     row_of = {id_: i for i, id_ in enumerate(ids)}
     n_aligned = n_used = 0
     i = 0
+    block_pairs = _MIN_PAIRS_PER_CALL          # grows while every speculated pair is used (rows that never merge)
     while i < n - 1:
         # ---- speculate a block of rows
         rows, budget = [], 0
         r = i
-        while r < n - 1 and (budget < _MIN_PAIRS_PER_CALL or not rows):
+        while r < n - 1 and (budget < block_pairs or not rows):
             rows.append(r)
             budget += n - 1 - r
             r += 1
+        used_before = n_used
         override = {row: new_consensuses[ids[row]] for row in rows if ids[row] in new_consensuses}
         table = _row_decisions(pool, rows, n, override, delta, delta_len, delta_iso_len_3, delta_iso_len_5, ctx)
         n_aligned += budget
@@ -202,6 +206,12 @@ def merge_consensuses(curr_best_seqs, work_dir, delta, delta_len, reads, max_seq
                     new_consensuses[id2] = generate_new_full_consensus(id1, id2, reads, curr_best_seqs, work_dir, max_seqs_to_spoa)
                     add_merged_reads(curr_best_seqs, id2, id1)
         i = rows[-1] + 1
+        # all speculated pairs consumed (no row broke early): the batch behaves like an all-pairs job, so issue it in
+        # launches that fill the GPU several times over; an early break shrinks the block again
+        if n_used - used_before == budget:
+            block_pairs = min(block_pairs * 4, _MAX_PAIRS_PER_CALL)
+        else:
+            block_pairs = _MIN_PAIRS_PER_CALL
     for id_ in curr_best_seqs:
         if id_ not in new_consensuses:
             new_consensuses[id_] = all_consensuses[id_]
