@@ -705,3 +705,39 @@ def test_small_batch_path_matches_regular_path(ctx):
         sc, eq, er, runs = oracle.sg_align(seqs[pa[7]], seqs[pb[7]], *params)
         assert (int(one["score"][0]), int(one["end_q"][0]), int(one["end_r"][0])) == (sc, eq, er)
         assert one["cigar"].tolist() == runs.tolist()
+
+
+def test_merge_consensuses_driver_on_gpu_equals_oracle_backed_run(ctx):
+    """The all-pairs driver (merge.merge_consensuses: speculative blocks + sequential replay) with the GPU behind
+    it against the same driver over the oracle-backed test double -- same merges, same regenerated consensuses."""
+    import copy
+    from fake_ctx import FakeContext
+    from isonform_b200 import merge, synth
+    rng = np.random.default_rng(401)
+    bases = [_rand_dna(rng, int(rng.integers(500, 900))) for _ in range(4)]
+    seqs = []
+    for i in range(48):
+        b = bases[i % 4]
+        s = synth.mutate(rng, b, 0.004 if i % 3 else 0.03)
+        seqs.append(s[int(rng.integers(0, 12)):len(s) - int(rng.integers(0, 12))])
+    seqs_by_id = {100 + i: s for i, s in enumerate(seqs)}
+    support = {100 + i: [100 + i] * (60 if i % 5 == 0 else 1) for i in range(len(seqs))}
+
+    def gen_all(all_c, alt, cbs, reads, work_dir, max_spoa):
+        for id_ in cbs:
+            all_c[id_] = seqs_by_id[id_]
+            alt.append((id_, seqs_by_id[id_]))
+
+    def regen(i1, i2, reads, cbs, wd, ms):
+        a, b = seqs_by_id[i1], seqs_by_id[i2]
+        return b[:len(b) // 2] + a[len(a) // 2:] if len(cbs[i2]) % 2 else b
+
+    results = []
+    for c in (ctx, FakeContext()):
+        cbs = copy.deepcopy(support)
+        stats = {}
+        new = merge.merge_consensuses(cbs, None, 0.15, 5, None, 200, 30, 50, generate_all_consensuses=gen_all,
+                                      generate_new_full_consensus=regen, ctx=c, stats=stats)
+        results.append((new, cbs, stats))
+    assert results[0][0] == results[1][0] and results[0][1] == results[1][1] and results[0][2] == results[1][2]
+    assert len(results[0][1]) < len(seqs), "the set must actually merge something"
