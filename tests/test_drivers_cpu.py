@@ -306,3 +306,32 @@ def test_super_batched_front_half_equals_per_batch():
         gdb, gdb1 = idx.database(), idx1.database()
         assert [[m1, m2, list(gdb[m1][m2])] for m1 in gdb for m2 in gdb[m1]] == \
                [[m1, m2, list(gdb1[m1][m2])] for m1 in gdb1 for m2 in gdb1[m1]]
+
+
+def test_merge_consensuses_block_grows_while_nothing_merges(monkeypatch):
+    """Rows that never merge consume every speculated pair, so the speculation block grows x4 per launch (a C2 batch
+    is issued in a handful of launches, not one per 8192 pairs); a merge resets it."""
+    calls = []
+
+    def no_merge(seqs, pa, pb, delta, delta_len, d3, d5, ctx=None):
+        calls.append(len(pa))
+        return np.zeros(len(pa), dtype=bool)
+
+    monkeypatch.setattr(merge.hotpath, "align_to_merge_pairs", no_merge)
+    monkeypatch.setattr(merge, "_MIN_PAIRS_PER_CALL", 50)
+    rng = np.random.default_rng(9)
+    seqs_by_id = {i: synth.random_dna(rng, 100 + i) for i in range(120)}
+    cbs = {i: [i] for i in seqs_by_id}
+
+    def gen_all(all_c, alt, cbs_, reads, work_dir, max_spoa):
+        for id_ in cbs_:
+            all_c[id_] = seqs_by_id[id_]
+            alt.append((id_, seqs_by_id[id_]))
+
+    stats = {}
+    out = merge.merge_consensuses(cbs, None, 0.15, 5, None, 200, 30, 50, generate_all_consensuses=gen_all,
+                                  generate_new_full_consensus=None, stats=stats)
+    total = 120 * 119 // 2
+    assert sum(calls) == total == stats["pairs_aligned"] == stats["pairs_used"]
+    assert len(calls) <= 6 and calls == sorted(calls[:-1]) + calls[-1:]        # 50-ish, x4, x4, ... then the remainder
+    assert out == seqs_by_id and len(cbs) == 120
