@@ -65,6 +65,14 @@ ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
  * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any
  * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
 ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
+/* Tie-break table of the aligner.  parasail is third-party and not vendored by the reference, so every
+ * tie-break of its sg_trace + cigar code (consensus.py:56-59) is a named switch here and in the oracle
+ * (isof_tiebreak_t in oracle/isof_oracle.c) instead of a hard-coded constant; all zero (the default) is the
+ * library as restated in DESIGN.md.  h_e_before_f: H source on ties DIAG > E > F instead of DIAG > F > E.
+ * gap_open_on_tie: a gap opens instead of extending when both score the same.  end_col_first: the end cell is
+ * searched in the last column first, then the last row.  swap_id: the CIGAR letters of the two gap states are
+ * swapped ('I' consumes s2).  Results are bit-identical to the oracle under each of the 16 tables. */
+ISOF_API int isof_set_tiebreak(isof_ctx *ctx, int h_e_before_f, int gap_open_on_tie, int end_col_first, int swap_id);
 /* Alignment batches whose trace exceeds the scratch budget are cut into chunks.  on=1 (default):
  * chunks rotate over three streams, each with its own scratch, so a chunk's tail (idle SMs while
  * its last pairs finish) and its traceback overlap the next chunks' DP.  on=0: one stream, one

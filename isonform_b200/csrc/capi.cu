@@ -154,6 +154,16 @@ int isof_set_packed(isof_ctx *ctx, int on)
     return ISOF_OK;
 }
 
+int isof_set_tiebreak(isof_ctx *ctx, int h_e_before_f, int gap_open_on_tie, int end_col_first, int swap_id)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->tb_h_e_before_f = h_e_before_f != 0;
+    ctx->tb_gap_open_on_tie = gap_open_on_tie != 0;
+    ctx->tb_end_col_first = end_col_first != 0;
+    ctx->tb_swap_id = swap_id != 0;
+    return ISOF_OK;
+}
+
 namespace { __global__ void selftest_kernel() { ISOF_ASSERT(threadIdx.x > 1000u, 30); } }
 
 int isof_debug_selftest(isof_ctx *ctx)

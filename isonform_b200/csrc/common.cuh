@@ -28,6 +28,8 @@ struct isof_ctx {
     size_t trace_free_at_first_use = 0;
     bool profiling = false;           // bracket every launch with CUDA events (isof_profile_*)
     bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
+    // tie-break table of the restated aligner (isof_set_tiebreak); all zero = the library as restated
+    int tb_h_e_before_f = 0, tb_gap_open_on_tie = 0, tb_end_col_first = 0, tb_swap_id = 0;
     bool overlap = true;              // pipeline trace chunks over NLANES streams, each with its own scratch
     static constexpr int NLANES = 3;  // pipeline depth: chunk c runs on stream c % NLANES
     cudaStream_t aux_stream[NLANES - 1] = {nullptr, nullptr};

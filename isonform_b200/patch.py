@@ -9,16 +9,20 @@ interface.
 """
 import functools
 
-from . import hotpath, merge, spans
+from . import bubbles, hotpath, merge, spans
 
 
 def install(main_globals=None, ctx=None, memo=None):
-    """Returns the AlignmentMemo shared by all patched alignment seams."""
+    """Returns the AlignmentMemo shared by all patched alignment seams (`memo.bubbles` is the
+    bubble-popping prefetcher with its per-iteration statistics)."""
     from modules import IsoformGeneration, batch_merging_parallel, consensus   # the reference tree
 
     memo = memo or merge.AlignmentMemo(ctx)
     # modules/consensus.py:55  (callers SimplifyGraph.py:644, IsoformGeneration.py:381)
     consensus.parasail_alignment = memo.parasail_alignment
+    # modules/SimplifyGraph.py:883-1151: one batched alignment call per bubble-popping iteration instead of one
+    # GPU call per candidate pair (hooks SimplifyGraph.generate_combinations, :938, and memoises run_spoa)
+    memo.bubbles = bubbles.BubblePrefetcher(memo).install()
     # modules/IsoformGeneration.py:380
     IsoformGeneration.align_to_merge = memo.align_to_merge
     # modules/IsoformGeneration.py:464 -- all-pairs loop with batched speculation

@@ -21,7 +21,12 @@ def build(force=False):
 
 class TieBreak(C.Structure):
     _fields_ = [("h_e_before_f", C.c_int32), ("gap_open_on_tie", C.c_int32),
-                ("end_col_first", C.c_int32)]
+                ("end_col_first", C.c_int32), ("swap_id", C.c_int32)]
+
+
+def all_tiebreaks():
+    """The 16 settings of the tie-break table, default first."""
+    return [TieBreak(a, b, c, d) for d in (0, 1) for c in (0, 1) for b in (0, 1) for a in (0, 1)]
 
 
 _lib = None

@@ -194,6 +194,11 @@ typedef struct {
      * greater (smallest i); equal score and end_ref==m-1 takes the smaller i.
      * 1: last COLUMN first (smallest i), then last row only if strictly greater (smallest j). */
     int32_t end_col_first;
+    /* CIGAR letters of the two gap states.  0: SAM convention with s1 = query -- the gap that walks the
+     * query axis i (state F) is 'I', the one that walks the ref axis j (state E) is 'D'; this is what
+     * the reference's cigar_to_seq (consensus.py:35-47) assumes.  1: letters swapped (the library's own
+     * state names: E = "INS" -> 'I', F = "DEL" -> 'D'). */
+    int32_t swap_id;
 } isof_tiebreak_t;
 
 /* BAM op codes used in the run encoding (len << 4 | op), as parasail's cigar->seq does. */
@@ -232,7 +237,7 @@ ISOF_API int32_t isof_oracle_sg_align_tb(const uint8_t *s1, int32_t n, const uin
                                          int32_t cigar_cap, int32_t *n_runs_out)
 {
     if (n <= 0 || m <= 0) return -1;               /* parasail rejects empty sequences */
-    isof_tiebreak_t tb = {0, 0, 0};
+    isof_tiebreak_t tb = {0, 0, 0, 0};
     if (tbk) tb = *tbk;
     const int32_t NEG = -(1 << 29);
     int32_t S[5][5];
@@ -310,12 +315,14 @@ ISOF_API int32_t isof_oracle_sg_align_tb(const uint8_t *s1, int32_t n, const uin
         }                                                                                          \
     } while (0)
     int32_t i = eq, j = er;
-    if (eq + 1 == n) PUSH(OP_D, m - 1 - j);        /* unaligned ref tail   */
-    else PUSH(OP_I, n - 1 - i);                    /* unaligned query tail */
+    const uint32_t op_e = tb.swap_id ? OP_I : OP_D;   /* E walks the ref axis j   */
+    const uint32_t op_f = tb.swap_id ? OP_D : OP_I;   /* F walks the query axis i */
+    if (eq + 1 == n) PUSH(op_e, m - 1 - j);        /* unaligned ref tail   */
+    else PUSH(op_f, n - 1 - i);                    /* unaligned query tail */
     int where = T_SRC_DIAG;
     while (i >= 0 || j >= 0) {
-        if (i < 0) { PUSH(OP_D, j + 1); break; }
-        if (j < 0) { PUSH(OP_I, i + 1); break; }
+        if (i < 0) { PUSH(op_e, j + 1); break; }
+        if (j < 0) { PUSH(op_f, i + 1); break; }
         uint8_t t = trace[(size_t)i * (size_t)m + (size_t)j];
         if (where == T_SRC_DIAG) {
             int src = t >> 2;
@@ -324,10 +331,10 @@ ISOF_API int32_t isof_oracle_sg_align_tb(const uint8_t *s1, int32_t n, const uin
                 --i; --j;
             } else where = src;
         } else if (where == T_SRC_E) {
-            PUSH(OP_D, 1); --j;
+            PUSH(op_e, 1); --j;
             where = (t & T_E_EXT) ? T_SRC_E : T_SRC_DIAG;
         } else {
-            PUSH(OP_I, 1); --i;
+            PUSH(op_f, 1); --i;
             where = (t & T_F_EXT) ? T_SRC_F : T_SRC_DIAG;
         }
     }

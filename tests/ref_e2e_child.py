@@ -42,7 +42,10 @@ def main():
     loader.exec_module(ref)
     from modules import IsoformGeneration
 
+    spoa_calls = [0]
+
     def fake_spoa(reads_file, out_file):           # deterministic stand-in for the absent spoa binary
+        spoa_calls[0] += 1
         seqs = [l.strip() for l in open(reads_file) if not l.startswith(">")]
         seqs.sort(key=lambda s: (len(s), s))
         return seqs[len(seqs) // 2]
@@ -61,10 +64,15 @@ def main():
                                  exact_instance_limit=0, set_w_dynamically=False, verbose=False, compression=False,
                                  delta_iso_len_3=30, delta_iso_len_5=50, parallel=True, slow=False)
     ref.main(args)
+    sys.stderr.write("SPOA_SPAWNS %d\n" % spoa_calls[0])
     if a.patched:
         c = stats["ctx"].calls
         sys.stderr.write("B200_SEAM_CALLS minimizers=%d spans=%d align_calls=%d pairs=%d memo_hits=%d memo_misses=%d\n"
                          % (c["minimizers"], c["spans"], c["align"], c["pairs"], stats["memo"].hits, stats["memo"].misses))
+        b = stats["memo"].bubbles.stats
+        sys.stderr.write("B200_BUBBLES iterations=%d speculated=%d prefetch_calls=%d prefetched=%d spoa_calls=%d spoa_hits=%d\n"
+                         % (b["iterations"], b["speculated_pairs"], b["prefetch_calls"], b["prefetched"], b["spoa_calls"],
+                            b["spoa_hits"]))
 
 
 if __name__ == "__main__":

@@ -77,11 +77,11 @@ def test_minimizers_empty_batch(ctx):
 
 
 # ------------------------------------------------------------------------------- alignment
-def _check_pairs(ctx, seqs, pa, pb, params):
+def _check_pairs(ctx, seqs, pa, pb, params, tiebreak=None):
     from isonform_b200 import hotpath
     res = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
     for p in range(len(pa)):
-        sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params)
+        sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params, tiebreak=tiebreak)
         got = res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]]
         assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er), (p, len(seqs[pa[p]]), len(seqs[pb[p]]))
         assert got.tolist() == runs.tolist(), (p, oracle.cigar_runs_to_string(got), oracle.cigar_runs_to_string(runs))
@@ -206,6 +206,70 @@ def test_align_features_vs_oracle(ctx):
         for p in range(len(pa)):
             tup = oracle.cigar_runs_to_tuples(res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]])
             assert bool(pop[p]) == oracle.parse_cigar_diversity(tup, 0.20, dl)
+
+
+def _tiebreak_cases():
+    """Pairs that exercise every tie of the recurrence and every kernel path: tie-heavy low-complexity strings,
+    random shapes around the stripe / lane boundaries, related reads (packed path, shared references), a wildcard
+    pair (32-bit WILD path), one pair beyond the 16-bit range."""
+    from isonform_b200 import synth
+    rng = np.random.default_rng(97)
+    seqs, pa, pb = [], [], []
+
+    def add(a, b):
+        seqs.extend([a, b]); pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    for i in range(60):
+        alpha = ["AC", "A", "ACG", "AAC"][i % 4]
+        add(_rand_dna(rng, int(rng.integers(1, 70)), alpha), _rand_dna(rng, int(rng.integers(1, 70)), alpha))
+    for (n, m) in [(1, 1), (1, 40), (40, 1), (8, 8), (31, 33), (255, 256), (257, 300), (300, 257), (513, 40), (40, 513),
+                   (700, 760)]:
+        x = _rand_dna(rng, max(n, m))
+        y = synth.mutate(rng, x, 0.06)
+        add(x[:n], (y + _rand_dna(rng, m))[:m])
+        add(_rand_dna(rng, n, "ACGGT"), _rand_dna(rng, m, "ACGGT"))
+    base = _rand_dna(rng, 420)
+    pool0 = len(seqs)
+    seqs.extend(synth.mutate(rng, base, 0.05) for _ in range(7))           # all pairs of related reads: shared references
+    for i in range(7):
+        for j in range(i + 1, 7):
+            pa.append(pool0 + i); pb.append(pool0 + j)
+    add(_rand_dna(rng, 150, "ACGTN"), _rand_dna(rng, 170, "ACGTNacgtX"))
+    add("X" * 40, lcg(45, 42))
+    return seqs, pa, pb
+
+
+@pytest.mark.parametrize("tb_index", range(16))
+def test_align_all_tiebreak_tables_vs_oracle(ctx, tb_index):
+    """The tie-break table (H-source order, open vs extend, end-cell order, I/D letters) is a switch of the CUDA
+    path, not a constant: under each of the 16 tables the GPU result equals the oracle's, on both arithmetic paths,
+    including the decision features and the reference's decisions evaluated from them."""
+    from isonform_b200 import hotpath
+    tb = oracle.all_tiebreaks()[tb_index]
+    seqs, pa, pb = _tiebreak_cases()
+    ctx.set_tiebreak(tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id)
+    try:
+        for params in [(2, -8, 12, 1), (2, -2, 12, 1), (1, -1, 1, 1), (2, -2, 2, 1), (2, -2, 0, 0)]:
+            for packed in (True, False):
+                ctx.set_packed(packed)
+                _check_pairs(ctx, seqs, pa, pb, params, tiebreak=tb)
+        ctx.set_packed(True)
+        # decision features under the table (IsoformGeneration.py:251-397, SimplifyGraph.py:175-196)
+        for dl in (5, 10):
+            res = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx, want_cigar=True, features_delta_len=dl)
+            merge = hotpath._merge_from_features(res["features"], 0.15, dl, 30, 50)
+            pop = hotpath._pop_from_features(res["features"], 0.20, dl)
+            for p in range(len(pa)):
+                s1, s2 = seqs[pa[p]], seqs[pb[p]]
+                a1, a2, cig, tup, score = oracle.parasail_alignment(s1, s2, 2, -2, 12, 1, tb)
+                f = res["features"][p]
+                sm = oracle.find_first_significant_match(a1, a2, 30, 0.7)
+                em = oracle.find_first_significant_match(a1[::-1], a2[::-1], 30, 0.7)
+                assert (int(f[4]), int(f[5])) == (sm, em), (tb_index, p, cig)
+                assert bool(merge[p]) == oracle.align_to_merge(s1, s2, 0.15, dl, 30, 50, tiebreak=tb), (tb_index, p)
+                assert bool(pop[p]) == oracle.parse_cigar_diversity(tup, 0.20, dl)
+    finally:
+        ctx.set_packed(True)
+        ctx.set_tiebreak(0, 0, 0, 0)
 
 
 def test_align_batch_form_and_errors(ctx):
