@@ -30,15 +30,20 @@ import itertools
 import sys
 
 
+class _NeedsSpoa(Exception):
+    """Raised inside a speculative consensus whose spoa result is not memoised yet."""
+
+
 class BubblePrefetcher:
     def __init__(self, memo, stats=None):
         self.memo = memo
         self.stats = stats if stats is not None else {}
         self.stats.update({"iterations": 0, "speculated_pairs": 0, "prefetch_calls": 0, "prefetched": 0,
-                           "spoa_calls": 0, "spoa_hits": 0, "certain": 0, "uncertain": 0})
+                           "spoa_calls": 0, "spoa_hits": 0, "certain": 0, "uncertain": 0, "skipped_for_spoa": 0})
         self._spoa_cache = {}
         self._orig = {}
         self._in_speculation = False
+        self._no_new_spoa = False
 
     # ------------------------------------------------------------------ wiring
     def install(self):
@@ -64,6 +69,8 @@ class BubblePrefetcher:
         if hit is not None:
             self.stats["spoa_hits"] += 1
             return hit
+        if self._no_new_spoa:
+            raise _NeedsSpoa()
         self.stats["spoa_calls"] += 1
         con = self._orig["run_spoa"](reads, spoa_out_file)
         self._spoa_cache[key] = con
@@ -106,8 +113,8 @@ class BubblePrefetcher:
         own nodes only.  Such CERTAIN combinations are speculated in full -- consensus strings included, so the
         `spoa` spawns they cost are the ones the replay needs anyway (memoised).  A combination that shares a node
         with an earlier candidate may be cut short by `marked`; it is speculated only when its consensus strings need
-        no spoa (paths of <= 2 reads, generate_consensus_path :562-573), so speculation never adds a subprocess
-        spawn.  Whatever the replay asks beyond that is a synchronous one-pair call."""
+        no NEW spoa run (paths of <= 2 reads, generate_consensus_path :562-573, or read sets whose consensus is
+        already memoised), so speculation never adds a subprocess spawn.  Whatever the replay asks beyond that is a synchronous one-pair call."""
         sg = self._sg
         recorded = []
 
@@ -136,8 +143,6 @@ class BubblePrefetcher:
                 self.stats["certain" if certain else "uncertain"] += 1
                 mega = len(all_paths) > 2
                 for p1, p2 in itertools.combinations(all_paths, 2):
-                    if not certain and (len(p1[1]) > 2 or len(p2[1]) > 2):
-                        continue                                  # would need spoa for a pair the loop may never reach
                     this_combi = (start, end, tuple(sorted(set(p1[1]) | set(p2[1]))))
                     if this_combi in not_viable_multibubble:
                         continue
@@ -151,7 +156,12 @@ class BubblePrefetcher:
                              node2: sg.get_consensus_positions(start, end, DG, p2[1])}
                     # reads of the reference's consensus cache fall through, writes stay in the scratch front map
                     cache = collections.ChainMap({}, multi_consensuses)
-                    sg.align_bubble_nodes(all_reads, infos, work_dir, k_size, 0, cache, mega, this_combi, delta_len)
+                    self._no_new_spoa = not certain
+                    try:
+                        sg.align_bubble_nodes(all_reads, infos, work_dir, k_size, 0, cache, mega, this_combi, delta_len)
+                    except _NeedsSpoa:                            # a spawn for a pair the loop may never reach: skip
+                        self.stats["skipped_for_spoa"] += 1
         finally:
+            self._no_new_spoa = False
             sg.consensus.parasail_alignment = real_seam
         return recorded

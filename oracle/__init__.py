@@ -10,7 +10,7 @@ The Python part restates the integer pair/span path (main:174-224, 308-338) and 
 decision functions (SimplifyGraph.py:175-196, IsoformGeneration.py:251-397).
 """
 from .capi import (  # noqa: F401
-    pyhash, minimizers, minimizers_batch, sg_align, sg_align_pairs, num_threads, TieBreak, all_tiebreaks,
+    pyhash, minimizers, minimizers_batch, sg_align, sg_align_pairs, num_threads, simd_lanes, simd_isa, TieBreak, all_tiebreaks,
     cigar_runs_to_string, cigar_runs_to_tuples, OPS, edit_distance, edit_distance_pairs,
 )
 from .pyside import (  # noqa: F401

@@ -64,6 +64,8 @@ def lib():
                                                       C.c_void_p, C.c_int]
         L.isof_oracle_edit_distance_pairs.restype = C.c_int64
         L.isof_oracle_num_threads.restype = C.c_int32
+        L.isof_oracle_simd_lanes.restype = C.c_int32
+        L.isof_oracle_simd_isa.restype = C.c_char_p
         del u8p
         _lib = L
     return _lib
@@ -162,6 +164,14 @@ def edit_distance_pairs(cat, off, ia, ib, threads=0):
 
 def num_threads():
     return int(lib().isof_oracle_num_threads())
+
+
+def simd_lanes():
+    return int(lib().isof_oracle_simd_lanes())
+
+
+def simd_isa():
+    return lib().isof_oracle_simd_isa().decode()
 
 
 def cigar_runs_to_string(runs):

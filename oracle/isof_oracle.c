@@ -400,6 +400,20 @@ ISOF_API int64_t isof_oracle_sg_align_pairs(const uint8_t *cat, const int64_t *o
     return err ? -1 : tot;
 }
 
+/* lanes of the inter-pair SIMD aligner and the widest instruction set its dispatcher will pick on this CPU */
+ISOF_API int32_t isof_oracle_simd_lanes(void) { return 32; }
+ISOF_API const char *isof_oracle_simd_isa(void)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx512bw")) return "AVX-512BW";
+    if (__builtin_cpu_supports("avx2")) return "AVX2";
+    return "baseline x86-64-v2";
+#else
+    return "scalar";
+#endif
+}
+
 ISOF_API int32_t isof_oracle_num_threads(void)
 {
 #ifdef _OPENMP
@@ -413,13 +427,13 @@ ISOF_API int32_t isof_oracle_num_threads(void)
 /* Inter-pair SIMD batch aligner (CPU baseline of bench.py).                                   */
 /*                                                                                            */
 /* Same recurrences, tie-breaks and cigar walk as isof_oracle_sg_align_tb with the default    */
-/* table, but 16 pairs advance in lock step in int16 lanes (the innermost loop runs over the   */
-/* lanes and is auto-vectorised: AVX2 where the CPU has it, via target_clones).  This is the   */
+/* table, but 32 pairs advance in lock step in int16 lanes (the innermost loop runs over the   */
+/* lanes and is auto-vectorised: AVX-512BW / AVX2 where the CPU has them, via target_clones).  This is the   */
 /* shape of a production CPU aligner (libparasail is SIMD too); the scalar function above      */
 /* stays the checker and tests/test_oracle_golden.py holds the two bit-identical.              */
 /* Falls back to the scalar routine for pairs outside the int16 range.                         */
 /* ------------------------------------------------------------------------------------------ */
-#define VL 16
+#define VL 32
 #define NEG16V (-16000)
 
 typedef struct {
@@ -430,7 +444,7 @@ typedef struct {
 } group_t;
 
 #if defined(__x86_64__) && defined(__GNUC__)
-#define ISOF_CLONES __attribute__((target_clones("avx2", "default")))
+#define ISOF_CLONES __attribute__((target_clones("arch=skylake-avx512", "avx2", "default")))
 #else
 #define ISOF_CLONES
 #endif
@@ -550,12 +564,20 @@ ISOF_API int64_t isof_oracle_sg_align_pairs_simd(const uint8_t *cat, const int64
                 ++lanes;
             } else { pp[v] = -1; nn[v] = 0; mm[v] = 0; }
         }
-        int16_t *q1 = (int16_t *)malloc(sizeof(int16_t) * (size_t)N * VL);
-        int16_t *c2 = (int16_t *)malloc(sizeof(int16_t) * (size_t)M * VL);
-        int16_t *H = (int16_t *)malloc(sizeof(int16_t) * (size_t)(M + 1) * VL);
-        int16_t *F = (int16_t *)malloc(sizeof(int16_t) * (size_t)M * VL);
-        uint8_t *trace = (uint8_t *)malloc((size_t)N * (size_t)M * VL);
-        if (!q1 || !c2 || !H || !F || !trace) { err = 1; free(q1); free(c2); free(H); free(F); free(trace); continue; }
+        /* per-thread grow-only scratch: a fresh 140 MB trace per group would spend a third of the time in page faults */
+        static _Thread_local int16_t *q1 = NULL, *c2 = NULL, *H = NULL, *F = NULL;
+        static _Thread_local uint8_t *trace = NULL;
+        static _Thread_local size_t capN = 0, capM = 0, capT = 0;
+        if ((size_t)N > capN) { free(q1); q1 = (int16_t *)malloc(sizeof(int16_t) * (size_t)N * VL); capN = q1 ? (size_t)N : 0; }
+        if ((size_t)M > capM) {
+            free(c2); free(H); free(F);
+            c2 = (int16_t *)malloc(sizeof(int16_t) * (size_t)M * VL);
+            H = (int16_t *)malloc(sizeof(int16_t) * (size_t)(M + 1) * VL);
+            F = (int16_t *)malloc(sizeof(int16_t) * (size_t)M * VL);
+            capM = (c2 && H && F) ? (size_t)M : 0;
+        }
+        if ((size_t)N * (size_t)M > capT) { free(trace); trace = (uint8_t *)malloc((size_t)N * (size_t)M * VL); capT = trace ? (size_t)N * (size_t)M : 0; }
+        if (!capN || !capM || !capT) { err = 1; continue; }
         for (int v = 0; v < VL; ++v) {
             const uint8_t *a = pp[v] >= 0 ? cat + off[ia[pp[v]]] : NULL;
             const uint8_t *b = pp[v] >= 0 ? cat + off[ib[pp[v]]] : NULL;
@@ -606,7 +628,6 @@ ISOF_API int64_t isof_oracle_sg_align_pairs_simd(const uint8_t *cat, const int64
             nr[p] = cnt;
             free(rev);
         }
-        free(q1); free(c2); free(H); free(F); free(trace);
     }
     /* everything the int16 lanes cannot hold goes through the scalar routine */
 #ifdef _OPENMP

@@ -31,7 +31,7 @@ def test_reference_main_with_patched_seams_writes_identical_outputs(tmp_path, se
     reads, _iso, _t = synth.make_cluster(seed=seed, gene_len=700, n_isoforms=3, n_reads=n_reads, eps=eps)
     fastq = str(tmp_path / "7_0.fastq")              # <cluster>_<batch>.fastq as isONform_parallel names it
     synth.write_fastq(fastq, reads)
-    _run(fastq, str(tmp_path / "ref"), 0)
+    r0 = _run(fastq, str(tmp_path / "ref"), 0)
     r = _run(fastq, str(tmp_path / "b200"), 1)
     for name in ("0_batch", "spoa0", "mapping0"):
         a = pickle.load(open(tmp_path / "ref" / name, "rb"))
@@ -44,3 +44,16 @@ def test_reference_main_with_patched_seams_writes_identical_outputs(tmp_path, se
     assert m, r.stderr[-2000:]
     # one minimizer launch and one span-index build for the whole batch; alignments went through the seam
     assert int(m.group(1)) == 1 and int(m.group(2)) == 1 and int(m.group(4)) > 0
+    # bubble popping (SimplifyGraph.py:883-1151) is prefetched: one batched alignment call per iteration at most, the
+    # bulk of the loop's alignments are memo hits, and speculation never costs an extra spoa spawn
+    b = re.search(r"B200_BUBBLES iterations=(\d+) speculated=(\d+) prefetch_calls=(\d+) prefetched=(\d+) spoa_calls=(\d+)",
+                  r.stderr)
+    hm = re.search(r"memo_hits=(\d+) memo_misses=(\d+)", r.stderr)
+    assert b and hm, r.stderr[-2000:]
+    iterations, prefetch_calls = int(b.group(1)), int(b.group(3))
+    hits, misses = int(hm.group(1)), int(hm.group(2))
+    assert iterations >= 1 and prefetch_calls <= iterations
+    assert hits > 0 and hits >= misses
+    spawns_ref = int(re.search(r"SPOA_SPAWNS (\d+)", r0.stderr).group(1))
+    spawns_b200 = int(re.search(r"SPOA_SPAWNS (\d+)", r.stderr).group(1))
+    assert spawns_b200 <= spawns_ref, (spawns_b200, spawns_ref)
