@@ -176,6 +176,27 @@ ISOF_API int isof_spans_batch_dev(isof_ctx *ctx, const uint8_t *bases, const int
                                   int32_t *rec_p2, int32_t *rec_count, int32_t *rec_bucket, int32_t *sorted_rec,
                                   int32_t *bucket_off, uint8_t *bucket_dropped, int64_t *n_rec, int64_t *n_buckets);
 
+/*
+ * Host-side helpers of the front half (plain C++, no GPU work; SURVEY.md scopes M6 to the host).
+ * isof_wis_picks replaces the per-read loop main:496-514 (sort by stop, fill_p2 main:227-239, solve_WIS
+ * main:242-263) for ALL reads of a batch: read r owns records read_rec_off[r] .. read_rec_off[r+1]-1 of the
+ * isof_spans_batch output; an interval is (rec_p1+k, rec_p2, weight rec_count) for records with rec_count > 0.
+ * Same IEEE-754 double arithmetic and tie-breaks as the reference's Python floats.  pick_rec receives the
+ * record indices WIS keeps, in increasing stop order per read; pick_off[n_reads+1] the per-read offsets.
+ * ISOF_ERR_RANGE: an interval start lies beyond the last stop (the reference raises IndexError there).
+ * isof_span_instances writes, for each picked record, the `seqs` array find_most_supported_span builds
+ * (main:324-337): (r_id, p1, p2) of the record, then of every other-read record of its bucket whose span differs
+ * by less than delta_len -- 3*rec_count values, so inst_off is the prefix sum of 3*rec_count[pick_rec].
+ * read_id maps the 0-based read index to the reference's r_id.
+ */
+ISOF_API int isof_wis_picks(int32_t n_reads, const int64_t *read_rec_off, const int32_t *rec_p1, const int32_t *rec_p2,
+                            const int32_t *rec_count, int32_t k, int32_t *pick_rec, int64_t pick_cap, int64_t *pick_off,
+                            int64_t *n_picks);
+ISOF_API int isof_span_instances(int64_t n_picks, const int32_t *pick_rec, const int32_t *rec_read, const int32_t *rec_p1,
+                                 const int32_t *rec_p2, const int32_t *rec_bucket, const int32_t *sorted_rec,
+                                 const int32_t *bucket_off, const int64_t *read_id, int32_t delta_len,
+                                 const int64_t *inst_off, uint32_t *inst);
+
 /* ------------------------------------------------------------------------------------------ */
 /* (b) semi-global affine alignment with traceback                                            */
 /* ------------------------------------------------------------------------------------------ */

@@ -38,7 +38,7 @@ class Profile(C.Structure):
 EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_debug_violations", "isof_debug_selftest",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
-           "isof_sg_features_pairs"]
+           "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances"]
 
 _lib = None
 _lib_debug = None
@@ -87,6 +87,8 @@ def load(debug=False):
                                           vp, vp, i32, C.POINTER(i64)]
     L.isof_sg_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp]
     L.isof_sg_features_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp]
+    L.isof_wis_picks.argtypes = [i32, vp, vp, vp, vp, i32, vp, i64, vp, C.POINTER(i64)]
+    L.isof_span_instances.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("isof_last_error",):
@@ -343,6 +345,46 @@ class Context:
                                                     gap_open, gap_ext, d_score, d_endq, d_endr, d_cigar, cigar_cap,
                                                     d_cigar_off, d_features, delta_len, C.byref(total)))
         return int(total.value)
+
+
+def wis_picks(read_rec_off, rec_p1, rec_p2, rec_count, k):
+    """(pick_rec int32[], pick_off int64[n_reads+1]): isof_wis_picks over a whole batch (host helper)."""
+    L = load()
+    read_rec_off = np.ascontiguousarray(read_rec_off, dtype=np.int64)
+    rec_p1 = np.ascontiguousarray(rec_p1, dtype=np.int32)
+    rec_p2 = np.ascontiguousarray(rec_p2, dtype=np.int32)
+    rec_count = np.ascontiguousarray(rec_count, dtype=np.int32)
+    n_reads = len(read_rec_off) - 1
+    cap = max(int(np.count_nonzero(rec_count > 0)), 1)
+    picks = np.empty(cap, np.int32)
+    off = np.zeros(n_reads + 1, np.int64)
+    n = C.c_int64(0)
+    rc = L.isof_wis_picks(n_reads, read_rec_off.ctypes.data, rec_p1.ctypes.data, rec_p2.ctypes.data, rec_count.ctypes.data,
+                          int(k), picks.ctypes.data, cap, off.ctypes.data, C.byref(n))
+    if rc == ERR_RANGE:
+        raise IndexError("list index out of range")          # what the reference's fill_p2 does on such input
+    if rc != ISOF_OK:
+        raise IsofError(rc, "isof_wis_picks failed")
+    return picks[:n.value], off
+
+
+def span_instances(pick_rec, arrays, read_id, delta_len):
+    """(inst uint32[], inst_off int64[n_picks+1]) for the picked records (isof_span_instances, host helper)."""
+    L = load()
+    pick_rec = np.ascontiguousarray(pick_rec, dtype=np.int32)
+    a = {k_: np.ascontiguousarray(arrays[k_], dtype=np.int32) for k_ in ("rec_read", "rec_p1", "rec_p2", "rec_count", "rec_bucket",
+                                                                        "sorted_rec", "bucket_off")}
+    read_id = np.ascontiguousarray(read_id, dtype=np.int64)
+    inst_off = np.zeros(len(pick_rec) + 1, np.int64)
+    np.cumsum(3 * a["rec_count"][pick_rec].astype(np.int64), out=inst_off[1:])
+    inst = np.empty(max(int(inst_off[-1]), 1), np.uint32)
+    rc = L.isof_span_instances(len(pick_rec), pick_rec.ctypes.data, a["rec_read"].ctypes.data, a["rec_p1"].ctypes.data,
+                               a["rec_p2"].ctypes.data, a["rec_bucket"].ctypes.data, a["sorted_rec"].ctypes.data,
+                               a["bucket_off"].ctypes.data, read_id.ctypes.data, int(delta_len), inst_off.ctypes.data,
+                               inst.ctypes.data)
+    if rc != ISOF_OK:
+        raise IsofError(rc, "isof_span_instances failed")
+    return inst[:inst_off[-1]], inst_off
 
 
 _default_ctx = {}

@@ -29,6 +29,34 @@ import collections
 import itertools
 import sys
 
+import numpy as np
+
+
+def generate_combinations(possible_starts, possible_ends, topo_nodes_dict, combis):
+    """Drop-in for SimplifyGraph.generate_combinations (:110-119), one of the two bookkeeping hot spots SURVEY.md
+    section 8f names (4 s per 1000-read batch: |starts| x |ends| Python set intersections per iteration).  Same
+    appended tuples in the same order; the read-support sets become rows of two 0/1 matrices and ONE integer matrix
+    product counts every intersection, so only the (start, end) pairs that really share >= 2 reads and respect the
+    topological order are touched in Python."""
+    if not possible_starts or not possible_ends:
+        return
+    reads = sorted({r for _n, supp in possible_starts for r in supp} | {r for _n, supp in possible_ends for r in supp})
+    col = {r: i for i, r in enumerate(reads)}
+    S = np.zeros((len(possible_starts), len(reads)), dtype=np.float32)
+    E = np.zeros((len(possible_ends), len(reads)), dtype=np.float32)
+    for i, (_n, supp) in enumerate(possible_starts):
+        S[i, [col[r] for r in supp]] = 1.0
+    for j, (_n, supp) in enumerate(possible_ends):
+        E[j, [col[r] for r in supp]] = 1.0
+    shared = S @ E.T                                       # exact: counts <= #reads << 2^24
+    ts = np.array([topo_nodes_dict[n] for n, _s in possible_starts])
+    te = np.array([topo_nodes_dict[n] for n, _s in possible_ends])
+    ok = (shared >= 2.0) & (ts[:, None] < te[None, :])
+    read_arr = np.array(reads, dtype=object)
+    for i, j in zip(*np.nonzero(ok)):                      # row-major: starts outer, ends inner, as the reference loops
+        inter = tuple(read_arr[np.nonzero((S[i] * E[j]) > 0)[0]].tolist())          # `reads` is sorted, so is this
+        combis.append((possible_starts[i][0], possible_ends[j][0], inter))
+
 
 class _NeedsSpoa(Exception):
     """Raised inside a speculative consensus whose spoa result is not memoised yet."""
@@ -78,7 +106,7 @@ class BubblePrefetcher:
 
     # ------------------------------------------------------------------ the per-iteration hook
     def _generate_combinations(self, possible_starts, possible_ends, topo_nodes_dict, combis):
-        self._orig["generate_combinations"](possible_starts, possible_ends, topo_nodes_dict, combis)
+        generate_combinations(possible_starts, possible_ends, topo_nodes_dict, combis)
         frame = sys._getframe(1)
         if frame.f_code.co_name != "new_bubble_popping_routine" or self._in_speculation:
             return

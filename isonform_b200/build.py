@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libisonform_b200.so")
 SO_DEBUG = os.path.join(HERE, "libisonform_b200_dbg.so")          # -DISOF_CHECK: device-side bounds assertions
-SOURCES = ["capi.cu", "minimizers.cu", "sg_align.cu", "sg_dp_tb1.cu", "sg_dp_tb2.cu", "sg_dp_tb3.cu", "spans.cu"]
+SOURCES = ["capi.cu", "minimizers.cu", "sg_align.cu", "sg_dp_tb1.cu", "sg_dp_tb2.cu", "sg_dp_tb3.cu", "spans.cu", "host_wis.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -46,8 +46,8 @@ def build(force=False, verbose=False, debug=None):
     extra = ["-DISOF_CHECK"] if debug else []
 
     def compile_one(src):
-        obj = os.path.join(CSRC, src.replace(".cu", ".dbg.o" if debug else ".o"))
-        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + (".dbg.o" if debug else ".o"))
+        cmd = [NVCC] + FLAGS + ["-Xcompiler", "-ffp-contract=off"] + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -17,9 +17,10 @@ import numpy as np
 from . import hotpath
 from ._lib import default_context
 
-# pairs per speculative launch: large enough to fill the GPU (148 SMs x 16 warps), small enough
-# that an early `break` wastes little
-_MIN_PAIRS_PER_CALL = 8192
+# pairs per speculative launch: large enough to fill the GPU several times over (148 SMs x 16 warps x 2 pairs = one
+# wave of 4736 pairs; a 64 k-pair launch takes ~0.15 s at C2 read lengths), which is also the most an early `break`
+# can waste -- cheaper than the extra launches and host round trips of smaller blocks
+_MIN_PAIRS_PER_CALL = 65536
 _MAX_PAIRS_PER_CALL = 1 << 19
 
 

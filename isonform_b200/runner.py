@@ -13,10 +13,16 @@ def read_batch(records):
 
 
 def batch_front_half(reads, k=20, w=31, xmin=40, xmax=80, delta_len=5, ctx=None):
-    """Returns (all_intervals_for_graph, new_all_reads, skipped_read_ids, SpanIndex)."""
+    """Returns (all_intervals_for_graph, new_all_reads, skipped_read_ids, SpanIndex).  The minimizer positions go from
+    kernel (a) to kernel (c) as arrays: the `{r_id: [(kmer, pos)]}` dict of the reference seam is not materialised."""
+    from ._lib import default_context, pack_sequences
+    ctx = ctx or default_context()
     xmin = max(xmin, 2 * k)                                      # main:623-625
-    M = hotpath.get_minimizers_and_positions(reads, w, k, "lex", ctx)
-    index = spans.SpanIndex(reads, M, k, xmin, xmax, delta_len, ctx)
+    ids = list(reads)
+    cat, off = pack_sequences([reads[r][1] for r in ids])
+    min_pos, min_off = ctx.minimizers_batch(cat, off, k, w)
+    arrays = ctx.spans_batch(cat, off, min_pos, min_off, k, xmin, xmax, delta_len)
+    index = spans.SpanIndex(reads, None, k, xmin, xmax, delta_len, _arrays=arrays, ids=ids)
     all_intervals_for_graph, new_all_reads, skipped = spans.batch_intervals_for_graph(index, reads)
     return all_intervals_for_graph, new_all_reads, skipped, index
 

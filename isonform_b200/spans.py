@@ -35,11 +35,12 @@ def minimizers_comb_iterator(minimizers, k, x_low, x_high):
 
 
 class SpanIndex:
-    def __init__(self, reads, M, k, x_low, x_high, delta_len, ctx=None, _arrays=None):
+    def __init__(self, reads, M, k, x_low, x_high, delta_len, ctx=None, _arrays=None, ids=None):
         """reads: {r_id: (acc, seq, qual)} in batch order; M: {r_id: [(kmer, pos)]} as returned by
-        get_minimizers_and_positions (same key order)."""
+        get_minimizers_and_positions (same key order).  Internal callers that already hold the library's span arrays
+        pass them as `_arrays` with the read ids in `ids` (M is then unused)."""
         self.k, self.x_low, self.x_high, self.delta_len = k, x_low, x_high, delta_len
-        self.ids = list(M)
+        self.ids = list(M) if ids is None else list(ids)
         self.id_of = np.array(self.ids, dtype=np.int64)
         self.row_of = {r: i for i, r in enumerate(self.ids)}
         self.reads = reads
@@ -276,7 +277,39 @@ def _solve_wis_arrays(starts, stops, ws):
 
 def batch_intervals_for_graph(index, reads):
     """The per-read loop of main:417-514 (with --exact): returns
-    (all_intervals_for_graph {graph_id: [(start, stop, count, instances)]}, new_all_reads, skipped r_ids)."""
+    (all_intervals_for_graph {graph_id: [(start, stop, count, instances)]}, new_all_reads, skipped r_ids).
+    WIS for all reads and the instance arrays of the picked intervals come from two calls into the library's host
+    helpers (csrc/host_wis.cpp); what is left here is building the Python objects the reference's graph code takes."""
+    from . import _lib
+    picks, pick_off = _lib.wis_picks(index.read_rec_off, index.rec_p1, index.rec_p2, index.rec_count, index.k)
+    inst, inst_off = _lib.span_instances(picks, index.__dict__, index.id_of, index.delta_len)
+    raw = memoryview(inst.tobytes())
+    starts = (index.rec_p1[picks].astype(np.int64) + index.k).tolist()
+    stops = index.rec_p2[picks].tolist()
+    counts = index.rec_count[picks].tolist()
+    ioff = (4 * inst_off).tolist()
+    poff = pick_off.tolist()
+    all_intervals_for_graph, new_all_reads, skipped = {}, {}, []
+    graph_id = 1
+    for r_id in sorted(reads):
+        i = index.row_of.get(r_id)
+        lo, hi = (poff[i], poff[i + 1]) if i is not None else (0, 0)
+        if hi == lo:
+            skipped.append(r_id)
+            continue
+        out = []
+        for x in range(lo, hi):
+            arr = array("I")
+            arr.frombytes(raw[ioff[x]:ioff[x + 1]])
+            out.append((starts[x], stops[x], counts[x], arr))
+        all_intervals_for_graph[graph_id] = out
+        new_all_reads[graph_id] = reads[r_id]
+        graph_id += 1
+    return all_intervals_for_graph, new_all_reads, skipped
+
+
+def batch_intervals_for_graph_py(index, reads):
+    """The same in numpy / Python (kept as the cross-check of the C++ helpers in the CPU tests)."""
     all_intervals_for_graph, new_all_reads, skipped = {}, {}, []
     graph_id = 1
     for r_id in sorted(reads):

@@ -77,3 +77,65 @@ def test_wis_mirror_matches_oracle_on_golden_intervals():
             if iv:
                 srt = sorted(iv, key=lambda x: x[1])
                 assert spans.solve_WIS(srt) == oracle.solve_WIS(srt)
+
+
+def test_generate_combinations_matrix_form_equals_reference_loop():
+    """bubbles.generate_combinations (one matrix product) against the reference's nested set-intersection loop
+    (SimplifyGraph.py:110-119), restated here: same tuples, same order."""
+    import numpy as np
+    from isonform_b200 import bubbles
+
+    def reference_loop(starts, ends, topo, combis):
+        for s in starts:
+            for e in ends:
+                if topo[s[0]] < topo[e[0]]:
+                    inter = tuple(sorted(set(s[1]).intersection(set(e[1]))))
+                    if len(inter) >= 2:
+                        combis.append((s[0], e[0], inter))
+
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        n_reads = int(rng.integers(2, 40))
+        nodes = ["n%d" % i for i in range(int(rng.integers(2, 30)))]
+        perm = rng.permutation(len(nodes))
+        topo = {n: int(perm[i]) for i, n in enumerate(nodes)}
+
+        def supp():
+            size = int(rng.integers(1, n_reads + 1))
+            return tuple(int(x) for x in rng.choice(np.arange(1, n_reads + 1), size=size, replace=False))
+        starts = [(n, supp()) for n in nodes if rng.random() < 0.6]
+        ends = [(n, supp()) for n in nodes if rng.random() < 0.6]
+        want, got = [], []
+        reference_loop(starts, ends, topo, want)
+        bubbles.generate_combinations(starts, ends, topo, got)
+        assert got == want, trial
+    got = []
+    bubbles.generate_combinations([], [("a", (1, 2))], {"a": 0}, got)
+    assert got == []
+
+
+def test_host_wis_and_instances_match_python_path():
+    """csrc/host_wis.cpp (isof_wis_picks / isof_span_instances: plain C++, runs without a GPU) against the numpy/Python
+    restatement of main:227-272,324-337 on random batches -- same picks, same instance arrays, same skipped reads."""
+    import sys as _sys
+    import os as _os
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    from fake_ctx import FakeContext
+    from isonform_b200 import hotpath, runner, spans, synth
+    for seed, n, eps, dl in ((3, 30, 0.01, 5), (4, 40, 0.05, 5), (9, 25, 0.0, 10), (10, 12, 0.1, 3)):
+        reads, _i, _t = synth.make_cluster(seed=seed, gene_len=800, n_isoforms=3, n_reads=n, eps=eps)
+        rd = runner.read_batch([(a, s, "I" * len(s)) for a, s in reads])
+        rd[len(rd) + 1] = ("short", "ACGTACGTAC", "I" * 10)                 # a read without any interval
+        ctx = FakeContext()
+        M = hotpath.get_minimizers_and_positions(rd, 31, 20, "lex", ctx)
+        idx = spans.SpanIndex(rd, M, 20, 40, 80, dl, ctx)
+        a = spans.batch_intervals_for_graph(idx, rd)
+        b = spans.batch_intervals_for_graph_py(idx, rd)
+        assert a[1] == b[1] and a[2] == b[2] and list(a[0]) == list(b[0])
+        for key in a[0]:
+            assert [(x, y, z, list(w)) for x, y, z, w in a[0][key]] == [(x, y, z, list(w)) for x, y, z, w in b[0][key]]
+        # the front half as the runner issues it (positions as arrays, no minimizer dict) gives the same
+        c = runner.batch_front_half(rd, 20, 31, 40, 80, dl, FakeContext())
+        assert c[2] == a[2] and list(c[0]) == list(a[0])
+        for key in a[0]:
+            assert [(x, y, z, list(w)) for x, y, z, w in c[0][key]] == [(x, y, z, list(w)) for x, y, z, w in a[0][key]]
