@@ -805,3 +805,57 @@ def test_merge_consensuses_driver_on_gpu_equals_oracle_backed_run(ctx):
         results.append((new, cbs, stats))
     assert results[0][0] == results[1][0] and results[0][1] == results[1][1] and results[0][2] == results[1][2]
     assert len(results[0][1]) < len(seqs), "the set must actually merge something"
+
+
+# ------------------------------------------------------------------------------- drop-in at the seams, on hardware
+@pytest.mark.parametrize("cap_index", [0, 1])
+def test_reference_seams_replayed_on_gpu(ctx, cap_index):
+    """tests/golden/seam_capture.json holds what the UNMODIFIED reference `main()` passed through every hot-path seam on
+    a synthetic batch (scripts/make_seam_capture.py, build container).  Here the recorded inputs go through the real GPU
+    context and every recorded output must come back: the reference's control flow is a deterministic function of
+    these values, so this is the entry-point drop-in claim proven on the B200."""
+    from isonform_b200 import hotpath, merge, runner
+    cap = load_golden("seam_capture.json")["captures"][cap_index]
+    pool, P = cap["pool"], cap["params"]
+    reads = {int(r): (acc, pool[si], "I" * len(pool[si])) for r, acc, si in cap["reads"]}
+    # (1) get_minimizers_and_positions (main:159)
+    M = hotpath.get_minimizers_and_positions(reads, P["w"], P["k"], "lex", ctx)
+    assert {str(r): [p for _m, p in M[r]] for r in M} == cap["minimizers"]
+    for r in M:
+        assert all(m == reads[r][1][p:p + P["k"]] for m, p in M[r])
+    # (2) the whole front half: what main() hands to generateGraphfromIntervals (main:531)
+    graph_iv, new_reads, _skipped, _index = runner.batch_front_half(reads, P["k"], P["w"], P["xmin"], P["xmax"], P["delta_len"], ctx)
+    got_iv = {str(g): [[a, b, c, list(arr)] for a, b, c, arr in v] for g, v in graph_iv.items()}
+    assert got_iv == cap["intervals_for_graph"]
+    assert {str(g): [v[0], v[1]] for g, v in new_reads.items()} == {g: [v[0], pool[v[1]]] for g, v in cap["new_all_reads"].items()}
+    # (3) every consensus.parasail_alignment call of bubble popping and isoform merging: one prefetch, then the per-pair seam
+    memo = merge.AlignmentMemo(ctx)
+    by_params = {}
+    for s1, s2, ma, mi, go, ge, _cig, _sc in cap["alignments"]:
+        by_params.setdefault((ma, mi, go, ge), []).append((pool[s1], pool[s2]))
+    for params, pairs in by_params.items():
+        memo.prefetch_alignments(pairs, *params)
+    for s1, s2, ma, mi, go, ge, cig, sc in cap["alignments"]:
+        a1, a2, got_cig, tuples, got_sc = memo.parasail_alignment(pool[s1], pool[s2], ma, mi, go, ge)
+        assert (got_cig, got_sc) == (cig, sc)
+        assert len(a1) == len(a2) == sum(l for l, _ in tuples)
+    assert memo.misses == 0
+    # (4) IsoformGeneration.align_to_merge decisions
+    for c1, c2, delta, dl, d3, d5, want in cap["merge_decisions"]:
+        assert hotpath.align_to_merge(pool[c1], pool[c2], delta, dl, d3, d5, ctx) == want
+    # (5) merge_consensuses (IsoformGeneration.py:464-507) through the speculative driver, consensus strings as recorded
+    mc = cap["merge"]
+    cbs = {int(i): list(v) for i, v in mc["curr_best_seqs_in"].items()}
+    mreads = {int(r): (v[0], pool[v[1]], "") for r, v in mc["reads"].items()}
+    regen = {(a, b): pool[s] for a, b, s in mc["regenerated"]}
+
+    def gen_all(all_c, alt, cur, rd, wd, ms):
+        for i, s in mc["all_consensuses"]:
+            all_c[i] = pool[s]
+            alt.append((i, pool[s]))
+
+    out = merge.merge_consensuses(cbs, None, mc["delta"], mc["delta_len"], mreads, P["max_seqs_to_spoa"], P["delta_iso_len_3"],
+                                  P["delta_iso_len_5"], generate_all_consensuses=gen_all,
+                                  generate_new_full_consensus=lambda i1, i2, rd, cur, wd, ms: regen[(i1, i2)], ctx=ctx)
+    assert {str(i): v for i, v in cbs.items()} == mc["curr_best_seqs_out"]
+    assert {str(i): s for i, s in out.items()} == {i: pool[s] for i, s in mc["new_consensuses"].items()}

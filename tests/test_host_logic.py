@@ -139,3 +139,15 @@ def test_host_wis_and_instances_match_python_path():
         assert c[2] == a[2] and list(c[0]) == list(a[0])
         for key in a[0]:
             assert [(x, y, z, list(w)) for x, y, z, w in c[0][key]] == [(x, y, z, list(w)) for x, y, z, w in a[0][key]]
+
+
+def test_seam_capture_replays_over_the_oracle_double():
+    """The recorded reference seams (tests/golden/seam_capture.json) replayed through the host logic over the
+    oracle-backed test double: pins the fixture and the host half on CPU; the `-m gpu` twin runs the real context."""
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+    import test_gpu_parity
+    from fake_ctx import FakeContext
+    for i in (0, 1):
+        test_gpu_parity.test_reference_seams_replayed_on_gpu(FakeContext(), i)
