@@ -474,7 +474,7 @@ def run_c5_points(ctx, lengths=(50, 100, 200, 500, 2000)):
     rows = []
     for L in lengths:
         nb = 2000
-        n_pairs = int(max(4000, min(200000, 2e10 / (L * L))))
+        n_pairs = int(max(4000, min(400000, 4e10 / (L * L))))
         base = [synth.random_dna(rng, L) for _ in range(nb)]
         muts = [synth.mutate(rng, x, 0.05) or "A" for x in base]
         pa = (np.arange(n_pairs) % nb).astype(np.int32)

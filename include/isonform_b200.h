@@ -65,6 +65,11 @@ ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
  * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any
  * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
 ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
+/* A call whose pairs are ALL short (both lengths <= 384, inside the 16-bit range) and numerous enough to fill the GPU
+ * (about 64 x SMs x (length/60)^2 pairs: a thread per task trades latency for throughput) takes the short-pair regime:
+ * one thread per task instead of a 32-lane wavefront per task (the bubble-popping sizes, SimplifyGraph.py:630-664).
+ * Identical results.  on=0 never, on=1 automatic (default), on=2 every all-short call (tests, A/B measurements). */
+ISOF_API int isof_set_short(isof_ctx *ctx, int on);
 /* Tie-break table of the aligner.  parasail is third-party and not vendored by the reference, so every
  * tie-break of its sg_trace + cigar code (consensus.py:56-59) is a named switch here and in the oracle
  * (isof_tiebreak_t in oracle/isof_oracle.c) instead of a hard-coded constant; all zero (the default) is the

@@ -35,7 +35,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_debug_violations", "isof_debug_selftest",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_debug_violations", "isof_debug_selftest",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances"]
@@ -68,6 +68,7 @@ def load(debug=False):
     L.isof_set_packed.argtypes = [vp, C.c_int]
     L.isof_set_overlap.argtypes = [vp, C.c_int]
     L.isof_set_tiebreak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.isof_set_short.argtypes = [vp, C.c_int]
     L.isof_debug_violations.argtypes = [vp, C.POINTER(C.c_uint)]
     L.isof_debug_selftest.argtypes = [vp]
     L.isof_profile_enable.argtypes = [vp, C.c_int]
@@ -156,6 +157,11 @@ class Context:
     def set_packed(self, on=True):
         """Enable (default) / disable the packed 16-bit DP path; results are identical either way."""
         self._check(self._L.isof_set_packed(self._h, 1 if on else 0))
+
+    def set_short(self, mode=1):
+        """Short-pair regime for all-short calls: 0/False never, 1/True when the call is large enough (default),
+        2 always (tests).  Results are identical either way."""
+        self._check(self._L.isof_set_short(self._h, int(mode)))
 
     def set_tiebreak(self, h_e_before_f=0, gap_open_on_tie=0, end_col_first=0, swap_id=0):
         """Tie-break table of the aligner (isof_set_tiebreak); all zero = the library as restated."""

@@ -154,6 +154,13 @@ int isof_set_packed(isof_ctx *ctx, int on)
     return ISOF_OK;
 }
 
+int isof_set_short(isof_ctx *ctx, int on)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->short_mode = on < 0 ? 0 : (on > 2 ? 2 : on);
+    return ISOF_OK;
+}
+
 int isof_set_tiebreak(isof_ctx *ctx, int h_e_before_f, int gap_open_on_tie, int end_col_first, int swap_id)
 {
     if (!ctx) return ISOF_ERR_ARG;

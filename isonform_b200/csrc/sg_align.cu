@@ -68,11 +68,11 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                             const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, int64_t P,
                             int32_t *__restrict__ pn, int32_t *__restrict__ pm, uint8_t *__restrict__ pwild,
                             int64_t *__restrict__ words, unsigned long long *__restrict__ misc, int h_max_min_len,
-                            int h_max_max_len)
+                            int h_max_max_len, int short_max)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0, padded = 0;
-    int mm = 0;
+    int mm = 0, mn = 0, not_short = 0, any_wild = 0;
     if (p < P) {
         int a = pa[p], b = pb[p];
         int n = 0, m = 0;
@@ -94,7 +94,10 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                 const int rr = need > 192 ? 8 : need > 128 ? 6 : need > 64 ? 4 : 2;
                 padded = (unsigned long long)((ns - 1) * SROWS + (elig ? rr * 32 : SROWS)) * m;
                 pwild[p] = (uint8_t)(wild | (elig << 1));
-                mm = m;
+                mm = m; mn = n;
+                // short-pair regime (sg_short.cu): both lengths small and inside the 16-bit range (wildcards allowed)
+                not_short = !(max(n, m) <= short_max && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len);
+                any_wild = wild;
             }
         }
         pn[p] = n; pm[p] = m;
@@ -105,10 +108,16 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
         cells += __shfl_down_sync(0xffffffffu, cells, d);
         padded += __shfl_down_sync(0xffffffffu, padded, d);
         mm = max(mm, __shfl_down_sync(0xffffffffu, mm, d));
+        mn = max(mn, __shfl_down_sync(0xffffffffu, mn, d));
+        not_short += __shfl_down_sync(0xffffffffu, not_short, d);
+        any_wild |= __shfl_down_sync(0xffffffffu, any_wild, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (cells) { atomicAdd(&misc[2], cells); atomicAdd(&misc[3], padded); }
         if (mm) atomicMax(&misc[1], (unsigned long long)mm);
+        if (mn) atomicMax(&misc[8], (unsigned long long)mn);
+        if (not_short) atomicAdd(&misc[9], (unsigned long long)not_short);
+        if (any_wild) atomicOr(&misc[10], 1ull);
     }
     if (p == P) words[P] = 0;
 }
@@ -163,15 +172,15 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
                   uint8_t *__restrict__ flags, int32_t *__restrict__ pn, int32_t *__restrict__ pm,
                   uint8_t *__restrict__ pwild, int64_t *__restrict__ ptrace, unsigned long long *__restrict__ misc,
                   int h_max_min_len, int h_max_max_len, int32_t *__restrict__ order,
-                  unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ ticket)
+                  unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ ticket, int short_max)
 {
     typedef cub::BlockScan<long long, 1024> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ uint32_t s_key[SMALL_P];
-    __shared__ unsigned long long s_stat[4];             // err, max m, cells, padded
+    __shared__ unsigned long long s_stat[7];             // err, max m, cells, padded, max n, not short, any wildcard
     __shared__ int s_nelig;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 4) s_stat[tid] = 0ull;
+    if (tid < 7) s_stat[tid] = 0ull;
     if (tid == 0) s_nelig = 0;
     // base codes + per-sequence wildcard flag (warp per sequence)
     for (int q = warp; q < n_seqs; q += 32) {
@@ -209,6 +218,9 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
                 atomicAdd(&s_stat[2], (unsigned long long)n * m);
                 atomicAdd(&s_stat[3], (unsigned long long)((ns - 1) * SROWS + (elig ? rr * 32 : SROWS)) * m);
                 atomicMax(&s_stat[1], (unsigned long long)m);
+                atomicMax(&s_stat[4], (unsigned long long)n);
+                if (!(max(n, m) <= short_max && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len)) atomicAdd(&s_stat[5], 1ull);
+                if (wild) atomicOr(&s_stat[6], 1ull);
                 pw = (uint8_t)(wild | (elig << 1));
                 if (elig) atomicAdd(&s_nelig, 1);
                 key = (elig ? 0u : 0x80000000u) | ((uint32_t)b & 0x7fffffffu);
@@ -234,6 +246,7 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
     if (tid == 0) {
         misc[0] = s_stat[0]; misc[1] = s_stat[1]; misc[2] = s_stat[2]; misc[3] = s_stat[3];
         misc[4] = 0ull; misc[5] = 0ull; misc[6] = 0ull;
+        misc[8] = s_stat[4]; misc[9] = s_stat[5]; misc[10] = s_stat[6];
         *n_elig = (unsigned long long)s_nelig;
         *ticket = 0ull;
     }
@@ -269,7 +282,7 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const uint32_t *trace = P.trace + (P.ptrace[p] - P.chunk_base);
-    uint32_t *tail = P.trace + (P.ptrace[p + 1] - P.chunk_base);     // runs go to tail[-1], tail[-2], ...
+    uint32_t *tail = run_tail(P, p);                                  // runs go to tail[-1], tail[-2], ...
     const int lay = P.playout[p];
     const int pc = lay & 15;                          // columns per step of the writer
     const bool split = (lay & 16) != 0;               // packed path: [src x8 | fe x8] 2-bit fields; 32-bit path: nibbles
@@ -363,8 +376,8 @@ small_finish_kernel(const AlignParams P, const int n_pairs, long long *__restric
     for (int p = warp; p < n_pairs; p += 32) {
         const int n = P.nruns[p];
         const long long dst = s_off[p];
-        const uint32_t *src = P.trace + (P.ptrace[p + 1] - P.chunk_base) - n;
-        ISOF_ASSERT(src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
+        const uint32_t *src = run_tail(P, p) - n;
+        ISOF_ASSERT(P.ptail || src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
         for (int x = lane; x < n; x += 32)
             if (dst + x < cigar_cap) cigar[dst + x] = src[x];
     }
@@ -383,8 +396,8 @@ __global__ void cigar_copy_kernel(const AlignParams P, const int64_t start, cons
     const int nr = P.nruns[p];
     if (lane == 0 && cigar_off) cigar_off[p] = dst;
     if (!cigar) return;
-    const uint32_t *src = P.trace + (P.ptrace[p + 1] - P.chunk_base) - nr;
-    ISOF_ASSERT(src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
+    const uint32_t *src = run_tail(P, p) - nr;
+    ISOF_ASSERT(P.ptail || src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
     for (int x = lane; x < nr; x += 32)
         if (dst + x < cigar_cap) cigar[dst + x] = src[x];
 }
@@ -450,7 +463,7 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const int nr = P.nruns[p];
-    const uint32_t *runs = P.trace + (P.ptrace[p + 1] - P.chunk_base) - nr;
+    const uint32_t *runs = run_tail(P, p) - nr;
     int32_t *f = feat + p * ISOF_N_FEATURES;
     // pass 1: parse_cigar_diversity features (SimplifyGraph.py:175-196)
     int alen = 0, nonmatch = 0, maxrun = 0;
@@ -548,7 +561,10 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
 
 }  // namespace
 
-unsigned isof_viol_align() { return isof_read_violations_tu() | isof_viol_dp_tb1() | isof_viol_dp_tb2() | isof_viol_dp_tb3(); }
+unsigned isof_viol_align()
+{
+    return isof_read_violations_tu() | isof_viol_dp_tb1() | isof_viol_dp_tb2() | isof_viol_dp_tb3() | isof_viol_short();
+}
 
 void isof_launch_dp_tb0(int blocks, cudaStream_t st, const AlignParams &A, int64_t start, int64_t end, unsigned long long *counter)
 {
@@ -595,7 +611,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     TRY(dev_reserve(ctx, ctx->b_nruns, sizeof(int32_t) * (size_t)P));
     TRY(dev_reserve(ctx, ctx->b_runoff, sizeof(int64_t) * (size_t)(P + 1)));
     TRY(dev_reserve(ctx, ctx->b_nruns64, sizeof(int64_t) * (size_t)(P + 1)));      // nruns as int64
-    TRY(dev_reserve(ctx, ctx->b_misc, 64));
+    TRY(dev_reserve(ctx, ctx->b_misc, 128));
     uint8_t *codes = (uint8_t *)ctx->b_codes.p, *flags = (uint8_t *)ctx->b_seqflags.p;
     int32_t *pn = (int32_t *)ctx->b_pn.p, *pm = (int32_t *)ctx->b_pm.p, *nruns = (int32_t *)ctx->b_nruns.p;
     uint8_t *pwild = (uint8_t *)ctx->b_status.p;
@@ -611,9 +627,10 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         unsigned long long *cnt0 = (unsigned long long *)ctx->b_counters.p + 3;          // counters[0] of a 1-chunk layout
         LaunchTimer t(ctx, SLOT_OTHER);
         small_plan_kernel<<<1, 1024, 0, st>>>(d_cat, d_off, n_seqs, d_pa, d_pb, (int)P, codes, flags, pn, pm, pwild, ptrace,
-                                              misc, h_max_min_len, h_max_max_len, (int32_t *)ctx->b_order.p, cnt0 + 3, cnt0);
+                                              misc, h_max_min_len, h_max_max_len, (int32_t *)ctx->b_order.p, cnt0 + 3, cnt0,
+                                              SHORT_MAX);
     } else {
-        CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 64, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 128, st));
         CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
         {
             LaunchTimer t(ctx, SLOT_OTHER);
@@ -623,7 +640,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         {
             LaunchTimer t(ctx, SLOT_OTHER);
             plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
-                                                                          words, misc, h_max_min_len, h_max_max_len);
+                                                                          words, misc, h_max_min_len, h_max_max_len, SHORT_MAX);
         }
         CUDA_TRY(ctx, cudaGetLastError());
         size_t tmp_bytes = 0;
@@ -639,10 +656,18 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     unsigned long long *pin = (unsigned long long *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(pin, misc, 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(pin + 4, ptrace + P, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(pin + 8, misc + 8, 24, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (pin[0] & 1) return isof_fail(ctx, ISOF_ERR_ARG, "pair index outside the sequence pool");
     if (pin[0] & 2) return isof_fail(ctx, ISOF_ERR_ARG, "empty sequence in a pair (parasail rejects it too)");
-    const int max_m = (int)pin[1];
+    const int max_m = (int)pin[1], max_n = (int)pin[8];
+    // Short-pair regime: a thread per task has ~10x the per-task latency of the 32-lane wavefront (a 100 x 100 group takes
+    // 0.3 ms whatever the pair count), so it only pays once the call holds enough groups to fill the machine; measured
+    // crossover (profiles/r02_short_crossover.jsonl): P ~ 64 x SMs x (L / 60)^2.  short_mode 2 forces it (tests).
+    const double len_ratio = (double)std::max((int)pin[1], (int)pin[8]) / 60.0;
+    const bool enough = ctx->short_mode == 2 || (double)P >= 64.0 * ctx->sm_count * len_ratio * len_ratio;
+    const bool all_short = pin[9] == 0 && !ctx->disable_packed && ctx->short_mode != 0 && h_max_min_len > 0 && enough;
+    const bool any_wild = pin[10] != 0;
     const int64_t total_words = (int64_t)pin[4];
     ctx->prof.dp_cells += (int64_t)pin[2];
     ctx->prof.dp_cells_padded += (int64_t)pin[3];
@@ -657,6 +682,96 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         size_t fr = 0, tot = 0;
         CUDA_TRY(ctx, cudaMemGetInfo(&fr, &tot));
         ctx->trace_free_at_first_use = fr + ctx->b_trace.cap;
+    }
+    AlignParams A;
+    A.cat = d_cat; A.codes = codes; A.seq_off = d_off; A.pa = d_pa; A.pb = d_pb; A.pn = pn; A.pm = pm; A.pwild = pwild;
+    A.ptrace = ptrace; A.trace = nullptr; A.bnd = nullptr; A.bnd_stride = 0;
+    A.score = d_score; A.endq = d_endq; A.endr = d_endr; A.nruns = nruns;
+    // ---- tagged constants under the tie-break table (DESIGN.md "parasail tie-break table").  The class tag of a gap
+    // state orders the H tie (larger wins; the diagonal is the largest), the flag inside the class orders open vs
+    // extend: the candidate that must win a tie carries the larger tag.
+    const bool e_first = ctx->tb_h_e_before_f != 0, open_tie = ctx->tb_gap_open_on_tie != 0;
+    const int S = 1 << TAG_BITS;
+    {
+        const int class_e = e_first ? 8 : 4, class_f = e_first ? 4 : 8;       // 32-bit path: flag of E in bit 0, of F in bit 1
+        A.c_eo = -gap_open * S + class_e + (open_tie ? 1 : 0);
+        A.c_ee = -gap_ext * S + class_e + (open_tie ? 0 : 1);
+        A.c_fo = -gap_open * S + class_f + (open_tie ? 2 : 0);
+        A.c_fe = -gap_ext * S + class_f + (open_tie ? 0 : 2);
+    }
+    A.c_sm = match * S + 12 - (3 << CODE_SHIFT);
+    A.c_sx = mismatch * S + 12;
+    auto pk = [](int v) { return ((uint32_t)(v & 0xffff)) | ((uint32_t)(v & 0xffff) << 16); };
+    {
+        // packed path: the stored E / F carry their class tag (TieBreakK<TB>), which doubles as the flag bit.  Default:
+        // opening candidates have tag 00 and extension keeps the class tag.  gap_open_on_tie: the opening candidate
+        // gets the class tag and the extension addend removes it.
+        const int tag_e = e_first ? 2 : 1, tag_f = e_first ? 1 : 2;
+        A.h_eo = pk(-4 * gap_open + (open_tie ? tag_e : 0));
+        A.h_ee = pk(-4 * gap_ext - (open_tie ? tag_e : 0));
+        A.h_fo = pk(-4 * gap_open + (open_tie ? tag_f : 0));
+        A.h_fe = pk(-4 * gap_ext - (open_tie ? tag_f : 0));
+    }
+    A.h_sm = pk(4 * match + 3 - (3 << CS16));
+    A.h_sx = pk(4 * mismatch + 3);
+    A.tb_src_e = e_first ? 2 : 1;
+    A.tb_open_tie = open_tie ? 1 : 0;
+    A.tb_end_col_first = ctx->tb_end_col_first ? 1 : 0;
+    A.tb_swap_id = ctx->tb_swap_id ? 1 : 0;
+    const int tb_variant = (e_first ? 1 : 0) | (open_tie ? 2 : 0);
+    A.ptail = nullptr;
+    A.chunk_base = 0;
+    int64_t *run_base = (int64_t *)(misc + 4);
+    CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
+    // ---- short-pair regime: every pair of the call is short (bubble popping, SimplifyGraph.py:630-664) -> one thread
+    // per task, no wavefront (sg_short.cu); falls through to the long path when the trace would not fit one buffer
+    if (all_short) {
+        const size_t fr = ctx->trace_free_at_first_use;
+        const size_t cap_bytes = ctx->trace_budget ? ctx->trace_budget : (size_t)(0.40 * (double)fr);
+        const int rc = isof_sg_short_path(ctx, A, P, max_n, max_m, any_wild, tb_variant, (int64_t)(cap_bytes / 4));
+        if (rc == ISOF_OK) {
+            if (d_features) {
+                LaunchTimer t(ctx, SLOT_TB);
+                sg_features_kernel<<<(unsigned)((P + 63) / 64), 64, 0, st>>>(A, 0, P, delta_len, d_features);
+            }
+            if (small) {
+                LaunchTimer t(ctx, SLOT_TB);
+                small_finish_kernel<<<1, 1024, 0, st>>>(A, (int)P, (long long *)run_base, d_cigar, (long long)cigar_cap,
+                                                        (long long *)d_cigar_off);
+            } else {
+                {
+                    LaunchTimer t(ctx, SLOT_TB);
+                    nruns_to_i64_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(nruns, 0, P, nruns64);
+                }
+                size_t tb2 = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tb2, nruns64, runoff, P, st);
+                TRY(dev_reserve(ctx, ctx->b_scan_tmp, tb2));
+                {
+                    LaunchTimer t(ctx, SLOT_TB);
+                    CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tb2, nruns64, runoff, P, st));
+                }
+                {
+                    LaunchTimer t(ctx, SLOT_TB);
+                    cigar_copy_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, st>>>(A, 0, P, runoff, run_base, d_cigar, cigar_cap,
+                                                                                       d_cigar_off);
+                }
+                {
+                    LaunchTimer t(ctx, SLOT_TB);
+                    advance_base_kernel<<<1, 1, 0, st>>>(run_base, runoff, nruns, 0, P, d_cigar_off, P);
+                }
+            }
+            CUDA_TRY(ctx, cudaGetLastError());
+            int64_t *pin64s = (int64_t *)ctx->pinned;
+            CUDA_TRY(ctx, cudaMemcpyAsync(pin64s, run_base, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (h_total_runs) *h_total_runs = pin64s[0];
+            ctx->prof.dp_cells_packed += (int64_t)pin[2];
+            if (d_cigar && pin64s[0] > cigar_cap)
+                return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap,
+                                 (long long)pin64s[0]);
+            return ISOF_OK;
+        }
+        if (rc != ISOF_ERR_NOMEM) return rc;
     }
     size_t budget_bytes = ctx->trace_budget;
     if (budget_bytes == 0) {
@@ -721,50 +836,13 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         }
     }
 
-    AlignParams A;
-    A.cat = d_cat; A.codes = codes; A.seq_off = d_off; A.pa = d_pa; A.pb = d_pb; A.pn = pn; A.pm = pm; A.pwild = pwild;
-    A.ptrace = ptrace; A.trace = (uint32_t *)ctx->b_trace.p; A.bnd = (int2 *)ctx->b_bnd.p; A.bnd_stride = bnd_stride;
-    A.score = d_score; A.endq = d_endq; A.endr = d_endr; A.nruns = nruns;
-    // ---- tagged constants under the tie-break table (DESIGN.md "parasail tie-break table").  The class tag of a gap
-    // state orders the H tie (larger wins; the diagonal is the largest), the flag inside the class orders open vs
-    // extend: the candidate that must win a tie carries the larger tag.
-    const bool e_first = ctx->tb_h_e_before_f != 0, open_tie = ctx->tb_gap_open_on_tie != 0;
-    const int S = 1 << TAG_BITS;
-    {
-        const int class_e = e_first ? 8 : 4, class_f = e_first ? 4 : 8;       // 32-bit path: flag of E in bit 0, of F in bit 1
-        A.c_eo = -gap_open * S + class_e + (open_tie ? 1 : 0);
-        A.c_ee = -gap_ext * S + class_e + (open_tie ? 0 : 1);
-        A.c_fo = -gap_open * S + class_f + (open_tie ? 2 : 0);
-        A.c_fe = -gap_ext * S + class_f + (open_tie ? 0 : 2);
-    }
-    A.c_sm = match * S + 12 - (3 << CODE_SHIFT);
-    A.c_sx = mismatch * S + 12;
-    auto pk = [](int v) { return ((uint32_t)(v & 0xffff)) | ((uint32_t)(v & 0xffff) << 16); };
-    {
-        // packed path: the stored E / F carry their class tag (TieBreakK<TB>), which doubles as the flag bit.  Default:
-        // opening candidates have tag 00 and extension keeps the class tag.  gap_open_on_tie: the opening candidate
-        // gets the class tag and the extension addend removes it.
-        const int tag_e = e_first ? 2 : 1, tag_f = e_first ? 1 : 2;
-        A.h_eo = pk(-4 * gap_open + (open_tie ? tag_e : 0));
-        A.h_ee = pk(-4 * gap_ext - (open_tie ? tag_e : 0));
-        A.h_fo = pk(-4 * gap_open + (open_tie ? tag_f : 0));
-        A.h_fe = pk(-4 * gap_ext - (open_tie ? tag_f : 0));
-    }
-    A.h_sm = pk(4 * match + 3 - (3 << CS16));
-    A.h_sx = pk(4 * mismatch + 3);
-    A.tb_src_e = e_first ? 2 : 1;
-    A.tb_open_tie = open_tie ? 1 : 0;
-    A.tb_end_col_first = ctx->tb_end_col_first ? 1 : 0;
-    A.tb_swap_id = ctx->tb_swap_id ? 1 : 0;
-    const int tb_variant = (e_first ? 1 : 0) | (open_tie ? 2 : 0);
+    A.trace = (uint32_t *)ctx->b_trace.p; A.bnd = (int2 *)ctx->b_bnd.p; A.bnd_stride = bnd_stride;
     TRY(dev_reserve(ctx, ctx->b_layout, (size_t)P * 2));
     A.playout = (uint8_t *)ctx->b_layout.p;
     A.plastrr = A.playout + P;
     A.h_max_min_len = h_max_min_len;
     A.h_max_max_len = h_max_max_len;
     A.chunk_words = 0;
-    int64_t *run_base = (int64_t *)(misc + 4);
-    CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
 
     // ---- reserve every per-lane scratch for the largest chunk up front: a reallocation inside the loop would
     // free memory that an earlier chunk of the same lane may still be using and stall the pipeline
@@ -789,6 +867,18 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     for (int w = 1; w < NL; ++w) lanes[w] = pipelined ? ctx->aux_stream[w - 1] : st;
     std::vector<cudaEvent_t> done((size_t)n_chunks, nullptr);
     cudaEvent_t fork = nullptr;
+    // Every exit from here on -- the CUDA_TRY / TRY early returns included -- goes through this guard: an error return
+    // first waits for all lanes, so that no kernel of the failed call still runs on an auxiliary stream when the next
+    // call reuses the per-lane scratch, and the events are destroyed on every path.
+    struct PipelineGuard {
+        cudaStream_t *lanes; int n_lanes; std::vector<cudaEvent_t> &done; cudaEvent_t &fork; bool joined = false;
+        ~PipelineGuard()
+        {
+            if (!joined) for (int w = 0; w < n_lanes; ++w) cudaStreamSynchronize(lanes[w]);
+            if (fork) cudaEventDestroy(fork);
+            for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
+        }
+    } guard{lanes, pipelined ? NL : 1, done, fork};
     if (pipelined) {
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventRecord(fork, st));
@@ -892,9 +982,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             CUDA_TRY(ctx, cudaStreamWaitEvent(st, tail, 0));
             cudaEventDestroy(tail);
         }
-        cudaEventDestroy(fork);
-        for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
     }
+    guard.joined = true;
     int64_t *pin64 = (int64_t *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(pin64, run_base, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));

@@ -54,7 +54,16 @@ struct AlignParams {
     int tb_open_tie;                       // 1: the gap flags of the trace mean "opened" (gap_open_on_tie), 0: "extended"
     int tb_end_col_first;                  // end cell: last column first
     int tb_swap_id;                        // CIGAR letters of the gap states swapped
+    const int64_t *ptail;                  // short-pair path: per pair, word offset one past its run slot (else nullptr)
 };
+
+constexpr int SHORT_MAX = 384;             // both lengths <= SHORT_MAX: candidate for the short-pair regime (sg_short.cu)
+
+// where the traceback leaves a pair's CIGAR runs (written backwards from this address)
+__device__ __forceinline__ uint32_t *run_tail(const AlignParams &P, const int64_t p)
+{
+    return P.ptail ? P.trace + P.ptail[p] : P.trace + (P.ptrace[p + 1] - P.chunk_base);
+}
 
 namespace {
 
@@ -769,3 +778,6 @@ void isof_launch_dp_tb3(int blocks, cudaStream_t st, const AlignParams &A, int64
 unsigned isof_viol_dp_tb1();
 unsigned isof_viol_dp_tb2();
 unsigned isof_viol_dp_tb3();
+unsigned isof_viol_short();
+int isof_sg_short_path(isof_ctx *ctx, AlignParams &A, int64_t P, int max_n, int max_m, bool any_wild, int tb_variant,
+                       int64_t budget_words);

@@ -636,6 +636,16 @@ def test_debug_build_bounds_assertions_stay_silent():
         b = hotpath.align_pairs(pool, ia, ib, 2, -2, 12, 1, ctx=dctx, features_delta_len=5)
         assert np.array_equal(a["cigar"], b["cigar"]) and np.array_equal(a["features"], b["features"])
         assert dctx.debug_violations()[0] == 0
+        # short-pair regime (thread-per-task kernel): ragged groups, wildcards, a partial last group
+        dctx.set_short(2)
+        for n_pairs, wild in ((130, False), (77, True)):
+            sseqs, spa, spb = _short_cases(np.random.default_rng(5 + n_pairs), n_pairs, wild)
+            res = hotpath.align_pairs(sseqs, spa, spb, 2, -8, 12, 1, ctx=dctx, features_delta_len=5)
+            for p in range(0, n_pairs, 9):
+                sc, _q, _r, runs = oracle.sg_align(sseqs[spa[p]], sseqs[spb[p]], 2, -8, 12, 1)
+                assert int(res["score"][p]) == sc
+                assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
+        assert dctx.debug_violations()[0] == 0
         # minimizers + spans
         reads = {i + 1: ("r", _rand_dna(rng, int(rng.integers(0, 900)), "ACGT" if i % 4 else "AC"), "") for i in range(80)}
         M = hotpath.get_minimizers_and_positions(reads, 31, 20, "lex", dctx)
@@ -859,3 +869,73 @@ def test_reference_seams_replayed_on_gpu(ctx, cap_index):
                                   generate_new_full_consensus=lambda i1, i2, rd, cur, wd, ms: regen[(i1, i2)], ctx=ctx)
     assert {str(i): v for i, v in cbs.items()} == mc["curr_best_seqs_out"]
     assert {str(i): s for i, s in out.items()} == {i: pool[s] for i, s in mc["new_consensuses"].items()}
+
+
+# ------------------------------------------------------------------------------- short-pair regime (sg_short.cu)
+def _short_cases(rng, n_pairs, wild):
+    from isonform_b200 import synth
+    seqs, pa, pb = [], [], []
+    alpha = "ACGTN" if wild else "ACGT"
+    for i in range(n_pairs):
+        n = int(rng.integers(1, 385)) if i % 7 else int(rng.integers(1, 20))
+        x = _rand_dna(rng, n, alpha if i % 5 == 0 else "ACGT")
+        kind = i % 4
+        if kind == 0:
+            y = _rand_dna(rng, int(rng.integers(1, 385)), "ACGT")
+        elif kind == 1:
+            y = (synth.mutate(rng, x, 0.08) or "A")[:384]
+        elif kind == 2:
+            y = _rand_dna(rng, int(rng.integers(1, 40)), "AC") + x[:200]
+        else:
+            y = x
+        if wild and i % 11 == 3:
+            y = y[:len(y) // 2] + "x" + y[len(y) // 2 + 1:]
+        seqs += [x, y[:384] or "C"]
+        pa.append(2 * i); pb.append(2 * i + 1)
+    return seqs, pa, pb
+
+
+@pytest.mark.parametrize("n_pairs,wild", [(1, False), (65, False), (700, True), (3001, False), (1500, True)])
+def test_short_pair_regime_matches_long_path_and_oracle(ctx, n_pairs, wild):
+    """All-short calls take the thread-per-task kernel; the same call forced onto the wavefront kernel and the oracle
+    must agree bit for bit (scores, end cells, CIGAR runs, decision features), for the fused (P <= 1024) and the regular
+    set-up, odd pair counts, wildcards, both bubble and isoform scores."""
+    from isonform_b200 import hotpath
+    rng = np.random.default_rng(1000 + n_pairs)
+    seqs, pa, pb = _short_cases(rng, n_pairs, wild)
+    for params in [(2, -8, 12, 1), (2, -2, 12, 1), (1, -1, 1, 1)]:
+        ctx.set_short(2)                                   # force the short kernel whatever the pair count
+        try:
+            a = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, features_delta_len=5)
+            plain = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
+            ctx.set_short(0)
+            b = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, features_delta_len=5)
+        finally:
+            ctx.set_short(1)
+        for key in ("score", "cigar_off", "cigar", "features"):
+            assert np.array_equal(a[key], b[key]), (params, key)
+        assert np.array_equal(plain["cigar"], a["cigar"]) and np.array_equal(plain["score"], a["score"])
+        step = max(1, n_pairs // 60)
+        for p in range(0, n_pairs, step):
+            sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params)
+            assert (int(plain["score"][p]), int(plain["end_q"][p]), int(plain["end_r"][p])) == (sc, eq, er), (params, p)
+            assert plain["cigar"][plain["cigar_off"][p]:plain["cigar_off"][p + 1]].tolist() == runs.tolist(), (params, p)
+
+
+@pytest.mark.parametrize("tb_index", [1, 2, 3, 4, 9, 15])
+def test_short_pair_regime_under_tiebreak_tables(ctx, tb_index):
+    tb = oracle.all_tiebreaks()[tb_index]
+    rng = np.random.default_rng(77)
+    seqs, pa, pb = [], [], []
+    for i in range(90):
+        alpha = ["AC", "A", "ACG", "AAC", "ACGT"][i % 5]
+        seqs += [_rand_dna(rng, int(rng.integers(1, 90)), alpha), _rand_dna(rng, int(rng.integers(1, 90)), alpha)]
+        pa.append(2 * i); pb.append(2 * i + 1)
+    ctx.set_tiebreak(tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id)
+    ctx.set_short(2)
+    try:
+        for params in [(2, -8, 12, 1), (1, -1, 1, 1), (2, -2, 2, 1), (2, -2, 0, 0)]:
+            _check_pairs(ctx, seqs, pa, pb, params, tiebreak=tb)
+    finally:
+        ctx.set_short(1)
+        ctx.set_tiebreak(0, 0, 0, 0)
