@@ -88,6 +88,10 @@ ISOF_API int isof_set_overlap(isof_ctx *ctx, int on);
  * bit per violated class instead of trapping.  Returns and clears the mask; bit 31 is set iff the assertions
  * are compiled in (the release library always reports 0). */
 ISOF_API int isof_debug_violations(isof_ctx *ctx, unsigned int *mask);
+/* Test knob of kernel (c): k-mers that do not pack into 2 bits per base (non-ACGT, lower case, k >= 32) are brought
+ * together by a 63-bit hash and then told apart by comparing bytes.  A small mask (e.g. 0xF) makes nearly all of them
+ * collide, so a test can prove that identity never depends on the hash.  Default: all 63 bits. */
+ISOF_API int isof_debug_set_span_hash_mask(isof_ctx *ctx, uint64_t mask);
 /* Launches a kernel whose only assertion is false (class 30): proves the reporting path end to end. */
 ISOF_API int isof_debug_selftest(isof_ctx *ctx);
 

@@ -35,7 +35,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_debug_violations", "isof_debug_selftest",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances"]
@@ -71,6 +71,7 @@ def load(debug=False):
     L.isof_set_short.argtypes = [vp, C.c_int]
     L.isof_debug_violations.argtypes = [vp, C.POINTER(C.c_uint)]
     L.isof_debug_selftest.argtypes = [vp]
+    L.isof_debug_set_span_hash_mask.argtypes = [vp, C.c_uint64]
     L.isof_profile_enable.argtypes = [vp, C.c_int]
     L.isof_profile_reset.argtypes = [vp]
     L.isof_profile_get.argtypes = [vp, C.POINTER(Profile)]
@@ -173,6 +174,10 @@ class Context:
         m = C.c_uint(0)
         self._check(self._L.isof_debug_violations(self._h, C.byref(m)))
         return int(m.value) & 0x7fffffff, bool(m.value & 0x80000000)
+
+    def debug_set_span_hash_mask(self, mask=0x7fffffffffffffff):
+        """Test knob: hash bits kernel (c) keeps for k-mers that do not 2-bit pack (forces collisions)."""
+        self._check(self._L.isof_debug_set_span_hash_mask(self._h, int(mask)))
 
     def debug_selftest(self):
         self._check(self._L.isof_debug_selftest(self._h))

@@ -154,6 +154,13 @@ int isof_set_packed(isof_ctx *ctx, int on)
     return ISOF_OK;
 }
 
+int isof_debug_set_span_hash_mask(isof_ctx *ctx, uint64_t mask)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->span_hash_mask = mask & 0x7fffffffffffffffULL;
+    return ISOF_OK;
+}
+
 int isof_set_short(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;
@@ -203,7 +210,8 @@ int isof_set_overlap(isof_ctx *ctx, int on)
         // share each): drop the buffers so that the next call re-reserves them and the total stays within the budget
         CUDA_TRY(ctx, cudaSetDevice(ctx->device));
         CUDA_TRY(ctx, cudaDeviceSynchronize());
-        DevBuf *bufs[] = {&ctx->b_trace, &ctx->b_trace_x[0], &ctx->b_trace_x[1]};
+        std::vector<DevBuf *> bufs = {&ctx->b_trace};
+        for (DevBuf &b : ctx->b_trace_x) bufs.push_back(&b);
         for (DevBuf *b : bufs)
             if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     }

@@ -28,12 +28,14 @@ struct isof_ctx {
     size_t trace_free_at_first_use = 0;
     bool profiling = false;           // bracket every launch with CUDA events (isof_profile_*)
     bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
+    uint64_t span_hash_mask = 0x7fffffffffffffffULL;      // test knob: fewer hash bits force collisions in kernel (c)
     int short_mode = 1;               // short-pair regime: 0 never, 1 when the call is large enough to pay (default), 2 always
     // tie-break table of the restated aligner (isof_set_tiebreak); all zero = the library as restated
     int tb_h_e_before_f = 0, tb_gap_open_on_tie = 0, tb_end_col_first = 0, tb_swap_id = 0;
     bool overlap = true;              // pipeline trace chunks over NLANES streams, each with its own scratch
     static constexpr int NLANES = 3;  // pipeline depth: chunk c runs on stream c % NLANES
-    cudaStream_t aux_stream[NLANES - 1] = {nullptr, nullptr};
+    static constexpr int MAX_LANES = 6;   // depth for batches whose occupancy is bound by trace memory (10 kb reads)
+    cudaStream_t aux_stream[MAX_LANES - 1] = {};
     isof_profile prof;
     // pending (start, stop, slot) event pairs when profiling
     struct Timed { cudaEvent_t a, b; int slot; };
@@ -41,8 +43,9 @@ struct isof_ctx {
     // scratch
     DevBuf b_codes, b_seqflags, b_pn, b_pm, b_words, b_nruns64, b_ptrace, b_scan_tmp, b_bnd, b_trace, b_nruns,
         b_counters, b_misc, b_runoff, b_status, b_layout, b_order, b_taskkey, b_short_g, b_short_p;
-    DevBuf b_taskkey_x[NLANES - 1];
-    DevBuf b_trace_x[NLANES - 1], b_bnd_x[NLANES - 1], b_runoff_x[NLANES - 1], b_nruns64_x[NLANES - 1], b_scan_tmp_x[NLANES - 1];
+    DevBuf b_taskkey_x[MAX_LANES - 1];
+    DevBuf b_trace_x[MAX_LANES - 1], b_bnd_x[MAX_LANES - 1], b_runoff_x[MAX_LANES - 1], b_nruns64_x[MAX_LANES - 1],
+        b_scan_tmp_x[MAX_LANES - 1];
     DevBuf b_h_bases, b_h_off, b_h_pa, b_h_pb, b_h_score, b_h_endq, b_h_endr, b_h_cig, b_h_cigoff, b_h_feat;
     DevBuf b_m_tmp, b_m_cnt, b_m_off;
     DevBuf b_s_mread, b_s_mkey, b_s_mpolya, b_s_mcnt, b_s_moff, b_s_key1, b_s_key2, b_s_keyt, b_s_keyo, b_s_idx0, b_s_idx1,
@@ -50,12 +53,16 @@ struct isof_ctx {
     DevBuf b_sh_minpos, b_sh_minoff, b_sh_rread, b_sh_rp1, b_sh_rp2, b_sh_rcount, b_sh_rbucket, b_sh_sorted, b_sh_boff, b_sh_bdrop;
     std::vector<DevBuf *> all_bufs()
     {
-        return {&b_codes, &b_seqflags, &b_pn, &b_pm, &b_words, &b_nruns64, &b_ptrace, &b_scan_tmp, &b_bnd, &b_trace, &b_nruns,
-                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_order, &b_taskkey, &b_short_g, &b_short_p, &b_taskkey_x[0], &b_taskkey_x[1], &b_trace_x[0], &b_trace_x[1], &b_bnd_x[0], &b_bnd_x[1], &b_runoff_x[0], &b_runoff_x[1], &b_nruns64_x[0], &b_nruns64_x[1], &b_scan_tmp_x[0], &b_scan_tmp_x[1], &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
+        std::vector<DevBuf *> v = {&b_codes, &b_seqflags, &b_pn, &b_pm, &b_words, &b_nruns64, &b_ptrace, &b_scan_tmp, &b_bnd, &b_trace, &b_nruns,
+                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_order, &b_taskkey, &b_short_g, &b_short_p, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
                 &b_h_endr, &b_h_cig, &b_h_cigoff, &b_h_feat, &b_m_tmp, &b_m_cnt, &b_m_off, &b_s_mread, &b_s_mkey,
                 &b_s_mpolya, &b_s_mcnt, &b_s_moff, &b_s_key1, &b_s_key2, &b_s_keyt, &b_s_keyo, &b_s_idx0, &b_s_idx1, &b_s_idx2,
                 &b_s_forb, &b_s_head, &b_s_bid, &b_s_sorttmp, &b_s_rbatch, &b_sh_batchoff, &b_sh_minpos, &b_sh_minoff, &b_sh_rread, &b_sh_rp1, &b_sh_rp2,
                 &b_sh_rcount, &b_sh_rbucket, &b_sh_sorted, &b_sh_boff, &b_sh_bdrop};
+        for (int w = 0; w < MAX_LANES - 1; ++w)
+            for (DevBuf *b : {&b_taskkey_x[w], &b_trace_x[w], &b_bnd_x[w], &b_runoff_x[w], &b_nruns64_x[w], &b_scan_tmp_x[w]})
+                v.push_back(b);
+        return v;
     }
     void *pinned = nullptr;           // small pinned staging for scalar read-backs
     size_t pinned_cap = 0;

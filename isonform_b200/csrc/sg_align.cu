@@ -68,7 +68,7 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                             const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, int64_t P,
                             int32_t *__restrict__ pn, int32_t *__restrict__ pm, uint8_t *__restrict__ pwild,
                             int64_t *__restrict__ words, unsigned long long *__restrict__ misc, int h_max_min_len,
-                            int h_max_max_len, int short_max)
+                            int h_max_max_len, int short_max, int rb_ok)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0, padded = 0;
@@ -86,14 +86,16 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                 int ns = (n + SROWS - 1) / SROWS;
                 w = (int64_t)ns * (m + 64) * 32 + TRACE_SLACK;        // covers the 1- and 2-column layouts
                 cells = (unsigned long long)n * m;
-                // bit0: a wildcard is present (32-bit WILD path); bit1: eligible for the packed 16-bit path
+                // bit0: a wildcard is present (32-bit WILD path); bit1: eligible for the packed 16-bit path; bit2: beyond
+                // the plain 16-bit range but fine for the re-based 16-bit lanes (long reads)
                 const int wild = flags[a] | flags[b];
                 const int elig = !wild && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len;
+                const int elig_rb = !wild && !elig && rb_ok;
                 // rows actually updated: full stripes + the compacted last stripe (2/4/6/8 rows per lane)
                 const int need = n - (ns - 1) * SROWS;
                 const int rr = need > 192 ? 8 : need > 128 ? 6 : need > 64 ? 4 : 2;
-                padded = (unsigned long long)((ns - 1) * SROWS + (elig ? rr * 32 : SROWS)) * m;
-                pwild[p] = (uint8_t)(wild | (elig << 1));
+                padded = (unsigned long long)((ns - 1) * SROWS + ((elig | elig_rb) ? rr * 32 : SROWS)) * m;
+                pwild[p] = (uint8_t)(wild | (elig << 1) | (elig_rb << 2));
                 mm = m; mn = n;
                 // short-pair regime (sg_short.cu): both lengths small and inside the 16-bit range (wildcards allowed)
                 not_short = !(max(n, m) <= short_max && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len);
@@ -126,31 +128,37 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
 // alignments of a task share their reference whenever the batch allows it (query-profile path)
 __global__ void task_key_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pb, int64_t start,
                                 int64_t cnt, uint32_t *__restrict__ key, int32_t *__restrict__ val,
-                                unsigned long long *__restrict__ n_elig)
+                                unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ n_rb)
 {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int el = 0;
+    int el = 0, rb = 0;
     if (x < cnt) {
         const int64_t p = start + x;
         el = (pwild[p] & 2) ? 1 : 0;
-        key[x] = (el ? 0u : 0x80000000u) | ((uint32_t)pb[p] & 0x7fffffffu);
+        rb = (pwild[p] & 4) ? 1 : 0;
+        // class 0: plain 16-bit, class 1: re-based 16-bit, class 2: 32-bit; inside a class by reference index
+        key[x] = (el ? 0u : rb ? 0x40000000u : 0x80000000u) | ((uint32_t)pb[p] & 0x3fffffffu);
         val[x] = (int32_t)p;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, el);
+    const unsigned m = __ballot_sync(0xffffffffu, el), m1 = __ballot_sync(0xffffffffu, rb);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_elig, (unsigned long long)__popc(m));
+    if ((threadIdx.x & 31) == 0 && m1) atomicAdd(n_rb, (unsigned long long)__popc(m1));
 }
 
 // statistics only: cells of the pairs that take the packed path in chunk [start,end)
 __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pn,
                                     const int32_t *__restrict__ pm, const int32_t *__restrict__ pb,
                                     const int32_t *__restrict__ order, const unsigned long long *__restrict__ n_elig,
-                                    int64_t start, int64_t end, unsigned long long *__restrict__ out)
+                                    const unsigned long long *__restrict__ n_rb, int64_t start, int64_t end,
+                                    unsigned long long *__restrict__ out)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t xA = start + 2 * t, xB = xA + 1;
+    const int64_t n0 = (int64_t)(*n_elig), n1 = (int64_t)(*n_rb);
+    // packed tasks of the plain class, then of the re-based class (which starts at n0 in the sorted order)
+    const int64_t xA = t < n0 / 2 ? start + 2 * t : start + n0 + 2 * (t - n0 / 2), xB = xA + 1;
     unsigned long long c = 0, cp = 0;               // packed path / of those, the query-profile variant
     const int64_t pA = xA < end ? order[xA] : 0, pB = xB < end ? order[xB] : 0;
-    if (xB < end && t < (int64_t)(*n_elig) / 2) {
+    if (xB < end && t < n0 / 2 + n1 / 2) {
         c = (unsigned long long)pn[pA] * pm[pA] + (unsigned long long)pn[pB] * pm[pB];
         if (pb[pA] == pb[pB]) cp = c;
     }
@@ -172,16 +180,17 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
                   uint8_t *__restrict__ flags, int32_t *__restrict__ pn, int32_t *__restrict__ pm,
                   uint8_t *__restrict__ pwild, int64_t *__restrict__ ptrace, unsigned long long *__restrict__ misc,
                   int h_max_min_len, int h_max_max_len, int32_t *__restrict__ order,
-                  unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ ticket, int short_max)
+                  unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ ticket, int short_max, int rb_ok,
+                  unsigned long long *__restrict__ n_rb, unsigned long long *__restrict__ rb_ticket)
 {
     typedef cub::BlockScan<long long, 1024> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ uint32_t s_key[SMALL_P];
     __shared__ unsigned long long s_stat[7];             // err, max m, cells, padded, max n, not short, any wildcard
-    __shared__ int s_nelig;
+    __shared__ int s_nelig, s_nrb;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 7) s_stat[tid] = 0ull;
-    if (tid == 0) s_nelig = 0;
+    if (tid == 0) { s_nelig = 0; s_nrb = 0; }
     // base codes + per-sequence wildcard flag (warp per sequence)
     for (int q = warp; q < n_seqs; q += 32) {
         const int64_t b = off[q], e = off[q + 1];
@@ -213,17 +222,19 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
                 w = (long long)ns * (m + 64) * 32 + TRACE_SLACK;
                 const int wild = flags[a] | flags[b];
                 const int elig = !wild && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len;
+                const int elig_rb = !wild && !elig && rb_ok;
                 const int need = n - (ns - 1) * SROWS;
                 const int rr = need > 192 ? 8 : need > 128 ? 6 : need > 64 ? 4 : 2;
                 atomicAdd(&s_stat[2], (unsigned long long)n * m);
-                atomicAdd(&s_stat[3], (unsigned long long)((ns - 1) * SROWS + (elig ? rr * 32 : SROWS)) * m);
+                atomicAdd(&s_stat[3], (unsigned long long)((ns - 1) * SROWS + ((elig | elig_rb) ? rr * 32 : SROWS)) * m);
                 atomicMax(&s_stat[1], (unsigned long long)m);
                 atomicMax(&s_stat[4], (unsigned long long)n);
                 if (!(max(n, m) <= short_max && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len)) atomicAdd(&s_stat[5], 1ull);
                 if (wild) atomicOr(&s_stat[6], 1ull);
-                pw = (uint8_t)(wild | (elig << 1));
+                pw = (uint8_t)(wild | (elig << 1) | (elig_rb << 2));
                 if (elig) atomicAdd(&s_nelig, 1);
-                key = (elig ? 0u : 0x80000000u) | ((uint32_t)b & 0x7fffffffu);
+                if (elig_rb) atomicAdd(&s_nrb, 1);
+                key = (elig ? 0u : elig_rb ? 0x40000000u : 0x80000000u) | ((uint32_t)b & 0x3fffffffu);
             }
         }
         pn[tid] = n; pm[tid] = m; pwild[tid] = pw;
@@ -249,6 +260,8 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
         misc[8] = s_stat[4]; misc[9] = s_stat[5]; misc[10] = s_stat[6];
         *n_elig = (unsigned long long)s_nelig;
         *ticket = 0ull;
+        *n_rb = (unsigned long long)s_nrb;
+        *rb_ticket = 0ull;
     }
 }
 
@@ -563,7 +576,8 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
 
 unsigned isof_viol_align()
 {
-    return isof_read_violations_tu() | isof_viol_dp_tb1() | isof_viol_dp_tb2() | isof_viol_dp_tb3() | isof_viol_short();
+    return isof_read_violations_tu() | isof_viol_dp_tb1() | isof_viol_dp_tb2() | isof_viol_dp_tb3() | isof_viol_short() |
+           isof_viol_dp_rb();
 }
 
 void isof_launch_dp_tb0(int blocks, cudaStream_t st, const AlignParams &A, int64_t start, int64_t end, unsigned long long *counter)
@@ -592,6 +606,12 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         const int room = 31000 / 4 - 2 * gap_open - std::abs(mismatch) - std::abs(match);
         h_max_max_len = room <= 0 ? 0 : (gap_ext > 0 ? room / gap_ext : INT_MAX);
     }
+    // ---- re-based 16-bit lanes for pairs beyond that range (dp_pair16<., RB>): the packed values follow a running base, so
+    // only the SPREAD of the scores inside the wavefront must fit: neighbouring cells differ by at most match + open (or
+    // open + ext), the wavefront spans 128 rows either side of the reference lane, 62 columns of lane skew and 64 columns
+    // of drift between two re-centrings (+32 slack)
+    int rb_ok = 0;
+    if (h_max_min_len > 0 && 4 * std::max(gap_open + gap_ext, match + gap_open) * (128 + 62 + 64 + 32) <= 24000) rb_ok = 1;
     if (P < 0 || n_seqs < 0) return isof_fail(ctx, ISOF_ERR_ARG, "negative count");
     if (match - mismatch > 256 || match - mismatch < 0 || gap_open < 0 || gap_ext < 0 ||
         std::abs(match) > 1024 || std::abs(mismatch) > 1024 || gap_open > 4096 || gap_ext > 4096)
@@ -623,12 +643,12 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     const bool small = P <= SMALL_P && n_bases <= SMALL_BASES;
     TRY(dev_reserve(ctx, ctx->b_order, sizeof(int32_t) * (size_t)P));
     if (small) {
-        TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * 3 * 3));
+        TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * 3 * 5));
         unsigned long long *cnt0 = (unsigned long long *)ctx->b_counters.p + 3;          // counters[0] of a 1-chunk layout
         LaunchTimer t(ctx, SLOT_OTHER);
         small_plan_kernel<<<1, 1024, 0, st>>>(d_cat, d_off, n_seqs, d_pa, d_pb, (int)P, codes, flags, pn, pm, pwild, ptrace,
                                               misc, h_max_min_len, h_max_max_len, (int32_t *)ctx->b_order.p, cnt0 + 3, cnt0,
-                                              SHORT_MAX);
+                                              SHORT_MAX, rb_ok, cnt0 + 6, cnt0 + 9);
     } else {
         CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 128, st));
         CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
@@ -640,7 +660,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         {
             LaunchTimer t(ctx, SLOT_OTHER);
             plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
-                                                                          words, misc, h_max_min_len, h_max_max_len, SHORT_MAX);
+                                                                          words, misc, h_max_min_len, h_max_max_len, SHORT_MAX, rb_ok);
         }
         CUDA_TRY(ctx, cudaGetLastError());
         size_t tmp_bytes = 0;
@@ -774,28 +794,38 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         if (rc != ISOF_ERR_NOMEM) return rc;
     }
     size_t budget_bytes = ctx->trace_budget;
+    bool memory_bound = false;            // the trace of the pairs that fill the machine does not fit: deeper pipeline
     if (budget_bytes == 0) {
         const double fr = (double)ctx->trace_free_at_first_use;
         const double want = 4.0 * (double)total_words / (double)P * (double)(ctx->sm_count * DP_CTAS_PER_SM * DP_WARPS) * 1.25 *
                             (double)isof_ctx::NLANES;
-        budget_bytes = (size_t)std::min(0.55 * fr, std::max(0.40 * fr, want));
+        // long pairs (10 kb reads: 36 MB of trace each) are occupancy-bound by trace memory: 2368 resident warps x 2
+        // alignments of the 16-bit lanes would need 175 GB; let such batches take up to 80 % of the free memory
+        budget_bytes = (size_t)std::min(0.80 * fr, std::max(0.40 * fr, want));
+        memory_bound = want > 0.80 * fr;
         if (budget_bytes < (64u << 20)) budget_bytes = 64u << 20;
     }
     int64_t budget_words = (int64_t)(budget_bytes / 4);
-    // pipelined mode: NLANES smaller buffers, chunk c runs on stream c % NLANES
-    constexpr int NL = isof_ctx::NLANES;
+    // pipelined mode: NL smaller buffers, chunk c runs on stream c % NL.  Memory-bound batches use twice as many, half as
+    // large: chunks then finish at staggered times, so buffers turn over continuously instead of three at once, and the
+    // latency-bound traceback of one chunk (few, very long walks) overlaps the DP of five others
+    const int NL = memory_bound ? isof_ctx::MAX_LANES : isof_ctx::NLANES;
     const bool want_overlap = ctx->overlap && total_words > budget_words / NL;
     if (want_overlap) budget_words /= NL;
     if (budget_words > total_words) budget_words = total_words;
     if (budget_words < 1) budget_words = 1;
     const bool single = total_words <= budget_words;          // everything fits one chunk: no device round trips
     const int n_chunks = single ? 1 : (int)(total_words / budget_words) + 1;
-    TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 3));
+    TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 5));
     int64_t *chunk_start_d = (int64_t *)ctx->b_counters.p;
     unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);      // task tickets per chunk
     unsigned long long *elig_counts = counters + n_chunks + 2;                                  // eligible pairs per chunk
-    const bool fused_small = small && single;          // tickets, eligible count and task order came from small_plan_kernel
-    if (!fused_small) CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 2, st));
+    unsigned long long *rb_counts = elig_counts + n_chunks + 2;                                 // re-based class per chunk
+    unsigned long long *rb_tickets = rb_counts + n_chunks + 2;                                  // its task tickets
+    const bool fused_small = small && single;          // tickets, class counts and task order came from small_plan_kernel
+    if (!fused_small) CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 4, st));
+    // a pair of the re-based class exists only if some pair exceeds the plain 16-bit range
+    const bool may_rb = rb_ok && (std::max(max_n, max_m) > h_max_max_len || std::min(max_n, max_m) > h_max_min_len);
     std::vector<int64_t> chunk_start((size_t)n_chunks + 1), start_off((size_t)n_chunks + 1);
     if (single) {
         chunk_start[0] = 0; chunk_start[1] = P;
@@ -862,7 +892,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     // ---- chunk pipeline.  Serial mode: everything on `st`.  Pipelined mode: chunk c runs on stream c % NLANES with
     // its own trace / boundary / scan scratch; the only cross-chunk dependency is the running CIGAR offset
     // (cigar_copy of chunk c needs advance_base of chunk c-1), carried by one event per chunk.
-    cudaStream_t lanes[NL];
+    cudaStream_t lanes[isof_ctx::MAX_LANES];
     lanes[0] = st;
     for (int w = 1; w < NL; ++w) lanes[w] = pipelined ? ctx->aux_stream[w - 1] : st;
     std::vector<cudaEvent_t> done((size_t)n_chunks, nullptr);
@@ -901,6 +931,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         if (fused_small) {
             A.order = (int32_t *)ctx->b_order.p;
             A.n_elig = elig_counts + c;
+            A.n_rb = rb_counts + c;
         } else {   // task order of the chunk: stable radix sort of the pair ids by (eligibility, reference)
             DevBuf &kb = w ? ctx->b_taskkey_x[w - 1] : ctx->b_taskkey;
             TRY(dev_reserve(ctx, kb, (sizeof(uint32_t) * 2 + sizeof(int32_t)) * (size_t)cnt + 64));
@@ -908,19 +939,20 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             int32_t *val_in = (int32_t *)(key_out + cnt);
             int32_t *order = (int32_t *)ctx->b_order.p;
             LaunchTimer t(ctx, SLOT_OTHER, cs);
-            task_key_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(pwild, d_pb, ps, cnt, key_in, val_in, elig_counts + c);
+            task_key_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(pwild, d_pb, ps, cnt, key_in, val_in, elig_counts + c, rb_counts + c);
             size_t tso = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tso, key_in, key_out, val_in, order + ps, (int)cnt, 0, 32, cs);
             TRY(dev_reserve(ctx, c_scan, tso));
             CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(c_scan.p, tso, key_in, key_out, val_in, order + ps, (int)cnt, 0, 32, cs));
             A.order = order;
             A.n_elig = elig_counts + c;
+            A.n_rb = rb_counts + c;
         }
         {
             LaunchTimer t(ctx, SLOT_DP, cs);
             const int64_t tasks = cnt;               // upper bound on tickets (all pairs single); CTAs are persistent anyway
             if (ctx->profiling)
-                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, A.order, A.n_elig, ps, pe, misc + 5);
+                packed_cells_kernel<<<(unsigned)((tasks + 255) / 256), 256, 0, cs>>>(pwild, pn, pm, d_pb, A.order, A.n_elig, A.n_rb, ps, pe, misc + 5);
             int blocks = (int)std::min<int64_t>((tasks + DP_WARPS - 1) / DP_WARPS, occ_blocks);
             switch (tb_variant) {
                 case 0: isof_launch_dp_tb0(blocks, cs, A, ps, pe, counters + c); break;
@@ -928,6 +960,11 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
                 case 2: isof_launch_dp_tb2(blocks, cs, A, ps, pe, counters + c); break;
                 default: isof_launch_dp_tb3(blocks, cs, A, ps, pe, counters + c); break;
             }
+        }
+        if (may_rb) {       // the chunk's re-based 16-bit tasks (long reads); exits at once when the class is empty
+            LaunchTimer t(ctx, SLOT_DP, cs);
+            const int blocks = (int)std::min<int64_t>((cnt / 2 + DP_WARPS) / DP_WARPS, occ_blocks);
+            isof_launch_dp_rb(tb_variant, blocks, cs, A, ps, rb_tickets + c);
         }
         {
             LaunchTimer t(ctx, SLOT_TB, cs);

@@ -49,6 +49,7 @@ struct AlignParams {
                                            // packed task t = (order[start+2t], order[start+2t+1]) -> partners share the
                                            // reference; the pairs behind the eligible ones are single 32-bit tasks
     const unsigned long long *n_elig;      // per chunk: number of packed-eligible pairs (device scalar)
+    const unsigned long long *n_rb;        // per chunk: number of pairs of the re-based 16-bit class (device scalar)
     // tie-break table, run-time part (the compile-time part is the TB template parameter of the DP kernel)
     int tb_src_e;                          // trace source code of state E (walks the ref axis): 1, or 2 under h_e_before_f
     int tb_open_tie;                       // 1: the gap flags of the trace mean "opened" (gap_open_on_tie), 0: "extended"
@@ -447,7 +448,17 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
     wB = __byte_perm(acc_ef, acc_h, 0x7632);
 }
 
-template <int TBV>
+// RB (re-based 16-bit lanes, for pairs beyond the plain 16-bit range such as 10 kb reads): the packed halves hold
+// value - base, where base (one 32-bit scalar per alignment, a multiple of 4 so that tags survive) follows the scores of
+// the wavefront.  Neighbouring DP cells differ by at most match + open per row / column (a gap of one more character
+// costs at most `open`, a diagonal step gains at most `match`), so the cells of a 256-row stripe and its 64-column lane
+// skew stay within +-12.6 k tagged units of lane 15's first row -- the warp re-centres on it every 32 steps (16 in fill
+// and drain), with saturating subtraction so that the -32000 sentinels stay sentinels.  Stripe boundary rows travel
+// through the line buffer as absolute values modulo 2^16 (one VIADD per value on either side): modular arithmetic
+// gives the right re-based value because the true one fits.  End-cell maxima are tracked as absolute 32-bit values.
+// Every comparison still happens between values of the same base, so scores, ties and trace bits are those of the
+// 32-bit path, bit for bit.
+template <int TBV, bool RB>
 __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
                                           int2 *__restrict__ bnd, uint4 *__restrict__ prof_warp)
 {
@@ -490,6 +501,8 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
         if (s == nsA - 1) { last_laneA = ((nA - 1) - s * SROWS) / RR; last_rA = ((nA - 1) - s * SROWS) % RR; if (lane == 0) P.plastrr[pA] = RR; }
         if (s == nsB - 1) { last_laneB = ((nB - 1) - s * SROWS) / RR; last_rB = ((nB - 1) - s * SROWS) % RR; if (lane == 0) P.plastrr[pB] = RR; }
         P16State S;
+        int baseA = 0, baseB = 0;                    // RB: true value = packed half + base; every stripe starts at 0
+        uint32_t basepk = 0u;                        // (baseA & 0xffff) | (baseB << 16)
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
             const uint32_t a = (i0 + r < nA) ? (uint32_t)qA[i0 + r] : 0u;
@@ -538,10 +551,38 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
 #pragma unroll
         for (int r = 0; r < RR; ++r) snap[r] = 0x80008000u;
 
+        // RB: re-centre every packed value of the warp on lane 15's first row (see the comment at the function head)
+        auto rebase = [&]() {
+            const uint32_t rep = __shfl_sync(FULL, S.Hl[0], 15);
+            const int dA = lo16(rep) & ~3, dB = hi16(rep) & ~3;
+            const uint32_t dpk = ((uint32_t)dA & 0xffffu) | ((uint32_t)dB << 16);
+            auto adj = [&](const uint32_t v) { return __vmaxs2(__vsubss2(v, dpk), NEG16); };
+#pragma unroll
+            for (int r = 0; r < RR; ++r) { S.Hl[r] = adj(S.Hl[r]); S.Eh[r] = adj(S.Eh[r]); }
+#pragma unroll
+            for (int c = 0; c < PC; ++c) {
+                S.Hbot[c] = adj(S.Hbot[c]); S.Fbot[c] = adj(S.Fbot[c]);
+                S.b_next[c].x = (int)adj((uint32_t)S.b_next[c].x); S.b_next[c].y = (int)adj((uint32_t)S.b_next[c].y);
+            }
+            S.diag0 = adj(S.diag0);
+            baseA += dA; baseB += dB;
+            basepk = __vadd2(basepk, dpk);
+        };
+        // boundary rows in the line buffer are absolute values modulo 2^16 (RB only)
+        auto bnd_load = [&](const int2 *src) {
+            int2 v = __ldcg(src);
+            if (RB) { v.x = (int)__vsub2((uint32_t)v.x, basepk); v.y = (int)__vsub2((uint32_t)v.y, basepk); }
+            return v;
+        };
+        auto bnd_value = [&](const uint32_t h, const uint32_t f) {
+            return RB ? make_int2((int)__vadd2(h, basepk), (int)__vadd2(f, basepk)) : make_int2((int)h, (int)f);
+        };
+
         // ---------------- general step (bounds checks + end-cell bookkeeping) ----------------
         auto general_step = [&](const int t, auto track_tag, auto row_tag) {
             constexpr bool TR = decltype(track_tag)::value;      // false: the step cannot reach a last column (fill steps before a steady range)
             constexpr bool TROW = decltype(row_tag)::value;      // false: not a last stripe, no last-row bookkeeping
+            if (RB && (t & 15) == 0) rebase();
             const int jb = PC * (t - lane);
             uint32_t rc[PC], hu[PC], fu[PC];
 #pragma unroll
@@ -559,7 +600,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                         const uint32_t a = (jn + c < mA) ? (uint32_t)rA[jn + c] : 0u;
                         const uint32_t b = (jn + c < mB) ? (uint32_t)rB[jn + c] : 0u;
                         S.rc_next[c] = PROF ? a : ((a << CS16) | (b << (CS16 + 16)));
-                        if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = __ldcg(&bnd[jn + c]);
+                        if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = bnd_load(&bnd[jn + c]);
                     }
                 }
             }
@@ -570,25 +611,36 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     p16_column<RR, PROF, TBV>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c], prof);
                     const int j = jb + c;
                     ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
-                    if (has_next && lane == 31 && j < m) bnd[j] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]);
+                    if (has_next && lane == 31 && j < m) bnd[j] = bnd_value(S.Hbot[c], S.Fbot[c]);
                     // last column of A / B: every lane passes it exactly once per stripe; keep the column (one LOP3 per
-                    // row) and fold it into the running maximum after the stripe's loop
+                    // row) and fold it into the running maximum after the stripe's loop (RB: the base may move before
+                    // then, so the column is folded right here as absolute values)
                     if (TR && j == mA - 1) {
 #pragma unroll
-                        for (int r = 0; r < RR; ++r) snap[r] = (snap[r] & 0xffff0000u) | (S.Hl[r] & 0x0000ffffu);
+                        for (int r = 0; r < RR; ++r) {
+                            if (RB) {
+                                const int v = lo16(S.Hl[r]) + baseA;
+                                if (liveA && i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
+                            } else snap[r] = (snap[r] & 0xffff0000u) | (S.Hl[r] & 0x0000ffffu);
+                        }
                     }
                     if (TR && j == mB - 1) {
 #pragma unroll
-                        for (int r = 0; r < RR; ++r) snap[r] = (snap[r] & 0x0000ffffu) | (S.Hl[r] & 0xffff0000u);
+                        for (int r = 0; r < RR; ++r) {
+                            if (RB) {
+                                const int v = hi16(S.Hl[r]) + baseB;
+                                if (liveB && i0 + r < nB && v > bcolB) { bcolB = v; bcolB_i = i0 + r; }
+                            } else snap[r] = (snap[r] & 0x0000ffffu) | (S.Hl[r] & 0xffff0000u);
+                        }
                     }
                     if (TROW && trackA && j < mA) {         // last row of A: smallest j wins ties
                         const uint32_t hv = pick_row<RR>(S.Hl, last_rA);
-                        const int v = lo16(hv);
+                        const int v = lo16(hv) + (RB ? baseA : 0);
                         if (v > browA) { browA = v; browA_j = j; }
                     }
                     if (TROW && trackB && j < mB) {
                         const uint32_t hv = pick_row<RR>(S.Hl, last_rB);
-                        const int v = hi16(hv);
+                        const int v = hi16(hv) + (RB ? baseB : 0);
                         if (v > browB) { browB = v; browB_j = j; }
                     }
                 }
@@ -636,7 +688,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 }
                 if (has_prev && lane == 0) {
 #pragma unroll
-                    for (int c = 0; c < PC; ++c) S.b_next[c] = __ldcg(pbn + c);
+                    for (int c = 0; c < PC; ++c) S.b_next[c] = bnd_load(pbn + c);
                 }
                 uint32_t wA[PC], wB[PC];
 #pragma unroll
@@ -646,12 +698,12 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                         const int j = PC * (t - lane) + c;
                         if (trackA) {
                             const uint32_t hv = pick_row<RR>(S.Hl, last_rA);
-                            const int v = lo16(hv);
+                            const int v = lo16(hv) + (RB ? baseA : 0);
                             if (v > browA) { browA = v; browA_j = j; }
                         }
                         if (trackB) {
                             const uint32_t hv = pick_row<RR>(S.Hl, last_rB);
-                            const int v = hi16(hv);
+                            const int v = hi16(hv) + (RB ? baseB : 0);
                             if (v > browB) { browB = v; browB_j = j; }
                         }
                     }
@@ -664,11 +716,23 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 *sB = make_uint2(wB[0], wB[1]);
                 if (has_next && lane == 31) {
 #pragma unroll
-                    for (int c = 0; c < PC; ++c) { ISOF_ASSERT(pbs + c < bnd + P.bnd_stride, CHK_BND); pbs[c] = make_int2((int)S.Hbot[c], (int)S.Fbot[c]); }
+                    for (int c = 0; c < PC; ++c) { ISOF_ASSERT(pbs + c < bnd + P.bnd_stride, CHK_BND); pbs[c] = bnd_value(S.Hbot[c], S.Fbot[c]); }
                 }
                 pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
             };
-            if (!track_stripe) {
+            if (RB) {
+                for (int t = 31; t < t2;) {
+                    rebase();
+                    const int te = min(t + 32, t2);
+                    if (!track_stripe) {
+#pragma unroll 2
+                        for (; t < te; ++t) steady_step(t, false);
+                    } else {
+#pragma unroll 2
+                        for (; t < te; ++t) steady_step(t, true);
+                    }
+                }
+            } else if (!track_stripe) {
 #pragma unroll 2
                 for (int t = 31; t < t2; ++t) steady_step(t, false);
             } else {
@@ -679,14 +743,14 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             else { for (int t = t2; t < T; ++t) general_step(t, std::true_type{}, std::false_type{}); }
         }
         // end cell, last column: smallest i wins ties (rows ascend within a lane and from stripe to stripe)
-        if (liveA) {
+        if (!RB && liveA) {
 #pragma unroll
             for (int r = 0; r < RR; ++r) {
                 const int v = lo16(snap[r]);
                 if (i0 + r < nA && v > bcolA) { bcolA = v; bcolA_i = i0 + r; }
             }
         }
-        if (liveB) {
+        if (!RB && liveB) {
 #pragma unroll
             for (int r = 0; r < RR; ++r) {
                 const int v = hi16(snap[r]);
@@ -751,9 +815,16 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
         const int64_t n_pk = (int64_t)(*P.n_elig) / 2;
         if ((int64_t)tkt < n_pk) {
             const int64_t xA = start + 2 * (int64_t)tkt;
-            dp_pair16<TBV>(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
+            dp_pair16<TBV, false>(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
         } else {
-            const int64_t x = start + 2 * n_pk + ((int64_t)tkt - n_pk);
+            // single 32-bit pairs: the odd one out of the plain-16 class, the odd one out of the re-based class (whose
+            // tasks sg_dp_rb_kernel takes), then everything that fits neither
+            const int64_t n0 = (int64_t)(*P.n_elig), n1 = (int64_t)(*P.n_rb);
+            const int64_t s = (int64_t)tkt - n_pk, odd0 = n0 & 1, odd1 = n1 & 1;
+            int64_t x;
+            if (s < odd0) x = start + n0 - 1;
+            else if (s < odd0 + odd1) x = start + n0 + n1 - 1;
+            else x = start + n0 + n1 + (s - odd0 - odd1);
             if (x >= end) break;
             dp_pair32(P, P.order[x], lane, bnd, s_prof[warp]);
         }
@@ -765,6 +836,26 @@ inline void launch_sg_dp(const int blocks, cudaStream_t st, const AlignParams &A
                          unsigned long long *counter)
 {
     sg_dp_kernel<TBV><<<blocks, DP_WARPS * 32, 0, st>>>(A, start, end, counter);
+}
+
+// The re-based class of a chunk: pairs order[start + n0 + 2k], order[start + n0 + 2k + 1], k < n1 / 2 (dp_pair16<., true>).
+// A kernel of its own: the extra live scalars of the re-based path would otherwise cost the plain path registers.
+template <int TBV>
+__global__ void __launch_bounds__(DP_WARPS * 32, DP_CTAS_PER_SM)
+sg_dp_rb_kernel(const AlignParams P, const int64_t start, unsigned long long *__restrict__ counter)
+{
+    __shared__ uint4 s_prof[DP_WARPS][4 * 2 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int2 *bnd = P.bnd + (size_t)(blockIdx.x * DP_WARPS + warp) * P.bnd_stride;
+    for (;;) {
+        unsigned long long tkt = 0;
+        if (lane == 0) tkt = atomicAdd(counter, 1ull);
+        tkt = __shfl_sync(0xffffffffu, tkt, 0);
+        const int64_t n0 = (int64_t)(*P.n_elig), n1 = (int64_t)(*P.n_rb);
+        if ((int64_t)tkt >= n1 / 2) break;
+        const int64_t xA = start + n0 + 2 * (int64_t)tkt;
+        dp_pair16<TBV, true>(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
+    }
 }
 
 }  // namespace
@@ -779,5 +870,7 @@ unsigned isof_viol_dp_tb1();
 unsigned isof_viol_dp_tb2();
 unsigned isof_viol_dp_tb3();
 unsigned isof_viol_short();
+unsigned isof_viol_dp_rb();
+void isof_launch_dp_rb(int tb_variant, int blocks, cudaStream_t st, const AlignParams &A, int64_t start, unsigned long long *counter);
 int isof_sg_short_path(isof_ctx *ctx, AlignParams &A, int64_t P, int max_n, int max_m, bool any_wild, int tb_variant,
                        int64_t budget_words);

@@ -11,8 +11,9 @@
 // a stable two-pass LSD radix sort on the two 64-bit k-mer keys groups them while keeping the
 // reference's insertion order inside every bucket.  k-mer identity: k <= 31 and pure upper-case
 // ACGT -> exact 2-bit packing; anything else (N, lower case, truncated k-mers of very short reads,
-// k >= 32) -> 63-bit SipHash with the top bit set (identity up to a 2^-63 collision, documented in
-// DESIGN.md).  Buckets that the reference drops (the polyA/polyA pair main:181, more than
+// k >= 32) -> a 63-bit SipHash brings candidates together and a resolution pass compares BYTES: the
+// final key of such a k-mer is the index of the first minimizer of the batch with the same string, so
+// identity is exact (span_resolve_kernel; runs only when a batch holds such k-mers).  Buckets that the reference drops (the polyA/polyA pair main:181, more than
 // 3*len(reads) occurrences main:206) are flagged; singletons are kept with size 1 (the host view
 // hides them as the reference deletes them, main:201-203).
 // The span search then counts, for every record, the other-read records of its bucket whose span
@@ -40,7 +41,8 @@ __device__ __forceinline__ int find_read(const int64_t *__restrict__ min_off, in
 __global__ void span_key_count_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ read_off, int R,
                                       const int32_t *__restrict__ min_pos, const int64_t *__restrict__ min_off, int64_t M,
                                       int k, int x_low, int x_high, int32_t *__restrict__ mread,
-                                      uint64_t *__restrict__ mkey, uint8_t *__restrict__ mpolya, int64_t *__restrict__ mcnt)
+                                      uint64_t *__restrict__ mkey, uint8_t *__restrict__ mpolya, int64_t *__restrict__ mcnt,
+                                      uint64_t hash_mask, unsigned long long *__restrict__ any_hashed)
 {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x > M) return;
@@ -69,7 +71,11 @@ __global__ void span_key_count_kernel(const uint8_t *__restrict__ bases, const i
         if (c != 'A') polya = false;
         key = (key << 2) | (uint64_t)(code & 3);
     }
-    if (!packable) key = ((uint64_t)py_siphash13_bytes(s, len) & 0x7fffffffffffffffULL) | 0x8000000000000000ULL;
+    if (!packable) {
+        // hash_mask < 2^63 - 1 is a test knob: it forces collisions so that the byte comparison below is exercised
+        key = ((uint64_t)py_siphash13_bytes(s, len) & 0x7fffffffffffffffULL & hash_mask) | 0x8000000000000000ULL;
+        atomicOr(any_hashed, 1ull);
+    }
     mkey[x] = key;
     mpolya[x] = polya ? 1 : 0;
     // partners: later minimizers of the same read with x_low < d <= x_high (positions increase)
@@ -81,6 +87,53 @@ __global__ void span_key_count_kernel(const uint8_t *__restrict__ bases, const i
         if (d > x_low) ++c;
     }
     mcnt[x] = c;
+}
+
+// ---- exact identity for k-mers that do not pack into 2 bits per base
+__global__ void span_hashkey_kernel(const uint64_t *__restrict__ mkey, int64_t M, uint64_t *__restrict__ skey,
+                                    uint32_t *__restrict__ sidx)
+{
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= M) return;
+    skey[x] = (mkey[x] >> 63) ? mkey[x] : 0ull;         // packed keys sort to the front and are left alone
+    sidx[x] = (uint32_t)x;
+}
+
+// One thread per run of equal hash keys (stable sort: minimizer indices ascend inside a run).  Every element gets the
+// key TOPBIT | (index of the first minimizer of the run with the same bytes): equal strings <=> equal keys, whatever
+// the hash did.  A run of identical strings (the common case: one repeated N-containing k-mer) costs one comparison
+// per element; distinct strings under one hash value cost one comparison per distinct representative.
+__global__ void span_resolve_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ read_off,
+                                    const int32_t *__restrict__ mread, const int32_t *__restrict__ min_pos, int k,
+                                    const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sidx, int64_t M,
+                                    uint64_t *__restrict__ mkey)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= M) return;
+    const uint64_t key = skey[s];
+    if (!(key >> 63) || (s > 0 && skey[s - 1] == key)) return;          // not the start of a run of hashed keys
+    const uint64_t TOP = 0x8000000000000000ULL;
+    for (int64_t e = s; e < M && skey[e] == key; ++e) {
+        const uint32_t xe = sidx[e];
+        const int64_t rbe = read_off[mread[xe]];
+        const int pe = min_pos[xe];
+        const int le = max(0, min(k, (int)(read_off[mread[xe] + 1] - rbe) - pe));
+        const uint8_t *be = bases + rbe + pe;
+        uint32_t repx = xe;
+        for (int64_t f = s; f < e; ++f) {
+            const uint32_t xf = sidx[f];
+            if (mkey[xf] != (TOP | (uint64_t)xf)) continue;              // not a representative
+            const int64_t rbf = read_off[mread[xf]];
+            const int pf = min_pos[xf];
+            const int lf = max(0, min(k, (int)(read_off[mread[xf] + 1] - rbf) - pf));
+            if (lf != le) continue;
+            const uint8_t *bf = bases + rbf + pf;
+            bool same = true;
+            for (int q = 0; q < le; ++q) if (be[q] != bf[q]) { same = false; break; }
+            if (same) { repx = xf; break; }
+        }
+        mkey[xe] = TOP | (uint64_t)repx;
+    }
 }
 
 __global__ void span_emit_kernel(const int32_t *__restrict__ min_pos, const int64_t *__restrict__ min_off, int64_t M,
@@ -228,6 +281,9 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
     TRY(dev_reserve(ctx, ctx->b_s_mpolya, (size_t)M));
     TRY(dev_reserve(ctx, ctx->b_s_mcnt, sizeof(int64_t) * (size_t)(M + 1)));
     TRY(dev_reserve(ctx, ctx->b_s_moff, sizeof(int64_t) * (size_t)(M + 1)));
+    TRY(dev_reserve(ctx, ctx->b_misc, 128));
+    unsigned long long *any_hashed = (unsigned long long *)ctx->b_misc.p + 12;
+    CUDA_TRY(ctx, cudaMemsetAsync(any_hashed, 0, 8, st));
     int32_t *mread = (int32_t *)ctx->b_s_mread.p;
     uint64_t *mkey = (uint64_t *)ctx->b_s_mkey.p;
     uint8_t *mpolya = (uint8_t *)ctx->b_s_mpolya.p;
@@ -235,7 +291,8 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
     {
         LaunchTimer t(ctx, SLOT_OTHER);
         span_key_count_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, st>>>(d_bases, d_read_off, R, d_min_pos, d_min_off, M,
-                                                                               k, x_low, x_high, mread, mkey, mpolya, mcnt);
+                                                                               k, x_low, x_high, mread, mkey, mpolya, mcnt,
+                                                                               ctx->span_hash_mask, any_hashed);
     }
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, mcnt, moff, M + 1, st);
@@ -246,8 +303,35 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
     }
     int64_t *pin = (int64_t *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(pin, moff + M, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(pin + 1, any_hashed, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     const int64_t G = pin[0];
+    if (pin[1] && G > 0) {
+        // some k-mers of this batch do not pack into 2 bits per base: replace their hash keys by exact identities
+        TRY(dev_reserve(ctx, ctx->b_s_keyt, sizeof(uint64_t) * (size_t)M));
+        TRY(dev_reserve(ctx, ctx->b_s_keyo, sizeof(uint64_t) * (size_t)M));
+        TRY(dev_reserve(ctx, ctx->b_s_idx0, sizeof(uint32_t) * (size_t)M));
+        TRY(dev_reserve(ctx, ctx->b_s_idx1, sizeof(uint32_t) * (size_t)M));
+        uint64_t *skey = (uint64_t *)ctx->b_s_keyt.p, *skey_o = (uint64_t *)ctx->b_s_keyo.p;
+        uint32_t *sidx = (uint32_t *)ctx->b_s_idx0.p, *sidx_o = (uint32_t *)ctx->b_s_idx1.p;
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            span_hashkey_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(mkey, M, skey, sidx);
+        }
+        size_t th = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, th, skey, skey_o, sidx, sidx_o, (int)M, 0, 64, st);
+        TRY(dev_reserve(ctx, ctx->b_s_sorttmp, th));
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_s_sorttmp.p, th, skey, skey_o, sidx, sidx_o, (int)M, 0, 64, st));
+        }
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            span_resolve_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_bases, d_read_off, mread, d_min_pos, k, skey_o, sidx_o,
+                                                                             M, mkey);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     *h_n_rec = G;
     if (G > rec_cap) return isof_fail(ctx, ISOF_ERR_CAPACITY, "record arrays hold %lld, %lld needed", (long long)rec_cap, (long long)G);
     if (G >= (1LL << 31)) return isof_fail(ctx, ISOF_ERR_RANGE, "more than 2^31 minimizer pairs in one batch");

@@ -616,6 +616,8 @@ def test_debug_build_bounds_assertions_stay_silent():
         seqs += ["ACGTN" * 30, "ACGT" * 40]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)      # wildcard -> 32-bit
         big = _rand_dna(rng, 4500)
         seqs += [big, synth.mutate(rng, big, 0.04)]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)   # > 16-bit range
+        big2 = _rand_dna(rng, 5100)
+        seqs += [big2[:4800], synth.mutate(rng, big2, 0.05)]; pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)   # a re-based task with the one above
         for packed in (True, False):
             dctx.set_packed(packed)
             for params in [(2, -2, 12, 1), (2, -8, 12, 1), (1, -1, 1, 1)]:
@@ -939,3 +941,89 @@ def test_short_pair_regime_under_tiebreak_tables(ctx, tb_index):
     finally:
         ctx.set_short(1)
         ctx.set_tiebreak(0, 0, 0, 0)
+
+
+# ------------------------------------------------------------------------------- re-based 16-bit lanes (long reads)
+def test_rebased_16bit_lanes_match_32bit_path_and_oracle(ctx):
+    """Pairs beyond the plain 16-bit score range (BASELINE config 4: 10 kb reads) run in 16-bit lanes that follow a
+    running base (dp_pair16<., RB>).  66 pairs -- C4 reads, identical sequences (score 2n: the largest value there is),
+    unrelated sequences (the most negative ones), exon-sized deletions and insertions, unequal lengths, a low-complexity
+    pair -- must equal the 32-bit path on every output and the oracle on a sample; under two more tie-break tables too."""
+    from isonform_b200 import hotpath, polya, synth
+    rng = np.random.default_rng(4242)
+    reads_l, _iso, _t = synth.make_config("C4", n_reads=10)
+    seqs = [polya.remove_read_polyA_ends(s, 12, 1) for _, s in reads_l]
+    ia, ib = [int(x) for x in np.triu_indices(10, 1)[0]], [int(x) for x in np.triu_indices(10, 1)[1]]       # 45 pairs
+
+    def add(a, b):
+        seqs.extend([a, b]); ia.append(len(seqs) - 2); ib.append(len(seqs) - 1)
+    x = _rand_dna(rng, 9000)
+    add(x, x)                                                    # identical: score 18000 (72000 in tagged units)
+    add(x, _rand_dna(rng, 8800))                                 # unrelated
+    add(x, x[:3000] + x[3600:])                                  # 600 bp deletion
+    add(x[:4000] + x[4500:], x)                                  # 500 bp insertion
+    add(x[2000:7000], x)                                         # contained: long free end gaps
+    add(x, x[1000:6200])
+    add(synth.mutate(rng, x, 0.12), x)
+    add(_rand_dna(rng, 5000, "AC"), _rand_dna(rng, 5200, "AC"))  # tie-heavy
+    for _ in range(13):
+        n = int(rng.integers(4200, 9000))
+        y = _rand_dna(rng, n)
+        z = synth.mutate(rng, y, float(rng.choice([0.01, 0.05, 0.1])))
+        if rng.random() < 0.5:
+            c = n // 3; z = z[:c] + z[c + int(rng.integers(50, 900)):]
+        add(y, z)
+    assert len(ia) == 66
+    for tb in (oracle.TieBreak(0, 0, 0, 0), oracle.TieBreak(1, 0, 1, 0), oracle.TieBreak(0, 1, 0, 1)):
+        ctx.set_tiebreak(tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id)
+        try:
+            ctx.set_packed(True)
+            a = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+            ctx.set_packed(False)                                # 32-bit path only
+            b = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+        finally:
+            ctx.set_packed(True)
+            ctx.set_tiebreak(0, 0, 0, 0)
+        for key in ("score", "cigar_off", "cigar", "features"):
+            assert np.array_equal(a[key], b[key]), (key, tb.h_e_before_f, tb.gap_open_on_tie)
+        ea = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx)          # end cells (default table only below)
+        if tb.h_e_before_f == 0 and tb.gap_open_on_tie == 0:
+            assert int(a["score"][45]) == 18000
+            for p in (0, 17, 44, 45, 46, 47, 48, 49, 50, 52, 60):
+                sc, eq, er, runs = oracle.sg_align(seqs[ia[p]], seqs[ib[p]], 2, -2, 12, 1)
+                assert (int(ea["score"][p]), int(ea["end_q"][p]), int(ea["end_r"][p])) == (sc, eq, er), p
+                assert ea["cigar"][ea["cigar_off"][p]:ea["cigar_off"][p + 1]].tolist() == runs.tolist(), p
+    prof0 = ctx.profile()
+    ctx.profile_enable(True); ctx.profile_reset()
+    hotpath.align_pairs(seqs, ia[:44], ib[:44], 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
+    pr = ctx.profile(); ctx.profile_enable(False)
+    assert pr["dp_cells_packed"] == pr["dp_cells"] > 0           # every pair of the call took the 16-bit lanes
+    del prof0
+
+
+# ------------------------------------------------------------------------------- kernel (c): exact k-mer identity
+@pytest.mark.parametrize("mask", [0x7fffffffffffffff, 0xF, 0x0])
+def test_spans_exact_kmer_identity_under_forced_hash_collisions(ctx, mask):
+    """k-mers that do not pack into 2 bits per base (N, lower case, k >= 32) are grouped by a hash and then told apart
+    by comparing bytes.  With the hash cut to 4 bits -- or to nothing: every such k-mer collides with every other --
+    the pair database, the span search and the WIS picks must still be the reference's (main:174-212, 308-338)."""
+    from isonform_b200 import synth
+    rng = np.random.default_rng(88)
+    base = _rand_dna(rng, 700)
+    # lower-case stretches, Ns and a lower-case/upper-case twin of the same region: distinct strings for the reference
+    low = base[:200] + base[200:330].lower() + base[330:450] + "N" + base[451:520] + "NN" + base[522:]
+    reads = {}
+    for i in range(9):
+        src = base if i % 3 == 0 else low
+        s = synth.mutate(rng, src, 0.01)                              # mutate keeps the case of untouched bases
+        reads[i + 1] = ("r%d" % i, s, "")
+    reads[10] = ("twin", low, "")
+    reads[11] = ("twin2", low, "")
+    reads[12] = ("upper", base, "")
+    ctx.debug_set_span_hash_mask(mask)
+    try:
+        _span_case_check(ctx, reads, 20, 31, 40, 80, 5)
+        _span_case_check(ctx, reads, 33, 45, 66, 120, 5)             # k >= 32: every k-mer goes through the byte comparison
+        _span_case_check(ctx, reads, 9, 20, 18, 60, 10)
+    finally:
+        ctx.debug_set_span_hash_mask()
