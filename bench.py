@@ -508,6 +508,12 @@ def run_seam_latency(ctx):
         for _ in range(n):
             hotpath.parasail_alignment(x, y, 2, -8, 12, 1, ctx=ctx)
         out["us_per_call_%dbp" % L] = (time.perf_counter() - t0) / n * 1e6
+        t0 = time.perf_counter()
+        for _ in range(n):
+            ctx.sg_align_one(x, y, 2, -8, 12, 1)
+        out["us_per_c_abi_call_%dbp" % L] = (time.perf_counter() - t0) / n * 1e6
+    out["note"] = ("hotpath.parasail_alignment = C ABI call + CIGAR string / aligned strings in Python; pairs whose trace fits 200 KB "
+                   "(up to ~500 x 500) take the fused one-launch kernel, longer ones the regular path")
     return out
 
 

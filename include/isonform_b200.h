@@ -65,6 +65,11 @@ ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
  * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any
  * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
 ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
+/* Host-buffer calls of at most 32 small pairs (trace <= 200 KB each, i.e. up to ~500 x 500) run as ONE fused launch: base
+ * codes, DP, traceback and features in one kernel with the trace in shared memory and inputs / outputs in mapped pinned
+ * memory -- the per-pair seams of the reference (a memo miss of consensus.parasail_alignment).  Identical results; on=0
+ * sends such calls through the regular path (tests, A/B measurements); default on=1. */
+ISOF_API int isof_set_fused_small(isof_ctx *ctx, int on);
 /* A call whose pairs are ALL short (both lengths <= 384, inside the 16-bit range) and numerous enough to fill the GPU
  * (about 64 x SMs x (length/60)^2 pairs: a thread per task trades latency for throughput) takes the short-pair regime:
  * one thread per task instead of a 32-lane wavefront per task (the bubble-popping sizes, SimplifyGraph.py:630-664).

@@ -35,7 +35,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances"]
@@ -69,6 +69,7 @@ def load(debug=False):
     L.isof_set_overlap.argtypes = [vp, C.c_int]
     L.isof_set_tiebreak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.isof_set_short.argtypes = [vp, C.c_int]
+    L.isof_set_fused_small.argtypes = [vp, C.c_int]
     L.isof_debug_violations.argtypes = [vp, C.POINTER(C.c_uint)]
     L.isof_debug_selftest.argtypes = [vp]
     L.isof_debug_set_span_hash_mask.argtypes = [vp, C.c_uint64]
@@ -158,6 +159,10 @@ class Context:
     def set_packed(self, on=True):
         """Enable (default) / disable the packed 16-bit DP path; results are identical either way."""
         self._check(self._L.isof_set_packed(self._h, 1 if on else 0))
+
+    def set_fused_small(self, on=True):
+        """One fused launch for tiny host-buffer calls (default on); results are identical either way."""
+        self._check(self._L.isof_set_fused_small(self._h, 1 if on else 0))
 
     def set_short(self, mode=1):
         """Short-pair regime for all-short calls: 0/False never, 1/True when the call is large enough (default),
@@ -334,6 +339,28 @@ class Context:
             break
         return {"score": score, "end_q": eq, "end_r": er, "cigar_off": coff,
                 "cigar": (cig[:coff[P]] if want_cigar else None), "features": feats}
+
+    def sg_align_one(self, s1, s2, match=2, mismatch=-2, gap_open=12, gap_ext=1):
+        """One pair, lean: (score, end_q, end_r, runs uint32[]) with pre-allocated buffers -- the per-pair seam
+        (consensus.parasail_alignment on a memo miss).  Goes through isof_sg_align_pairs, i.e. the fused tiny-call
+        kernel when the pair is small enough."""
+        b1 = s1.encode("latin-1") if isinstance(s1, str) else bytes(s1)
+        b2 = s2.encode("latin-1") if isinstance(s2, str) else bytes(s2)
+        n, m = len(b1), len(b2)
+        st = getattr(self, "_one", None)
+        if st is None or st["cap"] < n + m + 2:
+            cap = max(2 * (n + m + 2), 4096)
+            st = self._one = {"cap": cap, "off": np.zeros(3, np.int64), "pa": np.zeros(1, np.int32), "pb": np.ones(1, np.int32),
+                              "out": np.zeros(3, np.int32), "coff": np.zeros(2, np.int64), "runs": np.empty(cap, np.uint32)}
+            st["ptr"] = (st["off"].ctypes.data, st["pa"].ctypes.data, st["pb"].ctypes.data, st["out"].ctypes.data,
+                         st["out"].ctypes.data + 4, st["out"].ctypes.data + 8, st["runs"].ctypes.data, st["coff"].ctypes.data)
+        st["off"][1] = n
+        st["off"][2] = n + m
+        off_p, pa_p, pb_p, sc_p, eq_p, er_p, runs_p, coff_p = st["ptr"]
+        self._check(self._L.isof_sg_align_pairs(self._h, b1 + b2, off_p, 2, pa_p, pb_p, 1, match, mismatch, gap_open, gap_ext,
+                                                sc_p, eq_p, er_p, runs_p, st["cap"], coff_p))
+        out = st["out"]
+        return int(out[0]), int(out[1]), int(out[2]), st["runs"][:int(st["coff"][1])].copy()
 
     def sg_align_batch(self, s1_list, s2_list, match=2, mismatch=-2, gap_open=12, gap_ext=1):
         """The SURVEY 8b concatenated form (isof_sg_align_batch)."""

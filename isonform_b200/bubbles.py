@@ -23,7 +23,8 @@ combination loop (`generate_combinations`, :938).  After the reference has built
 `run_spoa` (IsoformGeneration.py:143-156) is memoised by the content of its input file: the
 speculation and the replay ask for the same consensus, and so do later iterations, so each distinct
 read set spawns `spoa` once.  Nothing in the reference tree is modified; `uninstall()` restores the
-three rebound attributes.
+rebound attributes.  The two bookkeeping hot spots of the same loop are replaced by equivalent, faster forms:
+`generate_combinations` (one matrix product) and `find_paths` (`PathFinder`: per-node lookup tables).
 """
 import collections
 import itertools
@@ -58,6 +59,65 @@ def generate_combinations(possible_starts, possible_ends, topo_nodes_dict, combi
         combis.append((possible_starts[i][0], possible_ends[j][0], inter))
 
 
+class PathFinder:
+    """Drop-in for SimplifyGraph.find_paths (:132-172), the second bookkeeping hot spot SURVEY.md section 8f names
+    (432 k calls per 1000-read batch).  Same walk, same results -- the set operations that fix the order in which reads
+    are popped are kept as they are -- but the step "first successor whose edge_supp LIST contains the read" (a scan
+    over the out-edges with a linear list search each) becomes one dictionary lookup in a per-node table
+    {read: (first such successor, frozenset(edge_supp))}, built on first use from DG's adjacency order.  The tables
+    are dropped whenever the graph changes (`invalidate`, called after every linearize_bubble)."""
+
+    def __init__(self):
+        self._tables = {}
+        self._graph = None
+
+    def invalidate(self):
+        self._tables.clear()
+
+    def _table(self, DG, node):
+        t = self._tables.get(node)
+        if t is None:
+            t = {}
+            for neighbor in DG.successors(node):
+                supp = DG[node][neighbor]['edge_supp']
+                entry = (neighbor, frozenset(supp))
+                for r in supp:
+                    if r not in t:
+                        t[r] = entry
+            self._tables[node] = t
+        return t
+
+    def find_paths(self, DG, startnode, endnode, support, all_paths, marked):
+        if DG is not self._graph:
+            self._graph = DG
+            self._tables.clear()
+        node_support_left = set(support)
+        all_supp = set(support)
+        while node_support_left:
+            node = startnode
+            read = node_support_left.pop()
+            current_node_support = node_support_left        # the reference aliases the set here (:141-142)
+            current_node_support.add(read)
+            visited_nodes = []
+            next_found = False
+            while node != endnode:
+                visited_nodes.append(node)
+                next_found = False
+                if node in marked:
+                    break
+                hit = self._table(DG, node).get(read)
+                if hit is None:
+                    break
+                node = hit[0]
+                current_node_support = current_node_support.intersection(hit[1])
+                next_found = True
+            if current_node_support and next_found:
+                node_support_left -= current_node_support
+                all_paths.append((visited_nodes, tuple(sorted(current_node_support)), all_supp - current_node_support))
+            else:
+                break
+
+
 class _NeedsSpoa(Exception):
     """Raised inside a speculative consensus whose spoa result is not memoised yet."""
 
@@ -72,22 +132,45 @@ class BubblePrefetcher:
         self._orig = {}
         self._in_speculation = False
         self._no_new_spoa = False
+        self.paths = PathFinder()
+        self.check_paths = False
 
     # ------------------------------------------------------------------ wiring
     def install(self):
         from modules import IsoformGeneration, SimplifyGraph        # the reference tree
         self._sg, self._ig = SimplifyGraph, IsoformGeneration
         self._orig = {"generate_combinations": SimplifyGraph.generate_combinations,
-                      "run_spoa": IsoformGeneration.run_spoa}
+                      "run_spoa": IsoformGeneration.run_spoa, "find_paths": SimplifyGraph.find_paths,
+                      "linearize_bubble": SimplifyGraph.linearize_bubble}
         SimplifyGraph.generate_combinations = self._generate_combinations
         IsoformGeneration.run_spoa = self._run_spoa
+        SimplifyGraph.find_paths = self._find_paths
+        SimplifyGraph.linearize_bubble = self._linearize_bubble
         return self
 
     def uninstall(self):
         if self._orig:
             self._sg.generate_combinations = self._orig["generate_combinations"]
             self._ig.run_spoa = self._orig["run_spoa"]
+            self._sg.find_paths = self._orig["find_paths"]
+            self._sg.linearize_bubble = self._orig["linearize_bubble"]
             self._orig = {}
+
+    # ------------------------------------------------------------------ SimplifyGraph.find_paths / linearize_bubble
+    def _find_paths(self, DG, startnode, endnode, support, all_paths, marked):
+        before = len(all_paths)
+        self.paths.find_paths(DG, startnode, endnode, support, all_paths, marked)
+        if self.check_paths:                      # test mode: the reference's own function must agree, call by call
+            want = []
+            self._orig["find_paths"](DG, startnode, endnode, support, want, marked)
+            assert all_paths[before:] == want, (startnode, endnode)
+            self.stats["find_paths_checked"] = self.stats.get("find_paths_checked", 0) + 1
+
+    def _linearize_bubble(self, *args, **kwargs):
+        try:
+            return self._orig["linearize_bubble"](*args, **kwargs)
+        finally:
+            self.paths.invalidate()               # the only place the routine rewires edges (:291, :507, :514)
 
     # ------------------------------------------------------------------ IsoformGeneration.run_spoa, memoised
     def _run_spoa(self, reads, spoa_out_file):

@@ -123,6 +123,7 @@ int isof_destroy(isof_ctx *ctx)
     flush_timers(ctx);
     for (DevBuf *b : ctx->all_bufs()) if (b->p) cudaFree(b->p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->fused_io) cudaFreeHost(ctx->fused_io);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (auto &as : ctx->aux_stream) if (as) cudaStreamDestroy(as);
     delete ctx;
@@ -158,6 +159,13 @@ int isof_debug_set_span_hash_mask(isof_ctx *ctx, uint64_t mask)
 {
     if (!ctx) return ISOF_ERR_ARG;
     ctx->span_hash_mask = mask & 0x7fffffffffffffffULL;
+    return ISOF_OK;
+}
+
+int isof_set_fused_small(isof_ctx *ctx, int on)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    ctx->disable_fused = (on == 0);
     return ISOF_OK;
 }
 
@@ -372,6 +380,12 @@ static int align_host(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_
     if (seq_off[0] != 0 || n_bases < 0) return isof_fail(ctx, ISOF_ERR_ARG, "seq_off must start at 0");
     if (P == 0) { if (cigar_off) cigar_off[0] = 0; return ISOF_OK; }
     if (!pair_a || !pair_b) return isof_fail(ctx, ISOF_ERR_ARG, "null pair list");
+    if (!ctx->disable_fused) {
+        // tiny calls (the per-pair seams): one fused launch, trace in shared memory, mapped I/O
+        const int frc = isof_sg_fused_small(ctx, seq_cat, seq_off, n_seqs, pair_a, pair_b, P, match, mismatch, gap_open, gap_ext,
+                                            delta_len, score, end_q, end_r, cigar_runs, cigar_cap, cigar_off, features);
+        if (frc != 1) return frc;
+    }
     TRY(h2d(ctx, ctx->b_h_bases, seq_cat, (size_t)n_bases));
     TRY(h2d(ctx, ctx->b_h_off, seq_off, sizeof(int64_t) * (size_t)(n_seqs + 1)));
     TRY(h2d(ctx, ctx->b_h_pa, pair_a, sizeof(int32_t) * (size_t)P));

@@ -64,6 +64,8 @@ struct isof_ctx {
                 v.push_back(b);
         return v;
     }
+    void *fused_io = nullptr;         // mapped pinned memory of the fused tiny-call path (inputs | outputs)
+    bool disable_fused = false;       // tiny calls through the regular path (tests / A-B measurements)
     void *pinned = nullptr;           // small pinned staging for scalar read-backs
     size_t pinned_cap = 0;
 };
@@ -179,6 +181,10 @@ int isof_spans_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_read
                     int64_t rec_cap, int32_t *d_rec_read, int32_t *d_rec_p1, int32_t *d_rec_p2, int32_t *d_rec_count,
                     int32_t *d_rec_bucket, int32_t *d_sorted_rec, int32_t *d_bucket_off, uint8_t *d_bucket_dropped,
                     int64_t *h_n_rec, int64_t *h_n_buckets, const int32_t *d_batch_read_off = nullptr, int32_t n_batches = 1);
+int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, const int32_t *pair_a,
+                        const int32_t *pair_b, int64_t P, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
+                        int32_t delta_len, int32_t *score, int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs,
+                        int64_t cigar_cap, int64_t *cigar_off, int32_t *features);
 int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off, int32_t n_seqs, int64_t n_bases,
                        const int32_t *d_pa, const int32_t *d_pb, int64_t P, int32_t match, int32_t mismatch,
                        int32_t gap_open, int32_t gap_ext, int32_t *d_score, int32_t *d_endq, int32_t *d_endr,

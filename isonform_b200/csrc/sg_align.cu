@@ -287,10 +287,10 @@ __global__ void chunk_bounds_kernel(const int64_t *__restrict__ ptrace, int64_t 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int upc(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
 
-__global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, const int64_t end)
+// SMEM: the trace lives in shared memory (fused small-call kernel): plain loads, no L2 prefetch
+template <bool SMEM>
+__device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64_t p)
 {
-    const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= end) return;
     const int n = P.pn[p], m = P.pm[p];
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
@@ -332,7 +332,7 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
         int l = (i >> 3) & 31, r = i & 7;
         if (s == last_s && rr_last != 8) { l = (i & 255) / rr_last; r = (i & 255) % rr_last; }
         const int jt = (pc == 1) ? j : (j >> 1), jc = (pc == 1) ? 0 : (j & 1);
-        {   // the path mostly follows the diagonal: pull the line it will need 16 steps from now into L2
+        if (!SMEM) {   // the path mostly follows the diagonal: pull the line it will need 16 steps from now into L2
             const int ip = i - 16, jp = j - 16;
             if (ip >= 0 && jp >= 0) {
                 const int sp_ = ip >> 8;
@@ -345,7 +345,7 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
         const uint32_t *wp = &trace[(((size_t)s * T + (jt + l)) * 32 + l) * pc + jc];
         ISOF_ASSERT(wp >= trace && wp < tail - TRACE_SLACK && wp < tail - nr, CHK_TRACE_LOAD);
         last_read = wp;
-        const uint32_t word = __ldcg(wp);
+        const uint32_t word = SMEM ? *wp : __ldcg(wp);
         const int nib = split ? ((((word >> (16 + 2 * r)) & 3) << 2) | ((word >> (2 * r)) & 3)) : ((word >> (4 * r)) & 15);
         if (where == 3) {
             const int src = nib >> 2;
@@ -366,6 +366,13 @@ __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, co
     if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; }
 #undef PUSH
     P.nruns[p] = nr;
+}
+
+__global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, const int64_t end)
+{
+    const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= end) return;
+    traceback_pair<false>(P, p);
 }
 
 // after the traceback of a small batch: CIGAR offsets (block scan of the run counts), coalesced copy of the runs,
@@ -467,17 +474,13 @@ struct AlnStream {
     }
 };
 
-__global__ void sg_features_kernel(const AlignParams P, const int64_t start, const int64_t end, int delta_len,
-                                   int32_t *__restrict__ feat)
+__device__ __forceinline__ void features_pair(const AlignParams &P, const int64_t p, const int delta_len, int32_t *__restrict__ f)
 {
-    const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= end) return;
     const int n = P.pn[p], m = P.pm[p];
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const int nr = P.nruns[p];
     const uint32_t *runs = run_tail(P, p) - nr;
-    int32_t *f = feat + p * ISOF_N_FEATURES;
     // pass 1: parse_cigar_diversity features (SimplifyGraph.py:175-196)
     int alen = 0, nonmatch = 0, maxrun = 0;
     for (int x = 0; x < nr; ++x) {
@@ -572,7 +575,189 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
     f[6] = structural; f[7] = miss_runs; f[8] = bm; f[9] = bn; f[10] = am; f[11] = an;
 }
 
+__global__ void sg_features_kernel(const AlignParams P, const int64_t start, const int64_t end, int delta_len,
+                                   int32_t *__restrict__ feat)
+{
+    const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= end) return;
+    features_pair(P, p, delta_len, feat + p * ISOF_N_FEATURES);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiny calls (the per-pair seams: a memo miss of consensus.parasail_alignment, one align_to_merge): ONE launch does
+// everything -- base codes, DP (32-bit wavefront path, one warp per pair), traceback, features -- with the trace in
+// SHARED memory (the traceback's dependent loads then cost ~30 cycles instead of an L2 round trip each) and inputs /
+// outputs in mapped pinned host memory (no memcpy calls: the kernel reads the sequences and writes the results over
+// PCIe itself).  The regular path spends 0.25 ms on such a call in five launches, eight small copies and two stream
+// synchronisations around a DP of 8 us.
+// ---------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const uint8_t *cat; const int64_t *off; const int32_t *pa, *pb;       // mapped host memory
+    int32_t *score, *endq, *endr, *nruns, *feat; uint32_t *runs; const int64_t *roff;
+    int2 *bnd; int64_t bnd_stride;
+    int c_eo, c_ee, c_fo, c_fe, c_sm, c_sx;
+    int tb_src_e, tb_open_tie, tb_end_col_first, tb_swap_id, delta_len;
+};
+
+__global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
+{
+    extern __shared__ uint4 fs_smem[];                          // [query profile 4 KB | trace words | cat | codes]
+    __shared__ int64_t s_off[3], s_ptrace[2];
+    __shared__ int32_t s_i32[8];                                 // pa pb pn pm score endq endr nruns
+    __shared__ uint8_t s_u8[4];                                  // pwild layout lastrr
+    const int p = blockIdx.x, lane = threadIdx.x;
+    const int ia = a.pa[p], ib = a.pb[p];
+    const int64_t oa = a.off[ia], ob = a.off[ib];
+    const int n = (int)(a.off[ia + 1] - oa), m = (int)(a.off[ib + 1] - ob);
+    const int ns = (n + SROWS - 1) / SROWS;
+    const int64_t words = (int64_t)ns * (m + 64) * 32 + TRACE_SLACK;
+    uint4 *prof = fs_smem;
+    uint32_t *trace = reinterpret_cast<uint32_t *>(fs_smem + 4 * 2 * 32);
+    uint8_t *s_cat = reinterpret_cast<uint8_t *>(trace + words);
+    uint8_t *s_codes = s_cat + ((n + m + 15) & ~15);
+    int wild = 0;
+    for (int x = lane; x < n + m; x += 32) {
+        const uint8_t c = x < n ? a.cat[oa + x] : a.cat[ob + (x - n)];
+        const int code = base_code(c);
+        s_cat[x] = c; s_codes[x] = (uint8_t)code;
+        wild |= (code == 4);
+    }
+    wild = __any_sync(0xffffffffu, wild);
+    if (lane == 0) {
+        s_off[0] = 0; s_off[1] = n; s_off[2] = n + m;
+        s_ptrace[0] = 0; s_ptrace[1] = words;
+        s_i32[0] = 0; s_i32[1] = 1; s_i32[2] = n; s_i32[3] = m;
+        s_u8[0] = (uint8_t)wild;
+    }
+    __syncwarp();
+    AlignParams P;
+    P.cat = s_cat; P.codes = s_codes; P.seq_off = s_off; P.pa = &s_i32[0]; P.pb = &s_i32[1]; P.pn = &s_i32[2]; P.pm = &s_i32[3];
+    P.pwild = &s_u8[0]; P.ptrace = s_ptrace; P.chunk_base = 0; P.trace = trace;
+    P.bnd = a.bnd + (size_t)p * a.bnd_stride; P.bnd_stride = a.bnd_stride;
+    P.score = &s_i32[4]; P.endq = &s_i32[5]; P.endr = &s_i32[6]; P.nruns = &s_i32[7];
+    P.c_eo = a.c_eo; P.c_ee = a.c_ee; P.c_fo = a.c_fo; P.c_fe = a.c_fe; P.c_sm = a.c_sm; P.c_sx = a.c_sx;
+    P.playout = &s_u8[1]; P.plastrr = &s_u8[2]; P.chunk_words = 0; P.order = nullptr; P.n_elig = nullptr; P.n_rb = nullptr;
+    P.tb_src_e = a.tb_src_e; P.tb_open_tie = a.tb_open_tie; P.tb_end_col_first = a.tb_end_col_first; P.tb_swap_id = a.tb_swap_id;
+    P.ptail = nullptr;
+    if (wild) dp_pair<true>(P, 0, lane, P.bnd, prof);
+    else dp_pair<false>(P, 0, lane, P.bnd, prof);
+    __syncwarp();
+    if (lane == 0) {
+        traceback_pair<true>(P, 0);
+        if (a.feat) features_pair(P, 0, a.delta_len, a.feat + (size_t)p * ISOF_N_FEATURES);
+        a.score[p] = s_i32[4]; a.endq[p] = s_i32[5]; a.endr[p] = s_i32[6]; a.nruns[p] = s_i32[7];
+    }
+    __syncwarp();
+    const int nr = s_i32[7];
+    const uint32_t *src = trace + words - nr;
+    uint32_t *dst = a.runs + a.roff[p];
+    for (int x = lane; x < nr; x += 32) dst[x] = src[x];
+}
+
 }  // namespace
+
+// Host buffers in, host buffers out, one launch.  Returns 1 when the call is not eligible (caller takes the regular path).
+int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, const int32_t *pair_a,
+                        const int32_t *pair_b, int64_t P, int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_ext,
+                        int32_t delta_len, int32_t *score, int32_t *end_q, int32_t *end_r, uint32_t *cigar_runs,
+                        int64_t cigar_cap, int64_t *cigar_off, int32_t *features)
+{
+    constexpr int64_t MAX_P = 32, MAX_SMEM = 200 * 1024, IO_BYTES = 512 * 1024;
+    if (P < 1 || P > MAX_P || ctx->profiling) return 1;
+    if (match - mismatch > 256 || match - mismatch < 0 || gap_open < 0 || gap_ext < 0 || std::abs(match) > 1024 ||
+        std::abs(mismatch) > 1024 || gap_open > 4096 || gap_ext > 4096)
+        return 1;                                          // the regular path reports the range error
+    // ---- plan on the host: lengths, validity, shared memory, run slots
+    int64_t in_bytes = 0, smem_max = 0, run_words = 0, bases = 0;
+    int max_m = 0;
+    int64_t roff[MAX_P + 1];
+    for (int64_t p = 0; p < P; ++p) {
+        const int a = pair_a[p], b = pair_b[p];
+        if (a < 0 || a >= n_seqs || b < 0 || b >= n_seqs) return 1;       // regular path: ISOF_ERR_ARG with its message
+        const int64_t n = seq_off[a + 1] - seq_off[a], m = seq_off[b + 1] - seq_off[b];
+        if (n <= 0 || m <= 0 || n > 4096 || m > 4096) return 1;
+        const int64_t ns = (n + SROWS - 1) / SROWS;
+        const int64_t words = ns * (m + 64) * 32 + TRACE_SLACK;
+        const int64_t smem = 4096 + words * 4 + 2 * ((n + m + 15) & ~15LL) + 64;
+        if (smem > MAX_SMEM) return 1;
+        smem_max = std::max(smem_max, smem);
+        roff[p] = run_words;
+        run_words += n + m + 2;
+        max_m = std::max(max_m, (int)m);
+        bases += n + m;
+    }
+    roff[P] = run_words;
+    const int64_t n_bases = seq_off[n_seqs];
+    in_bytes = 8 * (n_seqs + 1) + 8 * P + 8 * (P + 1) + n_bases + 64;
+    const int64_t out_bytes = 4 * (4 + ISOF_N_FEATURES) * P + 4 * run_words + 64;
+    if (in_bytes > IO_BYTES || out_bytes > IO_BYTES || n_seqs > 4096) return 1;
+    (void)bases;
+    if (!ctx->fused_io) {
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->fused_io, 2 * IO_BYTES, cudaHostAllocMapped));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(sg_fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_SMEM));
+    }
+    // ---- stage the inputs (mapped pinned memory: the kernel reads them over PCIe, no memcpy call)
+    uint8_t *in = (uint8_t *)ctx->fused_io, *out = in + IO_BYTES;
+    int64_t *h_off = (int64_t *)in;
+    int64_t *h_roff = h_off + (n_seqs + 1);
+    int32_t *h_pa = (int32_t *)(h_roff + (P + 1)), *h_pb = h_pa + P;
+    uint8_t *h_cat = (uint8_t *)(h_pb + P);
+    memcpy(h_off, seq_off, 8 * (size_t)(n_seqs + 1));
+    memcpy(h_roff, roff, 8 * (size_t)(P + 1));
+    memcpy(h_pa, pair_a, 4 * (size_t)P);
+    memcpy(h_pb, pair_b, 4 * (size_t)P);
+    memcpy(h_cat, seq_cat, (size_t)n_bases);
+    int32_t *o_score = (int32_t *)out, *o_endq = o_score + P, *o_endr = o_endq + P, *o_nruns = o_endr + P;
+    int32_t *o_feat = o_nruns + P;
+    uint32_t *o_runs = (uint32_t *)(o_feat + ISOF_N_FEATURES * P);
+    const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
+    TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)P));
+    FusedArgs a;
+    void *d_in = nullptr, *d_out = nullptr;
+    CUDA_TRY(ctx, cudaHostGetDevicePointer(&d_in, in, 0));
+    CUDA_TRY(ctx, cudaHostGetDevicePointer(&d_out, out, 0));
+    const ptrdiff_t din = (uint8_t *)d_in - in, dout = (uint8_t *)d_out - out;
+    a.off = (const int64_t *)((uint8_t *)h_off + din); a.roff = (const int64_t *)((uint8_t *)h_roff + din);
+    a.pa = (const int32_t *)((uint8_t *)h_pa + din); a.pb = (const int32_t *)((uint8_t *)h_pb + din);
+    a.cat = h_cat + din;
+    a.score = (int32_t *)((uint8_t *)o_score + dout); a.endq = (int32_t *)((uint8_t *)o_endq + dout);
+    a.endr = (int32_t *)((uint8_t *)o_endr + dout); a.nruns = (int32_t *)((uint8_t *)o_nruns + dout);
+    a.feat = features ? (int32_t *)((uint8_t *)o_feat + dout) : nullptr;
+    a.runs = (uint32_t *)((uint8_t *)o_runs + dout);
+    a.bnd = (int2 *)ctx->b_bnd.p; a.bnd_stride = bnd_stride;
+    const bool e_first = ctx->tb_h_e_before_f != 0, open_tie = ctx->tb_gap_open_on_tie != 0;
+    const int S = 1 << TAG_BITS, class_e = e_first ? 8 : 4, class_f = e_first ? 4 : 8;
+    a.c_eo = -gap_open * S + class_e + (open_tie ? 1 : 0);
+    a.c_ee = -gap_ext * S + class_e + (open_tie ? 0 : 1);
+    a.c_fo = -gap_open * S + class_f + (open_tie ? 2 : 0);
+    a.c_fe = -gap_ext * S + class_f + (open_tie ? 0 : 2);
+    a.c_sm = match * S + 12 - (3 << CODE_SHIFT);
+    a.c_sx = mismatch * S + 12;
+    a.tb_src_e = e_first ? 2 : 1; a.tb_open_tie = open_tie ? 1 : 0; a.tb_end_col_first = ctx->tb_end_col_first ? 1 : 0;
+    a.tb_swap_id = ctx->tb_swap_id ? 1 : 0; a.delta_len = delta_len;
+    ctx->prof.launches++; ctx->prof.dp_launches++;
+    sg_fused_small_kernel<<<(unsigned)P, 32, (size_t)smem_max, ctx->stream>>>(a);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // ---- results
+    int64_t total = 0;
+    for (int64_t p = 0; p < P; ++p) {
+        score[p] = o_score[p];
+        if (end_q) end_q[p] = o_endq[p];
+        if (end_r) end_r[p] = o_endr[p];
+        if (cigar_off) cigar_off[p] = total;
+        const int nr = o_nruns[p];
+        if (cigar_runs && total + nr <= cigar_cap) memcpy(cigar_runs + total, o_runs + roff[p], 4 * (size_t)nr);
+        total += nr;
+        const int64_t n = seq_off[pair_a[p] + 1] - seq_off[pair_a[p]], m = seq_off[pair_b[p] + 1] - seq_off[pair_b[p]];
+        ctx->prof.dp_cells += n * m;
+    }
+    if (cigar_off) cigar_off[P] = total;
+    if (features) memcpy(features, o_feat, 4 * (size_t)ISOF_N_FEATURES * (size_t)P);
+    if (cigar_runs && cigar_cap > 0 && total > cigar_cap)
+        return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap, (long long)total);
+    return ISOF_OK;
+}
 
 unsigned isof_viol_align()
 {

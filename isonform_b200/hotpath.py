@@ -91,10 +91,16 @@ def parasail_alignment(s1, s2, match_score=2, mismatch_penalty=-2, opening_penal
     (s1_alignment, s2_alignment, cigar_string, cigar_tuples, score)."""
     if len(s1) == 0 or len(s2) == 0:
         raise ValueError("parasail rejects empty sequences")
-    res = align_pairs([s1, s2], [0], [1], match_score, mismatch_penalty, opening_penalty, gap_ext, ctx)
-    cigar_string = runs_to_string(res["cigar"])
+    ctx = ctx or default_context()
+    one = getattr(ctx, "sg_align_one", None)
+    if one is not None:                       # lean single-pair call (pre-allocated buffers, fused tiny-call kernel)
+        score, _eq, _er, runs = one(s1, s2, match_score, mismatch_penalty, opening_penalty, gap_ext)
+    else:
+        res = align_pairs([s1, s2], [0], [1], match_score, mismatch_penalty, opening_penalty, gap_ext, ctx)
+        score, runs = int(res["score"][0]), res["cigar"]
+    cigar_string = runs_to_string(runs)
     a1, a2, tuples = cigar_to_seq(cigar_string, s1, s2)
-    return a1, a2, cigar_string, tuples, int(res["score"][0])
+    return a1, a2, cigar_string, tuples, score
 
 
 # ----------------------------------------------------------------------------------------------

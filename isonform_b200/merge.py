@@ -48,6 +48,12 @@ class AlignmentMemo:
         todo = [(a, b) for a, b in dict.fromkeys(pairs) if (a, b) + params not in self.cigars and a and b]
         if not todo:
             return 0
+        one = getattr(self._ctx(), "sg_align_one", None)
+        if len(todo) == 1 and one is not None:             # the memo-miss seam: lean single-pair call
+            a, b = todo[0]
+            score, _eq, _er, runs = one(a, b, *params)
+            self.cigars[(a, b) + params] = (hotpath.runs_to_string(runs), score)
+            return 1
         pool, pa, pb = _pool(todo)
         res = hotpath.align_pairs(pool, pa, pb, *params, ctx=self._ctx())
         off = res["cigar_off"]

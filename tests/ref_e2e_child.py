@@ -57,6 +57,7 @@ def main():
         from isonform_b200 import patch
         ctx = FakeContext()
         memo = patch.install(vars(ref), ctx=ctx)
+        memo.bubbles.check_paths = True           # every find_paths call is cross-checked against the reference's own
         stats = {"ctx": ctx, "memo": memo}
 
     args = types.SimpleNamespace(fastq=a.fastq, outfolder=a.outfolder, k=20, w=31, xmin=40, xmax=80, T=0.1, exact=True,
@@ -73,6 +74,7 @@ def main():
         sys.stderr.write("B200_BUBBLES iterations=%d speculated=%d prefetch_calls=%d prefetched=%d spoa_calls=%d spoa_hits=%d\n"
                          % (b["iterations"], b["speculated_pairs"], b["prefetch_calls"], b["prefetched"], b["spoa_calls"],
                             b["spoa_hits"]))
+        sys.stderr.write("B200_FIND_PATHS checked=%d\n" % b.get("find_paths_checked", 0))
 
 
 if __name__ == "__main__":

@@ -639,6 +639,13 @@ def test_debug_build_bounds_assertions_stay_silent():
         assert np.array_equal(a["cigar"], b["cigar"]) and np.array_equal(a["features"], b["features"])
         assert dctx.debug_violations()[0] == 0
         # short-pair regime (thread-per-task kernel): ragged groups, wildcards, a partial last group
+        # fused tiny-call kernel (trace in shared memory)
+        for (n, m) in [(1, 1), (99, 101), (257, 120), (480, 490), (130, 700)]:
+            x = _rand_dna(rng, max(n, m)); y = synth.mutate(rng, x, 0.06) + _rand_dna(rng, m)
+            res = hotpath.align_pairs([x[:n], y[:m]], [0], [1], 2, -8, 12, 1, ctx=dctx, features_delta_len=5)
+            sc, _q, _r, runs = oracle.sg_align(x[:n], y[:m], 2, -8, 12, 1)
+            assert int(res["score"][0]) == sc and res["cigar"].tolist() == runs.tolist()
+        assert dctx.debug_violations()[0] == 0
         dctx.set_short(2)
         for n_pairs, wild in ((130, False), (77, True)):
             sseqs, spa, spb = _short_cases(np.random.default_rng(5 + n_pairs), n_pairs, wild)
@@ -1027,3 +1034,58 @@ def test_spans_exact_kmer_identity_under_forced_hash_collisions(ctx, mask):
         _span_case_check(ctx, reads, 9, 20, 18, 60, 10)
     finally:
         ctx.debug_set_span_hash_mask()
+
+
+# ------------------------------------------------------------------------------- fused tiny-call path
+def test_fused_small_call_matches_regular_path_and_oracle(ctx):
+    """Host-buffer calls of a few small pairs run as one fused launch (trace in shared memory, mapped I/O).  Same
+    scores, end cells, CIGAR runs and features as the regular path and the oracle: single pairs from 1 x 1 to multi-stripe
+    shapes, wildcards and lower case, batches of up to 32 pairs, the capacity-retry protocol, a non-default tie-break
+    table, and shapes just beyond the fused limits (which must fall through to the regular path unnoticed)."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(2024)
+    cases = []
+    for (n, m) in [(1, 1), (1, 60), (60, 1), (7, 9), (99, 101), (256, 256), (257, 120), (300, 310), (520, 200), (130, 700),
+                   (480, 490), (800, 800), (20, 3000)]:
+        x = _rand_dna(rng, max(n, m))
+        y = synth.mutate(rng, x, 0.06) + _rand_dna(rng, m)
+        cases.append(([x[:n], y[:m]], [0], [1]))
+    cases.append((["ACGTNNACGTacgtACGTX" * 6, "ACGTACGTACGTacgt" * 7], [0], [1]))
+    cases.append((["X" * 40, lcg(45, 42)], [0, 1], [1, 0]))
+    pool = [synth.mutate(rng, _rand_dna(rng, 150), 0.05) for _ in range(12)] + ["ACGNNT" * 20]
+    ia, ib = np.triu_indices(len(pool), 1)
+    cases.append((pool, ia[:32].tolist(), ib[:32].tolist()))
+    cases.append((pool, ia[:33].tolist(), ib[:33].tolist()))             # 33 pairs: beyond the fused limit
+    for tb in ((0, 0, 0, 0), (1, 1, 1, 1)):
+        ctx.set_tiebreak(*tb)
+        try:
+            for seqs, pa, pb in cases:
+                for params in [(2, -8, 12, 1), (2, -2, 12, 1)]:
+                    ctx.set_fused_small(True)
+                    a = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
+                    af = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, want_cigar=True, features_delta_len=5)
+                    ctx.set_fused_small(False)
+                    b = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
+                    bf = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, want_cigar=True, features_delta_len=5)
+                    ctx.set_fused_small(True)
+                    for key in ("score", "end_q", "end_r", "cigar_off", "cigar"):
+                        assert np.array_equal(a[key], b[key]), (key, len(seqs[pa[0]]), len(seqs[pb[0]]), params, tb)
+                    for key in ("score", "cigar_off", "cigar", "features"):
+                        assert np.array_equal(af[key], bf[key]), (key, len(seqs[pa[0]]), len(seqs[pb[0]]), params, tb)
+        finally:
+            ctx.set_fused_small(True)
+            ctx.set_tiebreak(0, 0, 0, 0)
+    # against the oracle (default table) and through the reference-shaped seam
+    for seqs, pa, pb in cases[:15]:
+        res = hotpath.align_pairs(seqs, pa, pb, 2, -8, 12, 1, ctx=ctx)
+        for p in range(len(pa)):
+            sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], 2, -8, 12, 1)
+            assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er)
+            assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
+    cat, off = hotpath.pack_sequences(pool)
+    full = ctx.sg_align_pairs(cat, off, ia[:20], ib[:20])
+    small = ctx.sg_align_pairs(cat, off, ia[:20], ib[:20], cigar_cap=3)       # ISOF_ERR_CAPACITY + retry on the fused path
+    assert small["cigar"].tolist() == full["cigar"].tolist()
+    a1, a2, cig, tup, score = hotpath.parasail_alignment(pool[0], pool[1], 2, -8, 12, 1, ctx)
+    o = oracle.parasail_alignment(pool[0], pool[1], 2, -8, 12, 1)
+    assert (a1, a2, cig, tup, score) == (o[0], o[1], o[2], o[3], o[4])

@@ -54,6 +54,8 @@ def test_reference_main_with_patched_seams_writes_identical_outputs(tmp_path, se
     hits, misses = int(hm.group(1)), int(hm.group(2))
     assert iterations >= 1 and prefetch_calls <= iterations
     assert hits > 0 and hits >= misses
+    # PathFinder (the fast find_paths) agreed with the reference's own function on every call of the run
+    assert int(re.search(r"B200_FIND_PATHS checked=(\d+)", r.stderr).group(1)) > 100
     spawns_ref = int(re.search(r"SPOA_SPAWNS (\d+)", r0.stderr).group(1))
     spawns_b200 = int(re.search(r"SPOA_SPAWNS (\d+)", r.stderr).group(1))
     assert spawns_b200 <= spawns_ref, (spawns_b200, spawns_ref)
