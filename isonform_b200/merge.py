@@ -34,8 +34,13 @@ class AlignmentMemo:
     def __init__(self, ctx=None):
         self.ctx = ctx
         self.cigars = {}          # (s1, s2, match, mismatch, open, ext) -> (cigar_string, score)
-        self.merge_feats = {}     # (s1, s2, delta_len) -> int32[12]
+        self.merge_feats = {}     # (s1, s2, delta_len) -> int32[12] (own copy, not a view of a batch result)
         self.hits = self.misses = 0
+
+    def clear(self):
+        """Drop the memoised results (e.g. between batches: keys are whole consensus strings)."""
+        self.cigars.clear()
+        self.merge_feats.clear()
 
     def _ctx(self):
         if self.ctx is None:
@@ -85,7 +90,7 @@ class AlignmentMemo:
         pool, pa, pb = _pool(todo)
         res = hotpath.align_pairs(pool, pa, pb, 2, -2, 12, 1, ctx=self._ctx(), want_cigar=False, features_delta_len=delta_len)
         for p, (a, b) in enumerate(todo):
-            self.merge_feats[(a, b, delta_len)] = res["features"][p]
+            self.merge_feats[(a, b, delta_len)] = res["features"][p].copy()
         return len(todo)
 
     def align_to_merge(self, consensus1, consensus2, delta, delta_len, delta_iso_len_3, delta_iso_len_5):
@@ -94,6 +99,8 @@ class AlignmentMemo:
         f = self.merge_feats.get(key)
         if f is None:
             self.misses += 1
+            if len(consensus1) == 0 or len(consensus2) == 0:
+                raise ValueError("parasail rejects empty sequences")
             self.prefetch_merge([(consensus1, consensus2)], delta_len)
             f = self.merge_feats[key]
         else:
@@ -188,14 +195,14 @@ def merge_consensuses(curr_best_seqs, work_dir, delta, delta_len, reads, max_seq
             rows.append(r)
             budget += n - 1 - r
             r += 1
-        used_before = n_used
+        merged_in_block = False
         override = {row: new_consensuses[ids[row]] for row in rows if ids[row] in new_consensuses}
         table = _row_decisions(pool, rows, n, override, delta, delta_len, delta_iso_len_3, delta_iso_len_5, ctx)
         n_aligned += budget
         # ---- replay the reference loop over the block
         for row in rows:
             id1 = ids[row]
-            if id1 in new_consensuses and override.get(row) is not new_consensuses[id1]:
+            if id1 in new_consensuses and override.get(row, pool[row]) != new_consensuses[id1]:
                 # this row's left string changed while replaying an earlier row of the block
                 override2 = {row: new_consensuses[id1]}
                 table[row] = _row_decisions(pool, [row], n, override2, delta, delta_len, delta_iso_len_3, delta_iso_len_5,
@@ -205,6 +212,7 @@ def merge_consensuses(curr_best_seqs, work_dir, delta, delta_len, reads, max_seq
             hit = np.nonzero(dec)[0]
             n_used += (int(hit[0]) + 1) if len(hit) else len(dec)
             if len(hit):
+                merged_in_block = True
                 id2 = ids[row + 1 + int(hit[0])]
                 if len(curr_best_seqs[id2]) > 50:
                     add_merged_reads(curr_best_seqs, id2, id1)
@@ -215,7 +223,7 @@ def merge_consensuses(curr_best_seqs, work_dir, delta, delta_len, reads, max_seq
         i = rows[-1] + 1
         # all speculated pairs consumed (no row broke early): the batch behaves like an all-pairs job, so issue it in
         # launches that fill the GPU several times over; an early break shrinks the block again
-        if n_used - used_before == budget:
+        if not merged_in_block:
             block_pairs = min(block_pairs * 4, _MAX_PAIRS_PER_CALL)
         else:
             block_pairs = _MIN_PAIRS_PER_CALL

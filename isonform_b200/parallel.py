@@ -132,6 +132,8 @@ class InProcessRunner:
         """`isONform_parallel.main(args)` with the worker layer replaced (args: its argparse namespace)."""
         if args.outfolder and not os.path.exists(args.outfolder):
             os.makedirs(args.outfolder, exist_ok=True)
+        if self.world > 1 and getattr(args, "tmpdir", None):
+            args.tmpdir = os.path.join(args.tmpdir, "rank%d" % self.rank)      # every rank splits the clusters for itself
         if self.world > 1 and self.rank != 0:
             self.barrier()                 # rank 0 restructures the input folder first (:31-55 moves files)
         if self.world > 1 and self.rank == 0:
@@ -176,8 +178,9 @@ def main(argv=None):
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
         barrier = dist.barrier
     InProcessRunner(args.reference, barrier=barrier).run(args)
 

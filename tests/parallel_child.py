@@ -17,8 +17,16 @@ def main():
     ref = sys.argv[1]
     args = parallel.parser().parse_args(["--reference", ref] + sys.argv[2:])
     ctx = FakeContext()
-    runner = parallel.InProcessRunner(ref, ctx=ctx)
+    barrier = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:          # world_size-2 test: gloo carries the barriers
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        barrier = dist.barrier
+    runner = parallel.InProcessRunner(ref, ctx=ctx, barrier=barrier)
     runner.run(args)
+    if barrier is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     b = runner.memo.bubbles.stats
     sys.stderr.write("B200_PARALLEL " + json.dumps({"batches": runner.batches_run, "calls": ctx.calls, "memo_hits": runner.memo.hits,
                                                     "memo_misses": runner.memo.misses, "bubbles": b}) + "\n")
