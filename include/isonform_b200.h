@@ -211,6 +211,17 @@ ISOF_API int isof_span_instances(int64_t n_picks, const int32_t *pick_rec, const
                                  const int32_t *bucket_off, const int64_t *read_id, int32_t delta_len,
                                  const int64_t *inst_off, uint32_t *inst);
 
+/*
+ * In-process partial-order-alignment consensus (host C++, csrc/host_poa.cpp): stands where the
+ * reference spawns the external `spoa <reads.fa> -l 0 -r 0 -g -2` (IsoformGeneration.run_spoa, IsoformGeneration.py:143-156).
+ * Local alignment of each sequence to the growing graph, linear gap, heaviest-bundle consensus; an independent
+ * implementation with that command line's scoring (match 5, mismatch -4, gap -2), NOT a bit-exact spoa: use it on both
+ * sides of a comparison (scripts/isof_spoa is the same code as an executable).  Sequences are upper-cased; empty ones are
+ * skipped.  *out_len receives the consensus length (also on ISOF_ERR_CAPACITY).
+ */
+ISOF_API int isof_poa_consensus(const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, int32_t match,
+                                int32_t mismatch, int32_t gap, uint8_t *out, int64_t out_cap, int64_t *out_len);
+
 /* ------------------------------------------------------------------------------------------ */
 /* (b) semi-global affine alignment with traceback                                            */
 /* ------------------------------------------------------------------------------------------ */

@@ -38,7 +38,7 @@ class Profile(C.Structure):
 EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
-           "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances"]
+           "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances", "isof_poa_consensus"]
 
 _lib = None
 _lib_debug = None
@@ -92,6 +92,7 @@ def load(debug=False):
     L.isof_sg_features_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp]
     L.isof_wis_picks.argtypes = [i32, vp, vp, vp, vp, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_span_instances.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.isof_poa_consensus.argtypes = [vp, vp, i32, i32, i32, i32, vp, i64, C.POINTER(i64)]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("isof_last_error",):
@@ -383,6 +384,24 @@ class Context:
                                                     gap_open, gap_ext, d_score, d_endq, d_endr, d_cigar, cigar_cap,
                                                     d_cigar_off, d_features, delta_len, C.byref(total)))
         return int(total.value)
+
+
+def poa_consensus(seqs, match=5, mismatch=-4, gap=-2):
+    """Consensus string of a list of sequences (isof_poa_consensus, host helper; spoa's -l 0 -r 0 -g -2 scoring)."""
+    L = load()
+    cat, off = pack_sequences(seqs)
+    cap = int(2 * max((len(s) for s in seqs), default=0) + 64)
+    n = C.c_int64(0)
+    while True:
+        out = np.empty(max(cap, 1), np.uint8)
+        rc = L.isof_poa_consensus(cat.ctypes.data, off.ctypes.data, len(seqs), match, mismatch, gap, out.ctypes.data, cap,
+                                  C.byref(n))
+        if rc == ERR_CAPACITY:
+            cap = int(n.value)
+            continue
+        if rc != ISOF_OK:
+            raise IsofError(rc, "isof_poa_consensus failed")
+        return out[:n.value].tobytes().decode("latin-1")
 
 
 def wis_picks(read_rec_off, rec_p1, rec_p2, rec_count, k):

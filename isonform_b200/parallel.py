@@ -54,7 +54,7 @@ def batch_args(fastq, outfolder, params):
 
 
 class InProcessRunner:
-    def __init__(self, reference_dir, ctx=None, rank=None, world_size=None, barrier=None):
+    def __init__(self, reference_dir, ctx=None, rank=None, world_size=None, barrier=None, in_process_poa=False):
         if os.environ.get("PYTHONHASHSEED") != "0":
             raise RuntimeError("export PYTHONHASHSEED=0: the reference's minimizer order is CPython's hash(str) and the GPU "
                                "kernel implements it under that seed (the assignment at main:631 comes too late)")
@@ -64,7 +64,7 @@ class InProcessRunner:
         from . import patch
         self.main_mod = load_script(os.path.join(self.reference_dir, "main"), "isonform_reference_main")
         self.driver_mod = load_script(os.path.join(self.reference_dir, "isONform_parallel"), "isonform_reference_parallel")
-        self.memo = patch.install(vars(self.main_mod), ctx=ctx)
+        self.memo = patch.install(vars(self.main_mod), ctx=ctx, in_process_poa=in_process_poa)
         self.rank = int(os.environ.get("RANK", "0")) if rank is None else rank
         self.world = int(os.environ.get("WORLD_SIZE", "1")) if world_size is None else world_size
         self.barrier = barrier or (lambda: None)
@@ -169,6 +169,8 @@ def parser():
     p.add_argument("--delta_iso_len_5", type=int, default=50)
     p.add_argument("--tmpdir", type=str, default=None)
     p.add_argument("--write_fastq", action="store_true")
+    p.add_argument("--in_process_poa", action="store_true",
+                   help="consensus by the library's host POA instead of spawning the `spoa` binary (not bit-exact with spoa)")
     return p
 
 
@@ -182,7 +184,7 @@ def main(argv=None):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
         barrier = dist.barrier
-    InProcessRunner(args.reference, barrier=barrier).run(args)
+    InProcessRunner(args.reference, barrier=barrier, in_process_poa=args.in_process_poa).run(args)
 
 
 if __name__ == "__main__":

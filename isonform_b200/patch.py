@@ -12,12 +12,18 @@ import functools
 from . import bubbles, hotpath, merge, spans
 
 
-def install(main_globals=None, ctx=None, memo=None):
+def install(main_globals=None, ctx=None, memo=None, in_process_poa=False):
     """Returns the AlignmentMemo shared by all patched alignment seams (`memo.bubbles` is the
-    bubble-popping prefetcher with its per-iteration statistics)."""
+    bubble-popping prefetcher with its per-iteration statistics).
+    in_process_poa=True also replaces the `spoa` subprocess (IsoformGeneration.run_spoa, :143-156) by the library's host
+    POA: an independent consensus implementation, so outputs then match a reference run only if that run uses the same
+    code as its `spoa` (scripts/isof_spoa)."""
     from modules import IsoformGeneration, batch_merging_parallel, consensus   # the reference tree
 
     memo = memo or merge.AlignmentMemo(ctx)
+    if in_process_poa:
+        from . import poa
+        IsoformGeneration.run_spoa = poa.run_spoa          # before the prefetcher wraps it with its memo
     # modules/consensus.py:55  (callers SimplifyGraph.py:644, IsoformGeneration.py:381)
     consensus.parasail_alignment = memo.parasail_alignment
     # modules/SimplifyGraph.py:883-1151: one batched alignment call per bubble-popping iteration instead of one

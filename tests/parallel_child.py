@@ -22,7 +22,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("gloo")
         barrier = dist.barrier
-    runner = parallel.InProcessRunner(ref, ctx=ctx, barrier=barrier)
+    runner = parallel.InProcessRunner(ref, ctx=ctx, barrier=barrier, in_process_poa=args.in_process_poa)
     runner.run(args)
     if barrier is not None:
         import torch.distributed as dist

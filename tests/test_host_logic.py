@@ -151,3 +151,21 @@ def test_seam_capture_replays_over_the_oracle_double():
     from fake_ctx import FakeContext
     for i in (0, 1):
         test_gpu_parity.test_reference_seams_replayed_on_gpu(FakeContext(), i)
+
+
+def test_host_poa_consensus_properties():
+    """csrc/host_poa.cpp: deterministic; a single sequence is its own consensus; a majority base wins a column; the
+    consensus of noisy copies is far closer to the truth than any copy (30 copies at 5 % error: exact)."""
+    import numpy as np
+    import oracle
+    from isonform_b200 import poa, synth
+    assert poa.consensus(["ACGTACGT"]) == "ACGTACGT"
+    assert poa.consensus(["acgtacgt"]) == "ACGTACGT"
+    assert poa.consensus(["ACGTACGT", "ACGTTCGT", "ACGTACGT"]) == "ACGTACGT"
+    assert poa.consensus([]) == "" and poa.consensus(["", "ACGT"]) == "ACGT"
+    rng = np.random.default_rng(11)
+    truth = synth.random_dna(rng, 400)
+    copies = [synth.mutate(rng, truth, 0.05) for _ in range(30)]
+    con = poa.consensus(copies)
+    assert con == poa.consensus(list(copies))                       # deterministic
+    assert oracle.edit_distance(con, truth) <= 1 < min(oracle.edit_distance(c, truth) for c in copies)

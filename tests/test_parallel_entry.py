@@ -89,3 +89,29 @@ def test_two_ranks_shard_clusters_and_rank0_merges(tmp_path):
         assert open(tmp_path / "out_ref" / name).read() == open(tmp_path / "out_b200" / name).read(), name
     batches = [json.loads(re.search(r"B200_PARALLEL (\{.*\})", se).group(1))["batches"] for _so, se in outs]
     assert sum(batches) == 5 and min(batches) >= 1            # 2 + 1 + 2 batches, both ranks worked
+
+
+def test_in_process_poa_replaces_the_spoa_subprocess(tmp_path):
+    """with `--in_process_poa` no consensus spawns a process.  The unmodified reference runs with the
+    SAME POA code as its `spoa` executable (tests/stubs_poa/spoa -> scripts/isof_spoa); the final files must be
+    byte-identical, and the in-process run must not have called the executable at all."""
+    for name in ("in_ref", "in_b200"):
+        os.makedirs(tmp_path / name)
+    reads, _iso, _t = synth.make_cluster(seed=31, gene_len=500, n_isoforms=2, n_reads=36, eps=0.02)
+    synth.write_fastq(str(tmp_path / "in_ref" / "0.fastq"), reads)
+    synth.write_fastq(str(tmp_path / "in_b200" / "0.fastq"), reads)
+    env = _env()
+    env["PATH"] = os.pathsep.join([os.path.join(HERE, "stubs_poa"), env["PATH"]])
+    flags = ["--t", "1", "--iso_abundance", "2"]
+    r0 = subprocess.run([sys.executable, os.path.join(REF, "isONform_parallel"), "--fastq_folder", str(tmp_path / "in_ref"),
+                         "--outfolder", str(tmp_path / "out_ref")] + flags, capture_output=True, text=True, env=env,
+                        cwd=str(tmp_path), timeout=1500)
+    assert r0.returncode == 0, r0.stderr[-3000:] + r0.stdout[-2000:]
+    env_b = dict(env, PATH=os.pathsep.join([os.path.dirname(sys.executable), "/usr/bin", "/bin"]))      # no `spoa` on PATH at all
+    r1 = subprocess.run([sys.executable, os.path.join(HERE, "parallel_child.py"), REF, "--fastq_folder", str(tmp_path / "in_b200"),
+                         "--outfolder", str(tmp_path / "out_b200"), "--in_process_poa"] + flags, capture_output=True, text=True,
+                        env=env_b, cwd=str(tmp_path), timeout=1500)
+    assert r1.returncode == 0, r1.stderr[-3000:] + r1.stdout[-2000:]
+    for name in ("transcriptome.fasta", "transcriptome_mapping.txt", "transcriptome_support.txt"):
+        assert open(tmp_path / "out_ref" / name).read() == open(tmp_path / "out_b200" / name).read(), name
+    assert len(open(tmp_path / "out_b200" / "transcriptome.fasta").read()) > 0
