@@ -8,9 +8,11 @@
 // cell update as dp_pair16: tagged 4*score + 2-bit provenance, DPX max, trace bits gathered by IMADs), carrying the
 // bottom row of a block to the next one through a per-lane line buffer.  No shuffles, no fill/drain, no idle lanes:
 // the 64 alignments of a warp ("group") are sorted by shape, so all lanes run the same trip counts.
-//   trace      word[((rb * M + j) * 32 + lane) * 2 + half]   rb = row block, j = column, M = longest reference of
-//              the group -> every column step of a warp is one coalesced 256 B store; 0.5 B per cell, no padding
-//              steps (the long-pair layout spends (m/2 + 31) * 256 B per stripe whatever the row count)
+//   trace      uint4[(rb * M/2 + j/2) * 32 + lane] = {A(j even), B(j even), A(j odd), B(j odd)}   rb = row block, j =
+//              column, M = longest reference of the group (a multiple of 4) -> every two column steps of a warp are one
+//              coalesced 512 B store; 0.5 B per cell, no padding steps (the long-pair layout spends (m/2 + 31) * 256 B
+//              per stripe whatever the row count).  Two columns of an alignment share a 32 B sector, which halves
+//              the sector traffic of the traceback (it is bandwidth-bound on 32 B sectors at these sizes)
 //   boundary   bnd[(j * 32 + lane)] = (H, F) of the block's bottom row, per warp, L1/L2 resident
 //   CIGAR      traceback: one thread per pair (same walk as sg_traceback_kernel), runs written backwards into the
 //              pair's slot of the group's run area; features / CIGAR copy kernels are shared with the long path.
@@ -103,11 +105,11 @@ sg_dp_short_kernel(const ShortParams S, unsigned long long *__restrict__ counter
         const uint8_t *__restrict__ qB = S.codes + S.seq_off[S.pa[pB]];
         const uint8_t *__restrict__ rB = S.codes + S.seq_off[S.pb[pB]];
         const int64_t gbase = S.goff[g];
-        uint2 *__restrict__ tr = reinterpret_cast<uint2 *>(S.trace + gbase) + lane;
+        uint4 *__restrict__ tr = reinterpret_cast<uint4 *>(S.trace + gbase) + lane;
         const int64_t run_area = gbase + (int64_t)NRB * M * SHORT_GROUP;
         const int slot_words = NRB * R + M + 2;
-        if (hasA) { S.pbase[pA] = gbase + 2 * lane; S.pM[pA] = M; S.ptail[pA] = run_area + (int64_t)(lane + 1) * slot_words; }
-        if (hasB) { S.pbase[pB] = gbase + 2 * lane + 1; S.pM[pB] = M; S.ptail[pB] = run_area + (int64_t)(lane + 33) * slot_words; }
+        if (hasA) { S.pbase[pA] = gbase + 4 * lane; S.pM[pA] = M; S.ptail[pA] = run_area + (int64_t)(lane + 1) * slot_words; }
+        if (hasB) { S.pbase[pB] = gbase + 4 * lane + 1; S.pM[pB] = M; S.ptail[pB] = run_area + (int64_t)(lane + 33) * slot_words; }
         int bcolA = INT_MIN, bcolA_i = 0, browA = INT_MIN, browA_j = 0;
         int bcolB = INT_MIN, bcolB_i = 0, browB = INT_MIN, browB_j = 0;
         const int lastA_rb = (nA - 1) >> 3, lastA_r = (nA - 1) & 7, lastB_rb = (nB - 1) >> 3, lastB_r = (nB - 1) & 7;
@@ -134,7 +136,8 @@ sg_dp_short_kernel(const ShortParams S, unsigned long long *__restrict__ counter
             uint32_t a0 = (mA > 0) ? __ldg(wA) : 0u, b0 = (mB > 0) ? __ldg(wB) : 0u;
             uint2 b_next = make_uint2(0u, NEG16 | TAG_F);
             if (has_prev) b_next = bnd[0];
-            uint2 *__restrict__ tp = tr + (size_t)rb * M * 32;
+            uint4 *__restrict__ tp = tr + (size_t)rb * (M / 2) * 32;
+            uint32_t wA_even = 0u, wB_even = 0u;
             for (int j4 = 0; j4 < M; j4 += 4) {
                 // word k+1 starts at byte 4(k+1) - misalignment of the sequence: load it only while inside the sequence
                 const int nextA = j4 + 4 - (int)(shA >> 3), nextB = j4 + 4 - (int)(shB >> 3);
@@ -142,6 +145,9 @@ sg_dp_short_kernel(const ShortParams S, unsigned long long *__restrict__ counter
                 const uint32_t b1 = (nextB < mB) ? __ldg(wB + (j4 >> 2) + 1) : 0u;
                 const uint32_t bytesA = __funnelshift_r(a0, a1, shA), bytesB = __funnelshift_r(b0, b1, shB);
                 a0 = a1; b0 = b1;
+                // the word after next: into L1 now, so that the load above hits it one block later (no register held)
+                if (nextA + 4 < mA) asm volatile("prefetch.global.L1 [%0];" ::"l"(wA + (j4 >> 2) + 2));
+                if (nextB + 4 < mB) asm volatile("prefetch.global.L1 [%0];" ::"l"(wB + (j4 >> 2) + 2));
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int j = j4 + c;
@@ -149,6 +155,10 @@ sg_dp_short_kernel(const ShortParams S, unsigned long long *__restrict__ counter
                 uint32_t up = b_next.x, fup = b_next.y;
                 const uint32_t up0 = up;
                 if (has_prev && j + 1 < M) b_next = bnd[(size_t)(j + 1) * 32];
+                // ptxas sinks the load above to the end of the column (128 registers: it shortens the live range), which
+                // exposed an L2 round trip per column (ncu: a third of all stall samples on the move that consumes it);
+                // a prefetch three columns ahead costs no register and turns that load into an L1 hit
+                if (has_prev && j + 4 < M) asm volatile("prefetch.global.L1 [%0];" ::"l"(bnd + (size_t)(j + 4) * 32));
                 uint32_t diag = diag0;
                 uint32_t acc_ef = 0u, acc_h = 0u;
 #pragma unroll
@@ -182,8 +192,13 @@ sg_dp_short_kernel(const ShortParams S, unsigned long long *__restrict__ counter
                 }
                 diag0 = up0;
                 if (has_next) bnd[(size_t)j * 32] = make_uint2(up, fup);
-                ISOF_ASSERT((uint32_t *)(tp + (size_t)j * 32 + 1) <= S.trace + run_area, CHK_TRACE_STORE);
-                tp[(size_t)j * 32] = make_uint2(__byte_perm(acc_ef, acc_h, 0x5410), __byte_perm(acc_ef, acc_h, 0x7632));
+                if ((c & 1) == 0) {
+                    wA_even = __byte_perm(acc_ef, acc_h, 0x5410); wB_even = __byte_perm(acc_ef, acc_h, 0x7632);
+                } else {
+                    ISOF_ASSERT((uint32_t *)(tp + (size_t)(j >> 1) * 32 + 1) <= S.trace + run_area, CHK_TRACE_STORE);
+                    tp[(size_t)(j >> 1) * 32] = make_uint4(wA_even, wB_even, __byte_perm(acc_ef, acc_h, 0x5410),
+                                                           __byte_perm(acc_ef, acc_h, 0x7632));
+                }
                 // ---- end cell bookkeeping (restated library: running maxima of the last row / last column)
                 if (trackA && j < mA) {                    // last row of A: smallest j wins ties
                     const int v = lo16(pick_row<8>(Hl, lastA_r));
@@ -233,7 +248,7 @@ __global__ void sg_traceback_short_kernel(const AlignParams P, const int64_t *__
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const uint32_t *trace = P.trace + pbase[p];
-    const size_t col_stride = 64, rb_stride = (size_t)pM[p] * 64;
+    const size_t pair_stride = 128, rb_stride = (size_t)(pM[p] / 2) * 128;      // words per column pair / per row block
     uint32_t *tail = P.trace + P.ptail[p];
     int i = P.endq[p], j = P.endr[p];
     int nr = 0;
@@ -259,7 +274,7 @@ __global__ void sg_traceback_short_kernel(const AlignParams P, const int64_t *__
         if (i < 0) { PUSH(op_e, j + 1); break; }
         if (j < 0) { PUSH(op_f, i + 1); break; }
         const int r = i & 7;
-        const uint32_t *wp = trace + (size_t)(i >> 3) * rb_stride + (size_t)j * col_stride;
+        const uint32_t *wp = trace + (size_t)(i >> 3) * rb_stride + (size_t)(j >> 1) * pair_stride + (size_t)(j & 1) * 2;
         ISOF_ASSERT(wp >= P.trace && wp < tail - (n + m + 2), CHK_TRACE_LOAD);
         const uint32_t word = __ldcg(wp);
         const int nib = (((word >> (16 + 2 * r)) & 3) << 2) | ((word >> (2 * r)) & 3);
