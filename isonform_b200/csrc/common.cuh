@@ -65,6 +65,7 @@ struct isof_ctx {
         return v;
     }
     void *fused_io = nullptr;         // mapped pinned memory of the fused tiny-call path (inputs | outputs)
+    void *fused_io_dev = nullptr;     // its device address
     bool disable_fused = false;       // tiny calls through the regular path (tests / A-B measurements)
     void *pinned = nullptr;           // small pinned staging for scalar read-backs
     size_t pinned_cap = 0;

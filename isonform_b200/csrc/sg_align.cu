@@ -301,6 +301,9 @@ __device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64
     const bool split = (lay & 16) != 0;               // packed path: [src x8 | fe x8] 2-bit fields; 32-bit path: nibbles
     const int T = (m + pc - 1) / pc + 31;
     const int last_s = (n - 1) >> 8, rr_last = P.plastrr[p];   // rows per lane in the (possibly compacted) last stripe
+    // x / rr_last for x < 256 and rr_last in {2, 4, 6, 8} without an integer division in the walk: multiply-shift
+    // ((x * 171) >> 10 == x / 6 for x < 512)
+    const int rr_mul = rr_last == 6 ? 171 : 1, rr_sh = rr_last == 6 ? 10 : rr_last == 2 ? 1 : rr_last == 4 ? 2 : 3;
     int i = P.endq[p], j = P.endr[p];
     int nr = 0;
     uint32_t cur_op = 0xffu, cur_len = 0;
@@ -330,13 +333,13 @@ __device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64
         if (j < 0) { PUSH(op_f, i + 1); break; }
         const int s = i >> 8;
         int l = (i >> 3) & 31, r = i & 7;
-        if (s == last_s && rr_last != 8) { l = (i & 255) / rr_last; r = (i & 255) % rr_last; }
+        if (s == last_s && rr_last != 8) { l = ((i & 255) * rr_mul) >> rr_sh; r = (i & 255) - l * rr_last; }
         const int jt = (pc == 1) ? j : (j >> 1), jc = (pc == 1) ? 0 : (j & 1);
         if (!SMEM) {   // the path mostly follows the diagonal: pull the line it will need 16 steps from now into L2
             const int ip = i - 16, jp = j - 16;
             if (ip >= 0 && jp >= 0) {
                 const int sp_ = ip >> 8;
-                const int lp = (sp_ == last_s && rr_last != 8) ? (ip & 255) / rr_last : (ip >> 3) & 31;
+                const int lp = (sp_ == last_s && rr_last != 8) ? ((ip & 255) * rr_mul) >> rr_sh : (ip >> 3) & 31;
                 const int jtp = (pc == 1) ? jp : (jp >> 1);
                 const uint32_t *pf = &trace[(((size_t)sp_ * T + (jtp + lp)) * 32 + lp) * pc];
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
@@ -592,11 +595,13 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
 // synchronisations around a DP of 8 us.
 // ---------------------------------------------------------------------------------------------
 struct FusedArgs {
-    const uint8_t *cat; const int64_t *off; const int32_t *pa, *pb;       // mapped host memory
-    int32_t *score, *endq, *endr, *nruns, *feat; uint32_t *runs; const int64_t *roff;
+    const int4 *desc;                 // mapped host memory: per pair {n, m, byte offset of s1, of s2 | run slot, packed-eligible, 0, 0}
+    const uint8_t *in;                // mapped host memory: the sequences, each at a 16-byte aligned offset
+    int32_t *score, *endq, *endr, *nruns, *feat; uint32_t *runs;       // mapped host memory
     int2 *bnd; int64_t bnd_stride;
     int c_eo, c_ee, c_fo, c_fe, c_sm, c_sx;
-    int tb_src_e, tb_open_tie, tb_end_col_first, tb_swap_id, delta_len;
+    uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
+    int tb_src_e, tb_open_tie, tb_end_col_first, tb_swap_id, delta_len, tb_variant;
 };
 
 __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
@@ -606,25 +611,42 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __shared__ int32_t s_i32[8];                                 // pa pb pn pm score endq endr nruns
     __shared__ uint8_t s_u8[4];                                  // pwild layout lastrr
     const int p = blockIdx.x, lane = threadIdx.x;
-    const int ia = a.pa[p], ib = a.pb[p];
-    const int64_t oa = a.off[ia], ob = a.off[ib];
-    const int n = (int)(a.off[ia + 1] - oa), m = (int)(a.off[ib + 1] - ob);
+    const int4 d0 = a.desc[2 * p], d1 = a.desc[2 * p + 1];       // one broadcast read over PCIe
+    const int n = d0.x, m = d0.y;
     const int ns = (n + SROWS - 1) / SROWS;
     const int64_t words = (int64_t)ns * (m + 64) * 32 + TRACE_SLACK;
+    const int n16 = (n + 15) & ~15, m16 = (m + 15) & ~15;
     uint4 *prof = fs_smem;
     uint32_t *trace = reinterpret_cast<uint32_t *>(fs_smem + 4 * 2 * 32);
-    uint8_t *s_cat = reinterpret_cast<uint8_t *>(trace + words);
-    uint8_t *s_codes = s_cat + ((n + m + 15) & ~15);
+    uint8_t *s_cat = reinterpret_cast<uint8_t *>(trace + words);          // s1 at 0, s2 at n16 (16-byte aligned)
+    uint8_t *s_codes = s_cat + n16 + m16;
     int wild = 0;
-    for (int x = lane; x < n + m; x += 32) {
-        const uint8_t c = x < n ? a.cat[oa + x] : a.cat[ob + (x - n)];
-        const int code = base_code(c);
-        s_cat[x] = c; s_codes[x] = (uint8_t)code;
-        wild |= (code == 4);
+    // 16 bytes per lane and round: a 100 x 100 pair arrives in one PCIe round trip instead of seven
+    const int c1 = n16 >> 4, c2 = m16 >> 4;
+    for (int c = lane; c < c1 + c2; c += 32) {
+        const bool first = c < c1;
+        const int byte0 = first ? c * 16 : (c - c1) * 16, len = first ? n : m;
+        const uint4 v = *reinterpret_cast<const uint4 *>(a.in + (first ? d0.z : d0.w) + byte0);
+        const int so = first ? byte0 : n16 + byte0;
+        *reinterpret_cast<uint4 *>(s_cat + so) = v;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t cw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t cc = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int code = base_code((uint8_t)(w[q] >> (8 * b)));
+                cc |= (uint32_t)code << (8 * b);
+                wild |= (code == 4) && (byte0 + 4 * q + b < len);
+            }
+            cw[q] = cc;
+        }
+        *reinterpret_cast<uint4 *>(s_codes + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
     }
     wild = __any_sync(0xffffffffu, wild);
     if (lane == 0) {
-        s_off[0] = 0; s_off[1] = n; s_off[2] = n + m;
+        s_off[0] = 0; s_off[1] = n16; s_off[2] = n16 + m16;
         s_ptrace[0] = 0; s_ptrace[1] = words;
         s_i32[0] = 0; s_i32[1] = 1; s_i32[2] = n; s_i32[3] = m;
         s_u8[0] = (uint8_t)wild;
@@ -636,10 +658,16 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     P.bnd = a.bnd + (size_t)p * a.bnd_stride; P.bnd_stride = a.bnd_stride;
     P.score = &s_i32[4]; P.endq = &s_i32[5]; P.endr = &s_i32[6]; P.nruns = &s_i32[7];
     P.c_eo = a.c_eo; P.c_ee = a.c_ee; P.c_fo = a.c_fo; P.c_fe = a.c_fe; P.c_sm = a.c_sm; P.c_sx = a.c_sx;
+    P.h_eo = a.h_eo; P.h_ee = a.h_ee; P.h_fo = a.h_fo; P.h_fe = a.h_fe; P.h_sm = a.h_sm; P.h_sx = a.h_sx;
     P.playout = &s_u8[1]; P.plastrr = &s_u8[2]; P.chunk_words = 0; P.order = nullptr; P.n_elig = nullptr; P.n_rb = nullptr;
     P.tb_src_e = a.tb_src_e; P.tb_open_tie = a.tb_open_tie; P.tb_end_col_first = a.tb_end_col_first; P.tb_swap_id = a.tb_swap_id;
     P.ptail = nullptr;
-    if (wild) dp_pair<true>(P, 0, lane, P.bnd, prof);
+    // A lone pair inside the 16-bit range runs the PACKED path with itself in both halves (identical words go to the same
+    // trace addresses): that path compacts the last stripe to 2 / 4 / 6 rows per lane, so a 100-row query keeps 25 lanes
+    // busy with a 4-row dependency chain per step instead of 13 lanes with an 8-row one -- half the latency per step.
+    // (default tie-break table only: the other tables take the 32-bit path, whose constants are run-time values)
+    if (!wild && d1.y && a.tb_variant == 0) dp_pair16<0, false>(P, 0, 0, lane, P.bnd, prof);
+    else if (wild) dp_pair<true>(P, 0, lane, P.bnd, prof);
     else dp_pair<false>(P, 0, lane, P.bnd, prof);
     __syncwarp();
     if (lane == 0) {
@@ -650,7 +678,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __syncwarp();
     const int nr = s_i32[7];
     const uint32_t *src = trace + words - nr;
-    uint32_t *dst = a.runs + a.roff[p];
+    uint32_t *dst = a.runs + d1.x;
     for (int x = lane; x < nr; x += 32) dst[x] = src[x];
 }
 
@@ -667,10 +695,17 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     if (match - mismatch > 256 || match - mismatch < 0 || gap_open < 0 || gap_ext < 0 || std::abs(match) > 1024 ||
         std::abs(mismatch) > 1024 || gap_open > 4096 || gap_ext > 4096)
         return 1;                                          // the regular path reports the range error
-    // ---- plan on the host: lengths, validity, shared memory, run slots
-    int64_t in_bytes = 0, smem_max = 0, run_words = 0, bases = 0;
+    int h_max_min_len = 0, h_max_max_len = 0;              // packed 16-bit eligibility, as in isof_sg_align_core
+    if (!ctx->disable_packed && match > 0 && mismatch <= match && 4 * (match - mismatch) <= (1 << CS16)) {
+        h_max_min_len = (32767 - 16) / (4 * match);
+        const int room = 31000 / 4 - 2 * gap_open - std::abs(mismatch) - std::abs(match);
+        h_max_max_len = room <= 0 ? 0 : (gap_ext > 0 ? room / gap_ext : INT_MAX);
+    }
+    // ---- plan on the host: lengths, validity, shared memory, run slots, staging offsets
+    int64_t smem_max = 0, run_words = 0, in_bytes = 32 * P;
     int max_m = 0;
     int64_t roff[MAX_P + 1];
+    int32_t desc[MAX_P][8];
     for (int64_t p = 0; p < P; ++p) {
         const int a = pair_a[p], b = pair_b[p];
         if (a < 0 || a >= n_seqs || b < 0 || b >= n_seqs) return 1;       // regular path: ISOF_ERR_ARG with its message
@@ -678,48 +713,44 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
         if (n <= 0 || m <= 0 || n > 4096 || m > 4096) return 1;
         const int64_t ns = (n + SROWS - 1) / SROWS;
         const int64_t words = ns * (m + 64) * 32 + TRACE_SLACK;
-        const int64_t smem = 4096 + words * 4 + 2 * ((n + m + 15) & ~15LL) + 64;
+        const int64_t n16 = (n + 15) & ~15LL, m16 = (m + 15) & ~15LL;
+        const int64_t smem = 4096 + words * 4 + 2 * (n16 + m16) + 64;
         if (smem > MAX_SMEM) return 1;
         smem_max = std::max(smem_max, smem);
         roff[p] = run_words;
+        desc[p][0] = (int32_t)n; desc[p][1] = (int32_t)m; desc[p][2] = (int32_t)in_bytes; desc[p][3] = (int32_t)(in_bytes + n16);
+        desc[p][4] = (int32_t)run_words;
+        desc[p][5] = (std::min(n, m) <= h_max_min_len && std::max(n, m) <= h_max_max_len) ? 1 : 0;
+        desc[p][6] = desc[p][7] = 0;
+        in_bytes += n16 + m16;
         run_words += n + m + 2;
         max_m = std::max(max_m, (int)m);
-        bases += n + m;
     }
     roff[P] = run_words;
-    const int64_t n_bases = seq_off[n_seqs];
-    in_bytes = 8 * (n_seqs + 1) + 8 * P + 8 * (P + 1) + n_bases + 64;
     const int64_t out_bytes = 4 * (4 + ISOF_N_FEATURES) * P + 4 * run_words + 64;
-    if (in_bytes > IO_BYTES || out_bytes > IO_BYTES || n_seqs > 4096) return 1;
-    (void)bases;
+    if (in_bytes > IO_BYTES || out_bytes > IO_BYTES) return 1;
     if (!ctx->fused_io) {
         CUDA_TRY(ctx, cudaHostAlloc(&ctx->fused_io, 2 * IO_BYTES, cudaHostAllocMapped));
+        CUDA_TRY(ctx, cudaHostGetDevicePointer(&ctx->fused_io_dev, ctx->fused_io, 0));
         CUDA_TRY(ctx, cudaFuncSetAttribute(sg_fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_SMEM));
     }
     // ---- stage the inputs (mapped pinned memory: the kernel reads them over PCIe, no memcpy call)
     uint8_t *in = (uint8_t *)ctx->fused_io, *out = in + IO_BYTES;
-    int64_t *h_off = (int64_t *)in;
-    int64_t *h_roff = h_off + (n_seqs + 1);
-    int32_t *h_pa = (int32_t *)(h_roff + (P + 1)), *h_pb = h_pa + P;
-    uint8_t *h_cat = (uint8_t *)(h_pb + P);
-    memcpy(h_off, seq_off, 8 * (size_t)(n_seqs + 1));
-    memcpy(h_roff, roff, 8 * (size_t)(P + 1));
-    memcpy(h_pa, pair_a, 4 * (size_t)P);
-    memcpy(h_pb, pair_b, 4 * (size_t)P);
-    memcpy(h_cat, seq_cat, (size_t)n_bases);
+    uint8_t *d_in = (uint8_t *)ctx->fused_io_dev, *d_out = d_in + IO_BYTES;
+    memcpy(in, desc, 32 * (size_t)P);
+    for (int64_t p = 0; p < P; ++p) {
+        const int64_t n = desc[p][0], m = desc[p][1];
+        memcpy(in + desc[p][2], seq_cat + seq_off[pair_a[p]], (size_t)n);
+        memcpy(in + desc[p][3], seq_cat + seq_off[pair_b[p]], (size_t)m);
+    }
     int32_t *o_score = (int32_t *)out, *o_endq = o_score + P, *o_endr = o_endq + P, *o_nruns = o_endr + P;
     int32_t *o_feat = o_nruns + P;
     uint32_t *o_runs = (uint32_t *)(o_feat + ISOF_N_FEATURES * P);
-    const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
+    const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;       // touched by multi-stripe pairs only; grow-only reserve
     TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)P));
     FusedArgs a;
-    void *d_in = nullptr, *d_out = nullptr;
-    CUDA_TRY(ctx, cudaHostGetDevicePointer(&d_in, in, 0));
-    CUDA_TRY(ctx, cudaHostGetDevicePointer(&d_out, out, 0));
-    const ptrdiff_t din = (uint8_t *)d_in - in, dout = (uint8_t *)d_out - out;
-    a.off = (const int64_t *)((uint8_t *)h_off + din); a.roff = (const int64_t *)((uint8_t *)h_roff + din);
-    a.pa = (const int32_t *)((uint8_t *)h_pa + din); a.pb = (const int32_t *)((uint8_t *)h_pb + din);
-    a.cat = h_cat + din;
+    const ptrdiff_t dout = d_out - out;
+    a.desc = (const int4 *)d_in; a.in = d_in;
     a.score = (int32_t *)((uint8_t *)o_score + dout); a.endq = (int32_t *)((uint8_t *)o_endq + dout);
     a.endr = (int32_t *)((uint8_t *)o_endr + dout); a.nruns = (int32_t *)((uint8_t *)o_nruns + dout);
     a.feat = features ? (int32_t *)((uint8_t *)o_feat + dout) : nullptr;
@@ -733,6 +764,10 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     a.c_fe = -gap_ext * S + class_f + (open_tie ? 0 : 2);
     a.c_sm = match * S + 12 - (3 << CODE_SHIFT);
     a.c_sx = mismatch * S + 12;
+    auto pk = [](int v) { return ((uint32_t)(v & 0xffff)) | ((uint32_t)(v & 0xffff) << 16); };
+    a.h_eo = pk(-4 * gap_open); a.h_ee = pk(-4 * gap_ext); a.h_fo = a.h_eo; a.h_fe = a.h_ee;      // default table only (tb_variant 0)
+    a.h_sm = pk(4 * match + 3 - (3 << CS16)); a.h_sx = pk(4 * mismatch + 3);
+    a.tb_variant = (e_first ? 1 : 0) | (open_tie ? 2 : 0);
     a.tb_src_e = e_first ? 2 : 1; a.tb_open_tie = open_tie ? 1 : 0; a.tb_end_col_first = ctx->tb_end_col_first ? 1 : 0;
     a.tb_swap_id = ctx->tb_swap_id ? 1 : 0; a.delta_len = delta_len;
     ctx->prof.launches++; ctx->prof.dp_launches++;
@@ -749,8 +784,7 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
         const int nr = o_nruns[p];
         if (cigar_runs && total + nr <= cigar_cap) memcpy(cigar_runs + total, o_runs + roff[p], 4 * (size_t)nr);
         total += nr;
-        const int64_t n = seq_off[pair_a[p] + 1] - seq_off[pair_a[p]], m = seq_off[pair_b[p] + 1] - seq_off[pair_b[p]];
-        ctx->prof.dp_cells += n * m;
+        ctx->prof.dp_cells += (int64_t)desc[p][0] * desc[p][1];
     }
     if (cigar_off) cigar_off[P] = total;
     if (features) memcpy(features, o_feat, 4 * (size_t)ISOF_N_FEATURES * (size_t)P);
