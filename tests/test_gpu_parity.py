@@ -1089,3 +1089,59 @@ def test_fused_small_call_matches_regular_path_and_oracle(ctx):
     a1, a2, cig, tup, score = hotpath.parasail_alignment(pool[0], pool[1], 2, -8, 12, 1, ctx)
     o = oracle.parasail_alignment(pool[0], pool[1], 2, -8, 12, 1)
     assert (a1, a2, cig, tup, score) == (o[0], o[1], o[2], o[3], o[4])
+
+
+# ------------------------------------------------------------------------------- randomised differential test
+@pytest.mark.parametrize("seed", range(64))
+def test_randomised_regimes_vs_oracle(ctx, seed):
+    """Random batch compositions x random scoring parameters x random tie-break table x random regime switches (packed
+    on/off, short-pair kernel forced/never, fused tiny-call path on/off): every pair must equal the oracle under the same
+    table.  Catches interactions no hand-written case covers."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(7000 + seed)
+    n_pairs = int(rng.choice([1, 3, 17, 33, 64, 65, 130, 400]))
+    max_len = int(rng.choice([12, 60, 150, 384, 700]))
+    alphabet = str(rng.choice(["ACGT", "ACGT", "AC", "ACGTN", "ACGTacgtN"]))
+    seqs, pa, pb = [], [], []
+    for i in range(n_pairs):
+        n = int(rng.integers(1, max_len + 1))
+        x = _rand_dna(rng, n, alphabet)
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            y = _rand_dna(rng, int(rng.integers(1, max_len + 1)), alphabet)
+        elif kind == 1:
+            y = synth.mutate(rng, x, float(rng.choice([0.0, 0.02, 0.1]))) or "A"
+        elif kind == 2:
+            y = _rand_dna(rng, int(rng.integers(0, 30)), alphabet) + x[int(rng.integers(0, n)):]
+            y = y or "C"
+        else:
+            y = x[:int(rng.integers(1, n + 1))]
+        seqs += [x, y]
+        pa.append(2 * i); pb.append(2 * i + 1)
+    if rng.random() < 0.3:                                     # shared references: the query-profile path
+        pb = [pb[0]] * n_pairs
+    match = int(rng.integers(1, 4))
+    mismatch = -int(rng.integers(0, 9))
+    gap_open = int(rng.integers(0, 14))
+    gap_ext = int(rng.integers(0, 3))
+    params = (match, mismatch, gap_open, gap_ext)
+    tb = oracle.all_tiebreaks()[int(rng.integers(0, 16))]
+    packed, short_mode, fused = bool(rng.integers(0, 2)), int(rng.choice([0, 1, 2])), bool(rng.integers(0, 2))
+    ctx.set_tiebreak(tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id)
+    ctx.set_packed(packed); ctx.set_short(short_mode); ctx.set_fused_small(fused)
+    try:
+        res = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
+        feat = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, want_cigar=False, features_delta_len=5)
+    finally:
+        ctx.set_tiebreak(0, 0, 0, 0); ctx.set_packed(True); ctx.set_short(1); ctx.set_fused_small(True)
+    assert np.array_equal(res["score"], feat["score"])
+    for p in range(n_pairs):
+        sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params, tiebreak=tb)
+        got = res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]]
+        ctxt = (seed, p, params, (tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id), packed, short_mode, fused)
+        assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er), ctxt
+        assert got.tolist() == runs.tolist(), ctxt
+        tup = oracle.cigar_runs_to_tuples(runs)
+        f = feat["features"][p]
+        assert int(f[0]) == sum(l for l, _ in tup) and int(f[1]) == len(tup), ctxt
+        assert int(f[2]) == sum(l for l, o in tup if o != "=") and int(f[3]) == max([l for l, o in tup if o != "="] + [0]), ctxt
