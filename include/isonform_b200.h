@@ -65,6 +65,12 @@ ISOF_API int isof_set_trace_budget(isof_ctx *ctx, size_t bytes);
  * per warp, used when both fit the 16-bit tagged range and hold only ACGT) and a 32-bit path (any
  * length, wildcards).  on=0 forces the 32-bit path (A/B measurements, tests); default on=1. */
 ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
+/* Long pairs (beyond the plain 16-bit range, e.g. 10 kb reads) are occupancy-bound by trace memory: 37 MB per 8.5 kb pair.
+ * In feature-only calls their trace is therefore BANDED: only the diagonals between the main one and the one the free end
+ * gaps make room for (j - i between min(0, m-n) and max(0, m-n)), widened by `half_width` either side, are stored.  The DP
+ * itself is complete (scores are exact); a pair whose optimal path leaves the band is detected by the traceback and aligned
+ * again with the full trace, so results never depend on the band.  half_width = 0 turns banding off; default 1024. */
+ISOF_API int isof_set_band(isof_ctx *ctx, int half_width);
 /* Host-buffer calls of at most 32 small pairs (trace <= 200 KB each, i.e. up to ~500 x 500) run as ONE fused launch: base
  * codes, DP, traceback and features in one kernel with the trace in shared memory and inputs / outputs in mapped pinned
  * memory -- the per-pair seams of the reference (a memo miss of consensus.parasail_alignment).  Identical results; on=0
@@ -116,6 +122,7 @@ typedef struct {
     int64_t dp_cells_profile;    /* part of dp_cells_packed that used the shared-memory query profile */
     int64_t trace_bytes;         /* trace bytes written by the DP kernel                         */
     int64_t h2d_bytes, d2h_bytes;
+    int64_t band_pairs_retried;  /* pairs whose path left the banded trace and were aligned again with the full trace */
 } isof_profile;
 ISOF_API int isof_profile_enable(isof_ctx *ctx, int on);
 ISOF_API int isof_profile_reset(isof_ctx *ctx);

@@ -162,6 +162,13 @@ int isof_debug_set_span_hash_mask(isof_ctx *ctx, uint64_t mask)
     return ISOF_OK;
 }
 
+int isof_set_band(isof_ctx *ctx, int half_width)
+{
+    if (!ctx || half_width < 0) return ISOF_ERR_ARG;
+    ctx->band_w0 = half_width;
+    return ISOF_OK;
+}
+
 int isof_set_fused_small(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;

@@ -29,6 +29,7 @@ struct isof_ctx {
     bool profiling = false;           // bracket every launch with CUDA events (isof_profile_*)
     bool disable_packed = false;      // force the 32-bit DP path (tests / A-B measurements)
     uint64_t span_hash_mask = 0x7fffffffffffffffULL;      // test knob: fewer hash bits force collisions in kernel (c)
+    int band_w0 = 1024;               // half-width of the banded trace of long pairs beyond the free-end-gap diagonals; 0 = off
     int short_mode = 1;               // short-pair regime: 0 never, 1 when the call is large enough to pay (default), 2 always
     // tie-break table of the restated aligner (isof_set_tiebreak); all zero = the library as restated
     int tb_h_e_before_f = 0, tb_gap_open_on_tie = 0, tb_end_col_first = 0, tb_swap_id = 0;
@@ -42,7 +43,7 @@ struct isof_ctx {
     std::vector<Timed> timed;
     // scratch
     DevBuf b_codes, b_seqflags, b_pn, b_pm, b_words, b_nruns64, b_ptrace, b_scan_tmp, b_bnd, b_trace, b_nruns,
-        b_counters, b_misc, b_runoff, b_status, b_layout, b_order, b_taskkey, b_short_g, b_short_p;
+        b_counters, b_misc, b_runoff, b_status, b_layout, b_order, b_taskkey, b_short_g, b_short_p, b_band, b_fail_ids, b_fail;
     DevBuf b_taskkey_x[MAX_LANES - 1];
     DevBuf b_trace_x[MAX_LANES - 1], b_bnd_x[MAX_LANES - 1], b_runoff_x[MAX_LANES - 1], b_nruns64_x[MAX_LANES - 1],
         b_scan_tmp_x[MAX_LANES - 1];
@@ -54,7 +55,7 @@ struct isof_ctx {
     std::vector<DevBuf *> all_bufs()
     {
         std::vector<DevBuf *> v = {&b_codes, &b_seqflags, &b_pn, &b_pm, &b_words, &b_nruns64, &b_ptrace, &b_scan_tmp, &b_bnd, &b_trace, &b_nruns,
-                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_order, &b_taskkey, &b_short_g, &b_short_p, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
+                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_order, &b_taskkey, &b_short_g, &b_short_p, &b_band, &b_fail_ids, &b_fail, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
                 &b_h_endr, &b_h_cig, &b_h_cigoff, &b_h_feat, &b_m_tmp, &b_m_cnt, &b_m_off, &b_s_mread, &b_s_mkey,
                 &b_s_mpolya, &b_s_mcnt, &b_s_moff, &b_s_key1, &b_s_key2, &b_s_keyt, &b_s_keyo, &b_s_idx0, &b_s_idx1, &b_s_idx2,
                 &b_s_forb, &b_s_head, &b_s_bid, &b_s_sorttmp, &b_s_rbatch, &b_sh_batchoff, &b_sh_minpos, &b_sh_minoff, &b_sh_rread, &b_sh_rp1, &b_sh_rp2,

@@ -63,12 +63,26 @@ __global__ void encode_kernel(const uint8_t *__restrict__ cat, const int64_t *__
     }
 }
 
+// banded trace for a pair of the re-based class: keep the diagonals between the main one and the one the free end gaps
+// make room for, +- band_w0; worth it only when it is well below the whole matrix.  Returns the stored steps per stripe
+// (0 = not banded), sets the lowest kept diagonal and the trace words.
+__device__ __forceinline__ int band_plan(const int n, const int m, const int ns, const int band_w0, int &dmin_out, long long &w)
+{
+    const int dmin = min(0, m - n) - band_w0, dmax = max(0, m - n) + band_w0;
+    const int t_full = (m + 1) / 2 + 31, t_band = ((dmax - dmin + 320) >> 1) + 2;
+    dmin_out = 0;
+    if (band_w0 <= 0 || t_band + 64 >= t_full) return 0;
+    dmin_out = dmin;
+    w = (long long)ns * t_band * 64 + TRACE_SLACK;
+    return t_band;
+}
+
 // per pair: lengths, wildcard flag, trace words; misc[0]=error flags, misc[1]=max m, misc[2..3]=cells
 __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const uint8_t *__restrict__ flags,
                             const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, int64_t P,
                             int32_t *__restrict__ pn, int32_t *__restrict__ pm, uint8_t *__restrict__ pwild,
                             int64_t *__restrict__ words, unsigned long long *__restrict__ misc, int h_max_min_len,
-                            int h_max_max_len, int short_max, int rb_ok)
+                            int h_max_max_len, int short_max, int rb_ok, int band_w0, int32_t *__restrict__ pband)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0, padded = 0;
@@ -96,6 +110,13 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
                 const int rr = need > 192 ? 8 : need > 128 ? 6 : need > 64 ? 4 : 2;
                 padded = (unsigned long long)((ns - 1) * SROWS + ((elig | elig_rb) ? rr * 32 : SROWS)) * m;
                 pwild[p] = (uint8_t)(wild | (elig << 1) | (elig_rb << 2));
+                if (pband) {
+                    int bd = 0, tw = 0;
+                    long long wb = w;
+                    if (elig_rb) tw = band_plan(n, m, ns, band_w0, bd, wb);
+                    w = wb;
+                    pband[2 * p] = bd; pband[2 * p + 1] = tw;
+                }
                 mm = m; mn = n;
                 // short-pair regime (sg_short.cu): both lengths small and inside the 16-bit range (wildcards allowed)
                 not_short = !(max(n, m) <= short_max && min(n, m) <= h_max_min_len && max(n, m) <= h_max_max_len);
@@ -121,7 +142,35 @@ __global__ void plan_kernel(const int64_t *__restrict__ off, int n_seqs, const u
         if (not_short) atomicAdd(&misc[9], (unsigned long long)not_short);
         if (any_wild) atomicOr(&misc[10], 1ull);
     }
+    if (p < P && pband && pn[p] == 0) { pband[2 * p] = 0; pband[2 * p + 1] = 0; }
     if (p == P) words[P] = 0;
+}
+
+// pairs whose traceback left the band (nruns == -1): their ids, densely
+__global__ void collect_failed_kernel(const int32_t *__restrict__ nruns, int64_t P, int32_t *__restrict__ ids,
+                                      unsigned long long *__restrict__ count)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P && nruns[p] < 0) ids[atomicAdd(count, 1ull)] = (int32_t)p;
+}
+
+__global__ void gather_pairs_kernel(const int32_t *__restrict__ ids, int64_t n, const int32_t *__restrict__ pa,
+                                    const int32_t *__restrict__ pb, int32_t *__restrict__ pa2, int32_t *__restrict__ pb2)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { pa2[k] = pa[ids[k]]; pb2[k] = pb[ids[k]]; }
+}
+
+__global__ void scatter_results_kernel(const int32_t *__restrict__ ids, int64_t n, const int32_t *__restrict__ score2,
+                                       const int32_t *__restrict__ endq2, const int32_t *__restrict__ endr2,
+                                       const int32_t *__restrict__ feat2, int32_t *__restrict__ score, int32_t *__restrict__ endq,
+                                       int32_t *__restrict__ endr, int32_t *__restrict__ feat)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t p = ids[k];
+    score[p] = score2[k]; endq[p] = endq2[k]; endr[p] = endr2[k];
+    if (feat) for (int q = 0; q < ISOF_N_FEATURES; ++q) feat[p * ISOF_N_FEATURES + q] = feat2[k * ISOF_N_FEATURES + q];
 }
 
 // sort key of a pair inside its chunk: packed-eligible pairs first, then by reference index, so that the two
@@ -155,11 +204,14 @@ __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n0 = (int64_t)(*n_elig), n1 = (int64_t)(*n_rb);
     // packed tasks of the plain class, then of the re-based class (which starts at n0 in the sorted order)
-    const int64_t xA = t < n0 / 2 ? start + 2 * t : start + n0 + 2 * (t - n0 / 2), xB = xA + 1;
+    // (the odd pair of the re-based class runs as a task of its own, both halves on the same pair)
+    const bool plain = t < n0 / 2;
+    const int64_t u = t - n0 / 2;
+    const int64_t xA = plain ? start + 2 * t : start + n0 + 2 * u, xB = (plain || 2 * u + 1 < n1) ? xA + 1 : xA;
     unsigned long long c = 0, cp = 0;               // packed path / of those, the query-profile variant
     const int64_t pA = xA < end ? order[xA] : 0, pB = xB < end ? order[xB] : 0;
-    if (xB < end && t < n0 / 2 + n1 / 2) {
-        c = (unsigned long long)pn[pA] * pm[pA] + (unsigned long long)pn[pB] * pm[pB];
+    if (xB < end && t < n0 / 2 + (n1 + 1) / 2) {
+        c = (unsigned long long)pn[pA] * pm[pA] + (xB != xA ? (unsigned long long)pn[pB] * pm[pB] : 0ull);
         if (pb[pA] == pb[pB]) cp = c;
     }
     for (int d = 16; d; d >>= 1) { c += __shfl_down_sync(0xffffffffu, c, d); cp += __shfl_down_sync(0xffffffffu, cp, d); }
@@ -181,7 +233,8 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
                   uint8_t *__restrict__ pwild, int64_t *__restrict__ ptrace, unsigned long long *__restrict__ misc,
                   int h_max_min_len, int h_max_max_len, int32_t *__restrict__ order,
                   unsigned long long *__restrict__ n_elig, unsigned long long *__restrict__ ticket, int short_max, int rb_ok,
-                  unsigned long long *__restrict__ n_rb, unsigned long long *__restrict__ rb_ticket)
+                  unsigned long long *__restrict__ n_rb, unsigned long long *__restrict__ rb_ticket, int band_w0,
+                  int32_t *__restrict__ pband)
 {
     typedef cub::BlockScan<long long, 1024> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
@@ -212,6 +265,7 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
         int n = 0, m = 0;
         w = TRACE_SLACK;
         uint8_t pw = 0;
+        int bdm = 0, btw = 0;
         if (a < 0 || a >= n_seqs || b < 0 || b >= n_seqs) atomicOr(&s_stat[0], 1ull);
         else {
             n = (int)(off[a + 1] - off[a]);
@@ -235,9 +289,11 @@ small_plan_kernel(const uint8_t *__restrict__ cat, const int64_t *__restrict__ o
                 if (elig) atomicAdd(&s_nelig, 1);
                 if (elig_rb) atomicAdd(&s_nrb, 1);
                 key = (elig ? 0u : elig_rb ? 0x40000000u : 0x80000000u) | ((uint32_t)b & 0x3fffffffu);
+                if (pband && elig_rb) btw = band_plan(n, m, ns, band_w0, bdm, w);
             }
         }
         pn[tid] = n; pm[tid] = m; pwild[tid] = pw;
+        if (pband) { pband[2 * tid] = bdm; pband[2 * tid + 1] = btw; }
     }
     s_key[tid] = key;
     long long excl = 0, total = 0;
@@ -282,6 +338,30 @@ __global__ void chunk_bounds_kernel(const int64_t *__restrict__ ptrace, int64_t 
 }
 
 
+// banded second pass: run counts of the re-aligned pairs go back to their places, then the run offsets are rebuilt
+__global__ void scatter_nruns_kernel(const int32_t *__restrict__ ids, int64_t nf, const int32_t *__restrict__ nruns2,
+                                     int32_t *__restrict__ saved)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nf) saved[ids[k]] = nruns2[k];
+}
+
+__global__ void __launch_bounds__(1024) rebuild_offsets_kernel(const int32_t *__restrict__ nr, int64_t P, long long *__restrict__ cigar_off)
+{
+    typedef cub::BlockScan<long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    long long carry = 0;
+    for (int64_t base = 0; base < P; base += 1024) {
+        const int64_t p = base + threadIdx.x;
+        long long v = p < P ? (long long)max(nr[p], 0) : 0, excl, total;
+        Scan(tmp).ExclusiveSum(v, excl, total);
+        if (p < P) cigar_off[p] = carry + excl;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cigar_off[P] = carry;
+}
+
 // ---------------------------------------------------------------------------------------------
 // traceback -> reversed runs at the tail of the trace region
 // ---------------------------------------------------------------------------------------------
@@ -300,6 +380,9 @@ __device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64
     const int pc = lay & 15;                          // columns per step of the writer
     const bool split = (lay & 16) != 0;               // packed path: [src x8 | fe x8] 2-bit fields; 32-bit path: nibbles
     const int T = (m + pc - 1) / pc + 31;
+    // banded trace (AlignParams::pband): only the steps tlo(s) .. tlo(s)+tw-1 of every stripe were stored
+    const int band_dmin = (!SMEM && P.pband) ? P.pband[2 * p] : 0, tw = (!SMEM && P.pband) ? P.pband[2 * p + 1] : 0;
+    const int pitch = tw ? tw : T;
     const int last_s = (n - 1) >> 8, rr_last = P.plastrr[p];   // rows per lane in the (possibly compacted) last stripe
     // x / rr_last for x < 256 and rr_last in {2, 4, 6, 8} without an integer division in the walk: multiply-shift
     // ((x * 171) >> 10 == x / 6 for x < 512)
@@ -341,11 +424,19 @@ __device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64
                 const int sp_ = ip >> 8;
                 const int lp = (sp_ == last_s && rr_last != 8) ? ((ip & 255) * rr_mul) >> rr_sh : (ip >> 3) & 31;
                 const int jtp = (pc == 1) ? jp : (jp >> 1);
-                const uint32_t *pf = &trace[(((size_t)sp_ * T + (jtp + lp)) * 32 + lp) * pc];
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                const int tp_ = jtp + lp - (tw ? band_tlo(sp_, band_dmin) : 0);
+                if ((unsigned)tp_ < (unsigned)pitch) {
+                    const uint32_t *pf = &trace[(((size_t)sp_ * pitch + tp_) * 32 + lp) * pc];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                }
             }
         }
-        const uint32_t *wp = &trace[(((size_t)s * T + (jt + l)) * 32 + l) * pc + jc];
+        const int tt = jt + l - (tw ? band_tlo(s, band_dmin) : 0);
+        if (tw && (unsigned)tt >= (unsigned)tw) {     // the path left the band: this pair is re-aligned with the full trace
+            P.nruns[p] = -1;
+            return;
+        }
+        const uint32_t *wp = &trace[(((size_t)s * pitch + tt) * 32 + l) * pc + jc];
         ISOF_ASSERT(wp >= trace && wp < tail - TRACE_SLACK && wp < tail - nr, CHK_TRACE_LOAD);
         last_read = wp;
         const uint32_t word = SMEM ? *wp : __ldcg(wp);
@@ -388,7 +479,7 @@ small_finish_kernel(const AlignParams P, const int n_pairs, long long *__restric
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ long long s_off[SMALL_P + 1];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long nr = (tid < n_pairs) ? (long long)P.nruns[tid] : 0, excl = 0, total = 0;
+    long long nr = (tid < n_pairs) ? (long long)max(P.nruns[tid], 0) : 0, excl = 0, total = 0;
     Scan(scan_tmp).ExclusiveSum(nr, excl, total);
     s_off[tid] = excl;
     if (tid == 0) s_off[n_pairs] = total;
@@ -397,7 +488,7 @@ small_finish_kernel(const AlignParams P, const int n_pairs, long long *__restric
     if (tid == 0) *run_base = total;
     if (!cigar) return;
     for (int p = warp; p < n_pairs; p += 32) {
-        const int n = P.nruns[p];
+        const int n = max(P.nruns[p], 0);
         const long long dst = s_off[p];
         const uint32_t *src = run_tail(P, p) - n;
         ISOF_ASSERT(P.ptail || src >= P.trace + (P.ptrace[p] - P.chunk_base), CHK_CIGAR_COPY);
@@ -416,7 +507,7 @@ __global__ void cigar_copy_kernel(const AlignParams P, const int64_t start, cons
     const int64_t p = start + warp;
     if (p >= end) return;
     const int64_t dst = *run_base + local_off[p - start];
-    const int nr = P.nruns[p];
+    const int nr = max(P.nruns[p], 0);
     if (lane == 0 && cigar_off) cigar_off[p] = dst;
     if (!cigar) return;
     const uint32_t *src = run_tail(P, p) - nr;
@@ -428,14 +519,14 @@ __global__ void cigar_copy_kernel(const AlignParams P, const int64_t start, cons
 __global__ void advance_base_kernel(int64_t *run_base, const int64_t *local_off, const int32_t *nruns, int64_t start,
                                     int64_t end, int64_t *cigar_off, int64_t P)
 {
-    if (end > start) *run_base += local_off[end - 1 - start] + nruns[end - 1];
+    if (end > start) *run_base += local_off[end - 1 - start] + max(nruns[end - 1], 0);
     if (cigar_off && end == P) cigar_off[P] = *run_base;
 }
 
 __global__ void nruns_to_i64_kernel(const int32_t *nruns, int64_t start, int64_t count, int64_t *out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = nruns[start + i];
+    if (i < count) out[i] = max(nruns[start + i], 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -483,6 +574,7 @@ __device__ __forceinline__ void features_pair(const AlignParams &P, const int64_
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
     const int nr = P.nruns[p];
+    if (nr < 0) { f[0] = -1; return; }                // banded trace, path left the band: filled in by the second pass
     const uint32_t *runs = run_tail(P, p) - nr;
     // pass 1: parse_cigar_diversity features (SimplifyGraph.py:175-196)
     int alen = 0, nonmatch = 0, maxrun = 0;
@@ -662,6 +754,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     P.playout = &s_u8[1]; P.plastrr = &s_u8[2]; P.chunk_words = 0; P.order = nullptr; P.n_elig = nullptr; P.n_rb = nullptr;
     P.tb_src_e = a.tb_src_e; P.tb_open_tie = a.tb_open_tie; P.tb_end_col_first = a.tb_end_col_first; P.tb_swap_id = a.tb_swap_id;
     P.ptail = nullptr;
+    P.pband = nullptr;
     // A lone pair inside the 16-bit range runs the PACKED path with itself in both halves (identical words go to the same
     // trace addresses): that path compacts the last stripe to 2 / 4 / 6 rows per lane, so a 100-row query keeps 25 lanes
     // busy with a 4-row dependency chain per step instead of 13 lanes with an 8-row one -- half the latency per step.
@@ -851,6 +944,14 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     TRY(dev_reserve(ctx, ctx->b_runoff, sizeof(int64_t) * (size_t)(P + 1)));
     TRY(dev_reserve(ctx, ctx->b_nruns64, sizeof(int64_t) * (size_t)(P + 1)));      // nruns as int64
     TRY(dev_reserve(ctx, ctx->b_misc, 128));
+    // banded trace for the re-based class: feature-only calls (the CIGAR stream of a call that returns runs is laid out
+    // in pair order and could not be patched by a second pass)
+    const int band_w0 = (!d_cigar && d_features && rb_ok && d_endq && d_endr) ? ctx->band_w0 : 0;
+    int32_t *pband = nullptr;
+    if (band_w0 > 0) {
+        TRY(dev_reserve(ctx, ctx->b_band, sizeof(int32_t) * 2 * (size_t)P));
+        pband = (int32_t *)ctx->b_band.p;
+    }
     uint8_t *codes = (uint8_t *)ctx->b_codes.p, *flags = (uint8_t *)ctx->b_seqflags.p;
     int32_t *pn = (int32_t *)ctx->b_pn.p, *pm = (int32_t *)ctx->b_pm.p, *nruns = (int32_t *)ctx->b_nruns.p;
     uint8_t *pwild = (uint8_t *)ctx->b_status.p;
@@ -867,7 +968,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         LaunchTimer t(ctx, SLOT_OTHER);
         small_plan_kernel<<<1, 1024, 0, st>>>(d_cat, d_off, n_seqs, d_pa, d_pb, (int)P, codes, flags, pn, pm, pwild, ptrace,
                                               misc, h_max_min_len, h_max_max_len, (int32_t *)ctx->b_order.p, cnt0 + 3, cnt0,
-                                              SHORT_MAX, rb_ok, cnt0 + 6, cnt0 + 9);
+                                              SHORT_MAX, rb_ok, cnt0 + 6, cnt0 + 9, band_w0, pband);
     } else {
         CUDA_TRY(ctx, cudaMemsetAsync(misc, 0, 128, st));
         CUDA_TRY(ctx, cudaMemsetAsync(pwild, 0, (size_t)P, st));
@@ -879,7 +980,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         {
             LaunchTimer t(ctx, SLOT_OTHER);
             plan_kernel<<<(unsigned)((P + 1 + 255) / 256), 256, 0, st>>>(d_off, n_seqs, flags, d_pa, d_pb, P, pn, pm, pwild,
-                                                                          words, misc, h_max_min_len, h_max_max_len, SHORT_MAX, rb_ok);
+                                                                          words, misc, h_max_min_len, h_max_max_len, SHORT_MAX, rb_ok, band_w0,
+                                                                          pband);
         }
         CUDA_TRY(ctx, cudaGetLastError());
         size_t tmp_bytes = 0;
@@ -959,6 +1061,7 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     A.tb_swap_id = ctx->tb_swap_id ? 1 : 0;
     const int tb_variant = (e_first ? 1 : 0) | (open_tie ? 2 : 0);
     A.ptail = nullptr;
+    A.pband = pband;
     A.chunk_base = 0;
     int64_t *run_base = (int64_t *)(misc + 4);
     CUDA_TRY(ctx, cudaMemsetAsync(run_base, 0, 8, st));
@@ -1253,5 +1356,55 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     if (d_cigar && pin64[0] > cigar_cap)
         return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap,
                          (long long)pin64[0]);
+    if (pband) {
+        // ---- second pass of the banded trace: pairs whose optimal path left the band are aligned again with the full
+        // trace (same kernels, banding off) and their results scattered into place -- results stay exact
+        unsigned long long *fail_cnt = misc + 13;
+        CUDA_TRY(ctx, cudaMemsetAsync(fail_cnt, 0, 8, st));
+        TRY(dev_reserve(ctx, ctx->b_fail_ids, sizeof(int32_t) * (size_t)P));
+        int32_t *ids = (int32_t *)ctx->b_fail_ids.p;
+        {
+            LaunchTimer t(ctx, SLOT_OTHER);
+            collect_failed_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(nruns, P, ids, fail_cnt);
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(pin64, fail_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        const int64_t nf = pin64[0];
+        ctx->prof.band_pairs_retried += nf;
+        if (nf > 0) {
+            TRY(dev_reserve(ctx, ctx->b_fail, sizeof(int32_t) * (5 + ISOF_N_FEATURES) * (size_t)nf));
+            int32_t *pa2 = (int32_t *)ctx->b_fail.p, *pb2 = pa2 + nf, *score2 = pb2 + nf, *endq2 = score2 + nf, *endr2 = endq2 + nf;
+            int32_t *feat2 = endr2 + nf;
+            {
+                LaunchTimer t(ctx, SLOT_OTHER);
+                gather_pairs_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, d_pa, d_pb, pa2, pb2);
+            }
+            // the run counts of the first pass survive in the (now idle) band table; the second pass reuses `nruns`
+            int32_t *saved_nr = pband;
+            CUDA_TRY(ctx, cudaMemcpyAsync(saved_nr, nruns, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToDevice, st));
+            const int saved = ctx->band_w0;
+            ctx->band_w0 = 0;
+            const int rc2 = isof_sg_align_core(ctx, d_cat, d_off, n_seqs, n_bases, pa2, pb2, nf, match, mismatch, gap_open, gap_ext,
+                                               score2, endq2, endr2, nullptr, 0, nullptr, feat2, delta_len, nullptr);
+            ctx->band_w0 = saved;
+            if (rc2 != ISOF_OK) return rc2;
+            {
+                LaunchTimer t(ctx, SLOT_OTHER);
+                scatter_results_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, score2, endq2, endr2, feat2, d_score,
+                                                                                   d_endq, d_endr, d_features);
+                if (d_cigar_off) {
+                    scatter_nruns_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, nruns, saved_nr);
+                    rebuild_offsets_kernel<<<1, 1024, 0, st>>>(saved_nr, P, (long long *)d_cigar_off);
+                }
+            }
+            CUDA_TRY(ctx, cudaGetLastError());
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (h_total_runs && d_cigar_off) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(pin64, d_cigar_off + P, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(ctx, cudaStreamSynchronize(st));
+                *h_total_runs = pin64[0];
+            }
+        }
+    }
     return ISOF_OK;
 }

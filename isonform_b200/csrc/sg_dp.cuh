@@ -56,7 +56,15 @@ struct AlignParams {
     int tb_end_col_first;                  // end cell: last column first
     int tb_swap_id;                        // CIGAR letters of the gap states swapped
     const int64_t *ptail;                  // short-pair path: per pair, word offset one past its run slot (else nullptr)
+    // banded trace (re-based class, feature-only calls): per pair {dmin, Tw}; Tw = 0: the whole matrix is stored.  Only
+    // the cells with dmin <= j - i <= dmin + width are kept: per stripe s the steps tlo(s) .. tlo(s)+Tw-1 with
+    // tlo(s) = max(0, (256 s + dmin) >> 1); the traceback reports a pair whose path leaves the band (nruns = -1) and
+    // the host re-aligns those pairs with the full trace.
+    const int32_t *pband;
 };
+
+// first stored step of stripe s under a band starting at diagonal dmin
+__device__ __forceinline__ int band_tlo(const int s, const int dmin) { return max(0, (s * SROWS + dmin) >> 1); }
 
 constexpr int SHORT_MAX = 384;             // both lengths <= SHORT_MAX: candidate for the short-pair regime (sg_short.cu)
 
@@ -486,6 +494,9 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     // steady range of t: lane 31 has started (t >= 31) and lane 0's look-ahead block is inside both
     // references: PC*t + 2*PC <= mmin
     const int t_steady_end = (mmin - 2 * PC) / PC + 1;          // exclusive; may be <= 31 (then no steady range)
+    // banded trace (RB only; see AlignParams::pband): window of stored steps per stripe
+    int dminA = 0, twA = 0, dminB = 0, twB = 0;
+    if (RB && P.pband) { dminA = P.pband[2 * pA]; twA = P.pband[2 * pA + 1]; dminB = P.pband[2 * pB]; twB = P.pband[2 * pB + 1]; }
 
     // The last stripe of the task is compacted: with `need` rows left, every lane takes RR = 2, 4, 6 or 8
     // rows (the smallest that covers them), so no lane idles on padding rows.  Earlier stripes are full.
@@ -545,8 +556,11 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 if (has_prev && c < m) S.b_next[c] = __ldcg(&bnd[c]);
             }
         }
-        uint2 *tpA = reinterpret_cast<uint2 *>(traceA) + (size_t)s * TA * 32 + lane;
-        uint2 *tpB = reinterpret_cast<uint2 *>(traceB) + (size_t)s * TB * 32 + lane;
+        // banded pairs keep the steps tlo .. tlo + win - 1 of the stripe (stripe pitch = win); others all T steps
+        const int tloA = (RB && twA) ? band_tlo(s, dminA) : 0, winA = (RB && twA) ? twA : TA;
+        const int tloB = (RB && twB) ? band_tlo(s, dminB) : 0, winB = (RB && twB) ? twB : TB;
+        uint2 *tpA = reinterpret_cast<uint2 *>(traceA) + ((ptrdiff_t)s * winA - tloA) * 32 + lane;       // tp[t * 32]: step t
+        uint2 *tpB = reinterpret_cast<uint2 *>(traceB) + ((ptrdiff_t)s * winB - tloB) * 32 + lane;
         uint32_t snap[RR];                           // H of the last column (A low half, B high half), set in the drain
 #pragma unroll
         for (int r = 0; r < RR; ++r) snap[r] = 0x80008000u;
@@ -645,13 +659,15 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     }
                 }
                 S.diag0 = hu[PC - 1];
-                if (liveA && jb < mA) {
-                    ISOF_ASSERT((uint32_t *)(tpA + (size_t)t * 32 + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
-                    tpA[(size_t)t * 32] = make_uint2(wA[0], wA[1]);
+                if (liveA && jb < mA && (!RB || (unsigned)(t - tloA) < (unsigned)winA)) {
+                    ISOF_ASSERT((uint32_t *)(tpA + (ptrdiff_t)t * 32 + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                    ISOF_ASSERT((uint32_t *)(tpA + (ptrdiff_t)t * 32) >= traceA, CHK_TRACE_STORE);
+                    tpA[(ptrdiff_t)t * 32] = make_uint2(wA[0], wA[1]);
                 }
-                if (liveB && jb < mB) {
-                    ISOF_ASSERT((uint32_t *)(tpB + (size_t)t * 32 + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
-                    tpB[(size_t)t * 32] = make_uint2(wB[0], wB[1]);
+                if (liveB && jb < mB && (!RB || (unsigned)(t - tloB) < (unsigned)winB)) {
+                    ISOF_ASSERT((uint32_t *)(tpB + (ptrdiff_t)t * 32 + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                    ISOF_ASSERT((uint32_t *)(tpB + (ptrdiff_t)t * 32) >= traceB, CHK_TRACE_STORE);
+                    tpB[(ptrdiff_t)t * 32] = make_uint2(wB[0], wB[1]);
                 }
             }
         };
@@ -670,7 +686,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             const uint8_t *pb_ = rB + PC * (31 - lane) + PC;
             const int2 *pbn = bnd + PC * 31 + PC;                  // lane 0 only
             int2 *pbs = bnd + PC * (31 - 31);                      // lane 31 only: jb at t = 31
-            uint2 *sA = tpA + (size_t)31 * 32, *sB = tpB + (size_t)31 * 32;
+            uint2 *sA = tpA + (ptrdiff_t)31 * 32, *sB = tpB + (ptrdiff_t)31 * 32;
             auto steady_step = [&](const int t, const bool with_track) {
                 uint32_t rc[PC], hu[PC], fu[PC];
 #pragma unroll
@@ -709,11 +725,22 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     }
                 }
                 S.diag0 = hu[PC - 1];
-                ISOF_ASSERT((uint32_t *)(sA + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
-                ISOF_ASSERT((uint32_t *)(sB + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
-                ISOF_ASSERT((uint32_t *)sA >= traceA && (uint32_t *)sB >= traceB, CHK_TRACE_STORE);
-                *sA = make_uint2(wA[0], wA[1]);
-                *sB = make_uint2(wB[0], wB[1]);
+                if (!RB) {
+                    ISOF_ASSERT((uint32_t *)(sA + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                    ISOF_ASSERT((uint32_t *)(sB + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK, CHK_TRACE_STORE);
+                    ISOF_ASSERT((uint32_t *)sA >= traceA && (uint32_t *)sB >= traceB, CHK_TRACE_STORE);
+                    *sA = make_uint2(wA[0], wA[1]);
+                    *sB = make_uint2(wB[0], wB[1]);
+                } else {              // banded trace: the step is kept only inside the stripe's window (warp-uniform tests)
+                    if ((unsigned)(t - tloA) < (unsigned)winA) {
+                        ISOF_ASSERT((uint32_t *)(sA + 1) <= P.trace + (P.ptrace[pA + 1] - P.chunk_base) - TRACE_SLACK && (uint32_t *)sA >= traceA, CHK_TRACE_STORE);
+                        *sA = make_uint2(wA[0], wA[1]);
+                    }
+                    if ((unsigned)(t - tloB) < (unsigned)winB) {
+                        ISOF_ASSERT((uint32_t *)(sB + 1) <= P.trace + (P.ptrace[pB + 1] - P.chunk_base) - TRACE_SLACK && (uint32_t *)sB >= traceB, CHK_TRACE_STORE);
+                        *sB = make_uint2(wB[0], wB[1]);
+                    }
+                }
                 if (has_next && lane == 31) {
 #pragma unroll
                     for (int c = 0; c < PC; ++c) { ISOF_ASSERT(pbs + c < bnd + P.bnd_stride, CHK_BND); pbs[c] = bnd_value(S.Hbot[c], S.Fbot[c]); }
@@ -817,14 +844,13 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
             const int64_t xA = start + 2 * (int64_t)tkt;
             dp_pair16<TBV, false>(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
         } else {
-            // single 32-bit pairs: the odd one out of the plain-16 class, the odd one out of the re-based class (whose
-            // tasks sg_dp_rb_kernel takes), then everything that fits neither
+            // single 32-bit pairs: the odd one out of the plain-16 class, then everything that fits neither 16-bit class
+            // (sg_dp_rb_kernel takes the whole re-based class, its odd pair included: a banded trace has only that layout)
             const int64_t n0 = (int64_t)(*P.n_elig), n1 = (int64_t)(*P.n_rb);
-            const int64_t s = (int64_t)tkt - n_pk, odd0 = n0 & 1, odd1 = n1 & 1;
+            const int64_t s = (int64_t)tkt - n_pk, odd0 = n0 & 1;
             int64_t x;
             if (s < odd0) x = start + n0 - 1;
-            else if (s < odd0 + odd1) x = start + n0 + n1 - 1;
-            else x = start + n0 + n1 + (s - odd0 - odd1);
+            else x = start + n0 + n1 + (s - odd0);
             if (x >= end) break;
             dp_pair32(P, P.order[x], lane, bnd, s_prof[warp]);
         }
@@ -838,7 +864,7 @@ inline void launch_sg_dp(const int blocks, cudaStream_t st, const AlignParams &A
     sg_dp_kernel<TBV><<<blocks, DP_WARPS * 32, 0, st>>>(A, start, end, counter);
 }
 
-// The re-based class of a chunk: pairs order[start + n0 + 2k], order[start + n0 + 2k + 1], k < n1 / 2 (dp_pair16<., true>).
+// The re-based class of a chunk: pairs order[start + n0 + 2k], order[start + n0 + 2k + 1], k < (n1 + 1) / 2 (dp_pair16<., true>).
 // A kernel of its own: the extra live scalars of the re-based path would otherwise cost the plain path registers.
 template <int TBV>
 __global__ void __launch_bounds__(DP_WARPS * 32, DP_CTAS_PER_SM)
@@ -852,9 +878,10 @@ sg_dp_rb_kernel(const AlignParams P, const int64_t start, unsigned long long *__
         if (lane == 0) tkt = atomicAdd(counter, 1ull);
         tkt = __shfl_sync(0xffffffffu, tkt, 0);
         const int64_t n0 = (int64_t)(*P.n_elig), n1 = (int64_t)(*P.n_rb);
-        if ((int64_t)tkt >= n1 / 2) break;
-        const int64_t xA = start + n0 + 2 * (int64_t)tkt;
-        dp_pair16<TBV, true>(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
+        if ((int64_t)tkt >= (n1 + 1) / 2) break;
+        // the odd pair of the class runs with both halves on itself (same stores twice, same values)
+        const int64_t xA = start + n0 + 2 * (int64_t)tkt, xB = (2 * (int64_t)tkt + 1 < n1) ? xA + 1 : xA;
+        dp_pair16<TBV, true>(P, P.order[xA], P.order[xB], lane, bnd, s_prof[warp]);
     }
 }
 

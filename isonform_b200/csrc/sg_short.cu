@@ -392,6 +392,7 @@ int isof_sg_short_path(isof_ctx *ctx, AlignParams &A, int64_t P, int max_n, int 
     A.trace = (uint32_t *)ctx->b_trace.p;
     A.chunk_base = 0;
     A.ptail = ptail;
+    A.pband = nullptr;
     {
         LaunchTimer t(ctx, SLOT_TB);
         sg_traceback_short_kernel<<<(unsigned)((P + 63) / 64), 64, 0, st>>>(A, pbase, pM, P);

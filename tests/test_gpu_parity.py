@@ -655,6 +655,21 @@ def test_debug_build_bounds_assertions_stay_silent():
                 assert int(res["score"][p]) == sc
                 assert res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]].tolist() == runs.tolist()
         assert dctx.debug_violations()[0] == 0
+        # banded trace of long pairs (feature-only call), default and narrow band: stores stay inside the band window
+        dctx.set_short(1)
+        lx = _rand_dna(rng, 7000)
+        lseqs = [lx, synth.mutate(rng, lx, 0.05), lx[:2500] + lx[3000:], lx[1500:6800], synth.mutate(rng, lx[:5200], 0.08),
+                 _rand_dna(rng, 4700)]
+        lia, lib_ = np.triu_indices(len(lseqs), 1)
+        dctx.set_band(0)
+        want = hotpath.align_pairs(lseqs, lia, lib_, 2, -2, 12, 1, ctx=dctx, want_cigar=False, features_delta_len=5)
+        for hw in (1024, 64):
+            dctx.set_band(hw)
+            got = hotpath.align_pairs(lseqs, lia, lib_, 2, -2, 12, 1, ctx=dctx, want_cigar=False, features_delta_len=5)
+            assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["features"], want["features"])
+            assert np.array_equal(got["cigar_off"], want["cigar_off"])
+        dctx.set_band(1024)
+        assert dctx.debug_violations()[0] == 0
         # minimizers + spans
         reads = {i + 1: ("r", _rand_dna(rng, int(rng.integers(0, 900)), "ACGT" if i % 4 else "AC"), "") for i in range(80)}
         M = hotpath.get_minimizers_and_positions(reads, 31, 20, "lex", dctx)
@@ -1145,3 +1160,57 @@ def test_randomised_regimes_vs_oracle(ctx, seed):
         f = feat["features"][p]
         assert int(f[0]) == sum(l for l, _ in tup) and int(f[1]) == len(tup), ctxt
         assert int(f[2]) == sum(l for l, o in tup if o != "=") and int(f[3]) == max([l for l, o in tup if o != "="] + [0]), ctxt
+
+
+# ------------------------------------------------------------------------------- banded trace of long pairs
+@pytest.mark.parametrize("half_width", [1024, 96, 8])
+def test_banded_trace_of_long_pairs_never_changes_results(ctx, half_width):
+    """Feature-only calls store, for pairs of the re-based class, only a band of trace steps around the diagonals the
+    free end gaps make room for; a pair whose optimal path leaves the band is aligned again with the full trace
+    (isof_set_band).  Scores, features and run offsets must equal the unbanded call for every band width: 1024 (the
+    default: exon-sized indels stay inside), 96 and 8 (most pairs with an indel fail and take the second pass)."""
+    from isonform_b200 import hotpath, polya, synth
+    rng = np.random.default_rng(977 + half_width)
+    reads_l, _iso, _t = synth.make_config("C4", n_reads=8)
+    seqs = [polya.remove_read_polyA_ends(s, 12, 1) for _, s in reads_l]
+    ia, ib = [int(x) for x in np.triu_indices(8, 1)[0]], [int(x) for x in np.triu_indices(8, 1)[1]]          # 28 pairs
+
+    def add(a, b):
+        seqs.extend([a, b]); ia.append(len(seqs) - 2); ib.append(len(seqs) - 1)
+    x = _rand_dna(rng, 9000)
+    add(x, x)
+    add(x, x[:3000] + x[3600:])                                  # 600 bp deletion in the middle: path leaves a narrow band
+    add(x[:4000] + x[4500:], x)
+    add(x[:2000] + x[2400:6000] + _rand_dna(rng, 400) + x[6000:], x)        # deletion then insertion: ends on the main diagonal
+    add(x[2000:7000], x)                                         # contained: the band follows the free end gaps
+    add(x, x[1000:6200])
+    add(x, _rand_dna(rng, 8800))                                 # unrelated
+    add(_rand_dna(rng, 5000, "AC"), _rand_dna(rng, 5200, "AC"))
+    add(x[:300], x)                                              # short vs long (plain 16-bit class or re-based, never banded wrongly)
+    for _ in range(12):
+        n = int(rng.integers(4200, 9000))
+        y = _rand_dna(rng, n)
+        z = synth.mutate(rng, y, float(rng.choice([0.01, 0.05, 0.1])))
+        if rng.random() < 0.6:
+            c = int(rng.integers(200, n - 1200)); z = z[:c] + z[c + int(rng.integers(20, 900)):]
+        add(y, z) if rng.random() < 0.5 else add(z, y)
+    try:
+        ctx.set_band(0)
+        ref = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
+        ctx.set_band(half_width)
+        ctx.profile_enable(True); ctx.profile_reset()
+        got = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
+        pr = ctx.profile(); ctx.profile_enable(False)
+        # a call that returns the runs is never banded
+        full = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+    finally:
+        ctx.set_band(1024)
+        ctx.profile_enable(False)
+    for key in ("score", "features", "cigar_off"):
+        assert np.array_equal(got[key], ref[key]), (key, half_width)
+        assert np.array_equal(full[key], ref[key]), (key, half_width)
+    retried = pr["band_pairs_retried"]
+    if half_width == 1024:
+        assert retried <= 2, retried                             # only the unrelated / low-complexity pairs may wander
+    else:
+        assert retried >= 3, retried                             # the exon-sized indels do leave a narrow band
