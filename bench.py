@@ -458,13 +458,16 @@ def run_c4_sample(ctx, dev, n_reads=200):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.current_stream()
+    ctx.profile_reset()
     e0.record(stream)
     st.run()
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     return {"workload": wl["name"], "pairs": wl["n_pairs"], "mean_read_len": wl["n_bases"] / wl["n_reads"], "ms_per_step": ms,
-            "alignments_per_s": wl["n_pairs"] / ms * 1e3, "gcups": wl["cells"] / ms / 1e6}
+            "alignments_per_s": wl["n_pairs"] / ms * 1e3, "gcups": wl["cells"] / ms / 1e6,
+            "call": "feature-only (as merge_consensuses issues it): banded trace, exact via second pass",
+            "band_pairs_retried": ctx.profile()["band_pairs_retried"]}
 
 
 def run_c5_points(ctx, lengths=(50, 100, 200, 500, 2000)):

@@ -35,7 +35,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_set_band", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_fused_phases", "isof_set_band", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances", "isof_poa_consensus"]
@@ -71,6 +71,7 @@ def load(debug=False):
     L.isof_set_short.argtypes = [vp, C.c_int]
     L.isof_set_fused_small.argtypes = [vp, C.c_int]
     L.isof_set_band.argtypes = [vp, C.c_int]
+    L.isof_debug_fused_phases.argtypes = [vp, vp]
     L.isof_debug_violations.argtypes = [vp, C.POINTER(C.c_uint)]
     L.isof_debug_selftest.argtypes = [vp]
     L.isof_debug_set_span_hash_mask.argtypes = [vp, C.c_uint64]
@@ -165,6 +166,12 @@ class Context:
     def set_band(self, half_width=1024):
         """Half-width of the banded trace of long pairs in feature-only calls (0 = off); results never depend on it."""
         self._check(self._L.isof_set_band(self._h, int(half_width)))
+
+    def debug_fused_phases(self):
+        """SM cycles of the last fused small call's pair 0: (load+encode, DP, traceback, features+stores)."""
+        out = np.zeros(4, np.int64)
+        self._check(self._L.isof_debug_fused_phases(self._h, out.ctypes.data))
+        return tuple(int(x) for x in out)
 
     def set_fused_small(self, on=True):
         """One fused launch for tiny host-buffer calls (default on); results are identical either way."""

@@ -169,6 +169,14 @@ int isof_set_band(isof_ctx *ctx, int half_width)
     return ISOF_OK;
 }
 
+int isof_debug_fused_phases(isof_ctx *ctx, int64_t *cycles4)
+{
+    if (!ctx || !cycles4) return ISOF_ERR_ARG;
+    if (!ctx->fused_io) { memset(cycles4, 0, 32); return ISOF_OK; }
+    memcpy(cycles4, (const uint8_t *)ctx->fused_io + 2 * 512 * 1024 - 64, 32);
+    return ISOF_OK;
+}
+
 int isof_set_fused_small(isof_ctx *ctx, int on)
 {
     if (!ctx) return ISOF_ERR_ARG;

@@ -462,6 +462,106 @@ __device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64
     P.nruns[p] = nr;
 }
 
+// Warp-cooperative traceback of ONE pair whose trace lives in shared memory (fused small-call kernel).  The walk is a
+// chain of dependent loads and address arithmetic -- ~300 cycles per step for a lone thread, 17 us for a 100 x 100 pair,
+// as much as its DP.  But the trace holds the decision of EVERY cell, so the 32 lanes can look ahead: in state H lane k
+// reads the cell k steps down the diagonal; the leading lanes whose source is "diagonal" are all on the path, and their
+// = / X letters come from one ballot.  In a gap state lane k reads the cell k steps along the row (E) or column (F); the
+// leading lanes whose flag says "extended" stay in the gap.  One iteration (~one lone-thread step) thus covers a whole
+// diagonal stretch or a whole gap, up to 32 cells.  All lanes carry the same scalar state; same results as
+// traceback_pair by construction (tests compare the fused call with the regular path and the oracle).
+__device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const int64_t p, const int lane)
+{
+    constexpr unsigned FULLW = 0xffffffffu;
+    const int n = P.pn[p], m = P.pm[p];
+    const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
+    const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
+    const uint32_t *trace = P.trace + (P.ptrace[p] - P.chunk_base);
+    uint32_t *tail = run_tail(P, p);
+    const int lay = P.playout[p];
+    const int pc = lay & 15;
+    const bool split = (lay & 16) != 0;
+    const int T = (m + pc - 1) / pc + 31;
+    const int last_s = (n - 1) >> 8, rr_last = P.plastrr[p];
+    const int rr_mul = rr_last == 6 ? 171 : 1, rr_sh = rr_last == 6 ? 10 : rr_last == 2 ? 1 : rr_last == 4 ? 2 : 3;
+    int i = P.endq[p], j = P.endr[p];
+    int nr = 0;
+    uint32_t cur_op = 0xffu, cur_len = 0;
+#define PUSHW(op, len)                                                                             \
+    do {                                                                                           \
+        if ((len) > 0) {                                                                           \
+            if (cur_op == (uint32_t)(op)) cur_len += (uint32_t)(len);                              \
+            else {                                                                                 \
+                if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; } \
+                cur_op = (op); cur_len = (len);                                                    \
+            }                                                                                      \
+        }                                                                                          \
+    } while (0)
+    // the 4-bit decision of cell (ii, jj): [source 2 bits | gap flags 2 bits]
+    auto nibble = [&](const int ii, const int jj) {
+        const int s = ii >> 8;
+        int l = (ii >> 3) & 31, r = ii & 7;
+        if (s == last_s && rr_last != 8) { l = ((ii & 255) * rr_mul) >> rr_sh; r = (ii & 255) - l * rr_last; }
+        const int jt = (pc == 1) ? jj : (jj >> 1), jc = (pc == 1) ? 0 : (jj & 1);
+        const uint32_t *wp = &trace[(((size_t)s * T + jt + l) * 32 + l) * pc + jc];
+        ISOF_ASSERT(wp >= trace && wp < tail - TRACE_SLACK, CHK_TRACE_LOAD);
+        const uint32_t word = *wp;
+        return split ? (int)((((word >> (16 + 2 * r)) & 3) << 2) | ((word >> (2 * r)) & 3)) : (int)((word >> (4 * r)) & 15);
+    };
+    const int src_e = P.tb_src_e;
+    const int e_mask = split ? src_e : 1, f_mask = split ? 3 - src_e : 2;
+    const int flag_opened = P.tb_open_tie;
+    const uint32_t op_e = P.tb_swap_id ? ISOF_CIGAR_I : ISOF_CIGAR_D;
+    const uint32_t op_f = P.tb_swap_id ? ISOF_CIGAR_D : ISOF_CIGAR_I;
+    if (i + 1 == n) PUSHW(op_e, m - 1 - j);
+    else PUSHW(op_f, n - 1 - i);
+    int where = 3;
+    while (i >= 0 || j >= 0) {
+        if (i < 0) { PUSHW(op_e, j + 1); break; }
+        if (j < 0) { PUSHW(op_f, i + 1); break; }
+        if (where == 3) {
+            const int ii = i - lane, jj = j - lane;
+            const bool ok = ii >= 0 && jj >= 0;
+            int nib = 0;
+            bool eq = false;
+            if (ok) { nib = nibble(ii, jj); eq = upc(s1[ii]) == upc(s2[jj]); }
+            const unsigned diag = __ballot_sync(FULLW, ok && (nib >> 2) == 3);
+            const unsigned eqm = __ballot_sync(FULLW, eq);
+            const int nd = (diag == FULLW) ? 32 : __ffs((int)~diag) - 1;           // leading diagonal cells
+            if (nd == 0) { where = __shfl_sync(FULLW, nib, 0) >> 2; continue; }      // same cell again, now in its gap state
+            const unsigned mask = (nd == 32) ? FULLW : ((1u << nd) - 1u);
+            const unsigned e = eqm & mask;
+            int k = 0;
+            while (k < nd) {                                                      // one pass per run of = / X
+                const bool is_eq = (e >> k) & 1u;
+                const unsigned other = (is_eq ? ~e : e) & mask & ~((1u << k) - 1u);
+                const int k2 = other ? __ffs((int)other) - 1 : nd;
+                PUSHW(is_eq ? ISOF_CIGAR_EQ : ISOF_CIGAR_X, k2 - k);
+                k = k2;
+            }
+            i -= nd; j -= nd;
+        } else {
+            const bool in_e = (where == src_e);
+            const int ii = in_e ? i : i - lane, jj = in_e ? j - lane : j;
+            const bool ok = ii >= 0 && jj >= 0;
+            bool stay = false;
+            if (ok) stay = ((nibble(ii, jj) & (in_e ? e_mask : f_mask)) != 0) != (flag_opened != 0);
+            const unsigned okm = __ballot_sync(FULLW, ok);
+            const unsigned staym = __ballot_sync(FULLW, ok && stay);
+            const int ns = (staym == FULLW) ? 32 : __ffs((int)~staym) - 1;         // cells that keep the gap open
+            // the first cell that closes the gap is consumed too (when it exists), and the walk returns to H
+            const bool closes = ns < 32 && ((okm >> ns) & 1u);
+            const int steps = ns + (closes ? 1 : 0);
+            PUSHW(in_e ? op_e : op_f, steps);
+            if (in_e) j -= steps; else i -= steps;
+            if (closes) where = 3;
+        }
+    }
+    if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; }
+#undef PUSHW
+    if (lane == 0) P.nruns[p] = nr;
+}
+
 __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, const int64_t end)
 {
     const int64_t p = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -694,6 +794,7 @@ struct FusedArgs {
     int c_eo, c_ee, c_fo, c_fe, c_sm, c_sx;
     uint32_t h_eo, h_ee, h_fo, h_fe, h_sm, h_sx;
     int tb_src_e, tb_open_tie, tb_end_col_first, tb_swap_id, delta_len, tb_variant;
+    long long *stamps;                // mapped host memory: SM clock at the phase boundaries of pair 0 (latency accounting)
 };
 
 __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
@@ -703,6 +804,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __shared__ int32_t s_i32[8];                                 // pa pb pn pm score endq endr nruns
     __shared__ uint8_t s_u8[4];                                  // pwild layout lastrr
     const int p = blockIdx.x, lane = threadIdx.x;
+    const long long t_start = clock64();
     const int4 d0 = a.desc[2 * p], d1 = a.desc[2 * p + 1];       // one broadcast read over PCIe
     const int n = d0.x, m = d0.y;
     const int ns = (n + SROWS - 1) / SROWS;
@@ -737,6 +839,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
         *reinterpret_cast<uint4 *>(s_codes + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
     }
     wild = __any_sync(0xffffffffu, wild);
+    const long long t_loaded = clock64();
     if (lane == 0) {
         s_off[0] = 0; s_off[1] = n16; s_off[2] = n16 + m16;
         s_ptrace[0] = 0; s_ptrace[1] = words;
@@ -763,8 +866,12 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     else if (wild) dp_pair<true>(P, 0, lane, P.bnd, prof);
     else dp_pair<false>(P, 0, lane, P.bnd, prof);
     __syncwarp();
+    const long long t_dp = clock64();
+    long long t_tb = 0;
+    traceback_pair_warp(P, 0, lane);
+    __syncwarp();
     if (lane == 0) {
-        traceback_pair<true>(P, 0);
+        t_tb = clock64();
         if (a.feat) features_pair(P, 0, a.delta_len, a.feat + (size_t)p * ISOF_N_FEATURES);
         a.score[p] = s_i32[4]; a.endq[p] = s_i32[5]; a.endr[p] = s_i32[6]; a.nruns[p] = s_i32[7];
     }
@@ -773,6 +880,10 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     const uint32_t *src = trace + words - nr;
     uint32_t *dst = a.runs + d1.x;
     for (int x = lane; x < nr; x += 32) dst[x] = src[x];
+    if (p == 0 && lane == 0) {
+        a.stamps[0] = t_loaded - t_start; a.stamps[1] = t_dp - t_loaded; a.stamps[2] = t_tb - t_dp;
+        a.stamps[3] = clock64() - t_tb;
+    }
 }
 
 }  // namespace
@@ -820,7 +931,7 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
         max_m = std::max(max_m, (int)m);
     }
     roff[P] = run_words;
-    const int64_t out_bytes = 4 * (4 + ISOF_N_FEATURES) * P + 4 * run_words + 64;
+    const int64_t out_bytes = 4 * (4 + ISOF_N_FEATURES) * P + 4 * run_words + 64 + 64;       // + the phase clocks at the tail
     if (in_bytes > IO_BYTES || out_bytes > IO_BYTES) return 1;
     if (!ctx->fused_io) {
         CUDA_TRY(ctx, cudaHostAlloc(&ctx->fused_io, 2 * IO_BYTES, cudaHostAllocMapped));
@@ -849,6 +960,7 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     a.feat = features ? (int32_t *)((uint8_t *)o_feat + dout) : nullptr;
     a.runs = (uint32_t *)((uint8_t *)o_runs + dout);
     a.bnd = (int2 *)ctx->b_bnd.p; a.bnd_stride = bnd_stride;
+    a.stamps = (long long *)(d_out + IO_BYTES - 64);
     const bool e_first = ctx->tb_h_e_before_f != 0, open_tie = ctx->tb_gap_open_on_tie != 0;
     const int S = 1 << TAG_BITS, class_e = e_first ? 8 : 4, class_f = e_first ? 4 : 8;
     a.c_eo = -gap_open * S + class_e + (open_tie ? 1 : 0);
