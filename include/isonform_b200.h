@@ -76,9 +76,10 @@ ISOF_API int isof_set_band(isof_ctx *ctx, int half_width);
  * memory -- the per-pair seams of the reference (a memo miss of consensus.parasail_alignment).  Identical results; on=0
  * sends such calls through the regular path (tests, A/B measurements); default on=1. */
 ISOF_API int isof_set_fused_small(isof_ctx *ctx, int on);
-/* Latency accounting of the last fused small call (development aid): SM clock cycles pair 0 spent {fetching its inputs
- * over PCIe + encoding, in the DP, in the traceback, in features + result stores}. */
-ISOF_API int isof_debug_fused_phases(isof_ctx *ctx, int64_t *cycles4);
+/* Latency accounting of the last fused small call (development aid), 56 values: [0..3] SM clock cycles pair 0 spent
+ * {fetching its inputs over PCIe + encoding, in the DP, in the traceback, in features + result stores}; [8 + 2g], [9 + 2g]
+ * = begin / end of stripe g's DP in ns (%globaltimer) when the pair ran in chase mode (one block per stripe). */
+ISOF_API int isof_debug_fused_phases(isof_ctx *ctx, int64_t *values56);
 /* A call whose pairs are ALL short (both lengths <= 384, inside the 16-bit range) and numerous enough to fill the GPU
  * (about 64 x SMs x (length/60)^2 pairs: a thread per task trades latency for throughput) takes the short-pair regime:
  * one thread per task instead of a 32-lane wavefront per task (the bubble-popping sizes, SimplifyGraph.py:630-664).

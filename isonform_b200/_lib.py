@@ -168,10 +168,12 @@ class Context:
         self._check(self._L.isof_set_band(self._h, int(half_width)))
 
     def debug_fused_phases(self):
-        """SM cycles of the last fused small call's pair 0: (load+encode, DP, traceback, features+stores)."""
-        out = np.zeros(4, np.int64)
+        """Last fused small call, pair 0: SM cycles of (load+encode, DP, traceback, features+stores), then the list of
+        (begin, end) ns of every stripe's DP when the pair ran in chase mode."""
+        out = np.zeros(56, np.int64)
         self._check(self._L.isof_debug_fused_phases(self._h, out.ctypes.data))
-        return tuple(int(x) for x in out)
+        return tuple(int(x) for x in out[:4]) + ([(int(out[8 + 2 * g]), int(out[9 + 2 * g]), int(out[40 + g]) >> 40,
+                                                   int(out[40 + g]) & ((1 << 40) - 1)) for g in range(16)],)
 
     def set_fused_small(self, on=True):
         """One fused launch for tiny host-buffer calls (default on); results are identical either way."""

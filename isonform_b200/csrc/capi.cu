@@ -169,11 +169,11 @@ int isof_set_band(isof_ctx *ctx, int half_width)
     return ISOF_OK;
 }
 
-int isof_debug_fused_phases(isof_ctx *ctx, int64_t *cycles4)
+int isof_debug_fused_phases(isof_ctx *ctx, int64_t *cycles40)
 {
-    if (!ctx || !cycles4) return ISOF_ERR_ARG;
-    if (!ctx->fused_io) { memset(cycles4, 0, 32); return ISOF_OK; }
-    memcpy(cycles4, (const uint8_t *)ctx->fused_io + 2 * 512 * 1024 - 64, 32);
+    if (!ctx || !cycles40) return ISOF_ERR_ARG;
+    if (!ctx->fused_io) { memset(cycles40, 0, 448); return ISOF_OK; }
+    memcpy(cycles40, (const uint8_t *)ctx->fused_io + 2 * 512 * 1024 - 512, 448);
     return ISOF_OK;
 }
 

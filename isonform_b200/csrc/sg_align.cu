@@ -787,7 +787,11 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
 // synchronisations around a DP of 8 us.
 // ---------------------------------------------------------------------------------------------
 struct FusedArgs {
-    const int4 *desc;                 // mapped host memory: per pair {n, m, byte offset of s1, of s2 | run slot, packed-eligible, 0, 0}
+    const int4 *desc;                 // mapped host memory: per pair {n, m, byte offset of s1, of s2 | run slot, bit 0 packed-eligible + bit 1 chase,
+                                      //   1 + word offset of the pair's trace in `gtrace` (64 bit; 0 = trace in shared memory)}
+    uint32_t *gtrace;                 // device memory: traces of the pairs too large for shared memory
+    // chase mode (one block per stripe, see ChaseCtl): per (pair, stripe) completion flag and end-cell candidate
+    unsigned *done; int2 *acc; int n_stripes;
     const uint8_t *in;                // mapped host memory: the sequences, each at a 16-byte aligned offset
     int32_t *score, *endq, *endr, *nruns, *feat; uint32_t *runs;       // mapped host memory
     int2 *bnd; int64_t bnd_stride;
@@ -803,16 +807,21 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __shared__ int64_t s_off[3], s_ptrace[2];
     __shared__ int32_t s_i32[8];                                 // pa pb pn pm score endq endr nruns
     __shared__ uint8_t s_u8[4];                                  // pwild layout lastrr
-    const int p = blockIdx.x, lane = threadIdx.x;
+    __shared__ int2 s_ring[64];                                  // chase mode: settled batches of the boundary row
+    const int p = blockIdx.y, g = blockIdx.x, lane = threadIdx.x;
     const long long t_start = clock64();
     const int4 d0 = a.desc[2 * p], d1 = a.desc[2 * p + 1];       // one broadcast read over PCIe
     const int n = d0.x, m = d0.y;
     const int ns = (n + SROWS - 1) / SROWS;
+    const bool chase = (d1.y & 2) != 0;                          // one block per stripe; otherwise block 0 does the pair
+    if (g > 0 && (!chase || g >= ns)) return;
     const int64_t words = (int64_t)ns * (m + 64) * 32 + TRACE_SLACK;
     const int n16 = (n + 15) & ~15, m16 = (m + 15) & ~15;
     uint4 *prof = fs_smem;
-    uint32_t *trace = reinterpret_cast<uint32_t *>(fs_smem + 4 * 2 * 32);
-    uint8_t *s_cat = reinterpret_cast<uint8_t *>(trace + words);          // s1 at 0, s2 at n16 (16-byte aligned)
+    const long long goff = ((long long)(uint32_t)d1.z | ((long long)d1.w << 32)) - 1;       // < 0: shared memory
+    uint32_t *smem_words = reinterpret_cast<uint32_t *>(fs_smem + 4 * 2 * 32);
+    uint32_t *trace = goff < 0 ? smem_words : a.gtrace + goff;
+    uint8_t *s_cat = reinterpret_cast<uint8_t *>(goff < 0 ? smem_words + words : smem_words);   // s1 at 0, s2 at n16 (16-byte aligned)
     uint8_t *s_codes = s_cat + n16 + m16;
     int wild = 0;
     // 16 bytes per lane and round: a 100 x 100 pair arrives in one PCIe round trip instead of seven
@@ -850,7 +859,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     AlignParams P;
     P.cat = s_cat; P.codes = s_codes; P.seq_off = s_off; P.pa = &s_i32[0]; P.pb = &s_i32[1]; P.pn = &s_i32[2]; P.pm = &s_i32[3];
     P.pwild = &s_u8[0]; P.ptrace = s_ptrace; P.chunk_base = 0; P.trace = trace;
-    P.bnd = a.bnd + (size_t)p * a.bnd_stride; P.bnd_stride = a.bnd_stride;
+    P.bnd = a.bnd + (size_t)p * a.n_stripes * a.bnd_stride; P.bnd_stride = a.bnd_stride;
     P.score = &s_i32[4]; P.endq = &s_i32[5]; P.endr = &s_i32[6]; P.nruns = &s_i32[7];
     P.c_eo = a.c_eo; P.c_ee = a.c_ee; P.c_fo = a.c_fo; P.c_fe = a.c_fe; P.c_sm = a.c_sm; P.c_sx = a.c_sx;
     P.h_eo = a.h_eo; P.h_ee = a.h_ee; P.h_fo = a.h_fo; P.h_fe = a.h_fe; P.h_sm = a.h_sm; P.h_sx = a.h_sx;
@@ -862,7 +871,38 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     // trace addresses): that path compacts the last stripe to 2 / 4 / 6 rows per lane, so a 100-row query keeps 25 lanes
     // busy with a 4-row dependency chain per step instead of 13 lanes with an 8-row one -- half the latency per step.
     // (default tie-break table only: the other tables take the 32-bit path, whose constants are run-time values)
-    if (!wild && d1.y && a.tb_variant == 0) dp_pair16<0, false>(P, 0, 0, lane, P.bnd, prof);
+    if (chase) {
+        ChaseCtl ch;
+        const size_t slot = (size_t)p * a.n_stripes + g;
+        ch.s = g; ch.ring = s_ring; ch.spins = 0; ch.spin_cycles = 0;
+        ch.bnd_out = a.bnd + slot * a.bnd_stride; ch.bnd_in = ch.bnd_out - a.bnd_stride;      // bnd_in unused by stripe 0
+        long long g0 = 0, g1 = 0;
+        if (p == 0 && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+        dp_pair16<0, false, true>(P, 0, 0, lane, nullptr, prof, &ch);
+        if (p == 0 && lane == 0 && g < 16) {             // latency accounting: DP begin / end of every stripe of pair 0 (ns)
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+            a.stamps[8 + 2 * g] = g0; a.stamps[9 + 2 * g] = g1;
+            a.stamps[40 + g] = (ch.spins << 40) | ch.spin_cycles;
+        }
+        // the last column's best cell travels down the chain of stripes (ties: the smaller row, i.e. the earlier stripe)
+        int bcol = ch.bcol, bcol_i = ch.bcol_i;
+        if (lane == 0 && g > 0) {
+            while (ld_acquire_u32(a.done + slot - 1) == 0u) { }
+            const int2 prev = __ldcg(a.acc + slot - 1);
+            if (prev.x >= bcol) { bcol = prev.x; bcol_i = prev.y; }
+        }
+        __syncwarp();                                    // every lane's trace stores are ordered before lane 0's release
+        if (g + 1 < ns) {
+            if (lane == 0) { a.acc[slot] = make_int2(bcol, bcol_i); __threadfence(); st_release_u32(a.done + slot, 1u); }
+            return;
+        }
+        if (lane == 0) {                                 // last stripe: end cell, then the traceback below
+            int sc, eq, er;
+            pick_end_cell(P.tb_end_col_first, ch.brow, ch.brow_j, bcol, bcol_i, n, m, sc, eq, er);
+            s_i32[4] = sc >> 2; s_i32[5] = eq; s_i32[6] = er;
+        }
+    }
+    else if (!wild && (d1.y & 1) && a.tb_variant == 0) dp_pair16<0, false>(P, 0, 0, lane, P.bnd, prof);
     else if (wild) dp_pair<true>(P, 0, lane, P.bnd, prof);
     else dp_pair<false>(P, 0, lane, P.bnd, prof);
     __syncwarp();
@@ -880,7 +920,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     const uint32_t *src = trace + words - nr;
     uint32_t *dst = a.runs + d1.x;
     for (int x = lane; x < nr; x += 32) dst[x] = src[x];
-    if (p == 0 && lane == 0) {
+    if (p == 0 && lane == 0) {                          // (chase mode: the last stripe's block reports)
         a.stamps[0] = t_loaded - t_start; a.stamps[1] = t_dp - t_loaded; a.stamps[2] = t_tb - t_dp;
         a.stamps[3] = clock64() - t_tb;
     }
@@ -906,32 +946,58 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
         h_max_max_len = room <= 0 ? 0 : (gap_ext > 0 ? room / gap_ext : INT_MAX);
     }
     // ---- plan on the host: lengths, validity, shared memory, run slots, staging offsets
-    int64_t smem_max = 0, run_words = 0, in_bytes = 32 * P;
-    int max_m = 0;
+    int64_t smem_max = 0, run_words = 0, in_bytes = 32 * P, gwords = 0;
+    int max_m = 0, n_stripes = 1;
+    const bool default_table = !ctx->tb_h_e_before_f && !ctx->tb_gap_open_on_tie;
+    auto plain_acgt = [](const uint8_t *x, int64_t len) {
+        for (int64_t q = 0; q < len; ++q) {
+            const uint8_t c = x[q] & 0xdf;                 // upper case
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return false;
+        }
+        return true;
+    };
     int64_t roff[MAX_P + 1];
     int32_t desc[MAX_P][8];
+    bool chase_p[MAX_P];
     for (int64_t p = 0; p < P; ++p) {
         const int a = pair_a[p], b = pair_b[p];
         if (a < 0 || a >= n_seqs || b < 0 || b >= n_seqs) return 1;       // regular path: ISOF_ERR_ARG with its message
         const int64_t n = seq_off[a + 1] - seq_off[a], m = seq_off[b + 1] - seq_off[b];
         if (n <= 0 || m <= 0 || n > 4096 || m > 4096) return 1;
         const int64_t ns = (n + SROWS - 1) / SROWS;
+        // several stripes: one block per stripe, chasing its predecessor (packed path, default table, no wildcard)
+        chase_p[p] = ns >= 2 && std::min(n, m) <= h_max_min_len && std::max(n, m) <= h_max_max_len && default_table &&
+                     plain_acgt(seq_cat + seq_off[a], n) && plain_acgt(seq_cat + seq_off[b], m);
+        if (chase_p[p]) n_stripes = std::max(n_stripes, (int)ns);
+    }
+    for (int64_t p = 0; p < P; ++p) {
+        const int a = pair_a[p], b = pair_b[p];
+        const int64_t n = seq_off[a + 1] - seq_off[a], m = seq_off[b + 1] - seq_off[b];
+        const int64_t ns = (n + SROWS - 1) / SROWS;
         const int64_t words = ns * (m + 64) * 32 + TRACE_SLACK;
         const int64_t n16 = (n + 15) & ~15LL, m16 = (m + 15) & ~15LL;
-        const int64_t smem = 4096 + words * 4 + 2 * (n16 + m16) + 64;
-        if (smem > MAX_SMEM) return 1;
+        int64_t smem = 4096 + words * 4 + 2 * (n16 + m16) + 64, goff1 = 0;
+        const bool packed_ok = std::min(n, m) <= h_max_min_len && std::max(n, m) <= h_max_max_len;
+        const bool chase = chase_p[p];
+        // trace in device memory (the lanes' look-ahead hides its latency): too large for shared memory, or a chase call --
+        // the stripes' blocks sit on different SMs, and all blocks of the launch share one shared-memory size
+        if (smem > MAX_SMEM || n_stripes > 1) {
+            smem = 4096 + 2 * (n16 + m16) + 64;
+            goff1 = gwords + 1;
+            gwords += (words + 31) & ~31LL;
+        }
         smem_max = std::max(smem_max, smem);
         roff[p] = run_words;
         desc[p][0] = (int32_t)n; desc[p][1] = (int32_t)m; desc[p][2] = (int32_t)in_bytes; desc[p][3] = (int32_t)(in_bytes + n16);
         desc[p][4] = (int32_t)run_words;
-        desc[p][5] = (std::min(n, m) <= h_max_min_len && std::max(n, m) <= h_max_max_len) ? 1 : 0;
-        desc[p][6] = desc[p][7] = 0;
+        desc[p][5] = (packed_ok ? 1 : 0) | (chase ? 2 : 0);
+        desc[p][6] = (int32_t)(uint32_t)(goff1 & 0xffffffffLL); desc[p][7] = (int32_t)(goff1 >> 32);
         in_bytes += n16 + m16;
         run_words += n + m + 2;
         max_m = std::max(max_m, (int)m);
     }
     roff[P] = run_words;
-    const int64_t out_bytes = 4 * (4 + ISOF_N_FEATURES) * P + 4 * run_words + 64 + 64;       // + the phase clocks at the tail
+    const int64_t out_bytes = 4 * (4 + ISOF_N_FEATURES) * P + 4 * run_words + 64 + 512;      // + the phase clocks at the tail
     if (in_bytes > IO_BYTES || out_bytes > IO_BYTES) return 1;
     if (!ctx->fused_io) {
         CUDA_TRY(ctx, cudaHostAlloc(&ctx->fused_io, 2 * IO_BYTES, cudaHostAllocMapped));
@@ -951,7 +1017,7 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     int32_t *o_feat = o_nruns + P;
     uint32_t *o_runs = (uint32_t *)(o_feat + ISOF_N_FEATURES * P);
     const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;       // touched by multi-stripe pairs only; grow-only reserve
-    TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)P * (size_t)n_stripes));
     FusedArgs a;
     const ptrdiff_t dout = d_out - out;
     a.desc = (const int4 *)d_in; a.in = d_in;
@@ -960,7 +1026,21 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     a.feat = features ? (int32_t *)((uint8_t *)o_feat + dout) : nullptr;
     a.runs = (uint32_t *)((uint8_t *)o_runs + dout);
     a.bnd = (int2 *)ctx->b_bnd.p; a.bnd_stride = bnd_stride;
-    a.stamps = (long long *)(d_out + IO_BYTES - 64);
+    a.n_stripes = n_stripes; a.done = nullptr; a.acc = nullptr;
+    if (n_stripes > 1) {
+        const size_t slots = (size_t)P * (size_t)n_stripes;
+        TRY(dev_reserve(ctx, ctx->b_chase, 16 * slots));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->b_chase.p, 0, 4 * slots, ctx->stream));       // done flags
+        a.done = (unsigned *)ctx->b_chase.p; a.acc = (int2 *)((uint8_t *)ctx->b_chase.p + 8 * slots);
+        // boundary lines start "empty" (CHASE_EMPTY in every word)
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->b_bnd.p, 0x80, sizeof(int2) * (size_t)bnd_stride * slots, ctx->stream));
+    }
+    a.gtrace = nullptr;
+    if (gwords) {
+        TRY(dev_reserve(ctx, ctx->b_trace, sizeof(uint32_t) * (size_t)gwords));
+        a.gtrace = (uint32_t *)ctx->b_trace.p;
+    }
+    a.stamps = (long long *)(d_out + IO_BYTES - 512);
     const bool e_first = ctx->tb_h_e_before_f != 0, open_tie = ctx->tb_gap_open_on_tie != 0;
     const int S = 1 << TAG_BITS, class_e = e_first ? 8 : 4, class_f = e_first ? 4 : 8;
     a.c_eo = -gap_open * S + class_e + (open_tie ? 1 : 0);
@@ -976,7 +1056,7 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     a.tb_src_e = e_first ? 2 : 1; a.tb_open_tie = open_tie ? 1 : 0; a.tb_end_col_first = ctx->tb_end_col_first ? 1 : 0;
     a.tb_swap_id = ctx->tb_swap_id ? 1 : 0; a.delta_len = delta_len;
     ctx->prof.launches++; ctx->prof.dp_launches++;
-    sg_fused_small_kernel<<<(unsigned)P, 32, (size_t)smem_max, ctx->stream>>>(a);
+    sg_fused_small_kernel<<<dim3((unsigned)n_stripes, (unsigned)P), 32, (size_t)smem_max, ctx->stream>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // ---- results

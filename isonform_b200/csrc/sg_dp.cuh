@@ -466,11 +466,52 @@ __device__ __forceinline__ void p16_column(P16State &S, const P16Const &K, const
 // gives the right re-based value because the true one fits.  End-cell maxima are tracked as absolute 32-bit values.
 // Every comparison still happens between values of the same base, so scores, ties and trace bits are those of the
 // 32-bit path, bit for bit.
-template <int TBV, bool RB>
+// CHASE (lone pairs of the fused small-call kernel): one warp per STRIPE, each in a block of its own.  The warp of stripe
+// s reads the boundary row that the warp of stripe s - 1 is still writing -- every stripe has its own line buffer -- and
+// follows it at the distance of the lane skew.  No flags and no fences on that path: the line buffers start out filled
+// with a value no boundary cell can hold (CHASE_EMPTY: H = -32640 in both halves, below every reachable score), a
+// boundary cell is ONE 8-byte store, and the consumer's lane 0 simply re-reads (ld.volatile, L2) until the cell is there.
+// A 4000 x 4000 pair then takes ~T + 15 * 35 steps instead of 16 * T.  The warp returns its end-cell candidates instead of
+// writing results.  (A first version published "columns written so far" with st.release every 8 steps: each release had
+// to wait for the warp's outstanding trace stores, and the chain ran 6x slower than this one.)
+constexpr uint32_t CHASE_EMPTY = 0x80808080u;          // cudaMemset(line buffers, 0x80)
+struct ChaseCtl {
+    int s;                             // the one stripe this warp computes
+    int2 *bnd_in, *bnd_out;            // boundary rows: stripe s-1's bottom row (read), this stripe's (written)
+    int2 *ring;                        // shared memory, 64 entries: the settled batches of the boundary row
+    int bcol, bcol_i, brow, brow_j;    // out: best of the last column over this stripe's rows; best of the last row
+    long long spins, spin_cycles;      // out (latency accounting): re-reads of a batch that was not there yet, cycles spent on them
+};
+__device__ __forceinline__ int2 ld_volatile_int2(const int2 *p)
+{
+    int2 v;
+    // no "memory" clobber: the compiler stays free to schedule the step's other loads (profile, codes) across this one
+    asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, const unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int TBV, bool RB, bool CHASE = false>
 __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA, const int64_t pB, const int lane,
-                                          int2 *__restrict__ bnd, uint4 *__restrict__ prof_warp)
+                                          int2 *__restrict__ bnd, uint4 *__restrict__ prof_warp, ChaseCtl *ch = nullptr)
 {
     const unsigned FULL = 0xffffffffu;
+    const int2 *__restrict__ bnd_r = CHASE ? ch->bnd_in : bnd;       // boundary row read by lane 0
+    int2 *__restrict__ bnd_w = CHASE ? ch->bnd_out : bnd;            // boundary row written by lane 31
+    static_assert(!(CHASE && RB), "chase mode exists for the plain 16-bit lanes only");
+    auto bnd_put = [&](int2 *dst, const int2 v) {
+        if (CHASE) __stcg(dst, v); else *dst = v;
+    };
     const int nA = P.pn[pA], mA = P.pm[pA], nB = P.pn[pB], mB = P.pm[pB];
     const uint8_t *__restrict__ qA = P.codes + P.seq_off[P.pa[pA]];
     const uint8_t *__restrict__ rA = P.codes + P.seq_off[P.pb[pA]];
@@ -482,6 +523,37 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     const int T = (m + PC - 1) / PC + 31, TA = (mA + PC - 1) / PC + 31, TB = (mB + PC - 1) / PC + 31;
     const int nsA = (nA + SROWS - 1) / SROWS, nsB = (nB + SROWS - 1) / SROWS, ns = max(nsA, nsB);
     int last_laneA = 0, last_rA = 0, last_laneB = 0, last_rB = 0;       // set in the alignment's last stripe
+    // CHASE: the boundary row comes in batches of 32 columns, one per lane, fetched a batch (16 steps) ahead of its use so
+    // that the L2 round trip -- longer than a step -- never sits on the step's critical path; lane 0 picks its columns out
+    // of the batch with shuffles.  A batch is re-read until none of its cells holds the empty marker.
+    int2 ch_cur = make_int2(0, 0), ch_next = make_int2(0, 0);
+    int ch_col0 = 0;                                                 // first column of ch_cur
+    auto chase_issue = [&](const int col0) {                         // this lane's cell of the batch starting at col0
+        const int col = col0 + lane;
+        return (col < m) ? ld_volatile_int2(bnd_r + col) : make_int2(0, 0);
+    };
+    auto chase_settle = [&](int2 &v, const int col0) {
+        const int col = col0 + lane;
+        const long long c0 = clock64();
+        while (__any_sync(FULL, col < m && (uint32_t)v.x == CHASE_EMPTY)) {
+            if (col < m && (uint32_t)v.x == CHASE_EMPTY) v = ld_volatile_int2(bnd_r + col);
+            ++ch->spins;
+        }
+        ch->spin_cycles += clock64() - c0;
+    };
+    // boundary cell of column `col` (warp-uniform) for lane 0: a settled batch is parked in a 64-entry ring in shared
+    // memory, from which lane 0 reads like the other modes read the line buffer; the batches rotate when col runs past
+    auto chase_take = [&](const int col) {
+        if (col - ch_col0 >= 32) {
+            ch_col0 += 32;
+            ch_cur = ch_next;
+            chase_settle(ch_cur, ch_col0);
+            ch->ring[(ch_col0 + lane) & 63] = ch_cur;
+            __syncwarp();
+            ch_next = chase_issue(ch_col0 + 32);
+        }
+        return ch->ring[col & 63];
+    };
     P16Const K;
     // the F constants equal the E constants (same penalties, tags come from the stored values): one register each
     // (under gap_open_on_tie the opening / extension addends carry the state's own tag and differ)
@@ -553,8 +625,20 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             if (lane == 0) {
                 const uint32_t a = (c < mA) ? (uint32_t)rA[c] : 0u, b = (c < mB) ? (uint32_t)rB[c] : 0u;
                 S.rc_next[c] = PROF ? a : ((a << CS16) | (b << (CS16 + 16)));
-                if (has_prev && c < m) S.b_next[c] = __ldcg(&bnd[c]);
+                if (!CHASE && has_prev && c < m) S.b_next[c] = __ldcg(&bnd_r[c]);
             }
+        }
+        if (CHASE && has_prev) {                     // first two batches of the boundary row; columns 0 .. PC-1 feed step 0
+            ch_col0 = 0;
+            ch_cur = chase_issue(0);
+            ch_next = chase_issue(32);
+            chase_settle(ch_cur, 0);
+            __syncwarp();
+            ch->ring[lane] = ch_cur;
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < PC; ++c)
+                if (lane == 0 && c < m) S.b_next[c] = ch->ring[c];
         }
         // banded pairs keep the steps tlo .. tlo + win - 1 of the stripe (stripe pitch = win); others all T steps
         const int tloA = (RB && twA) ? band_tlo(s, dminA) : 0, winA = (RB && twA) ? twA : TA;
@@ -604,7 +688,16 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 rc[c] = S.rc_next[c];
                 hu[c] = __shfl_up_sync(FULL, S.Hbot[c], 1);
                 fu[c] = __shfl_up_sync(FULL, S.Fbot[c], 1);
-                if (lane == 0) { hu[c] = (uint32_t)S.b_next[c].x; fu[c] = (uint32_t)S.b_next[c].y; }
+                if (lane == 0) {
+                    hu[c] = (uint32_t)S.b_next[c].x; fu[c] = (uint32_t)S.b_next[c].y;
+                }
+            }
+            if (CHASE && has_prev && PC * (t + 1) < m) {          // lane 0's boundary cells of the next step (warp-uniform)
+#pragma unroll
+                for (int c = 0; c < PC; ++c) {
+                    const int col = PC * (t + 1) + c;
+                    if (col < m) { const int2 v = chase_take(col); if (lane == 0) S.b_next[c] = v; }
+                }
             }
             {
                 const int jn = jb + PC;
@@ -614,7 +707,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                         const uint32_t a = (jn + c < mA) ? (uint32_t)rA[jn + c] : 0u;
                         const uint32_t b = (jn + c < mB) ? (uint32_t)rB[jn + c] : 0u;
                         S.rc_next[c] = PROF ? a : ((a << CS16) | (b << (CS16 + 16)));
-                        if (has_prev && lane == 0 && jn + c < m) S.b_next[c] = bnd_load(&bnd[jn + c]);
+                        if (!CHASE && has_prev && lane == 0 && jn + c < m) S.b_next[c] = bnd_load(&bnd_r[jn + c]);
                     }
                 }
             }
@@ -625,7 +718,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     p16_column<RR, PROF, TBV>(S, K, rc[c], hu[c], fu[c], (c == 0) ? S.diag0 : hu[c - 1], S.Hbot[c], S.Fbot[c], wA[c], wB[c], prof);
                     const int j = jb + c;
                     ISOF_ASSERT(j < P.bnd_stride, CHK_BND);
-                    if (has_next && lane == 31 && j < m) bnd[j] = bnd_value(S.Hbot[c], S.Fbot[c]);
+                    if (has_next && lane == 31 && j < m) bnd_put(&bnd_w[j], bnd_value(S.Hbot[c], S.Fbot[c]));
                     // last column of A / B: every lane passes it exactly once per stripe; keep the column (one LOP3 per
                     // row) and fold it into the running maximum after the stripe's loop (RB: the base may move before
                     // then, so the column is folded right here as absolute values)
@@ -684,8 +777,8 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             // and there only the running maximum of the last row (the last column is reached in the drain)
             const uint8_t *pa_ = rA + PC * (31 - lane) + PC;       // look-ahead block of step t = 31
             const uint8_t *pb_ = rB + PC * (31 - lane) + PC;
-            const int2 *pbn = bnd + PC * 31 + PC;                  // lane 0 only
-            int2 *pbs = bnd + PC * (31 - 31);                      // lane 31 only: jb at t = 31
+            const int2 *pbn = bnd_r + PC * 31 + PC;                // lane 0 only
+            int2 *pbs = bnd_w + PC * (31 - 31);                    // lane 31 only: jb at t = 31
             uint2 *sA = tpA + (ptrdiff_t)31 * 32, *sB = tpB + (ptrdiff_t)31 * 32;
             auto steady_step = [&](const int t, const bool with_track) {
                 uint32_t rc[PC], hu[PC], fu[PC];
@@ -694,7 +787,9 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     rc[c] = S.rc_next[c];
                     hu[c] = __shfl_up_sync(FULL, S.Hbot[c], 1);
                     fu[c] = __shfl_up_sync(FULL, S.Fbot[c], 1);
-                    if (lane == 0) { hu[c] = (uint32_t)S.b_next[c].x; fu[c] = (uint32_t)S.b_next[c].y; }
+                    if (lane == 0) {
+                        hu[c] = (uint32_t)S.b_next[c].x; fu[c] = (uint32_t)S.b_next[c].y;
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < PC; ++c)
@@ -702,7 +797,12 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                     ISOF_ASSERT(pa_ + c < rA + mA && pb_ + c < rB + mB && pa_ >= rA && pb_ >= rB, CHK_SEQ_LOAD);
                     S.rc_next[c] = PROF ? (uint32_t)pa_[c] : (((uint32_t)pa_[c] << CS16) | ((uint32_t)pb_[c] << (CS16 + 16)));
                 }
-                if (has_prev && lane == 0) {
+                if (CHASE) {
+                    if (has_prev) {
+#pragma unroll
+                        for (int c = 0; c < PC; ++c) { const int2 v = chase_take(PC * (t + 1) + c); if (lane == 0) S.b_next[c] = v; }
+                    }
+                } else if (has_prev && lane == 0) {
 #pragma unroll
                     for (int c = 0; c < PC; ++c) S.b_next[c] = bnd_load(pbn + c);
                 }
@@ -743,7 +843,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 }
                 if (has_next && lane == 31) {
 #pragma unroll
-                    for (int c = 0; c < PC; ++c) { ISOF_ASSERT(pbs + c < bnd + P.bnd_stride, CHK_BND); pbs[c] = bnd_value(S.Hbot[c], S.Fbot[c]); }
+                    for (int c = 0; c < PC; ++c) { ISOF_ASSERT(pbs + c < bnd_w + P.bnd_stride, CHK_BND); bnd_put(&pbs[c], bnd_value(S.Hbot[c], S.Fbot[c])); }
                 }
                 pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
             };
@@ -786,7 +886,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
         }
         __syncwarp();
     };
-    for (int s = 0; s < ns; ++s) {
+    for (int s = CHASE ? ch->s : 0; s < (CHASE ? ch->s + 1 : ns); ++s) {
         const int need = max(min(nA - s * SROWS, SROWS), min(nB - s * SROWS, SROWS));
         if (same_ref) {
             if (need > 192) run_stripe(std::integral_constant<int, 8>{}, std::true_type{}, s);
@@ -809,6 +909,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
         ov = __shfl_xor_sync(FULL, bcolB, d); oi = __shfl_xor_sync(FULL, bcolB_i, d);
         if (ov > bcolB || (ov == bcolB && oi < bcolB_i)) { bcolB = ov; bcolB_i = oi; }
     }
+    if (CHASE) { ch->bcol = bcolA; ch->bcol_i = bcolA_i; ch->brow = browA; ch->brow_j = browA_j; return; }
     if (lane == 0) {
         int sc, eq, er;
         pick_end_cell(P.tb_end_col_first, browA, browA_j, bcolA, bcolA_i, nA, mA, sc, eq, er);

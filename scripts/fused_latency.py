@@ -7,7 +7,7 @@ from isonform_b200 import _lib, synth
 ctx = _lib.Context(0)
 rng = np.random.default_rng(1)
 MHZ = 1965.0
-for L in (30, 100, 250, 500, 1000):
+for L in (30, 100, 250, 500, 1000, 2000, 4000):
     x = synth.random_dna(rng, L); y = synth.mutate(rng, x, 0.05)
     for _ in range(20):
         ctx.sg_align_one(x, y, 2, -8, 12, 1)
@@ -28,4 +28,9 @@ for L in (30, 100, 250, 500, 1000):
         f(*args)
     bare = (time.perf_counter() - t0) / 300 * 1e6
     print("L=%d  sg_align_one %.1f us  bare C call %.1f us  kernel phases us: load %.1f dp %.1f traceback %.1f finish %.1f (sum %.1f)"
-          % (L, one, bare, ph[0] / MHZ, ph[1] / MHZ, ph[2] / MHZ, ph[3] / MHZ, sum(ph) / MHZ), flush=True)
+          % (L, one, bare, ph[0] / MHZ, ph[1] / MHZ, ph[2] / MHZ, ph[3] / MHZ, sum(ph[:4]) / MHZ), flush=True)
+    st = [x for x in ph[4] if x[1] > 0]
+    if L >= 500 and st:
+        t0s = min(x[0] for x in st)
+        print("      stripes (begin us, end us, batch re-reads, us spent on them): " +
+              " ".join("(%.0f %.0f %d %.0f)" % ((b - t0s) / 1e3, (e - t0s) / 1e3, sp, cyc / MHZ) for b, e, sp, cyc in st), flush=True)

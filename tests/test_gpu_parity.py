@@ -640,7 +640,7 @@ def test_debug_build_bounds_assertions_stay_silent():
         assert dctx.debug_violations()[0] == 0
         # short-pair regime (thread-per-task kernel): ragged groups, wildcards, a partial last group
         # fused tiny-call kernel (trace in shared memory)
-        for (n, m) in [(1, 1), (99, 101), (257, 120), (480, 490), (130, 700)]:
+        for (n, m) in [(1, 1), (99, 101), (257, 120), (480, 490), (130, 700), (1300, 1250), (600, 2100)]:
             x = _rand_dna(rng, max(n, m)); y = synth.mutate(rng, x, 0.06) + _rand_dna(rng, m)
             res = hotpath.align_pairs([x[:n], y[:m]], [0], [1], 2, -8, 12, 1, ctx=dctx, features_delta_len=5)
             sc, _q, _r, runs = oracle.sg_align(x[:n], y[:m], 2, -8, 12, 1)
@@ -1056,12 +1056,13 @@ def test_fused_small_call_matches_regular_path_and_oracle(ctx):
     """Host-buffer calls of a few small pairs run as one fused launch (trace in shared memory, mapped I/O).  Same
     scores, end cells, CIGAR runs and features as the regular path and the oracle: single pairs from 1 x 1 to multi-stripe
     shapes, wildcards and lower case, batches of up to 32 pairs, the capacity-retry protocol, a non-default tie-break
-    table, and shapes just beyond the fused limits (which must fall through to the regular path unnoticed)."""
+    table, pairs whose trace does not fit shared memory (it then lives in device memory, up to 4096 x 4096), and shapes
+    just beyond the fused limits (which must fall through to the regular path unnoticed)."""
     from isonform_b200 import hotpath, synth
     rng = np.random.default_rng(2024)
     cases = []
     for (n, m) in [(1, 1), (1, 60), (60, 1), (7, 9), (99, 101), (256, 256), (257, 120), (300, 310), (520, 200), (130, 700),
-                   (480, 490), (800, 800), (20, 3000)]:
+                   (480, 490), (800, 800), (20, 3000), (1500, 1400), (4096, 700), (2500, 2600), (4097, 300)]:
         x = _rand_dna(rng, max(n, m))
         y = synth.mutate(rng, x, 0.06) + _rand_dna(rng, m)
         cases.append(([x[:n], y[:m]], [0], [1]))
@@ -1091,7 +1092,7 @@ def test_fused_small_call_matches_regular_path_and_oracle(ctx):
             ctx.set_fused_small(True)
             ctx.set_tiebreak(0, 0, 0, 0)
     # against the oracle (default table) and through the reference-shaped seam
-    for seqs, pa, pb in cases[:15]:
+    for seqs, pa, pb in cases[:19]:
         res = hotpath.align_pairs(seqs, pa, pb, 2, -8, 12, 1, ctx=ctx)
         for p in range(len(pa)):
             sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], 2, -8, 12, 1)
