@@ -434,6 +434,7 @@ def run_entry(ctx, wl):
     import torch
     from isonform_b200 import runner
     reads = runner.read_batch([(a, s, "I" * len(s)) for a, s in wl["reads"]])
+    runner.batch_hot_path(reads, K_SIZE, W_SIZE, X_MIN, X_MAX, DELTA_LEN, ctx=ctx, stats={})       # warm-up pass (scratch growth)
     stats = {}
     ctx.profile_reset()
     torch.cuda.synchronize()
@@ -515,8 +516,9 @@ def run_seam_latency(ctx):
         for _ in range(n):
             ctx.sg_align_one(x, y, 2, -8, 12, 1)
         out["us_per_c_abi_call_%dbp" % L] = (time.perf_counter() - t0) / n * 1e6
-    out["note"] = ("hotpath.parasail_alignment = C ABI call + CIGAR string / aligned strings in Python; pairs whose trace fits 200 KB "
-                   "(up to ~500 x 500) take the fused one-launch kernel, longer ones the regular path")
+    out["note"] = ("hotpath.parasail_alignment = C ABI call + CIGAR string / aligned strings in Python; calls of <= 32 pairs up to "
+                   "4096 x 4096 take the fused one-launch kernel (trace in shared memory up to ~500 x 500, warp-cooperative "
+                   "traceback, one warp per 256-row stripe chasing its predecessor for multi-stripe pairs)")
     return out
 
 
