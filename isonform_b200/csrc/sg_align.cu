@@ -1326,48 +1326,68 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     const int NL = memory_bound ? isof_ctx::MAX_LANES : isof_ctx::NLANES;
     const bool want_overlap = ctx->overlap && total_words > budget_words / NL;
     if (want_overlap) budget_words /= NL;
-    if (budget_words > total_words) budget_words = total_words;
-    if (budget_words < 1) budget_words = 1;
-    const bool single = total_words <= budget_words;          // everything fits one chunk: no device round trips
-    const int n_chunks = single ? 1 : (int)(total_words / budget_words) + 1;
-    TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 5));
-    int64_t *chunk_start_d = (int64_t *)ctx->b_counters.p;
-    unsigned long long *counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);      // task tickets per chunk
-    unsigned long long *elig_counts = counters + n_chunks + 2;                                  // eligible pairs per chunk
-    unsigned long long *rb_counts = elig_counts + n_chunks + 2;                                 // re-based class per chunk
-    unsigned long long *rb_tickets = rb_counts + n_chunks + 2;                                  // its task tickets
-    const bool fused_small = small && single;          // tickets, class counts and task order came from small_plan_kernel
-    if (!fused_small) CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 4, st));
+    // a chunk holds the pairs that START inside its slice of the trace offsets, so it can exceed the slice by one pair
+    const int64_t pair_max_words = (int64_t)((max_n + SROWS - 1) / SROWS) * (max_m + 64) * 32 + TRACE_SLACK;
+    if (want_overlap && ctx->trace_budget == 0) {
+        // lanes left by an earlier call (e.g. the first pass of a banded call, whose chunks were a sliver smaller): plan
+        // the chunks to fit them rather than free and re-allocate tens of GB while the other lanes fill the memory
+        size_t lane_cap = ctx->b_trace.cap;
+        for (int w = 1; w < NL; ++w) lane_cap = std::min(lane_cap, ctx->b_trace_x[w - 1].cap);
+        const int64_t fit = (int64_t)(lane_cap / 4) - pair_max_words;
+        if (fit >= budget_words / 2 && fit < budget_words) budget_words = fit;
+    }
+    bool single = false, pipelined = false, fused_small = false;
+    int n_chunks = 1;
+    int64_t *chunk_start_d = nullptr;
+    unsigned long long *counters = nullptr, *elig_counts = nullptr, *rb_counts = nullptr, *rb_tickets = nullptr;
     // a pair of the re-based class exists only if some pair exceeds the plain 16-bit range
     const bool may_rb = rb_ok && (std::max(max_n, max_m) > h_max_max_len || std::min(max_n, max_m) > h_max_min_len);
-    std::vector<int64_t> chunk_start((size_t)n_chunks + 1), start_off((size_t)n_chunks + 1);
-    if (single) {
-        chunk_start[0] = 0; chunk_start[1] = P;
-        start_off[0] = 0; start_off[1] = total_words;
-    } else {
-        {
-            LaunchTimer t(ctx, SLOT_OTHER);
-            chunk_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(ptrace, P, budget_words, n_chunks, chunk_start_d);
+    std::vector<int64_t> chunk_start, start_off;
+    for (int attempt = 0;; ++attempt) {
+        if (budget_words > total_words) budget_words = total_words;
+        if (budget_words < 1) budget_words = 1;
+        single = total_words <= budget_words;              // everything fits one chunk: no device round trips
+        n_chunks = single ? 1 : (int)(total_words / budget_words) + 1;
+        TRY(dev_reserve(ctx, ctx->b_counters, sizeof(int64_t) * (size_t)(n_chunks + 2) * 5));
+        chunk_start_d = (int64_t *)ctx->b_counters.p;
+        counters = (unsigned long long *)(chunk_start_d + n_chunks + 2);       // task tickets per chunk
+        elig_counts = counters + n_chunks + 2;                                  // eligible pairs per chunk
+        rb_counts = elig_counts + n_chunks + 2;                                 // re-based class per chunk
+        rb_tickets = rb_counts + n_chunks + 2;                                  // its task tickets
+        fused_small = small && single;                     // tickets, class counts and task order came from small_plan_kernel
+        if (!fused_small) CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, sizeof(int64_t) * (size_t)(n_chunks + 2) * 4, st));
+        chunk_start.assign((size_t)n_chunks + 1, 0);
+        start_off.assign((size_t)n_chunks + 1, 0);
+        if (single) {
+            chunk_start[0] = 0; chunk_start[1] = P;
+            start_off[0] = 0; start_off[1] = total_words;
+        } else {
+            {
+                LaunchTimer t(ctx, SLOT_OTHER);
+                chunk_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(ptrace, P, budget_words, n_chunks, chunk_start_d);
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(chunk_start.data(), chunk_start_d, sizeof(int64_t) * (size_t)(n_chunks + 1),
+                                          cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            // the largest chunk decides the scratch size: offsets of chunk starts are needed on the host
+            for (int c = 0; c <= n_chunks; ++c)
+                CUDA_TRY(ctx, cudaMemcpyAsync(&start_off[c], ptrace + chunk_start[c], 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
         }
-        CUDA_TRY(ctx, cudaMemcpyAsync(chunk_start.data(), chunk_start_d, sizeof(int64_t) * (size_t)(n_chunks + 1),
-                                      cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        // the largest chunk decides the scratch size: offsets of chunk starts are needed on the host
-        for (int c = 0; c <= n_chunks; ++c)
-            CUDA_TRY(ctx, cudaMemcpyAsync(&start_off[c], ptrace + chunk_start[c], 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    }
-    int64_t max_chunk_words = 0;
-    for (int c = 0; c < n_chunks; ++c) max_chunk_words = std::max(max_chunk_words, start_off[c + 1] - start_off[c]);
-    const bool pipelined = want_overlap && n_chunks > 1;
-    for (int w = 0; w < (pipelined ? NL : 1); ++w) {
-        DevBuf *tb = w ? &ctx->b_trace_x[w - 1] : &ctx->b_trace;
-        if ((size_t)max_chunk_words * 4 > tb->cap) {
-            int rc = dev_reserve(ctx, *tb, (size_t)max_chunk_words * 4);
-            if (rc != ISOF_OK)
-                return isof_fail(ctx, ISOF_ERR_NOMEM, "trace scratch of %lld bytes does not fit (largest pair/chunk)",
-                                 (long long)max_chunk_words * 4);
+        int64_t max_chunk_words = 0;
+        for (int c = 0; c < n_chunks; ++c) max_chunk_words = std::max(max_chunk_words, start_off[c + 1] - start_off[c]);
+        pipelined = want_overlap && n_chunks > 1;
+        bool fits = true;
+        for (int w = 0; w < (pipelined ? NL : 1) && fits; ++w) {
+            DevBuf *tb = w ? &ctx->b_trace_x[w - 1] : &ctx->b_trace;
+            if ((size_t)max_chunk_words * 4 > tb->cap) fits = dev_reserve(ctx, *tb, (size_t)max_chunk_words * 4) == ISOF_OK;
         }
+        if (fits) break;
+        // the device is fuller than at first use (the caller's own tensors, a fragmented heap): plan smaller chunks
+        if (attempt == 3 || budget_words <= pair_max_words)
+            return isof_fail(ctx, ISOF_ERR_NOMEM, "trace scratch of %lld bytes does not fit (largest pair/chunk)",
+                             (long long)max_chunk_words * 4);
+        budget_words = std::max(budget_words / 2, pair_max_words);
     }
     const int occ_blocks = ctx->sm_count * DP_CTAS_PER_SM;   // resident CTAs (persistent: one launch fills the GPU once)
     const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;
