@@ -127,6 +127,7 @@ typedef struct {
     int64_t trace_bytes;         /* trace bytes written by the DP kernel                         */
     int64_t h2d_bytes, d2h_bytes;
     int64_t band_pairs_retried;  /* pairs whose path left the banded trace and were aligned again with the full trace */
+    int64_t trace_replans;       /* times the trace chunks were planned again, smaller, because a lane did not fit the device */
 } isof_profile;
 ISOF_API int isof_profile_enable(isof_ctx *ctx, int on);
 ISOF_API int isof_profile_reset(isof_ctx *ctx);

@@ -29,7 +29,7 @@ class Profile(C.Structure):
                 ("traceback_ms", C.c_double), ("minimizer_ms", C.c_double), ("other_ms", C.c_double),
                 ("dp_cells", C.c_int64), ("dp_cells_padded", C.c_int64), ("dp_cells_packed", C.c_int64), ("dp_cells_profile", C.c_int64),
                 ("trace_bytes", C.c_int64),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("band_pairs_retried", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("band_pairs_retried", C.c_int64), ("trace_replans", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1388,6 +1388,12 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             return isof_fail(ctx, ISOF_ERR_NOMEM, "trace scratch of %lld bytes does not fit (largest pair/chunk)",
                              (long long)max_chunk_words * 4);
         budget_words = std::max(budget_words / 2, pair_max_words);
+        ctx->prof.trace_replans++;
+        // hand every lane back first: a lane that did get its (too large) share would otherwise keep it
+        for (int w = 0; w < isof_ctx::MAX_LANES; ++w) {
+            DevBuf *tb = w ? &ctx->b_trace_x[w - 1] : &ctx->b_trace;
+            if (tb->p) { CUDA_TRY(ctx, cudaFree(tb->p)); tb->p = nullptr; tb->cap = 0; }
+        }
     }
     const int occ_blocks = ctx->sm_count * DP_CTAS_PER_SM;   // resident CTAs (persistent: one launch fills the GPU once)
     const int64_t bnd_stride = ((int64_t)max_m + 128) & ~63LL;

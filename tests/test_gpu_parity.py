@@ -1215,3 +1215,37 @@ def test_banded_trace_of_long_pairs_never_changes_results(ctx, half_width):
         assert retried <= 2, retried                             # only the unrelated / low-complexity pairs may wander
     else:
         assert retried >= 3, retried                             # the exon-sized indels do leave a narrow band
+
+
+def test_trace_lanes_shrink_when_the_device_fills_up_after_first_use():
+    """The trace budget is sized from the memory that was free when the context first aligned.  If the host framework
+    has since filled the device (here: a torch tensor that leaves ~24 GB), the lanes no longer fit: the call must re-plan
+    with smaller chunks -- handing back the lanes it already got -- and return the same results, not ISOF_ERR_NOMEM."""
+    import torch
+    from isonform_b200 import _lib, hotpath, synth
+    rng = np.random.default_rng(31)
+    base = _rand_dna(rng, 2400)
+    pool = [synth.mutate(rng, base, 0.05) for _ in range(260)]
+    ib, ia = np.tril_indices(len(pool), -1)                      # 33 670 pairs, ~97 GB of trace: many chunks
+    c = _lib.Context(0)
+    hog = None
+    try:
+        hotpath.align_pairs(pool[:40], ia[:700], ib[:700], 2, -2, 12, 1, ctx=c)              # first use: budget from the free memory now
+        free, _total = torch.cuda.mem_get_info()
+        if free < (60 << 30):
+            pytest.skip("needs a mostly empty device")
+        hog = torch.empty(free - (24 << 30), dtype=torch.uint8, device="cuda")
+        c.profile_reset()
+        got = hotpath.align_pairs(pool, ia, ib, 2, -2, 12, 1, ctx=c, want_cigar=False, features_delta_len=5)
+        assert c.profile()["trace_replans"] >= 1
+        del hog
+        hog = None
+        torch.cuda.empty_cache()
+        want = hotpath.align_pairs(pool, ia, ib, 2, -2, 12, 1, ctx=c, want_cigar=False, features_delta_len=5)
+        assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["features"], want["features"])
+        sc, _q, _r, _runs = oracle.sg_align(pool[ia[777]], pool[ib[777]], 2, -2, 12, 1)
+        assert int(got["score"][777]) == sc
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+        c.close()
