@@ -238,12 +238,17 @@ sg_dp_short_kernel(const ShortParams S, unsigned long long *__restrict__ counter
     }
 }
 
-// traceback over the short layout: same walk as sg_traceback_kernel, other addresses
+// traceback over the short layout: same walk as sg_traceback_kernel, other addresses.  Threads take the pairs in the
+// sorted order of the DP groups: the 32 threads of a warp then walk the 32 alignments of one half of one group, whose
+// trace words for the same cell sit 16 bytes apart -- pairs of similar shape stay near each other on their way up the
+// diagonal, so a warp's loads fall into a few neighbouring lines instead of 32 unrelated sectors
 __global__ void sg_traceback_short_kernel(const AlignParams P, const int64_t *__restrict__ pbase,
-                                          const int32_t *__restrict__ pM, const int64_t n_pairs)
+                                          const int32_t *__restrict__ pM, const int32_t *__restrict__ order,
+                                          const int64_t n_pairs)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_pairs) return;
+    const int64_t p = order[x];
     const int n = P.pn[p], m = P.pm[p];
     const uint8_t *s1 = P.cat + P.seq_off[P.pa[p]];
     const uint8_t *s2 = P.cat + P.seq_off[P.pb[p]];
@@ -395,7 +400,7 @@ int isof_sg_short_path(isof_ctx *ctx, AlignParams &A, int64_t P, int max_n, int 
     A.pband = nullptr;
     {
         LaunchTimer t(ctx, SLOT_TB);
-        sg_traceback_short_kernel<<<(unsigned)((P + 63) / 64), 64, 0, st>>>(A, pbase, pM, P);
+        sg_traceback_short_kernel<<<(unsigned)((P + 63) / 64), 64, 0, st>>>(A, pbase, pM, order, P);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return ISOF_OK;
