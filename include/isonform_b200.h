@@ -71,6 +71,12 @@ ISOF_API int isof_set_packed(isof_ctx *ctx, int on);
  * itself is complete (scores are exact); a pair whose optimal path leaves the band is detected by the traceback and aligned
  * again with the full trace, so results never depend on the band.  half_width = 0 turns banding off; default 1024. */
 ISOF_API int isof_set_band(isof_ctx *ctx, int half_width);
+/* Traceback of the regular (chunked) path.  mode 1 = one WARP per pair -- the trace holds the decision of every cell, so
+ * the 32 lanes look ahead along the diagonal (state H) or along the gap and one iteration covers up to 32 steps of the
+ * walk: 2x faster on its own, but its many warps take the slots the next chunk's DP waits for; mode 0 = one thread per
+ * pair (light, latency-bound: fits the gaps of a pipelined step); mode 2 (default) = warp per pair for chunks of up to 4096
+ * pairs (small calls, long reads), thread per pair beyond.  Same results in every mode. */
+ISOF_API int isof_set_traceback_warp(isof_ctx *ctx, int mode);
 /* Host-buffer calls of at most 32 small pairs (trace <= 200 KB each, i.e. up to ~500 x 500) run as ONE fused launch: base
  * codes, DP, traceback and features in one kernel with the trace in shared memory and inputs / outputs in mapped pinned
  * memory -- the per-pair seams of the reference (a memo miss of consensus.parasail_alignment).  Identical results; on=0

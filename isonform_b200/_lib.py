@@ -35,7 +35,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_fused_phases", "isof_set_band", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_fused_phases", "isof_set_band", "isof_set_traceback_warp", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances", "isof_poa_consensus"]
@@ -71,6 +71,7 @@ def load(debug=False):
     L.isof_set_short.argtypes = [vp, C.c_int]
     L.isof_set_fused_small.argtypes = [vp, C.c_int]
     L.isof_set_band.argtypes = [vp, C.c_int]
+    L.isof_set_traceback_warp.argtypes = [vp, C.c_int]
     L.isof_debug_fused_phases.argtypes = [vp, vp]
     L.isof_debug_violations.argtypes = [vp, C.POINTER(C.c_uint)]
     L.isof_debug_selftest.argtypes = [vp]
@@ -162,6 +163,11 @@ class Context:
     def set_packed(self, on=True):
         """Enable (default) / disable the packed 16-bit DP path; results are identical either way."""
         self._check(self._L.isof_set_packed(self._h, 1 if on else 0))
+
+    def set_traceback_warp(self, mode=2):
+        """Regular path's traceback: True/1 = one warp per pair with look-ahead, False/0 = one thread per pair, 2 = by chunk
+        size (default).  Same results."""
+        self._check(self._L.isof_set_traceback_warp(self._h, int(mode)))
 
     def set_band(self, half_width=1024):
         """Half-width of the banded trace of long pairs in feature-only calls (0 = off); results never depend on it."""

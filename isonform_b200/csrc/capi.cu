@@ -162,6 +162,13 @@ int isof_debug_set_span_hash_mask(isof_ctx *ctx, uint64_t mask)
     return ISOF_OK;
 }
 
+int isof_set_traceback_warp(isof_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return ISOF_ERR_ARG;
+    ctx->tb_warp = mode;
+    return ISOF_OK;
+}
+
 int isof_set_band(isof_ctx *ctx, int half_width)
 {
     if (!ctx || half_width < 0) return ISOF_ERR_ARG;

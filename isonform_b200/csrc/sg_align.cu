@@ -470,6 +470,10 @@ __device__ __forceinline__ void traceback_pair(const AlignParams &P, const int64
 // leading lanes whose flag says "extended" stay in the gap.  One iteration (~one lone-thread step) thus covers a whole
 // diagonal stretch or a whole gap, up to 32 cells.  All lanes carry the same scalar state; same results as
 // traceback_pair by construction (tests compare the fused call with the regular path and the oracle).
+// SMEM = false: the trace lives in device memory (regular path, one warp per pair): loads bypass L1, the trace may be
+// banded (AlignParams::pband) -- a cell outside the band ends a look-ahead, and the walk itself stepping on one reports
+// nruns = -1 (second pass with the full trace).
+template <bool SMEM>
 __device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const int64_t p, const int lane)
 {
     constexpr unsigned FULLW = 0xffffffffu;
@@ -482,6 +486,8 @@ __device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const 
     const int pc = lay & 15;
     const bool split = (lay & 16) != 0;
     const int T = (m + pc - 1) / pc + 31;
+    const int band_dmin = (!SMEM && P.pband) ? P.pband[2 * p] : 0, tw = (!SMEM && P.pband) ? P.pband[2 * p + 1] : 0;
+    const int pitch = tw ? tw : T;
     const int last_s = (n - 1) >> 8, rr_last = P.plastrr[p];
     const int rr_mul = rr_last == 6 ? 171 : 1, rr_sh = rr_last == 6 ? 10 : rr_last == 2 ? 1 : rr_last == 4 ? 2 : 3;
     int i = P.endq[p], j = P.endr[p];
@@ -492,20 +498,22 @@ __device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const 
         if ((len) > 0) {                                                                           \
             if (cur_op == (uint32_t)(op)) cur_len += (uint32_t)(len);                              \
             else {                                                                                 \
-                if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; } \
+                if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); if (lane == 0) tail[-nr] = (cur_len << 4) | cur_op; } \
                 cur_op = (op); cur_len = (len);                                                    \
             }                                                                                      \
         }                                                                                          \
     } while (0)
-    // the 4-bit decision of cell (ii, jj): [source 2 bits | gap flags 2 bits]
+    // the 4-bit decision of cell (ii, jj): [source 2 bits | gap flags 2 bits]; -1 when a banded trace does not hold the cell
     auto nibble = [&](const int ii, const int jj) {
         const int s = ii >> 8;
         int l = (ii >> 3) & 31, r = ii & 7;
         if (s == last_s && rr_last != 8) { l = ((ii & 255) * rr_mul) >> rr_sh; r = (ii & 255) - l * rr_last; }
         const int jt = (pc == 1) ? jj : (jj >> 1), jc = (pc == 1) ? 0 : (jj & 1);
-        const uint32_t *wp = &trace[(((size_t)s * T + jt + l) * 32 + l) * pc + jc];
+        const int tt = jt + l - (tw ? band_tlo(s, band_dmin) : 0);
+        if (tw && (unsigned)tt >= (unsigned)tw) return -1;
+        const uint32_t *wp = &trace[(((size_t)s * pitch + tt) * 32 + l) * pc + jc];
         ISOF_ASSERT(wp >= trace && wp < tail - TRACE_SLACK, CHK_TRACE_LOAD);
-        const uint32_t word = *wp;
+        const uint32_t word = SMEM ? *wp : __ldcg(wp);
         return split ? (int)((((word >> (16 + 2 * r)) & 3) << 2) | ((word >> (2 * r)) & 3)) : (int)((word >> (4 * r)) & 15);
     };
     const int src_e = P.tb_src_e;
@@ -522,13 +530,18 @@ __device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const 
         if (where == 3) {
             const int ii = i - lane, jj = j - lane;
             const bool ok = ii >= 0 && jj >= 0;
-            int nib = 0;
+            int nib = -1;
             bool eq = false;
             if (ok) { nib = nibble(ii, jj); eq = upc(s1[ii]) == upc(s2[jj]); }
-            const unsigned diag = __ballot_sync(FULLW, ok && (nib >> 2) == 3);
+            const unsigned diag = __ballot_sync(FULLW, nib >= 0 && (nib >> 2) == 3);
             const unsigned eqm = __ballot_sync(FULLW, eq);
             const int nd = (diag == FULLW) ? 32 : __ffs((int)~diag) - 1;           // leading diagonal cells
-            if (nd == 0) { where = __shfl_sync(FULLW, nib, 0) >> 2; continue; }      // same cell again, now in its gap state
+            if (nd == 0) {                                                         // same cell again, now in its gap state
+                const int nib0 = __shfl_sync(FULLW, nib, 0);
+                if (nib0 < 0) { if (lane == 0) P.nruns[p] = -1; return; }           // the path left the band
+                where = nib0 >> 2;
+                continue;
+            }
             const unsigned mask = (nd == 32) ? FULLW : ((1u << nd) - 1u);
             const unsigned e = eqm & mask;
             int k = 0;
@@ -545,9 +558,11 @@ __device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const 
             const int ii = in_e ? i : i - lane, jj = in_e ? j - lane : j;
             const bool ok = ii >= 0 && jj >= 0;
             bool stay = false;
-            if (ok) stay = ((nibble(ii, jj) & (in_e ? e_mask : f_mask)) != 0) != (flag_opened != 0);
-            const unsigned okm = __ballot_sync(FULLW, ok);
-            const unsigned staym = __ballot_sync(FULLW, ok && stay);
+            int nib = -1;
+            if (ok) { nib = nibble(ii, jj); stay = ((nib & (in_e ? e_mask : f_mask)) != 0) != (flag_opened != 0); }
+            if (__shfl_sync(FULLW, nib, 0) < 0) { if (lane == 0) P.nruns[p] = -1; return; }       // the path left the band
+            const unsigned okm = __ballot_sync(FULLW, nib >= 0);
+            const unsigned staym = __ballot_sync(FULLW, nib >= 0 && stay);
             const int ns = (staym == FULLW) ? 32 : __ffs((int)~staym) - 1;         // cells that keep the gap open
             // the first cell that closes the gap is consumed too (when it exists), and the walk returns to H
             const bool closes = ns < 32 && ((okm >> ns) & 1u);
@@ -557,9 +572,17 @@ __device__ __forceinline__ void traceback_pair_warp(const AlignParams &P, const 
             if (closes) where = 3;
         }
     }
-    if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); tail[-nr] = (cur_len << 4) | cur_op; }
+    if (cur_len) { ++nr; ISOF_ASSERT(tail - nr >= trace, CHK_TAIL_OVERLAP); if (lane == 0) tail[-nr] = (cur_len << 4) | cur_op; }
 #undef PUSHW
     if (lane == 0) P.nruns[p] = nr;
+}
+
+// one warp per pair (regular path)
+__global__ void __launch_bounds__(128) sg_traceback_warp_kernel(const AlignParams P, const int64_t start, const int64_t end)
+{
+    const int64_t p = start + (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (p >= end) return;
+    traceback_pair_warp<false>(P, p, threadIdx.x & 31);
 }
 
 __global__ void sg_traceback_kernel(const AlignParams P, const int64_t start, const int64_t end)
@@ -908,7 +931,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __syncwarp();
     const long long t_dp = clock64();
     long long t_tb = 0;
-    traceback_pair_warp(P, 0, lane);
+    traceback_pair_warp<true>(P, 0, lane);
     __syncwarp();
     if (lane == 0) {
         t_tb = clock64();
@@ -1508,7 +1531,11 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         }
         {
             LaunchTimer t(ctx, SLOT_TB, cs);
-            sg_traceback_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, cs>>>(A, ps, pe);
+            // one warp per pair is the faster walk (look-ahead), one thread per pair the lighter one: in a pipelined step a
+            // chunk of 18 k pairs as 18 k warps takes the slots the next chunk's DP is waiting for (C2: -3 % on the step)
+            const bool warp_tb = ctx->tb_warp == 1 || (ctx->tb_warp == 2 && cnt <= 4096);
+            if (warp_tb) sg_traceback_warp_kernel<<<(unsigned)((cnt + 3) / 4), 128, 0, cs>>>(A, ps, pe);
+            else sg_traceback_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, cs>>>(A, ps, pe);
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (d_features) {

@@ -1249,3 +1249,51 @@ def test_trace_lanes_shrink_when_the_device_fills_up_after_first_use():
         del hog
         torch.cuda.empty_cache()
         c.close()
+
+
+def test_warp_traceback_equals_thread_traceback(ctx):
+    """The regular path's traceback runs one warp per pair (look-ahead along the diagonal / the gap); the round-1
+    thread-per-pair kernel stays selectable.  Same runs, features and scores on a mixed batch: packed, 32-bit (wildcards),
+    re-based and banded pairs, compacted last stripes, exon-sized gaps longer than one look-ahead, many chunks."""
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(99)
+    seqs, pa, pb = [], [], []
+
+    def add(a, b):
+        seqs.extend([a, b]); pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    for (n, m) in [(1, 1), (3, 70), (70, 3), (255, 257), (257, 255), (700, 1500), (1500, 700), (2047, 2049), (33, 2000)]:
+        x = _rand_dna(rng, max(n, m)); y = synth.mutate(rng, x, 0.07) + _rand_dna(rng, m)
+        add(x[:n], y[:m])
+    x = _rand_dna(rng, 3000)
+    add(x, x[:1000] + x[1400:])                                  # 400 bp gap: 13 look-aheads long
+    add(x[:500] + x[1500:], x)
+    add("ACGTN" * 200, "ACGT" * 260)                             # wildcards: 32-bit path, nibble layout
+    add("AC" * 600, "AC" * 630)                                  # tie-heavy
+    big = _rand_dna(rng, 6000)
+    add(big, synth.mutate(rng, big, 0.05))                       # re-based class
+    add(big[:2000] + big[2300:], synth.mutate(rng, big, 0.03))
+    base = _rand_dna(rng, 1100)
+    pool = [synth.mutate(rng, base, 0.05) for _ in range(24)]
+    o = len(seqs)
+    seqs += pool
+    ib, ia = np.tril_indices(len(pool), -1)
+    pa += (ia + o).tolist(); pb += (ib + o).tolist()
+    for budget in (0, 8 << 20):
+        ctx.set_trace_budget(budget)
+        try:
+            ctx.set_traceback_warp(True)
+            a = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+            af = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
+            ctx.set_traceback_warp(False)
+            b = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+            bf = hotpath.align_pairs(seqs, pa, pb, 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
+        finally:
+            ctx.set_traceback_warp(2)
+            ctx.set_trace_budget(0)
+        for key in ("score", "cigar_off", "cigar", "features"):
+            assert np.array_equal(a[key], b[key]), (key, budget)
+        for key in ("score", "cigar_off", "features"):
+            assert np.array_equal(af[key], bf[key]) and np.array_equal(af[key], a[key]), (key, budget)
+    for p in range(15):
+        sc, _q, _r, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], 2, -2, 12, 1)
+        assert int(a["score"][p]) == sc and a["cigar"][a["cigar_off"][p]:a["cigar_off"][p + 1]].tolist() == runs.tolist(), p
