@@ -486,7 +486,9 @@ __device__ __forceinline__ int2 ld_volatile_int2(const int2 *p)
 {
     int2 v;
     // no "memory" clobber: the compiler stays free to schedule the step's other loads (profile, codes) across this one
-    asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    // a WEAK load that bypasses L1 (L2 is the point of coherence): fresh data on every execution, and -- unlike
+    // ld.volatile / ld.relaxed.gpu -- no ordering against the warp's outstanding trace stores
+    asm volatile("ld.global.cg.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
 
@@ -543,16 +545,30 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     };
     // boundary cell of column `col` (warp-uniform) for lane 0: a settled batch is parked in a 64-entry ring in shared
     // memory, from which lane 0 reads like the other modes read the line buffer; the batches rotate when col runs past
-    auto chase_take = [&](const int col) {
+    // the ring is addressed in the shared window directly (a generic pointer costs an S2UR per access: the shared window
+    // base of the CTA -- ~100 cycles on the critical path of a lone warp's step)
+    const uint32_t ring_sa = CHASE ? (uint32_t)__cvta_generic_to_shared(ch->ring) : 0u;
+    auto ring_put = [&](const int col, const int2 v) {
+        asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(ring_sa + ((uint32_t)(col & 63) << 3)), "r"(v.x), "r"(v.y) : "memory");
+    };
+    auto ring_get = [&](const int col) {
+        int2 v;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(ring_sa + ((uint32_t)(col & 63) << 3)));
+        return v;
+    };
+    auto chase_rotate = [&](const int col) {
         if (col - ch_col0 >= 32) {
             ch_col0 += 32;
             ch_cur = ch_next;
             chase_settle(ch_cur, ch_col0);
-            ch->ring[(ch_col0 + lane) & 63] = ch_cur;
+            ring_put(ch_col0 + lane, ch_cur);
             __syncwarp();
             ch_next = chase_issue(ch_col0 + 32);
         }
-        return ch->ring[col & 63];
+    };
+    auto chase_take = [&](const int col) {
+        chase_rotate(col);
+        return ring_get(col);
     };
     P16Const K;
     // the F constants equal the E constants (same penalties, tags come from the stored values): one register each
@@ -634,11 +650,13 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
             ch_next = chase_issue(32);
             chase_settle(ch_cur, 0);
             __syncwarp();
-            ch->ring[lane] = ch_cur;
+            ring_put(lane, ch_cur);
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < PC; ++c)
-                if (lane == 0 && c < m) S.b_next[c] = ch->ring[c];
+            for (int c = 0; c < PC; ++c) {
+                const int2 v = ring_get(c);
+                if (lane == 0 && c < m) S.b_next[c] = v;
+            }
         }
         // banded pairs keep the steps tlo .. tlo + win - 1 of the stripe (stripe pitch = win); others all T steps
         const int tloA = (RB && twA) ? band_tlo(s, dminA) : 0, winA = (RB && twA) ? twA : TA;
@@ -800,7 +818,7 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 if (CHASE) {
                     if (has_prev) {
 #pragma unroll
-                        for (int c = 0; c < PC; ++c) { const int2 v = chase_take(PC * (t + 1) + c); if (lane == 0) S.b_next[c] = v; }
+                        for (int c = 0; c < PC; ++c) { const int2 v = ring_get(PC * (t + 1) + c); if (lane == 0) S.b_next[c] = v; }
                     }
                 } else if (has_prev && lane == 0) {
 #pragma unroll
@@ -847,7 +865,21 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
                 }
                 pa_ += PC; pb_ += PC; pbn += PC; pbs += PC; sA += 32; sB += 32;
             };
-            if (RB) {
+            if (CHASE && has_prev) {
+                // blocks of steps that stay inside one batch of the boundary row: the rotation (settle the next batch, park
+                // it in the ring, issue the one after) happens between blocks, the steps themselves only read the ring
+                for (int t = 31; t < t2;) {
+                    chase_rotate(PC * (t + 1));
+                    const int te = min(t2, (ch_col0 + 32) / PC - 1);          // first step whose look-ahead leaves the batch
+                    if (!track_stripe) {
+#pragma unroll 2
+                        for (; t < te; ++t) steady_step(t, false);
+                    } else {
+#pragma unroll 2
+                        for (; t < te; ++t) steady_step(t, true);
+                    }
+                }
+            } else if (RB) {
                 for (int t = 31; t < t2;) {
                     rebase();
                     const int te = min(t + 32, t2);
