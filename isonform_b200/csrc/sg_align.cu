@@ -810,7 +810,7 @@ __global__ void sg_features_kernel(const AlignParams P, const int64_t start, con
 // synchronisations around a DP of 8 us.
 // ---------------------------------------------------------------------------------------------
 struct FusedArgs {
-    const int4 *desc;                 // mapped host memory: per pair {n, m, byte offset of s1, of s2 | run slot, bit 0 packed-eligible + bit 1 chase,
+    int4 desc[64];                    // kernel parameter (no PCIe read): per pair {n, m, byte offset of s1, of s2 | run slot, bit 0 packed-eligible + bit 1 chase,
                                       //   1 + word offset of the pair's trace in `gtrace` (64 bit; 0 = trace in shared memory)}
     uint32_t *gtrace;                 // device memory: traces of the pairs too large for shared memory
     // chase mode (one block per stripe, see ChaseCtl): per (pair, stripe) completion flag and end-cell candidate
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __shared__ int2 s_ring[64];                                  // chase mode: settled batches of the boundary row
     const int p = blockIdx.y, g = blockIdx.x, lane = threadIdx.x;
     const long long t_start = clock64();
-    const int4 d0 = a.desc[2 * p], d1 = a.desc[2 * p + 1];       // one broadcast read over PCIe
+    const int4 d0 = a.desc[2 * p], d1 = a.desc[2 * p + 1];       // kernel parameters: constant bank
     const int n = d0.x, m = d0.y;
     const int ns = (n + SROWS - 1) / SROWS;
     const bool chase = (d1.y & 2) != 0;                          // one block per stripe; otherwise block 0 does the pair
@@ -849,10 +849,21 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     int wild = 0;
     // 16 bytes per lane and round: a 100 x 100 pair arrives in one PCIe round trip instead of seven
     const int c1 = n16 >> 4, c2 = m16 >> 4;
-    for (int c = lane; c < c1 + c2; c += 32) {
+    // (four loads in flight per lane: every round is a PCIe round trip of ~3 us, an 8 KB pair would take 16 of them)
+    for (int cb = lane; cb < c1 + c2; cb += 128) {
+      uint4 vq[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+          const int c = cb + 32 * q4;
+          if (c < c1 + c2) vq[q4] = *reinterpret_cast<const uint4 *>(a.in + (c < c1 ? d0.z + c * 16 : d0.w + (c - c1) * 16));
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int c = cb + 32 * q4;
+        if (c >= c1 + c2) break;
         const bool first = c < c1;
         const int byte0 = first ? c * 16 : (c - c1) * 16, len = first ? n : m;
-        const uint4 v = *reinterpret_cast<const uint4 *>(a.in + (first ? d0.z : d0.w) + byte0);
+        const uint4 v = vq[q4];
         const int so = first ? byte0 : n16 + byte0;
         *reinterpret_cast<uint4 *>(s_cat + so) = v;
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -869,6 +880,7 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
             cw[q] = cc;
         }
         *reinterpret_cast<uint4 *>(s_codes + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      }
     }
     wild = __any_sync(0xffffffffu, wild);
     const long long t_loaded = clock64();
@@ -969,7 +981,7 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
         h_max_max_len = room <= 0 ? 0 : (gap_ext > 0 ? room / gap_ext : INT_MAX);
     }
     // ---- plan on the host: lengths, validity, shared memory, run slots, staging offsets
-    int64_t smem_max = 0, run_words = 0, in_bytes = 32 * P, gwords = 0;
+    int64_t smem_max = 0, run_words = 0, in_bytes = 0, gwords = 0;
     int max_m = 0, n_stripes = 1;
     const bool default_table = !ctx->tb_h_e_before_f && !ctx->tb_gap_open_on_tie;
     auto plain_acgt = [](const uint8_t *x, int64_t len) {
@@ -1030,7 +1042,6 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     // ---- stage the inputs (mapped pinned memory: the kernel reads them over PCIe, no memcpy call)
     uint8_t *in = (uint8_t *)ctx->fused_io, *out = in + IO_BYTES;
     uint8_t *d_in = (uint8_t *)ctx->fused_io_dev, *d_out = d_in + IO_BYTES;
-    memcpy(in, desc, 32 * (size_t)P);
     for (int64_t p = 0; p < P; ++p) {
         const int64_t n = desc[p][0], m = desc[p][1];
         memcpy(in + desc[p][2], seq_cat + seq_off[pair_a[p]], (size_t)n);
@@ -1043,7 +1054,8 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     TRY(dev_reserve(ctx, ctx->b_bnd, sizeof(int2) * (size_t)bnd_stride * (size_t)P * (size_t)n_stripes));
     FusedArgs a;
     const ptrdiff_t dout = d_out - out;
-    a.desc = (const int4 *)d_in; a.in = d_in;
+    memcpy(a.desc, desc, 32 * (size_t)P);
+    a.in = d_in;
     a.score = (int32_t *)((uint8_t *)o_score + dout); a.endq = (int32_t *)((uint8_t *)o_endq + dout);
     a.endr = (int32_t *)((uint8_t *)o_endr + dout); a.nruns = (int32_t *)((uint8_t *)o_nruns + dout);
     a.feat = features ? (int32_t *)((uint8_t *)o_feat + dout) : nullptr;
