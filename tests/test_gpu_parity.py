@@ -1,6 +1,7 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
 same seeded inputs, and against the committed golden fixtures."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -1108,15 +1109,18 @@ def test_fused_small_call_matches_regular_path_and_oracle(ctx):
 
 
 # ------------------------------------------------------------------------------- randomised differential test
-@pytest.mark.parametrize("seed", range(64))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ISOF_FUZZ_SEEDS", "64"))))
 def test_randomised_regimes_vs_oracle(ctx, seed):
     """Random batch compositions x random scoring parameters x random tie-break table x random regime switches (packed
-    on/off, short-pair kernel forced/never, fused tiny-call path on/off): every pair must equal the oracle under the same
-    table.  Catches interactions no hand-written case covers."""
+    on/off, short-pair kernel forced/never, fused tiny-call path on/off -- incl. its multi-stripe chase mode --, traceback
+    per thread / per warp, trace band width): every pair must equal the oracle under the same table.  Catches
+    interactions no hand-written case covers.  ISOF_FUZZ_SEEDS=N widens the sweep (development)."""
     from isonform_b200 import hotpath, synth
     rng = np.random.default_rng(7000 + seed)
     n_pairs = int(rng.choice([1, 3, 17, 33, 64, 65, 130, 400]))
-    max_len = int(rng.choice([12, 60, 150, 384, 700]))
+    max_len = int(rng.choice([12, 60, 150, 384, 700, 1500, 3000]))
+    if max_len >= 1500:
+        n_pairs = min(n_pairs, 33 if max_len == 1500 else 17)
     alphabet = str(rng.choice(["ACGT", "ACGT", "AC", "ACGTN", "ACGTacgtN"]))
     seqs, pa, pb = [], [], []
     for i in range(n_pairs):
@@ -1143,18 +1147,22 @@ def test_randomised_regimes_vs_oracle(ctx, seed):
     params = (match, mismatch, gap_open, gap_ext)
     tb = oracle.all_tiebreaks()[int(rng.integers(0, 16))]
     packed, short_mode, fused = bool(rng.integers(0, 2)), int(rng.choice([0, 1, 2])), bool(rng.integers(0, 2))
+    tb_mode, band = int(rng.choice([0, 1, 2])), int(rng.choice([0, 64, 1024]))
     ctx.set_tiebreak(tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id)
     ctx.set_packed(packed); ctx.set_short(short_mode); ctx.set_fused_small(fused)
+    ctx.set_traceback_warp(tb_mode); ctx.set_band(band)
     try:
         res = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx)
         feat = hotpath.align_pairs(seqs, pa, pb, *params, ctx=ctx, want_cigar=False, features_delta_len=5)
     finally:
         ctx.set_tiebreak(0, 0, 0, 0); ctx.set_packed(True); ctx.set_short(1); ctx.set_fused_small(True)
+        ctx.set_traceback_warp(2); ctx.set_band(1024)
     assert np.array_equal(res["score"], feat["score"])
     for p in range(n_pairs):
         sc, eq, er, runs = oracle.sg_align(seqs[pa[p]], seqs[pb[p]], *params, tiebreak=tb)
         got = res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]]
-        ctxt = (seed, p, params, (tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id), packed, short_mode, fused)
+        ctxt = (seed, p, params, (tb.h_e_before_f, tb.gap_open_on_tie, tb.end_col_first, tb.swap_id), packed, short_mode, fused,
+                tb_mode, band, len(seqs[pa[p]]), len(seqs[pb[p]]))
         assert (int(res["score"][p]), int(res["end_q"][p]), int(res["end_r"][p])) == (sc, eq, er), ctxt
         assert got.tolist() == runs.tolist(), ctxt
         tup = oracle.cigar_runs_to_tuples(runs)
