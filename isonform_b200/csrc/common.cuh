@@ -45,7 +45,7 @@ struct isof_ctx {
     std::vector<Timed> timed;
     // scratch
     DevBuf b_codes, b_seqflags, b_pn, b_pm, b_words, b_nruns64, b_ptrace, b_scan_tmp, b_bnd, b_trace, b_nruns,
-        b_counters, b_misc, b_runoff, b_status, b_layout, b_order, b_taskkey, b_short_g, b_short_p, b_band, b_fail_ids, b_fail, b_chase;
+        b_counters, b_misc, b_runoff, b_status, b_layout, b_order, b_taskkey, b_short_g, b_short_p, b_band, b_fail_ids, b_fail, b_chase, b_splice;
     DevBuf b_taskkey_x[MAX_LANES - 1];
     DevBuf b_trace_x[MAX_LANES - 1], b_bnd_x[MAX_LANES - 1], b_runoff_x[MAX_LANES - 1], b_nruns64_x[MAX_LANES - 1],
         b_scan_tmp_x[MAX_LANES - 1];
@@ -57,7 +57,7 @@ struct isof_ctx {
     std::vector<DevBuf *> all_bufs()
     {
         std::vector<DevBuf *> v = {&b_codes, &b_seqflags, &b_pn, &b_pm, &b_words, &b_nruns64, &b_ptrace, &b_scan_tmp, &b_bnd, &b_trace, &b_nruns,
-                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_order, &b_taskkey, &b_short_g, &b_short_p, &b_band, &b_fail_ids, &b_fail, &b_chase, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
+                &b_counters, &b_misc, &b_runoff, &b_status, &b_layout, &b_order, &b_taskkey, &b_short_g, &b_short_p, &b_band, &b_fail_ids, &b_fail, &b_chase, &b_splice, &b_h_bases, &b_h_off, &b_h_pa, &b_h_pb, &b_h_score, &b_h_endq,
                 &b_h_endr, &b_h_cig, &b_h_cigoff, &b_h_feat, &b_m_tmp, &b_m_cnt, &b_m_off, &b_s_mread, &b_s_mkey,
                 &b_s_mpolya, &b_s_mcnt, &b_s_moff, &b_s_key1, &b_s_key2, &b_s_keyt, &b_s_keyo, &b_s_idx0, &b_s_idx1, &b_s_idx2,
                 &b_s_forb, &b_s_head, &b_s_bid, &b_s_sorttmp, &b_s_rbatch, &b_sh_batchoff, &b_sh_minpos, &b_sh_minoff, &b_sh_rread, &b_sh_rp1, &b_sh_rp2,

@@ -173,6 +173,29 @@ __global__ void scatter_results_kernel(const int32_t *__restrict__ ids, int64_t 
     if (feat) for (int q = 0; q < ISOF_N_FEATURES; ++q) feat[p * ISOF_N_FEATURES + q] = feat2[k * ISOF_N_FEATURES + q];
 }
 
+// banded second pass of a call that returns the runs: pair p's runs move from their place in the first pass's stream
+// (`old_stream` + old_off[p]) -- or, for a re-aligned pair, from the second pass's stream -- to the rebuilt offsets
+__global__ void mark_failed_kernel(const int32_t *__restrict__ ids, int64_t nf, int32_t *__restrict__ kidx)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nf) kidx[ids[k]] = (int32_t)k;
+}
+
+__global__ void splice_runs_kernel(const uint32_t *__restrict__ old_stream, const int64_t *__restrict__ old_off,
+                                   const uint32_t *__restrict__ cig2, const int64_t *__restrict__ off2,
+                                   const int32_t *__restrict__ kidx, const int64_t *__restrict__ new_off, int64_t P,
+                                   uint32_t *__restrict__ out)
+{
+    const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int lane = threadIdx.x & 31;
+    const int k = kidx[p];
+    const uint32_t *src = k >= 0 ? cig2 + off2[k] : old_stream + old_off[p];
+    uint32_t *dst = out + new_off[p];
+    const int64_t len = new_off[p + 1] - new_off[p];
+    for (int64_t x = lane; x < len; x += 32) dst[x] = src[x];
+}
+
 // sort key of a pair inside its chunk: packed-eligible pairs first, then by reference index, so that the two
 // alignments of a task share their reference whenever the batch allows it (query-profile path)
 __global__ void task_key_kernel(const uint8_t *__restrict__ pwild, const int32_t *__restrict__ pb, int64_t start,
@@ -1172,8 +1195,8 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
     TRY(dev_reserve(ctx, ctx->b_nruns64, sizeof(int64_t) * (size_t)(P + 1)));      // nruns as int64
     TRY(dev_reserve(ctx, ctx->b_misc, 128));
     // banded trace for the re-based class: feature-only calls (the CIGAR stream of a call that returns runs is laid out
-    // in pair order and could not be patched by a second pass)
-    const int band_w0 = (!d_cigar && d_features && rb_ok && d_endq && d_endr) ? ctx->band_w0 : 0;
+    // is then spliced together from the two passes, which needs the offsets)
+    const int band_w0 = ((!d_cigar || d_cigar_off) && rb_ok && d_endq && d_endr) ? ctx->band_w0 : 0;
     int32_t *pband = nullptr;
     if (band_w0 > 0) {
         TRY(dev_reserve(ctx, ctx->b_band, sizeof(int32_t) * 2 * (size_t)P));
@@ -1629,9 +1652,31 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
         const int64_t nf = pin64[0];
         ctx->prof.band_pairs_retried += nf;
         if (nf > 0) {
-            TRY(dev_reserve(ctx, ctx->b_fail, sizeof(int32_t) * (5 + ISOF_N_FEATURES) * (size_t)nf));
-            int32_t *pa2 = (int32_t *)ctx->b_fail.p, *pb2 = pa2 + nf, *score2 = pb2 + nf, *endq2 = score2 + nf, *endr2 = endq2 + nf;
+            TRY(dev_reserve(ctx, ctx->b_fail, sizeof(int32_t) * (5 + ISOF_N_FEATURES) * (size_t)nf + sizeof(int64_t) * (size_t)(nf + 2)));
+            int64_t *off2 = (int64_t *)ctx->b_fail.p;                 // run offsets of the second pass (nf + 1)
+            int32_t *pa2 = (int32_t *)(off2 + nf + 2), *pb2 = pa2 + nf, *score2 = pb2 + nf, *endq2 = score2 + nf, *endr2 = endq2 + nf;
             int32_t *feat2 = endr2 + nf;
+            // a call that returns the runs: the first pass's stream and offsets are set aside, the second pass writes a
+            // stream of its own, and both are spliced into the caller's buffer at the rebuilt offsets
+            uint32_t *old_stream = nullptr, *cig2 = nullptr;
+            int64_t *old_off = nullptr;
+            int32_t *kidx = nullptr;
+            int64_t cap2 = 0, first_total = 0;
+            if (d_cigar) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(pin64 + 4, d_cigar_off + P, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(ctx, cudaStreamSynchronize(st));
+                first_total = pin64[4];
+                cap2 = nf * ((int64_t)max_n + max_m + 2);
+                TRY(dev_reserve(ctx, ctx->b_splice, sizeof(uint32_t) * (size_t)(first_total + cap2) + sizeof(int64_t) * (size_t)(P + 1) +
+                                                        sizeof(int32_t) * (size_t)P + 64));
+                old_off = (int64_t *)ctx->b_splice.p;
+                old_stream = (uint32_t *)(old_off + P + 1);
+                cig2 = old_stream + first_total;
+                kidx = (int32_t *)(cig2 + cap2);
+                CUDA_TRY(ctx, cudaMemcpyAsync(old_off, d_cigar_off, sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyDeviceToDevice, st));
+                CUDA_TRY(ctx, cudaMemcpyAsync(old_stream, d_cigar, sizeof(uint32_t) * (size_t)first_total, cudaMemcpyDeviceToDevice, st));
+                CUDA_TRY(ctx, cudaMemsetAsync(kidx, 0xff, sizeof(int32_t) * (size_t)P, st));
+            }
             {
                 LaunchTimer t(ctx, SLOT_OTHER);
                 gather_pairs_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, d_pa, d_pb, pa2, pb2);
@@ -1642,13 +1687,15 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             const int saved = ctx->band_w0;
             ctx->band_w0 = 0;
             const int rc2 = isof_sg_align_core(ctx, d_cat, d_off, n_seqs, n_bases, pa2, pb2, nf, match, mismatch, gap_open, gap_ext,
-                                               score2, endq2, endr2, nullptr, 0, nullptr, feat2, delta_len, nullptr);
+                                               score2, endq2, endr2, cig2, cap2, d_cigar ? off2 : nullptr,
+                                               d_features ? feat2 : nullptr, delta_len, nullptr);
             ctx->band_w0 = saved;
             if (rc2 != ISOF_OK) return rc2;
             {
                 LaunchTimer t(ctx, SLOT_OTHER);
-                scatter_results_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, score2, endq2, endr2, feat2, d_score,
-                                                                                   d_endq, d_endr, d_features);
+                scatter_results_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, score2, endq2, endr2,
+                                                                                   d_features ? feat2 : nullptr, d_score, d_endq,
+                                                                                   d_endr, d_features);
                 if (d_cigar_off) {
                     scatter_nruns_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, nruns, saved_nr);
                     rebuild_offsets_kernel<<<1, 1024, 0, st>>>(saved_nr, P, (long long *)d_cigar_off);
@@ -1656,10 +1703,20 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
             }
             CUDA_TRY(ctx, cudaGetLastError());
             CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            if (h_total_runs && d_cigar_off) {
+            if ((h_total_runs || d_cigar) && d_cigar_off) {
                 CUDA_TRY(ctx, cudaMemcpyAsync(pin64, d_cigar_off + P, 8, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(ctx, cudaStreamSynchronize(st));
-                *h_total_runs = pin64[0];
+                if (h_total_runs) *h_total_runs = pin64[0];
+            }
+            if (d_cigar) {
+                if (pin64[0] > cigar_cap)
+                    return isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar_runs holds %lld runs, %lld needed", (long long)cigar_cap,
+                                     (long long)pin64[0]);
+                LaunchTimer t(ctx, SLOT_TB);
+                mark_failed_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(ids, nf, kidx);
+                splice_runs_kernel<<<(unsigned)((P + 3) / 4), 128, 0, st>>>(old_stream, old_off, cig2, off2, kidx, d_cigar_off, P, d_cigar);
+                CUDA_TRY(ctx, cudaGetLastError());
+                CUDA_TRY(ctx, cudaStreamSynchronize(st));
             }
         }
     }

@@ -1206,18 +1206,28 @@ def test_banded_trace_of_long_pairs_never_changes_results(ctx, half_width):
     try:
         ctx.set_band(0)
         ref = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
+        ref_full = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+        ref_runs = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx)
         ctx.set_band(half_width)
         ctx.profile_enable(True); ctx.profile_reset()
         got = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, want_cigar=False, features_delta_len=5)
         pr = ctx.profile(); ctx.profile_enable(False)
-        # a call that returns the runs is never banded
+        # a call that returns the runs: the stream is spliced together from the two passes
         full = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx, features_delta_len=5)
+        runs = hotpath.align_pairs(seqs, ia, ib, 2, -2, 12, 1, ctx=ctx)
+        cat, off = hotpath.pack_sequences(seqs)
+        tight = ctx.sg_align_pairs(cat, off, np.asarray(ia, np.int32), np.asarray(ib, np.int32), 2, -2, 12, 1, cigar_cap=1000)
     finally:
         ctx.set_band(1024)
         ctx.profile_enable(False)
     for key in ("score", "features", "cigar_off"):
         assert np.array_equal(got[key], ref[key]), (key, half_width)
         assert np.array_equal(full[key], ref[key]), (key, half_width)
+    for key in ("score", "features", "cigar_off", "cigar"):
+        assert np.array_equal(full[key], ref_full[key]), (key, half_width)
+    for key in ("score", "end_q", "end_r", "cigar_off", "cigar"):
+        assert np.array_equal(runs[key], ref_runs[key]), (key, half_width)
+        assert np.array_equal(tight[key], ref_runs[key]), (key, half_width)      # capacity-retry protocol across both passes
     retried = pr["band_pairs_retried"]
     if half_width == 1024:
         assert retried <= 2, retried                             # only the unrelated / low-complexity pairs may wander
