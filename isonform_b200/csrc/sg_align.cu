@@ -227,13 +227,15 @@ __global__ void packed_cells_kernel(const uint8_t *__restrict__ pwild, const int
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n0 = (int64_t)(*n_elig), n1 = (int64_t)(*n_rb);
     // packed tasks of the plain class, then of the re-based class (which starts at n0 in the sorted order)
-    // (the odd pair of the re-based class runs as a task of its own, both halves on the same pair)
-    const bool plain = t < n0 / 2;
-    const int64_t u = t - n0 / 2;
-    const int64_t xA = plain ? start + 2 * t : start + n0 + 2 * u, xB = (plain || 2 * u + 1 < n1) ? xA + 1 : xA;
+    // (the odd pair of a class runs as a task of its own, both halves on the same pair)
+    const int64_t t0 = (n0 + 1) / 2;
+    const bool plain = t < t0;
+    const int64_t u = t - t0;
+    const int64_t xA = plain ? start + 2 * t : start + n0 + 2 * u;
+    const int64_t xB = (plain ? 2 * t + 1 < n0 : 2 * u + 1 < n1) ? xA + 1 : xA;
     unsigned long long c = 0, cp = 0;               // packed path / of those, the query-profile variant
     const int64_t pA = xA < end ? order[xA] : 0, pB = xB < end ? order[xB] : 0;
-    if (xB < end && t < n0 / 2 + (n1 + 1) / 2) {
+    if (xB < end && t < t0 + (n1 + 1) / 2) {
         c = (unsigned long long)pn[pA] * pm[pA] + (xB != xA ? (unsigned long long)pn[pB] * pm[pB] : 0ull);
         if (pb[pA] == pb[pB]) cp = c;
     }

@@ -971,19 +971,19 @@ sg_dp_kernel(const AlignParams P, const int64_t start, const int64_t end, unsign
         unsigned long long tkt = 0;
         if (lane == 0) tkt = atomicAdd(counter, 1ull);
         tkt = __shfl_sync(0xffffffffu, tkt, 0);
-        // tickets [0, n_pk): packed tasks over the eligible pairs; the rest: one 32-bit pair per ticket
-        const int64_t n_pk = (int64_t)(*P.n_elig) / 2;
+        // tickets [0, n_pk): packed tasks over the eligible pairs (the odd pair of the class runs with both halves on
+        // itself: a lone 2.7 kb pair on the 32-bit path is a 7 ms tail of one warp); the rest: one 32-bit pair per ticket
+        const int64_t n0 = (int64_t)(*P.n_elig);
+        const int64_t n_pk = (n0 + 1) / 2;
         if ((int64_t)tkt < n_pk) {
-            const int64_t xA = start + 2 * (int64_t)tkt;
-            dp_pair16<TBV, false>(P, P.order[xA], P.order[xA + 1], lane, bnd, s_prof[warp]);
+            const int64_t xA = start + 2 * (int64_t)tkt, xB = (2 * (int64_t)tkt + 1 < n0) ? xA + 1 : xA;
+            dp_pair16<TBV, false>(P, P.order[xA], P.order[xB], lane, bnd, s_prof[warp]);
         } else {
-            // single 32-bit pairs: the odd one out of the plain-16 class, then everything that fits neither 16-bit class
-            // (sg_dp_rb_kernel takes the whole re-based class, its odd pair included: a banded trace has only that layout)
-            const int64_t n0 = (int64_t)(*P.n_elig), n1 = (int64_t)(*P.n_rb);
-            const int64_t s = (int64_t)tkt - n_pk, odd0 = n0 & 1;
-            int64_t x;
-            if (s < odd0) x = start + n0 - 1;
-            else x = start + n0 + n1 + (s - odd0);
+            // single 32-bit pairs: everything that fits neither 16-bit class (sg_dp_rb_kernel takes the whole re-based
+            // class, its odd pair included: a banded trace has only that layout)
+            const int64_t n1 = (int64_t)(*P.n_rb);
+            const int64_t s = (int64_t)tkt - n_pk;
+            const int64_t x = start + n0 + n1 + s;
             if (x >= end) break;
             dp_pair32(P, P.order[x], lane, bnd, s_prof[warp]);
         }
