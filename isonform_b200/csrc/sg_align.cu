@@ -840,6 +840,7 @@ struct FusedArgs {
     uint32_t *gtrace;                 // device memory: traces of the pairs too large for shared memory
     // chase mode (one block per stripe, see ChaseCtl): per (pair, stripe) completion flag and end-cell candidate
     unsigned *done; int2 *acc; int n_stripes;
+    unsigned *ticket;                 // chase mode: blocks take their (pair, stripe) in the order they START
     const uint8_t *in;                // mapped host memory: the sequences, each at a 16-byte aligned offset
     int32_t *score, *endq, *endr, *nruns, *feat; uint32_t *runs;       // mapped host memory
     int2 *bnd; int64_t bnd_stride;
@@ -856,7 +857,18 @@ __global__ void __launch_bounds__(32) sg_fused_small_kernel(const FusedArgs a)
     __shared__ int32_t s_i32[8];                                 // pa pb pn pm score endq endr nruns
     __shared__ uint8_t s_u8[4];                                  // pwild layout lastrr
     __shared__ int2 s_ring[64];                                  // chase mode: settled batches of the boundary row
-    const int p = blockIdx.y, g = blockIdx.x, lane = threadIdx.x;
+    const int lane = threadIdx.x;
+    int p = blockIdx.y, g = blockIdx.x;
+    if (a.n_stripes > 1) {
+        // A stripe's block waits for the block of the stripe before it.  The hardware usually starts blocks in index order,
+        // but nothing guarantees it, and a waiting block whose predecessor never becomes resident would hang the device:
+        // (pair, stripe) is therefore assigned by a ticket taken at block start (as in decoupled look-back scans) -- the
+        // block a waiter depends on has taken its ticket earlier, so it is running.
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        p = (int)(t / (unsigned)a.n_stripes); g = (int)(t % (unsigned)a.n_stripes);
+    }
     const long long t_start = clock64();
     const int4 d0 = a.desc[2 * p], d1 = a.desc[2 * p + 1];       // kernel parameters: constant bank
     const int n = d0.x, m = d0.y;
@@ -1086,12 +1098,13 @@ int isof_sg_fused_small(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *se
     a.feat = features ? (int32_t *)((uint8_t *)o_feat + dout) : nullptr;
     a.runs = (uint32_t *)((uint8_t *)o_runs + dout);
     a.bnd = (int2 *)ctx->b_bnd.p; a.bnd_stride = bnd_stride;
-    a.n_stripes = n_stripes; a.done = nullptr; a.acc = nullptr;
+    a.n_stripes = n_stripes; a.done = nullptr; a.acc = nullptr; a.ticket = nullptr;
     if (n_stripes > 1) {
         const size_t slots = (size_t)P * (size_t)n_stripes;
-        TRY(dev_reserve(ctx, ctx->b_chase, 16 * slots));
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->b_chase.p, 0, 4 * slots, ctx->stream));       // done flags
-        a.done = (unsigned *)ctx->b_chase.p; a.acc = (int2 *)((uint8_t *)ctx->b_chase.p + 8 * slots);
+        TRY(dev_reserve(ctx, ctx->b_chase, 16 * slots + 16));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->b_chase.p, 0, 4 * slots + 16, ctx->stream));  // done flags + the ticket counter
+        a.done = (unsigned *)ctx->b_chase.p; a.ticket = a.done + slots;
+        a.acc = (int2 *)((uint8_t *)ctx->b_chase.p + 8 * slots + 16);
         // boundary lines start "empty" (CHASE_EMPTY in every word)
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->b_bnd.p, 0x80, sizeof(int2) * (size_t)bnd_stride * slots, ctx->stream));
     }
