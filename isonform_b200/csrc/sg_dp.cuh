@@ -537,8 +537,9 @@ __device__ __forceinline__ void dp_pair16(const AlignParams &P, const int64_t pA
     auto chase_settle = [&](int2 &v, const int col0) {
         const int col = col0 + lane;
         const long long c0 = clock64();
-        while (__any_sync(FULL, col < m && (uint32_t)v.x == CHASE_EMPTY)) {
-            if (col < m && (uint32_t)v.x == CHASE_EMPTY) v = ld_volatile_int2(bnd_r + col);
+        // (both words are checked: an 8-byte store lands as one piece in practice, but PTX does not promise it for vectors)
+        while (__any_sync(FULL, col < m && ((uint32_t)v.x == CHASE_EMPTY || (uint32_t)v.y == CHASE_EMPTY))) {
+            if (col < m && ((uint32_t)v.x == CHASE_EMPTY || (uint32_t)v.y == CHASE_EMPTY)) v = ld_volatile_int2(bnd_r + col);
             ++ch->spins;
         }
         ch->spin_cycles += clock64() - c0;
