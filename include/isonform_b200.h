@@ -294,6 +294,32 @@ ISOF_API int isof_sg_features_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const
                            int32_t mismatch, int32_t gap_open, int32_t gap_ext, int32_t delta_len, int32_t *score,
                            int32_t *features, uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off);
 
+/* ------------------------------------------------------------------------------------------ */
+/* (b') unit-cost global edit distance, Myers / Hyyro bit-parallel                            */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * What edlib.align(query, target, mode="NW", task="distance" | "path", k=k) returns, for a batch of pairs drawn from a
+ * sequence pool.  The reference declares edlib (setup.py:81, README.md:25) and has no call site for it (SURVEY.md section
+ * 0.2): this entry point serves BASELINE config 5 (interval-pair sweep against a CPU Myers) and north_star's kernel (b);
+ * the reference's decisions stay with isof_sg_* above.  query = pool[pair_a[p]] (rows), target = pool[pair_b[p]].
+ * Bytes compare by value (case-sensitive, like edlib without additionalEqualities); empty sequences are allowed.
+ *   k            < 0: no bound; else a distance above k is reported as -1 (and the pair gets no path), as edlib does
+ *   dist         per pair
+ *   cigar_off    NULL: distances only (no trace is stored).  Else n_pairs+1 offsets into cigar_runs (filled even on
+ *                ISOF_ERR_CAPACITY; cigar_runs may then be NULL to learn the size)
+ *   cigar_runs   (len<<4|op) runs in alignment order with ops ISOF_CIGAR_EQ / _X / _I (consumes the query) / _D (consumes
+ *                the target): edlib's extended CIGAR.  One optimal path; ties prefer the diagonal, then I, then D, walking
+ *                back from the end (edlib documents no tie rule; the distance is the contract, the path is one witness).
+ */
+ISOF_API int isof_edit_distance_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs,
+                                      const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs, int32_t k, int32_t *dist,
+                                      uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off);
+/* Device-pointer variant; `n_bases` = seq_off[n_seqs]; *n_runs_total is a HOST pointer (may be NULL). */
+ISOF_API int isof_edit_distance_pairs_dev(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs,
+                                          int64_t n_bases, const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs,
+                                          int32_t k, int32_t *dist, uint32_t *cigar_runs, int64_t cigar_cap,
+                                          int64_t *cigar_off, int64_t *n_runs_total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ class Profile(C.Structure):
 EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_fused_phases", "isof_set_band", "isof_set_traceback_warp", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
-           "isof_sg_features_pairs", "isof_wis_picks", "isof_span_instances", "isof_poa_consensus"]
+           "isof_sg_features_pairs", "isof_edit_distance_pairs", "isof_edit_distance_pairs_dev", "isof_wis_picks", "isof_span_instances", "isof_poa_consensus"]
 
 _lib = None
 _lib_debug = None
@@ -93,6 +93,8 @@ def load(debug=False):
                                           vp, vp, i32, C.POINTER(i64)]
     L.isof_sg_align_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp]
     L.isof_sg_features_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp]
+    L.isof_edit_distance_pairs.argtypes = [vp, vp, vp, i32, vp, vp, i64, i32, vp, vp, i64, vp]
+    L.isof_edit_distance_pairs_dev.argtypes = [vp, vp, vp, i32, i64, vp, vp, i64, i32, vp, vp, i64, vp, C.POINTER(i64)]
     L.isof_wis_picks.argtypes = [i32, vp, vp, vp, vp, i32, vp, i64, vp, C.POINTER(i64)]
     L.isof_span_instances.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.isof_poa_consensus.argtypes = [vp, vp, i32, i32, i32, i32, vp, i64, C.POINTER(i64)]
@@ -403,6 +405,45 @@ class Context:
         self._check(self._L.isof_sg_align_pairs_dev(self._h, d_cat, d_off, n_seqs, n_bases, d_pa, d_pb, P, match, mismatch,
                                                     gap_open, gap_ext, d_score, d_endq, d_endr, d_cigar, cigar_cap,
                                                     d_cigar_off, d_features, delta_len, C.byref(total)))
+        return int(total.value)
+
+
+    # ------------------------------------------------------------------ (b') unit-cost edit distance
+    def edit_distance_pairs(self, cat, off, pair_a, pair_b, k=-1, want_cigar=False):
+        """Global unit-cost edit distance of pool[pair_a[p]] (query) against pool[pair_b[p]] (target): what
+        edlib.align(q, t, mode="NW", task="distance"|"path", k=k) computes.  Returns dict(dist int32[P] (-1 above k),
+        cigar_off, cigar) -- the last two None unless want_cigar."""
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+        pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+        P = len(pa)
+        if len(pb) != P:
+            raise ValueError("pair_a and pair_b differ in length")
+        dist = np.empty(P, np.int32)
+        if not want_cigar:
+            self._check(self._L.isof_edit_distance_pairs(self._h, cat.ctypes.data, off.ctypes.data, len(off) - 1, pa.ctypes.data,
+                                                         pb.ctypes.data, P, int(k), dist.ctypes.data, None, 0, None))
+            return {"dist": dist, "cigar_off": None, "cigar": None}
+        coff = np.zeros(P + 1, np.int64)
+        cap = 64 * P + (1 << 16)
+        while True:
+            cig = np.empty(max(cap, 1), np.uint32)
+            rc = self._L.isof_edit_distance_pairs(self._h, cat.ctypes.data, off.ctypes.data, len(off) - 1, pa.ctypes.data,
+                                                  pb.ctypes.data, P, int(k), dist.ctypes.data, cig.ctypes.data, cap,
+                                                  coff.ctypes.data)
+            if rc == ERR_CAPACITY:
+                cap = int(coff[P])
+                continue
+            self._check(rc)
+            break
+        return {"dist": dist, "cigar_off": coff, "cigar": cig[:coff[P]]}
+
+    def edit_distance_pairs_dev(self, d_cat, d_off, n_seqs, n_bases, d_pa, d_pb, P, k, d_dist, d_cigar=None, cigar_cap=0,
+                                d_cigar_off=None):
+        total = C.c_int64(0)
+        self._check(self._L.isof_edit_distance_pairs_dev(self._h, d_cat, d_off, n_seqs, n_bases, d_pa, d_pb, P, int(k), d_dist,
+                                                         d_cigar, cigar_cap, d_cigar_off, C.byref(total)))
         return int(total.value)
 
 

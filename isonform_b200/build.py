@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libisonform_b200.so")
 SO_DEBUG = os.path.join(HERE, "libisonform_b200_dbg.so")          # -DISOF_CHECK: device-side bounds assertions
-SOURCES = ["capi.cu", "minimizers.cu", "sg_align.cu", "sg_dp_tb1.cu", "sg_dp_tb2.cu", "sg_dp_tb3.cu", "sg_dp_rb.cu", "sg_dp_rb2.cu", "sg_short.cu", "spans.cu", "host_wis.cpp", "host_poa.cpp"]
+SOURCES = ["capi.cu", "minimizers.cu", "sg_align.cu", "sg_dp_tb1.cu", "sg_dp_tb2.cu", "sg_dp_tb3.cu", "sg_dp_rb.cu", "sg_dp_rb2.cu", "sg_short.cu", "myers.cu", "spans.cu", "host_wis.cpp", "host_poa.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -224,7 +224,7 @@ int isof_debug_violations(isof_ctx *ctx, unsigned int *mask)
     if (!ctx || !mask) return ISOF_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaDeviceSynchronize());
-    *mask = isof_viol_align() | isof_viol_minimizers() | isof_viol_spans() | isof_read_violations_tu();
+    *mask = isof_viol_align() | isof_viol_minimizers() | isof_viol_spans() | isof_viol_myers() | isof_read_violations_tu();
 #ifdef ISOF_CHECK
     *mask |= 0x80000000u;             // this library was built with the assertions compiled in
 #endif
@@ -474,6 +474,55 @@ int isof_sg_align_batch(isof_ctx *ctx, const uint8_t *s1_cat, const int64_t *s1_
     for (int32_t p = 0; p < n_pairs; ++p) { pa[p] = p; pb[p] = n_pairs + p; }
     return isof_sg_align_pairs(ctx, cat.data(), off.data(), 2 * n_pairs, pa.data(), pb.data(), n_pairs, match, mismatch,
                                gap_open, gap_ext, score, end_q, end_r, cigar_runs, cigar_cap, cigar_off);
+}
+
+// ---- (b') unit-cost global edit distance (myers.cu)
+int isof_edit_distance_pairs_dev(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, int64_t n_bases,
+                                 const int32_t *pair_a, const int32_t *pair_b, int64_t n_pairs, int32_t k, int32_t *dist,
+                                 uint32_t *cigar_runs, int64_t cigar_cap, int64_t *cigar_off, int64_t *n_runs_total)
+{
+    if (!ctx || !dist || !seq_off || (n_pairs > 0 && (!pair_a || !pair_b))) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    if (cigar_runs && !cigar_off) return isof_fail(ctx, ISOF_ERR_ARG, "cigar_runs without cigar_off");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return isof_edit_distance_core(ctx, seq_cat, seq_off, n_seqs, n_bases, pair_a, pair_b, n_pairs, k, dist, cigar_runs, cigar_cap,
+                                   cigar_off, n_runs_total);
+}
+
+int isof_edit_distance_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const int64_t *seq_off, int32_t n_seqs, const int32_t *pair_a,
+                             const int32_t *pair_b, int64_t P, int32_t k, int32_t *dist, uint32_t *cigar_runs, int64_t cigar_cap,
+                             int64_t *cigar_off)
+{
+    if (!ctx || !seq_off || n_seqs < 0 || P < 0 || !dist) return isof_fail(ctx, ISOF_ERR_ARG, "null argument");
+    if (cigar_runs && !cigar_off) return isof_fail(ctx, ISOF_ERR_ARG, "cigar_runs without cigar_off");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_bases = seq_off[n_seqs];
+    if (seq_off[0] != 0 || n_bases < 0) return isof_fail(ctx, ISOF_ERR_ARG, "seq_off must start at 0");
+    if (P == 0) { if (cigar_off) cigar_off[0] = 0; return ISOF_OK; }
+    if (!pair_a || !pair_b) return isof_fail(ctx, ISOF_ERR_ARG, "null pair list");
+    TRY(h2d(ctx, ctx->b_h_bases, seq_cat, (size_t)n_bases));
+    TRY(h2d(ctx, ctx->b_h_off, seq_off, sizeof(int64_t) * (size_t)(n_seqs + 1)));
+    TRY(h2d(ctx, ctx->b_h_pa, pair_a, sizeof(int32_t) * (size_t)P));
+    TRY(h2d(ctx, ctx->b_h_pb, pair_b, sizeof(int32_t) * (size_t)P));
+    TRY(dev_reserve(ctx, ctx->b_h_dist, sizeof(int32_t) * (size_t)P));
+    if (cigar_off) TRY(dev_reserve(ctx, ctx->b_h_cigoff, sizeof(int64_t) * (size_t)(P + 1)));
+    uint32_t *d_cig = nullptr;
+    if (cigar_runs && cigar_cap > 0) {
+        TRY(dev_reserve(ctx, ctx->b_h_cig, sizeof(uint32_t) * (size_t)cigar_cap));
+        d_cig = (uint32_t *)ctx->b_h_cig.p;
+    }
+    int64_t total = 0;
+    const int rc = isof_edit_distance_core(ctx, (const uint8_t *)ctx->b_h_bases.p, (const int64_t *)ctx->b_h_off.p, n_seqs, n_bases,
+                                           (const int32_t *)ctx->b_h_pa.p, (const int32_t *)ctx->b_h_pb.p, P, k,
+                                           (int32_t *)ctx->b_h_dist.p, d_cig, d_cig ? cigar_cap : 0,
+                                           cigar_off ? (int64_t *)ctx->b_h_cigoff.p : nullptr, &total);
+    if (rc != ISOF_OK && rc != ISOF_ERR_CAPACITY) return rc;
+    int rc2 = rc;
+    if (cigar_runs && !d_cig && total > 0) rc2 = isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar buffer too small: need %lld runs", (long long)total);
+    TRY(d2h(ctx, dist, ctx->b_h_dist.p, sizeof(int32_t) * (size_t)P));
+    if (cigar_off) TRY(d2h(ctx, cigar_off, ctx->b_h_cigoff.p, sizeof(int64_t) * (size_t)(P + 1)));
+    if (d_cig && rc == ISOF_OK) TRY(d2h(ctx, cigar_runs, d_cig, sizeof(uint32_t) * (size_t)total));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc2;
 }
 
 }  // extern "C"

@@ -53,6 +53,8 @@ struct isof_ctx {
     DevBuf b_m_tmp, b_m_cnt, b_m_off;
     DevBuf b_s_mread, b_s_mkey, b_s_mpolya, b_s_mcnt, b_s_moff, b_s_key1, b_s_key2, b_s_keyt, b_s_keyo, b_s_idx0, b_s_idx1,
         b_s_idx2, b_s_forb, b_s_head, b_s_bid, b_s_sorttmp, b_s_rbatch, b_sh_batchoff;
+    DevBuf b_ed[13];                  // kernel (b'), myers.cu: codes, symbols, layout, plan, sort, tasks, trace, runs
+    DevBuf b_h_dist;
     DevBuf b_sh_minpos, b_sh_minoff, b_sh_rread, b_sh_rp1, b_sh_rp2, b_sh_rcount, b_sh_rbucket, b_sh_sorted, b_sh_boff, b_sh_bdrop;
     std::vector<DevBuf *> all_bufs()
     {
@@ -65,6 +67,8 @@ struct isof_ctx {
         for (int w = 0; w < MAX_LANES - 1; ++w)
             for (DevBuf *b : {&b_taskkey_x[w], &b_trace_x[w], &b_bnd_x[w], &b_runoff_x[w], &b_nruns64_x[w], &b_scan_tmp_x[w]})
                 v.push_back(b);
+        for (DevBuf &b : b_ed) v.push_back(&b);
+        v.push_back(&b_h_dist);
         return v;
     }
     void *fused_io = nullptr;         // mapped pinned memory of the fused tiny-call path (inputs | outputs)
@@ -175,6 +179,7 @@ struct LaunchTimer {
 unsigned isof_viol_align();
 unsigned isof_viol_minimizers();
 unsigned isof_viol_spans();
+unsigned isof_viol_myers();
 
 // internal entry points implemented in the .cu files
 int isof_minimizers_core(isof_ctx *ctx, const uint8_t *d_bases, const int64_t *d_off, int32_t R, int64_t n_bases,
@@ -194,3 +199,6 @@ int isof_sg_align_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off
                        int32_t gap_open, int32_t gap_ext, int32_t *d_score, int32_t *d_endq, int32_t *d_endr,
                        uint32_t *d_cigar, int64_t cigar_cap, int64_t *d_cigar_off, int32_t *d_features,
                        int32_t delta_len, int64_t *h_total_runs);
+int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *d_off, int32_t n_seqs, int64_t n_bases,
+                            const int32_t *d_pa, const int32_t *d_pb, int64_t P, int32_t k, int32_t *d_dist,
+                            uint32_t *d_cigar, int64_t cigar_cap, int64_t *d_cigar_off, int64_t *h_total_runs);

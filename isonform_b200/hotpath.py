@@ -10,7 +10,7 @@ Same names, argument meaning and error behaviour as the reference functions they
     parse_cigar_diversity_isoform_level_new                   modules/IsoformGeneration.py:251-397
 
 plus the batched forms the drivers use (`align_pairs`, `align_to_merge_pairs`,
-`bubble_decisions`).  Every numeric result comes from the GPU; the host only evaluates the
+`bubble_decisions`) and `edit_distance_pairs` / `edlib_align` (edlib's interface: setup.py:81, no call site).  Every numeric result comes from the GPU; the host only evaluates the
 reference's float comparisons on the integer features the kernels emit.
 """
 import re
@@ -101,6 +101,34 @@ def parasail_alignment(s1, s2, match_score=2, mismatch_penalty=-2, opening_penal
     cigar_string = runs_to_string(runs)
     a1, a2, tuples = cigar_to_seq(cigar_string, s1, s2)
     return a1, a2, cigar_string, tuples, score
+
+
+# ----------------------------------------------------------------------------------------------
+# (b') unit-cost edit distance -- edlib's shape (declared by the reference's setup.py:81, never called)
+# ----------------------------------------------------------------------------------------------
+def edit_distance_pairs(seqs, pair_a, pair_b, k=-1, task="distance", ctx=None):
+    """Batched edlib.align(seqs[a], seqs[b], mode="NW", task=task, k=k): a list of dicts with edlib's keys
+    {"editDistance": int (-1 above k), "cigar": extended CIGAR string or None}.  One library call (Myers/Hyyro
+    bit-parallel kernel, csrc/myers.cu)."""
+    if task not in ("distance", "path"):
+        raise ValueError("task must be 'distance' or 'path'")
+    ctx = ctx or default_context()
+    cat, off = pack_sequences(seqs)
+    res = ctx.edit_distance_pairs(cat, off, pair_a, pair_b, k=k, want_cigar=(task == "path"))
+    out = []
+    for p, d in enumerate(res["dist"]):
+        cig = None
+        if task == "path" and d >= 0:
+            cig = runs_to_string(res["cigar"][res["cigar_off"][p]:res["cigar_off"][p + 1]])
+        out.append({"editDistance": int(d), "cigar": cig})
+    return out
+
+
+def edlib_align(query, target, mode="NW", task="distance", k=-1, ctx=None):
+    """One pair with edlib.align's signature (global mode only: the kernel computes NW)."""
+    if mode != "NW":
+        raise ValueError("only mode='NW' (global) is implemented")
+    return edit_distance_pairs([query, target], [0], [1], k=k, task=task, ctx=ctx)[0]
 
 
 # ----------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ decision functions (SimplifyGraph.py:175-196, IsoformGeneration.py:251-397).
 """
 from .capi import (  # noqa: F401
     pyhash, minimizers, minimizers_batch, sg_align, sg_align_pairs, num_threads, simd_lanes, simd_isa, TieBreak, all_tiebreaks,
-    cigar_runs_to_string, cigar_runs_to_tuples, OPS, edit_distance, edit_distance_pairs,
+    cigar_runs_to_string, cigar_runs_to_tuples, OPS, edit_distance, edit_distance_pairs, edit_path,
 )
 from .pyside import (  # noqa: F401
     get_kmer_minimizers, get_minimizers_and_positions, minimizers_comb_iterator,

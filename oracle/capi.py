@@ -63,6 +63,9 @@ def lib():
         L.isof_oracle_edit_distance_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                       C.c_void_p, C.c_int]
         L.isof_oracle_edit_distance_pairs.restype = C.c_int64
+        L.isof_oracle_edit_path.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int32)]
+        L.isof_oracle_edit_path.restype = C.c_int64
         L.isof_oracle_num_threads.restype = C.c_int32
         L.isof_oracle_simd_lanes.restype = C.c_int32
         L.isof_oracle_simd_isa.restype = C.c_char_p
@@ -148,6 +151,18 @@ def edit_distance(s1, s2):
     """Global unit-cost edit distance (Myers/Hyyro bit-vector); config 5's "edlib CPU" stand-in."""
     a, b = _b(s1), _b(s2)
     return int(lib().isof_oracle_edit_distance(a, len(a), b, len(b)))
+
+
+def edit_path(s1, s2):
+    """(distance, uint32 runs) of one optimal global unit-cost alignment: plain O(nm) matrix, walked back preferring
+    the diagonal, then 'I' (consumes s1), then 'D' -- the checker of isof_edit_distance_pairs' path."""
+    a, b = _b(s1), _b(s2)
+    runs = np.empty(len(a) + len(b) + 2, np.uint32)
+    d = C.c_int32(0)
+    nr = lib().isof_oracle_edit_path(a, len(a), b, len(b), runs.ctypes.data, len(runs), C.byref(d))
+    if nr < 0:
+        raise MemoryError("oracle edit_path")
+    return int(d.value), runs[:nr].copy()
 
 
 def edit_distance_pairs(cat, off, ia, ib, threads=0):

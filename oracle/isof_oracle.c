@@ -712,6 +712,61 @@ ISOF_API int32_t isof_oracle_edit_distance(const uint8_t *q, int32_t n, const ui
     return (int32_t)bottom;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * One optimal global unit-cost alignment path as (len << 4 | op) runs in alignment order, ops 7 '=' / 8 'X' /
+ * 1 'I' (consumes q) / 2 'D' (consumes t) -- the extended CIGAR of edlib's task="path".  Plain O(nm) matrix
+ * (Wagner-Fischer), walked back from (n, m) preferring the diagonal, then up ('I'), then left ('D').
+ * edlib has no call site in the reference (setup.py:81 only) and documents no tie rule: the checker for
+ * isof_edit_distance_pairs' path.  Returns the number of runs (also when it exceeds cap; nothing is
+ * written beyond cap), -1 on allocation failure; *dist_out receives D(n, m).
+ * ------------------------------------------------------------------------------------------- */
+ISOF_API int64_t isof_oracle_edit_path(const uint8_t *q, int32_t n, const uint8_t *t, int32_t m, uint32_t *runs,
+                                       int64_t cap, int32_t *dist_out)
+{
+    const size_t W = (size_t)m + 1;
+    int32_t *D = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1) * W);
+    uint32_t *rev = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + (size_t)m + 2));
+    if (!D || !rev) { free(D); free(rev); return -1; }
+    for (int32_t j = 0; j <= m; ++j) D[j] = j;
+    for (int32_t i = 1; i <= n; ++i) {
+        int32_t *row = D + (size_t)i * W;
+        const int32_t *up = row - W;
+        row[0] = i;
+        for (int32_t j = 1; j <= m; ++j) {
+            int32_t v = up[j - 1] + (q[i - 1] != t[j - 1]);
+            if (up[j] + 1 < v) v = up[j] + 1;
+            if (row[j - 1] + 1 < v) v = row[j - 1] + 1;
+            row[j] = v;
+        }
+    }
+    if (dist_out) *dist_out = D[(size_t)n * W + m];
+    int64_t nr = 0;
+    uint32_t cur_op = 0xff, cur_len = 0;
+    int32_t i = n, j = m;
+    while (i > 0 || j > 0) {
+        uint32_t op;
+        uint32_t len = 1;
+        if (i > 0 && j > 0) {
+            const int32_t here = D[(size_t)i * W + j];
+            const int neq = q[i - 1] != t[j - 1];
+            if (here == D[(size_t)(i - 1) * W + j - 1] + neq) { op = neq ? 8u : 7u; --i; --j; }
+            else if (here == D[(size_t)(i - 1) * W + j] + 1) { op = 1u; --i; }
+            else { op = 2u; --j; }
+        } else if (i > 0) { op = 1u; len = (uint32_t)i; i = 0; }
+        else { op = 2u; len = (uint32_t)j; j = 0; }
+        if (op == cur_op) cur_len += len;
+        else {
+            if (cur_len) rev[nr++] = (cur_len << 4) | cur_op;
+            cur_op = op;
+            cur_len = len;
+        }
+    }
+    if (cur_len) rev[nr++] = (cur_len << 4) | cur_op;
+    for (int64_t x = 0; x < nr && x < cap; ++x) runs[x] = rev[nr - 1 - x];
+    free(D); free(rev);
+    return nr;
+}
+
 ISOF_API int64_t isof_oracle_edit_distance_pairs(const uint8_t *cat, const int64_t *off, const int32_t *ia,
                                                  const int32_t *ib, int64_t P, int32_t *dist, int threads)
 {

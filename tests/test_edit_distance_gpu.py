@@ -1,0 +1,232 @@
+"""Kernel (b'), csrc/myers.cu: batched global unit-cost edit distance (Myers/Hyyro bit-parallel) through the C ABI against
+the oracle's Myers restatement (itself checked against a plain O(nm) DP in test_oracle_edit_distance.py) and, for the
+path, against the oracle's plain-matrix traceback with the same tie rule.  edlib has no call site in the reference
+(setup.py:81 only): the integer distance is the contract; the textbook known answers pin both sides."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+KNOWN = [("kitten", "sitting", 3), ("Saturday", "Sunday", 3), ("", "abc", 3), ("abc", "", 3), ("", "", 0),
+         ("GATTACA", "GATTACA", 0), ("intention", "execution", 5), ("ACGT", "TGCA", 4), ("a", "b", 1)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from isonform_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _rand(rng, n, alphabet="ACGT"):
+    return "".join(alphabet[int(x)] for x in rng.integers(0, len(alphabet), size=n))
+
+
+def _mutate(rng, s, rate, alphabet="ACGT"):
+    out = []
+    for ch in s:
+        r = rng.random()
+        if r < rate / 3:
+            continue
+        if r < 2 * rate / 3:
+            out.append(alphabet[int(rng.integers(0, len(alphabet)))])
+            continue
+        out.append(ch)
+        if r > 1 - rate / 3:
+            out.append(alphabet[int(rng.integers(0, len(alphabet)))])
+    return "".join(out)
+
+
+def _pool(seqs):
+    from isonform_b200._lib import pack_sequences
+    return pack_sequences(seqs)
+
+
+def _apply(runs, q, t):
+    """Walk a (len<<4|op) run list over q and t: returns (cost, consumed_q, consumed_t, letters_ok)."""
+    i = j = cost = 0
+    ok = True
+    for r in runs:
+        ln, op = int(r) >> 4, int(r) & 15
+        if op == 7:
+            ok &= q[i:i + ln] == t[j:j + ln]
+            i += ln; j += ln
+        elif op == 8:
+            ok &= all(a != b for a, b in zip(q[i:i + ln], t[j:j + ln]))
+            i += ln; j += ln; cost += ln
+        elif op == 1:
+            i += ln; cost += ln
+        elif op == 2:
+            j += ln; cost += ln
+        else:
+            ok = False
+    return cost, i, j, ok
+
+
+def test_known_answers(ctx):
+    from isonform_b200 import hotpath
+    for a, b, d in KNOWN:
+        assert oracle.edit_distance(a, b) == d
+        assert hotpath.edlib_align(a, b, ctx=ctx)["editDistance"] == d, (a, b)
+        r = hotpath.edlib_align(a, b, task="path", ctx=ctx)
+        assert r["editDistance"] == d
+        assert r["cigar"] == oracle.cigar_runs_to_string(oracle.edit_path(a, b)[1]), (a, b)
+
+
+def test_distance_vs_oracle_all_group_sizes_and_stripes(ctx):
+    """Every class of the kernel (1, 2, 4, 8, 16, 32 lanes per pair; 1 to 4 stripes of 1024 rows), word and stripe
+    boundaries, ragged targets inside a warp, similar and unrelated pairs."""
+    rng = np.random.default_rng(101)
+    seqs = [""]
+    edges = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049,
+             3100, 4097]
+    for n in edges:
+        s = _rand(rng, n)
+        seqs += [s, _mutate(rng, s, 0.1), _mutate(rng, s, 0.3)]
+    for _ in range(120):
+        n = int(rng.integers(1, 700))
+        s = _rand(rng, n)
+        seqs += [s, _mutate(rng, s, float(rng.random()) * 0.4)]
+    seqs += ["A" * 300, "A" * 1500, "AC" * 700, "ACGT" * 1000, "T" * 40]
+    cat, off = _pool(seqs)
+    S = len(seqs)
+    pa = rng.integers(0, S, 6000).astype(np.int32)
+    pb = rng.integers(0, S, 6000).astype(np.int32)
+    # neighbours (a sequence and its mutated copies) so that small distances occur in every class
+    nb = np.arange(S - 1, dtype=np.int32)
+    pa = np.concatenate([pa, nb, nb + 1, nb])
+    pb = np.concatenate([pb, nb + 1, nb, nb])
+    got = ctx.edit_distance_pairs(cat, off, pa, pb)["dist"]
+    want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, [(int(p), len(seqs[pa[p]]), len(seqs[pb[p]]), int(got[p]), int(want[p])) for p in bad[:10]]
+
+
+def test_arbitrary_bytes_and_case(ctx):
+    """Bytes compare by value: lower case differs from upper case, N equals only N, any byte value is a symbol."""
+    rng = np.random.default_rng(7)
+    seqs = [bytes(rng.integers(0, 256, int(rng.integers(0, 400))).astype(np.uint8)) for _ in range(60)]
+    seqs += [b"ACGTNacgtn" * 20, b"acgtnACGTN" * 20, b"\x00" * 70, b"\x00\xff" * 35, b"N" * 100, b"n" * 100]
+    cat, off = _pool(seqs)
+    S = len(seqs)
+    pa = np.repeat(np.arange(S, dtype=np.int32), S)
+    pb = np.tile(np.arange(S, dtype=np.int32), S)
+    got = ctx.edit_distance_pairs(cat, off, pa, pb)["dist"]
+    want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    assert (got == want).all()
+    assert got[(S - 2) * S + (S - 1)] == 100           # 'N' * 100 vs 'n' * 100
+
+
+def test_threshold_k(ctx):
+    rng = np.random.default_rng(9)
+    seqs = []
+    for _ in range(100):
+        s = _rand(rng, int(rng.integers(1, 1500)))
+        seqs += [s, _mutate(rng, s, 0.05)]
+    cat, off = _pool(seqs)
+    pa = np.arange(0, 200, 2, dtype=np.int32)
+    pb = pa + 1
+    full = ctx.edit_distance_pairs(cat, off, pa, pb)["dist"]
+    for k in (0, 5, 40, 10 ** 6):
+        got = ctx.edit_distance_pairs(cat, off, pa, pb, k=k)["dist"]
+        assert (got == np.where(full <= k, full, -1)).all()
+    r = ctx.edit_distance_pairs(cat, off, pa, pb, k=5, want_cigar=True)
+    n_runs = np.diff(r["cigar_off"])
+    assert ((n_runs == 0) == (r["dist"] < 0)).all()            # no path above k; every other pair (non-empty) has runs
+
+
+def test_path_vs_oracle(ctx):
+    """Runs equal the oracle's plain-matrix traceback (diagonal, then I, then D) and are a valid witness of the distance."""
+    rng = np.random.default_rng(33)
+    seqs = ["", "A", "ACGT"]
+    for n in [1, 31, 32, 33, 64, 65, 100, 128, 129, 256, 300, 512, 513, 1024, 1025, 1500, 2049, 2600]:
+        s = _rand(rng, n)
+        seqs += [s, _mutate(rng, s, 0.08), _mutate(rng, s, 0.3), s[n // 3:], s[: 2 * n // 3] + _rand(rng, 40)]
+    seqs += ["A" * 200, "A" * 230, "AC" * 100, "CA" * 100]
+    cat, off = _pool(seqs)
+    S = len(seqs)
+    pa = rng.integers(0, S, 700).astype(np.int32)
+    pb = rng.integers(0, S, 700).astype(np.int32)
+    nb = np.arange(S - 1, dtype=np.int32)
+    pa = np.concatenate([pa, nb, nb + 1, nb])
+    pb = np.concatenate([pb, nb + 1, nb, nb])
+    r = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+    want_d = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    assert (r["dist"] == want_d).all()
+    for p in range(len(pa)):
+        q, t = seqs[pa[p]], seqs[pb[p]]
+        runs = r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]]
+        cost, i, j, ok = _apply(runs, q, t)
+        assert ok and i == len(q) and j == len(t) and cost == int(want_d[p]), (p, len(q), len(t))
+        if len(q) * len(t) <= 1_500_000 or p % 9 == 0:
+            d, want = oracle.edit_path(q, t)
+            assert d == int(want_d[p])
+            assert runs.tolist() == want.tolist(), (p, len(q), len(t))
+
+
+def test_path_capacity_protocol_and_chunked_trace(ctx):
+    """ISOF_ERR_CAPACITY reports the needed size; a trace budget smaller than the call forces chunks (the DP then runs
+    once for the run counts and once for the runs) with identical output."""
+    from isonform_b200 import _lib
+    rng = np.random.default_rng(5)
+    seqs = []
+    for _ in range(60):
+        s = _rand(rng, int(rng.integers(50, 900)))
+        seqs += [s, _mutate(rng, s, 0.15)]
+    cat, off = _pool(seqs)
+    pa = rng.integers(0, len(seqs), 500).astype(np.int32)
+    pb = rng.integers(0, len(seqs), 500).astype(np.int32)
+    ref = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+    L = ctx._L
+    dist = np.empty(len(pa), np.int32)
+    coff = np.zeros(len(pa) + 1, np.int64)
+    small = np.empty(10, np.uint32)
+    rc = L.isof_edit_distance_pairs(ctx._h, cat.ctypes.data, off.ctypes.data, len(off) - 1, pa.ctypes.data, pb.ctypes.data,
+                                    len(pa), -1, dist.ctypes.data, small.ctypes.data, 10, coff.ctypes.data)
+    assert rc == _lib.ERR_CAPACITY and coff[-1] == len(ref["cigar"]) and (coff == ref["cigar_off"]).all()
+    c2 = _lib.Context(0)
+    try:
+        c2.set_trace_budget(3 << 20)
+        r2 = c2.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+        assert c2.profile()["dp_launches"] > 2
+    finally:
+        c2.close()
+    assert (r2["dist"] == ref["dist"]).all() and (r2["cigar_off"] == ref["cigar_off"]).all()
+    assert (r2["cigar"] == ref["cigar"]).all()
+
+
+def test_bad_arguments(ctx):
+    from isonform_b200 import _lib
+    cat, off = _pool(["ACGT", "AC"])
+    with pytest.raises(_lib.IsofError):
+        ctx.edit_distance_pairs(cat, off, [0], [2])
+    with pytest.raises(_lib.IsofError):
+        ctx.edit_distance_pairs(cat, off, [-1], [0])
+    assert len(ctx.edit_distance_pairs(cat, off, [], [])["dist"]) == 0
+
+
+def test_large_batch_checksum_property(ctx):
+    """Full-size property check (no oracle at this size in seconds): symmetry d(a,b) = d(b,a), d(a,a) = 0,
+    | |a| - |b| | <= d <= max(|a|, |b|), triangle inequality on sampled triples; 200 k pairs of 100-300 bp."""
+    rng = np.random.default_rng(77)
+    base = [_rand(rng, int(rng.integers(100, 300))) for _ in range(40)]
+    seqs = [_mutate(rng, base[i % 40], 0.1) for i in range(2000)]
+    cat, off = _pool(seqs)
+    lens = np.diff(off)
+    pa = rng.integers(0, 2000, 200_000).astype(np.int32)
+    pb = rng.integers(0, 2000, 200_000).astype(np.int32)
+    d_ab = ctx.edit_distance_pairs(cat, off, pa, pb)["dist"]
+    d_ba = ctx.edit_distance_pairs(cat, off, pb, pa)["dist"]
+    assert (d_ab == d_ba).all()
+    assert (d_ab[pa == pb] == 0).all()
+    assert (d_ab >= np.abs(lens[pa] - lens[pb])).all() and (d_ab <= np.maximum(lens[pa], lens[pb])).all()
+    pc = rng.integers(0, 2000, 200_000).astype(np.int32)
+    d_bc = ctx.edit_distance_pairs(cat, off, pb, pc)["dist"]
+    d_ac = ctx.edit_distance_pairs(cat, off, pa, pc)["dist"]
+    assert (d_ac <= d_ab + d_bc).all()
+    sub = rng.integers(0, 200_000, 3000)
+    want = oracle.edit_distance_pairs(cat, off, pa[sub], pb[sub], threads=8)
+    assert (d_ab[sub] == want).all()

@@ -45,3 +45,51 @@ def test_edit_distance_pairs_batch():
     d = oracle.edit_distance_pairs(cat, off, ia, ib, threads=2)
     for p in range(0, 100, 7):
         assert int(d[p]) == _dp(seqs[ia[p]], seqs[ib[p]])
+
+
+def _path_py(a, b):
+    """Plain matrix + traceback (diagonal, then up = 'I', then left = 'D') in Python, small sizes only."""
+    n, m = len(a), len(b)
+    D = [[0] * (m + 1) for _ in range(n + 1)]
+    for j in range(m + 1):
+        D[0][j] = j
+    for i in range(1, n + 1):
+        D[i][0] = i
+        for j in range(1, m + 1):
+            D[i][j] = min(D[i - 1][j - 1] + (a[i - 1] != b[j - 1]), D[i - 1][j] + 1, D[i][j - 1] + 1)
+    ops = []
+    i, j = n, m
+    while i > 0 or j > 0:
+        if i > 0 and j > 0 and D[i][j] == D[i - 1][j - 1] + (a[i - 1] != b[j - 1]):
+            ops.append("X" if a[i - 1] != b[j - 1] else "=")
+            i -= 1; j -= 1
+        elif i > 0 and (j == 0 or D[i][j] == D[i - 1][j] + 1):
+            ops.append("I"); i -= 1
+        else:
+            ops.append("D"); j -= 1
+    ops.reverse()
+    out, k = "", 0
+    while k < len(ops):
+        e = k
+        while e < len(ops) and ops[e] == ops[k]:
+            e += 1
+        out += "%d%s" % (e - k, ops[k])
+        k = e
+    return D[n][m], out
+
+
+def test_edit_path_vs_python_and_known_answers():
+    rng = np.random.default_rng(8)
+    for a, b, d in [("kitten", "sitting", 3), ("Saturday", "Sunday", 3), ("", "abc", 3), ("abc", "", 3), ("", "", 0),
+                    ("intention", "execution", 5)]:
+        got_d, runs = oracle.edit_path(a, b)
+        assert got_d == d == oracle.edit_distance(a, b)
+        assert oracle.cigar_runs_to_string(runs) == _path_py(a, b)[1]
+    for _ in range(60):
+        n, m = int(rng.integers(0, 90)), int(rng.integers(0, 90))
+        a = "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+        b = "".join("ACGT"[x] for x in rng.integers(0, 4, m)) if rng.random() < 0.4 else a[m // 3:] + a[:m // 4]
+        d, runs = oracle.edit_path(a, b)
+        want_d, want = _path_py(a, b)
+        assert d == want_d == oracle.edit_distance(a, b)
+        assert oracle.cigar_runs_to_string(runs) == want
