@@ -426,7 +426,12 @@ class Context:
                                                          pb.ctypes.data, P, int(k), dist.ctypes.data, None, 0, None))
             return {"dist": dist, "cigar_off": None, "cigar": None}
         coff = np.zeros(P + 1, np.int64)
-        cap = 64 * P + (1 << 16)
+        # a path has at most n+m runs; unrelated sequences come close to half of that, noisy copies stay far below.  A
+        # too small buffer costs a second full run (ISOF_ERR_CAPACITY), an untouched tail of np.empty costs nothing
+        lens = np.diff(off).astype(np.int64)
+        ok = P and len(lens) and pa.min() >= 0 and pb.min() >= 0 and max(pa.max(), pb.max()) < len(lens)
+        worst = int(lens.take(pa).sum() + lens.take(pb).sum()) + 2 * P if ok else 1
+        cap = int(min(worst, worst // 2 + 64 * P + (1 << 16)))
         while True:
             cig = np.empty(max(cap, 1), np.uint32)
             rc = self._L.isof_edit_distance_pairs(self._h, cat.ctypes.data, off.ctypes.data, len(off) - 1, pa.ctypes.data,

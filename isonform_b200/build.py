@@ -46,8 +46,12 @@ def build(force=False, verbose=False, debug=None):
     objs = []
     extra = ["-DISOF_CHECK"] if debug else []
 
+    headers = [d for d in deps if d.endswith((".cuh", ".h"))]
+
     def compile_one(src):
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + (".dbg.o" if debug else ".o"))
+        if not force and not verbose and not _stale(obj, headers + [os.path.join(CSRC, src)]):
+            return obj                       # only the sources that changed (or all of them after a header change)
         cmd = [NVCC] + FLAGS + ["-Xcompiler", "-ffp-contract=off"] + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

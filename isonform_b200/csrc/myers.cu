@@ -28,23 +28,28 @@
 
 namespace {
 
-constexpr int ED_WARPS = 4;                // warps per block of the DP kernel
+constexpr int ED_WARPS = 4;                // warps per block of the DP kernel (fewer when the symbol tables are large)
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int ED_NC = 14;                  // classes: (lanes per pair G, words per lane W)
+
+// class -> lg2(G), W.  Biggest first; a pair of n rows holds ceil(n/32) words: up to 4 stay in ONE thread (G = 1, W = their
+// number), more are spread over the smallest power-of-two group whose lanes then hold 3 or 4 words each.
+__device__ __constant__ const int8_t ED_LGG[ED_NC] = {5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 0, 0, 0, 0};
+__device__ __constant__ const int8_t ED_W[ED_NC] = {4, 3, 4, 3, 4, 3, 4, 3, 4, 3, 4, 3, 2, 1};
 
 struct EdLayout {                          // written on the device, read back once per call
-    int32_t cls_start[7];                  // sorted position where class c starts; class c runs groups of G = 32 >> c lanes
-    int32_t task_start[7];                 // first task of class c
+    int32_t cls_start[ED_NC + 1];          // sorted position where class c starts
+    int32_t task_start[ED_NC + 1];         // first task of class c (a task = one warp = 32 / G pairs)
     int32_t n_sym;                         // distinct byte values in the pool
     int32_t max_m_multi;                   // longest target among multi-stripe pairs (line-buffer size)
     int32_t err;                           // bit 0: pair index outside the pool, bit 1: sequence longer than 2^31-1
     int32_t pad;
-    int64_t total_words;                   // trace size of the whole call in uint2 units
 };
 
 struct EdDesc {                            // where the traceback finds a pair's trace
     int64_t tbase;                         // uint2 index of the task's trace inside the chunk
     int32_t m_max;                         // column pitch of the task
-    int32_t lane0;                         // first lane of the pair's group
+    int32_t lane0_cls;                     // first lane of the pair's group | class << 8
 };
 
 struct EdArgs {
@@ -104,16 +109,20 @@ __global__ void ed_encode_kernel(const uint8_t *__restrict__ cat, int64_t n_base
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// plan: lengths, class (group size), sort key
+// plan: lengths, class (group size, words per lane), sort key
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ed_class_of(int n)            // class c -> G = 32 >> c
+__host__ __device__ __forceinline__ int ed_class_of(int64_t n, int64_t *stripes)
 {
-    if (n > 512) return 0;
-    if (n > 256) return 1;
-    if (n > 128) return 2;
-    if (n > 64) return 3;
-    if (n > 32) return 4;
-    return 5;
+    const int64_t wt = (n + 31) >> 5;                                  // words of the query
+    *stripes = 1;
+    if (wt <= 4) return wt <= 1 ? 13 : (int)(14 - wt);                // one thread per pair: W = 1..4 -> class 13..10
+    const int64_t ns = (wt + 127) >> 7;                                // stripes of at most 128 words (32 lanes x 4)
+    const int pw = (int)((wt + ns - 1) / ns);                          // words per stripe, 5..128
+    int lg = 1;
+    while ((4 << lg) < pw) ++lg;                                       // smallest group with <= 4 words per lane
+    const int w = (pw + (1 << lg) - 1) >> lg;                          // 3 or 4
+    *stripes = (n + ((int64_t)1024 * w) - 1) / ((int64_t)1024 * w);    // as the kernel counts them (G = 32 only when > 1)
+    return (5 - lg) * 2 + (4 - w);
 }
 
 __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, const int32_t *__restrict__ pa,
@@ -121,8 +130,8 @@ __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, 
                                unsigned long long *__restrict__ keys, int32_t *__restrict__ idx, unsigned int *__restrict__ cnt,
                                EdLayout *lay)
 {
-    __shared__ unsigned int s_cnt[6];
-    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+    __shared__ unsigned int s_cnt[ED_NC];
+    if (threadIdx.x < ED_NC) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) {
@@ -133,36 +142,36 @@ __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, 
         if (n < 0 || m < 0 || n > 0x7fffffff || m > 0x7fffffff) { atomicOr(&lay->err, 2); n = m = 0; }
         pn[p] = (int32_t)n;
         pm[p] = (int32_t)m;
-        const int c = ed_class_of((int)n);
-        const unsigned long long stripes = c == 0 ? (unsigned long long)((n + 1023) >> 10) : 1ull;
-        const unsigned long long cost = stripes * (unsigned long long)m;                 // < 2^53
+        int64_t stripes;
+        const int c = ed_class_of(n, &stripes);
+        const unsigned long long cost = (unsigned long long)stripes * (unsigned long long)m;      // < 2^53
         keys[p] = ((unsigned long long)c << 56) | (0x00ffffffffffffffull - cost);        // ascending: big groups, long targets first
         idx[p] = (int32_t)p;
         atomicAdd(&s_cnt[c], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 6 && s_cnt[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < ED_NC && s_cnt[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 __global__ void ed_layout_kernel(const unsigned int *__restrict__ cnt, EdLayout *lay)
 {
     int32_t cs = 0, ts = 0;
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < ED_NC; ++c) {
         lay->cls_start[c] = cs;
         lay->task_start[c] = ts;
-        const int32_t per = 1 << c;                                                       // pairs per task = 32 / G
+        const int32_t per = 32 >> ED_LGG[c];                                              // pairs per task = 32 / G
         cs += (int32_t)cnt[c];
         ts += ((int32_t)cnt[c] + per - 1) / per;
     }
-    lay->cls_start[6] = cs;
-    lay->task_start[6] = ts;
+    lay->cls_start[ED_NC] = cs;
+    lay->task_start[ED_NC] = ts;
 }
 
 __device__ __forceinline__ int ed_task_class(const EdLayout *lay, int t)
 {
     int c = 0;
 #pragma unroll
-    for (int x = 1; x < 6; ++x) c += (t >= lay->task_start[x]) ? 1 : 0;
+    for (int x = 1; x < ED_NC; ++x) c += (t >= lay->task_start[x]) ? 1 : 0;
     return c;
 }
 
@@ -173,12 +182,13 @@ __global__ void ed_task_kernel(EdLayout *lay, const int32_t *__restrict__ order,
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_slots) return;
     int64_t words = 0;
-    if (t < lay->task_start[6]) {
+    if (t < lay->task_start[ED_NC]) {
         const int c = ed_task_class(lay, (int)t);
-        const int pair = order[lay->cls_start[c] + ((int)t - lay->task_start[c]) * (1 << c)];
-        const int64_t stripes = c == 0 ? (((int64_t)pn[pair] + 1023) >> 10) : 1;
+        const int pair = order[lay->cls_start[c] + ((int)t - lay->task_start[c]) * (32 >> ED_LGG[c])];
+        int64_t stripes;
+        ed_class_of(pn[pair], &stripes);
         if (stripes > 1) atomicMax(&lay->max_m_multi, pm[pair]);
-        if (want_trace) words = stripes * (int64_t)pm[pair] * 32;
+        if (want_trace) words = stripes * (int64_t)pm[pair] * 32 * ED_W[c];
     }
     task_words[t] = words;
 }
@@ -186,11 +196,64 @@ __global__ void ed_task_kernel(EdLayout *lay, const int32_t *__restrict__ order,
 // ---------------------------------------------------------------------------------------------------------------
 // the DP
 // ---------------------------------------------------------------------------------------------------------------
-template <int G, bool TRACE>
+// s = x + y over W words; returns the carry out of the top word
+template <int W>
+__device__ __forceinline__ uint32_t ed_add(const uint32_t (&x)[W], const uint32_t (&y)[W], uint32_t (&s)[W])
+{
+    uint32_t co;
+    if constexpr (W == 1)
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(s[0]), "=r"(co) : "r"(x[0]), "r"(y[0]));
+    else if constexpr (W == 2)
+        asm("add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 %1, %4, %6;\n\taddc.u32 %2, 0, 0;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(y[0]), "r"(y[1]));
+    else if constexpr (W == 3)
+        asm("add.cc.u32 %0, %4, %7;\n\taddc.cc.u32 %1, %5, %8;\n\taddc.cc.u32 %2, %6, %9;\n\taddc.u32 %3, 0, 0;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(co)
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(y[0]), "r"(y[1]), "r"(y[2]));
+    else
+        asm("add.cc.u32 %0, %5, %9;\n\taddc.cc.u32 %1, %6, %10;\n\taddc.cc.u32 %2, %7, %11;\n\taddc.cc.u32 %3, %8, %12;\n\t"
+            "addc.u32 %4, 0, 0;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(co)
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+    return co;
+}
+
+// s += c (0 or 1), rippling through the words
+template <int W>
+__device__ __forceinline__ void ed_add_carry(uint32_t (&s)[W], uint32_t c)
+{
+    if constexpr (W == 1)
+        s[0] += c;
+    else if constexpr (W == 2)
+        asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(s[0]), "+r"(s[1]) : "r"(c));
+    else if constexpr (W == 3)
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 %2, %2, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]) : "r"(c));
+    else
+        asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;"
+            : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]) : "r"(c));
+}
+
+template <int W>
+__device__ __forceinline__ void ed_load_eq(const uint32_t *p, uint32_t (&e)[W])
+{
+    if constexpr (W == 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+    } else if constexpr (W == 2) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        e[0] = v.x; e[1] = v.y;
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) e[w] = p[w];
+    }
+}
+
+template <int G, int W, bool TRACE>
 __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const int c, uint32_t *__restrict__ peq,
                                             uint32_t *__restrict__ lb, const int lane)
 {
     constexpr int PPT = 32 / G;
+    constexpr int RL = 32 * W;                                         // rows per lane
     const int gl = lane % G, slot = lane / G;
     const EdLayout *lay = a.lay;
     const int sidx = lay->cls_start[c] + (t - lay->task_start[c]) * PPT + slot;
@@ -205,19 +268,25 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
         tb = a.off[a.pb[pair]];
     }
     const int m_max = (int)__reduce_max_sync(FULL, (unsigned)m);
-    const int ns = (G == 32) ? max(1, (int)(((int64_t)n + 1023) >> 10)) : 1;       // G == 32: one pair per warp, uniform
+    const int ns = (G == 32) ? max(1, (int)(((int64_t)n + 32 * RL - 1) / (32 * RL))) : 1;     // G == 32: one pair per warp, uniform
     const int64_t tbase = TRACE ? a.task_off[t] - a.trace_base : 0;
     const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
+    uint32_t *my_eq = peq + lane * W;                                  // Eq[symbol][lane][word]: symbol pitch 32 * W words
     int acc = 0;
     for (int s = 0; s < ns; ++s) {
-        // ---- match vectors of this stripe: Eq[symbol][lane], each lane fills its own column of the table
-        for (int y = 0; y < a.n_sym; ++y) peq[y * 32 + lane] = 0;
-        const int64_t r0 = (int64_t)s * 1024 + gl * 32;
-        const int nv = (int)min((int64_t)32, max((int64_t)0, (int64_t)n - r0));
-        for (int r = 0; r < nv; ++r) peq[(int)a.codes[qb + r0 + r] * 32 + lane] |= 1u << r;
+        // ---- match vectors of this stripe, each lane fills its own words of the table
+        for (int y = 0; y < a.n_sym; ++y)
+#pragma unroll
+            for (int w = 0; w < W; ++w) my_eq[y * 32 * W + w] = 0;
+        const int64_t r0 = (int64_t)s * 32 * RL + gl * RL;
+        const int nv = (int)min((int64_t)RL, max((int64_t)0, (int64_t)n - r0));      // valid rows of this lane
+        for (int r = 0; r < nv; ++r) my_eq[(int)a.codes[qb + r0 + r] * 32 * W + (r >> 5)] |= 1u << (r & 31);
         __syncwarp();
-        uint32_t pv = ~0u, mv = 0u, hist = 0u;
-        const bool rd = s > 0, wr = s + 1 < ns;
+        uint32_t pv[W], mv[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { pv[w] = ~0u; mv[w] = 0u; }
+        uint32_t hist = 0u;
+        const bool rd = (G == 32) && s > 0, wr = (G == 32) && s + 1 < ns;
         for (int j0 = 0; j0 < m_max; j0 += 16) {
             const uint32_t hw = rd ? lb[j0 >> 4] : 0x55555555u;        // horizontal delta entering row 0: +1 per column at the top
 #pragma unroll
@@ -234,53 +303,87 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
                 for (int u = 0; u < 4; ++u) {
                     const int j = j4 + u;
                     const bool act = j < m;
-                    const uint32_t ch = act ? ((c4 >> (8 * u)) & 0xffu) : 0u;
-                    const uint32_t eq0 = peq[ch * 32 + lane];
-                    const uint32_t inb = (hw >> (2 * (j & 15))) & 3u;  // bit 0: +1, bit 1: -1 (group lane 0 only)
-                    uint32_t eq = eq0;
-                    if (G == 1 || gl == 0) eq |= inb >> 1;
-                    const uint32_t xv = eq0 | mv;
-                    const uint32_t x = eq & pv;
-                    uint32_t sum = x + pv;
+                    // symbols read past m belong to the next sequence or the padding: valid table rows, results discarded
+                    const uint32_t ch = __byte_perm(c4, 0, 0x4440 + u);
+                    uint32_t eq0[W], eq[W], x[W], sum[W], ph[W], mh[W];
+                    ed_load_eq<W>(my_eq + ch * (32 * W), eq0);
+                    const uint32_t inb = (G == 32) ? ((hw >> (2 * (j & 15))) & 3u) : 1u;   // bit 0: +1, bit 1: -1
+#pragma unroll
+                    for (int w = 0; w < W; ++w) eq[w] = eq0[w];
+                    if (G == 1 || gl == 0) eq[0] |= inb >> 1;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) x[w] = eq[w] & pv[w];
+                    const uint32_t co = ed_add<W>(x, pv, sum);
                     if (G > 1) {
-                        // carries between the words of the group: generate / propagate votes, lookahead by one addition
+                        // carries between the lanes of the group: generate / propagate votes, lookahead by one addition
+                        uint32_t all = sum[0];
+#pragma unroll
+                        for (int w = 1; w < W; ++w) all &= sum[w];
                         const bool top = gl == G - 1;
-                        const unsigned gm = __ballot_sync(FULL, !top && sum < x);
-                        const unsigned pm_ = __ballot_sync(FULL, !top && sum == 0xffffffffu);
-                        const unsigned cy = (((pm_ | gm) + gm) ^ pm_);
-                        sum += (cy >> lane) & 1u;
+                        const unsigned gm = __ballot_sync(FULL, !top && co != 0u);
+                        const unsigned pk = __ballot_sync(FULL, !top && all == 0xffffffffu);
+                        const unsigned cy = (((pk | gm) + gm) ^ pk);
+                        ed_add_carry<W>(sum, (cy >> lane) & 1u);
                     }
-                    const uint32_t xh = (sum ^ pv) | eq;
-                    const uint32_t ph = mv | ~(xh | pv);
-                    const uint32_t mh = pv & xh;
-                    const uint32_t t2 = (ph >> 31) | ((mh >> 31) << 1);
-                    uint32_t up = inb;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const uint32_t xh = (sum[w] ^ pv[w]) | eq[w];
+                        ph[w] = mv[w] | ~(xh | pv[w]);
+                        mh[w] = pv[w] & xh;
+                    }
+                    // bit 31 of the lane's top words for the lane above: byte 0 <- ph, byte 1 <- mh
+                    const uint32_t t2 = __byte_perm(ph[W - 1], mh[W - 1], 0x0073);
+                    uint32_t up = ((inb & 1u) << 7) | ((inb & 2u) << 14);
                     if (G > 1) {
                         const uint32_t below = __shfl_up_sync(FULL, t2, 1);
                         if (gl != 0) up = below;
                     }
-                    const uint32_t ph2 = (ph << 1) | (up & 1u);
-                    const uint32_t mh2 = (mh << 1) | (up >> 1);
-                    const uint32_t pvn = mh2 | ~(xv | ph2);
-                    const uint32_t mvn = ph2 & xv;
-                    if (TRACE && act) {
+                    uint32_t pcar = up << 24, mcar = up << 16;           // bit 31 = the bit shifted in
+                    uint32_t dg[W], pvn[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const uint32_t ph2 = __funnelshift_l(pcar, ph[w], 1);
+                        const uint32_t mh2 = __funnelshift_l(mcar, mh[w], 1);
+                        pcar = ph[w];
+                        mcar = mh[w];
+                        const uint32_t xv = eq0[w] | mv[w];
+                        pvn[w] = mh2 | ~(xv | ph2);
+                        const uint32_t mvn = ph2 & xv;
                         // diagonal move optimal: match, or D(i,j) - D(i-1,j-1) = dh(i,j) + dv(i,j-1) = 1
-                        const uint32_t dg = eq0 | (ph & ~(pv | mv)) | (pv & ~(ph | mh));
-                        ISOF_ASSERT(tbase + ((int64_t)s * m_max + j) * 32 + lane < a.trace_cap, CHK_TRACE_STORE);
-                        a.trace[tbase + ((int64_t)s * m_max + j) * 32 + lane] = make_uint2(dg, pvn);
+                        if (TRACE) dg[w] = eq0[w] | (ph[w] & ~(pv[w] | mv[w])) | (pv[w] & ~(ph[w] | mh[w]));
+                        mv[w] = act ? mvn : mv[w];
                     }
-                    if (G == 32) hist |= t2 << (2 * (j & 15));
-                    pv = act ? pvn : pv;
-                    mv = act ? mvn : mv;
+                    if (TRACE && act) {
+                        const int64_t ti = tbase + (((int64_t)s * m_max + j) * 32 + lane) * W;
+                        ISOF_ASSERT(ti + W <= a.trace_cap, CHK_TRACE_STORE);
+                        if constexpr (W == 4) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(a.trace + ti);
+                            dst[0] = make_uint4(dg[0], pvn[0], dg[1], pvn[1]);
+                            dst[1] = make_uint4(dg[2], pvn[2], dg[3], pvn[3]);
+                        } else if constexpr (W == 2) {
+                            *reinterpret_cast<uint4 *>(a.trace + ti) = make_uint4(dg[0], pvn[0], dg[1], pvn[1]);
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < W; ++w) a.trace[ti + w] = make_uint2(dg[w], pvn[w]);
+                        }
+                    }
+#pragma unroll
+                    for (int w = 0; w < W; ++w) pv[w] = act ? pvn[w] : pv[w];
+                    if (G == 32 && wr) hist |= (((t2 >> 7) & 1u) | ((t2 >> 14) & 2u)) << (2 * (j & 15));
                 }
             }
-            if (G == 32) {
-                if (wr && lane == 31) lb[j0 >> 4] = hist;              // bottom row of the stripe: the next stripe's carry-in
+            if (G == 32 && wr) {
+                if (lane == 31) lb[j0 >> 4] = hist;                    // bottom row of the stripe: the next stripe's carry-in
                 hist = 0u;
             }
         }
-        const uint32_t rows = nv >= 32 ? ~0u : ((1u << nv) - 1u);
-        int d = __popc(pv & rows) - __popc(mv & rows);
+        int d = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int nw = min(32, max(0, nv - 32 * w));
+            const uint32_t rows = nw >= 32 ? ~0u : ((1u << nw) - 1u);
+            d += __popc(pv[w] & rows) - __popc(mv[w] & rows);
+        }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
         acc += d;
@@ -290,27 +393,36 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
         int dist = m + acc;                                            // D(0,m) = m, then down the last column
         if (a.k >= 0 && dist > a.k) dist = -1;
         a.dist[pair] = dist;
-        if (TRACE) a.desc[pair] = EdDesc{tbase, m_max, slot * G};
+        if (TRACE) a.desc[pair] = EdDesc{tbase, m_max, (slot * G) | (c << 8)};
     }
 }
 
 template <bool TRACE>
 __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
 {
-    extern __shared__ uint32_t ed_smem[];
+    extern __shared__ uint4 ed_smem4[];
+    uint32_t *ed_smem = reinterpret_cast<uint32_t *>(ed_smem4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = a.t0 + blockIdx.x * ED_WARPS + warp;
+    const int t = a.t0 + blockIdx.x * (blockDim.x >> 5) + warp;
     if (t >= a.t1) return;
-    uint32_t *peq = ed_smem + (size_t)warp * (a.n_sym * 32 + a.lb_words);
-    uint32_t *lb = peq + a.n_sym * 32;
+    uint32_t *peq = ed_smem + (size_t)warp * (a.n_sym * 128 + a.lb_words);       // sized for W = 4; 16-byte aligned (lb_words % 4 == 0)
+    uint32_t *lb = peq + a.n_sym * 128;
     const int c = ed_task_class(a.lay, t);
     switch (c) {
-    case 0: ed_run_task<32, TRACE>(a, t, c, peq, lb, lane); break;
-    case 1: ed_run_task<16, TRACE>(a, t, c, peq, lb, lane); break;
-    case 2: ed_run_task<8, TRACE>(a, t, c, peq, lb, lane); break;
-    case 3: ed_run_task<4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 4: ed_run_task<2, TRACE>(a, t, c, peq, lb, lane); break;
-    default: ed_run_task<1, TRACE>(a, t, c, peq, lb, lane); break;
+    case 0: ed_run_task<32, 4, TRACE>(a, t, c, peq, lb, lane); break;
+    case 1: ed_run_task<32, 3, TRACE>(a, t, c, peq, lb, lane); break;
+    case 2: ed_run_task<16, 4, TRACE>(a, t, c, peq, lb, lane); break;
+    case 3: ed_run_task<16, 3, TRACE>(a, t, c, peq, lb, lane); break;
+    case 4: ed_run_task<8, 4, TRACE>(a, t, c, peq, lb, lane); break;
+    case 5: ed_run_task<8, 3, TRACE>(a, t, c, peq, lb, lane); break;
+    case 6: ed_run_task<4, 4, TRACE>(a, t, c, peq, lb, lane); break;
+    case 7: ed_run_task<4, 3, TRACE>(a, t, c, peq, lb, lane); break;
+    case 8: ed_run_task<2, 4, TRACE>(a, t, c, peq, lb, lane); break;
+    case 9: ed_run_task<2, 3, TRACE>(a, t, c, peq, lb, lane); break;
+    case 10: ed_run_task<1, 4, TRACE>(a, t, c, peq, lb, lane); break;
+    case 11: ed_run_task<1, 3, TRACE>(a, t, c, peq, lb, lane); break;
+    case 12: ed_run_task<1, 2, TRACE>(a, t, c, peq, lb, lane); break;
+    default: ed_run_task<1, 1, TRACE>(a, t, c, peq, lb, lane); break;
     }
 }
 
@@ -326,8 +438,9 @@ __global__ void ed_traceback_kernel(const EdArgs a, int64_t *__restrict__ nruns6
     if (t >= a.t1) return;
     const EdLayout *lay = a.lay;
     const int c = ed_task_class(lay, t);
-    if (slot >= (1 << c)) return;
-    const int sidx = lay->cls_start[c] + (t - lay->task_start[c]) * (1 << c) + slot;
+    const int ppt = 32 >> ED_LGG[c];
+    if (slot >= ppt) return;
+    const int sidx = lay->cls_start[c] + (t - lay->task_start[c]) * ppt + slot;
     if (sidx >= lay->cls_start[c + 1]) return;
     const int pair = a.order[sidx];
     if (a.dist[pair] < 0) {
@@ -335,6 +448,8 @@ __global__ void ed_traceback_kernel(const EdArgs a, int64_t *__restrict__ nruns6
         return;
     }
     const EdDesc d = a.desc[pair];
+    const int W = ED_W[c], lane0 = d.lane0_cls & 255;
+    const int rows_stripe = (32 * W) << ED_LGG[c];
     const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
     int i = a.pn[pair], j = a.pm[pair];
     int64_t count = 0, wpos = WRITE ? cigar_off[pair + 1] - 1 : 0;
@@ -350,8 +465,10 @@ __global__ void ed_traceback_kernel(const EdArgs a, int64_t *__restrict__ nruns6
     };
     while (i > 0 && j > 0) {
         const int r = i - 1;
-        ISOF_ASSERT(d.tbase + ((int64_t)(r >> 10) * d.m_max + (j - 1)) * 32 + d.lane0 + ((r & 1023) >> 5) < a.trace_cap, CHK_TRACE_LOAD);
-        const uint2 w = a.trace[d.tbase + ((int64_t)(r >> 10) * d.m_max + (j - 1)) * 32 + d.lane0 + ((r & 1023) >> 5)];
+        const int s = r / rows_stripe, wi = (r - s * rows_stripe) >> 5;           // word of the stripe
+        const int64_t ti = d.tbase + (((int64_t)s * d.m_max + (j - 1)) * 32 + lane0 + wi / W) * W + wi % W;
+        ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
+        const uint2 w = a.trace[ti];
         const uint32_t bit = 1u << (r & 31);
         if (w.x & bit) {
             emit(q[i - 1] == tg[j - 1] ? (uint32_t)ISOF_CIGAR_EQ : (uint32_t)ISOF_CIGAR_X, 1);
@@ -370,13 +487,13 @@ __global__ void ed_traceback_kernel(const EdArgs a, int64_t *__restrict__ nruns6
     if (!WRITE) nruns64[pair] = count;
 }
 
-int ed_launch_dp(isof_ctx *ctx, EdArgs &a, bool trace, size_t smem)
+int ed_launch_dp(isof_ctx *ctx, EdArgs &a, bool trace, size_t smem_warp, int wpb)
 {
-    const int blocks = (a.t1 - a.t0 + ED_WARPS - 1) / ED_WARPS;
+    const int blocks = (a.t1 - a.t0 + wpb - 1) / wpb;
     if (blocks <= 0) return ISOF_OK;
     LaunchTimer lt(ctx, SLOT_DP);
-    if (trace) ed_dp_kernel<true><<<blocks, ED_WARPS * 32, smem, ctx->stream>>>(a);
-    else ed_dp_kernel<false><<<blocks, ED_WARPS * 32, smem, ctx->stream>>>(a);
+    if (trace) ed_dp_kernel<true><<<blocks, wpb * 32, smem_warp * wpb, ctx->stream>>>(a);
+    else ed_dp_kernel<false><<<blocks, wpb * 32, smem_warp * wpb, ctx->stream>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
     return ISOF_OK;
 }
@@ -401,7 +518,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     DevBuf *B = ctx->b_ed;
     TRY(dev_reserve(ctx, B[0], (size_t)n_bases + 32));                       // codes
-    TRY(dev_reserve(ctx, B[1], 512));                                        // present[8] | cnt[6] | lut[256]
+    TRY(dev_reserve(ctx, B[1], 512));                                        // present[8] | cnt[ED_NC] | lut[256]
     TRY(dev_reserve(ctx, B[2], sizeof(EdLayout)));
     TRY(dev_reserve(ctx, B[3], sizeof(int32_t) * (size_t)P));                // pn
     TRY(dev_reserve(ctx, B[4], sizeof(int32_t) * (size_t)P));                // pm
@@ -410,7 +527,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     TRY(dev_reserve(ctx, B[7], sizeof(int64_t) * (size_t)(P + 1) * 2));      // task_words | task_off
     uint8_t *codes = (uint8_t *)B[0].p;
     unsigned int *present = (unsigned int *)B[1].p, *cnt = present + 8;
-    uint8_t *lut = (uint8_t *)(present + 16);
+    uint8_t *lut = (uint8_t *)(present + 32);
     EdLayout *lay = (EdLayout *)B[2].p;
     int32_t *pn = (int32_t *)B[3].p, *pm = (int32_t *)B[4].p;
     unsigned long long *keys = (unsigned long long *)B[5].p, *keys_out = keys + P;
@@ -438,12 +555,12 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     CUDA_TRY(ctx, cudaGetLastError());
     size_t tmp_sort = 0, tmp_scan = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 59, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 60, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, task_words, task_off, (int)(P + 1), st);
     TRY(dev_reserve(ctx, B[8], std::max(tmp_sort, tmp_scan)));
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
-        CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(B[8].p, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 59, st));
+        CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(B[8].p, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 60, st));
     }
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
@@ -466,14 +583,16 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (h_lay->err & 1) return isof_fail(ctx, ISOF_ERR_ARG, "pair index outside the sequence pool");
     if (h_lay->err & 2) return isof_fail(ctx, ISOF_ERR_ARG, "sequence longer than 2^31-1");
-    const int T = h_lay->task_start[6];
+    const int T = h_lay->task_start[ED_NC];
     const int n_sym = std::max(h_lay->n_sym, 1);
-    const int lb_words = h_lay->max_m_multi > 0 ? (h_lay->max_m_multi + 15) / 16 + 1 : 0;
+    const int lb_words = h_lay->max_m_multi > 0 ? (((h_lay->max_m_multi + 15) / 16 + 1 + 3) & ~3) : 0;
     const int64_t total_words = *h_total;
-    const size_t smem = (size_t)ED_WARPS * ((size_t)n_sym * 32 + (size_t)lb_words) * sizeof(uint32_t);
+    const size_t smem_warp = ((size_t)n_sym * 128 + (size_t)lb_words) * sizeof(uint32_t);
+    const int wpb = (int)std::max<size_t>(1, std::min<size_t>(ED_WARPS, (200 * 1024) / smem_warp));
+    const size_t smem = smem_warp * wpb;
     if (smem > 200 * 1024)
         return isof_fail(ctx, ISOF_ERR_NOMEM, "edit distance: %d symbols and a %d-column multi-stripe target need %zu bytes of "
-                         "shared memory per block", n_sym, h_lay->max_m_multi, smem);
+                         "shared memory per warp", n_sym, h_lay->max_m_multi, smem_warp);
     if (smem > 48 * 1024) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(ed_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(ctx, cudaFuncSetAttribute(ed_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -482,7 +601,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     a.codes = codes; a.off = d_off; a.pa = d_pa; a.pb = d_pb; a.order = order; a.pn = pn; a.pm = pm; a.lay = lay;
     a.task_off = task_off; a.trace = nullptr; a.trace_base = 0; a.trace_cap = 0; a.t0 = 0; a.t1 = T; a.n_sym = n_sym; a.lb_words = lb_words;
     a.dist = d_dist; a.desc = nullptr; a.k = k;
-    if (!want_path) return ed_launch_dp(ctx, a, false, smem);
+    if (!want_path) return ed_launch_dp(ctx, a, false, smem_warp, wpb);
 
     // ---- path: trace chunks
     TRY(dev_reserve(ctx, B[9], sizeof(EdDesc) * (size_t)P));
@@ -529,7 +648,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
         a.t0 = cuts[x];
         a.t1 = cuts[x + 1];
         a.trace_base = chunk_base[x];
-        if (!write || !single) TRY(ed_launch_dp(ctx, a, true, smem));
+        if (!write || !single) TRY(ed_launch_dp(ctx, a, true, smem_warp, wpb));
         const int64_t threads = (int64_t)(a.t1 - a.t0) * 32;
         LaunchTimer lt(ctx, SLOT_TB);
         if (write) ed_traceback_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a, nruns64, d_cigar_off, d_cigar);
