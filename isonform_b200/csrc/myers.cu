@@ -20,7 +20,7 @@
 // Symbols: the bytes of the pool are renumbered densely (only values that occur), the match vectors Eq[symbol][lane] of a
 // stripe sit in shared memory, one conflict-free word load per column.
 // Path: per cell two bits -- "diagonal move is optimal" (match, or mismatch and D(i,j) = D(i-1,j-1) + 1) and "vertical
-// delta is +1" -- stored as one coalesced 256-byte row per warp and column (0.25 B per cell); the traceback prefers
+// delta is +1" -- stored as one coalesced row of 256 W bytes per warp and column (0.25 B per cell); the traceback prefers
 // diagonal, then up ('I', consumes the query), then left ('D').
 #include "common.cuh"
 
@@ -128,7 +128,7 @@ __host__ __device__ __forceinline__ int ed_class_of(int64_t n, int64_t *stripes)
 __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, const int32_t *__restrict__ pa,
                                const int32_t *__restrict__ pb, int64_t P, int32_t *__restrict__ pn, int32_t *__restrict__ pm,
                                unsigned long long *__restrict__ keys, int32_t *__restrict__ idx, unsigned int *__restrict__ cnt,
-                               EdLayout *lay)
+                               EdLayout *lay, int64_t *__restrict__ ops_words)
 {
     __shared__ unsigned int s_cnt[ED_NC];
     if (threadIdx.x < ED_NC) s_cnt[threadIdx.x] = 0;
@@ -147,6 +147,7 @@ __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, 
         const unsigned long long cost = (unsigned long long)stripes * (unsigned long long)m;      // < 2^53
         keys[p] = ((unsigned long long)c << 56) | (0x00ffffffffffffffull - cost);        // ascending: big groups, long targets first
         idx[p] = (int32_t)p;
+        if (ops_words) ops_words[p] = ((n + m + 15) >> 4) + 1;                              // 2 bits per step of the path
         atomicAdd(&s_cnt[c], 1u);
     }
     __syncthreads();
@@ -354,6 +355,9 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
                         mv[w] = act ? mvn : mv[w];
                     }
                     if (TRACE && act) {
+                        // one coalesced row of 256 * W bytes per warp and column.  (Blocks of four columns per 32-byte sector
+                        // cut the traceback's DRAM reads 4x but made these stores 16-byte pieces at a 128-byte stride: the DP
+                        // ran 1.7x slower and the walk, which is latency-bound, gained 15 %.)
                         const int64_t ti = tbase + (((int64_t)s * m_max + j) * 32 + lane) * W;
                         ISOF_ASSERT(ti + W <= a.trace_cap, CHK_TRACE_STORE);
                         if constexpr (W == 4) {
@@ -427,24 +431,23 @@ __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// traceback: one thread per pair; pass 1 counts the runs, pass 2 writes them (alignment order) at their final place
+// traceback: one thread per pair walks the trace ONCE and leaves the path as 2-bit steps (16 per word, walk order) in a
+// small per-pair scratch plus its run count; after the scan of the counts ed_runs_kernel turns the steps into runs at
+// their final place (alignment order).  The walk is bound by 32-byte sector traffic on a trace that does not fit L2, so
+// it is not repeated -- and a chunked call needs its DP only once.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool WRITE>
-__global__ void ed_traceback_kernel(const EdArgs a, int64_t *__restrict__ nruns64, const int64_t *__restrict__ cigar_off,
-                                    uint32_t *__restrict__ cigar)
+__global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const int64_t sidx1, int64_t *__restrict__ nruns64,
+                                    const int64_t *__restrict__ ops_off, uint32_t *__restrict__ ops, int4 *__restrict__ hdr)
 {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = a.t0 + (int)(tid >> 5), slot = (int)(tid & 31);
-    if (t >= a.t1) return;
-    const EdLayout *lay = a.lay;
-    const int c = ed_task_class(lay, t);
-    const int ppt = 32 >> ED_LGG[c];
-    if (slot >= ppt) return;
-    const int sidx = lay->cls_start[c] + (t - lay->task_start[c]) * ppt + slot;
-    if (sidx >= lay->cls_start[c + 1]) return;
+    // one thread per pair of the chunk, in sorted order: every lane of a warp walks (the trace is addressed through the
+    // pair's descriptor, not through its task)
+    const int64_t sidx = sidx0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= sidx1) return;
     const int pair = a.order[sidx];
+    const int c = a.desc[pair].lane0_cls >> 8;
     if (a.dist[pair] < 0) {
-        if (!WRITE) nruns64[pair] = 0;
+        nruns64[pair] = 0;
+        hdr[pair] = make_int4(0, 0, 0, 0);
         return;
     }
     const EdDesc d = a.desc[pair];
@@ -452,39 +455,91 @@ __global__ void ed_traceback_kernel(const EdArgs a, int64_t *__restrict__ nruns6
     const int rows_stripe = (32 * W) << ED_LGG[c];
     const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
     int i = a.pn[pair], j = a.pm[pair];
-    int64_t count = 0, wpos = WRITE ? cigar_off[pair + 1] - 1 : 0;
-    uint32_t cur_op = 0xffu, cur_len = 0;
+    uint32_t *out = ops + ops_off[pair];
+    int64_t count = 0;
+    int steps = 0;
+    uint32_t cur_op = 0xffu, acc = 0u;
+    auto step = [&](uint32_t code) {                                   // 0 '=', 1 'X', 2 'I', 3 'D'
+        count += (code != cur_op) ? 1 : 0;
+        cur_op = code;
+        acc |= code << (2 * (steps & 15));
+        if ((++steps & 15) == 0) { out[(steps >> 4) - 1] = acc; acc = 0u; }
+    };
+    // Most steps are diagonal, so the cells of the next steps ALONG THE DIAGONAL are fetched together (independent loads,
+    // one latency) and consumed while the path stays on it; a gap step ends the batch.  The look-ahead doubles after a
+    // batch that was consumed whole and starts over after a gap: unrelated pairs waste no sectors, noisy copies run 8 deep.
+    constexpr int TBK = 8;
+    const bool multi = ED_LGG[c] == 5;
+    int kcur = 1;
+    while (i > 0 && j > 0) {
+        uint2 w[TBK];
+        bool eqc[TBK];
+        const int kmax = min(kcur, min(i, j));
+#pragma unroll
+        for (int k = 0; k < TBK; ++k) {
+            if (k < kmax) {
+                const int r = i - 1 - k;
+                const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;       // word of the stripe
+                const int jc = j - 1 - k;
+                const int64_t ti = d.tbase + (((int64_t)s * d.m_max + jc) * 32 + lane0 + wi / W) * W + wi % W;
+                ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
+                w[k] = a.trace[ti];
+                eqc[k] = q[r] == tg[jc];
+            }
+        }
+        kcur = min(TBK, kcur * 2);
+        bool on = true;                                                // still on the prefetched diagonal
+#pragma unroll
+        for (int k = 0; k < TBK; ++k) {                                // no break: w[] and eqc[] stay in registers
+            if (on && k < kmax) {
+                const uint32_t bit = 1u << ((i - 1) & 31);
+                if (w[k].x & bit) {
+                    step(eqc[k] ? 0u : 1u);
+                    --i; --j;
+                } else {
+                    if (w[k].y & bit) { step(2u); --i; }
+                    else { step(3u); --j; }
+                    kcur = 1;
+                    on = false;
+                }
+            }
+        }
+    }
+    if (steps & 15) out[steps >> 4] = acc;
+    // the rest of the first row / column is one run
+    if (i > 0) count += (cur_op != 2u) ? 1 : 0;
+    if (j > 0) count += (cur_op != 3u) ? 1 : 0;
+    nruns64[pair] = count;
+    hdr[pair] = make_int4(steps, i, j, 0);
+}
+
+__global__ void ed_runs_kernel(int64_t P, const int64_t *__restrict__ ops_off, const uint32_t *__restrict__ ops,
+                               const int4 *__restrict__ hdr, const int64_t *__restrict__ cigar_off, uint32_t *__restrict__ cigar)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int4 h = hdr[p];
+    const uint32_t *in = ops + ops_off[p];
+    int64_t wpos = cigar_off[p + 1] - 1;
+    uint32_t cur_op = 0xffu, cur_len = 0, word = 0;
     auto emit = [&](uint32_t op, uint32_t len) {
         if (op == cur_op) { cur_len += len; return; }
         if (cur_len) {
-            if (WRITE) cigar[wpos--] = (cur_len << 4) | cur_op;
-            ++count;
+            ISOF_ASSERT(wpos >= cigar_off[p], CHK_CIGAR_COPY);
+            cigar[wpos--] = (cur_len << 4) | cur_op;
         }
         cur_op = op;
         cur_len = len;
     };
-    while (i > 0 && j > 0) {
-        const int r = i - 1;
-        const int s = r / rows_stripe, wi = (r - s * rows_stripe) >> 5;           // word of the stripe
-        const int64_t ti = d.tbase + (((int64_t)s * d.m_max + (j - 1)) * 32 + lane0 + wi / W) * W + wi % W;
-        ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
-        const uint2 w = a.trace[ti];
-        const uint32_t bit = 1u << (r & 31);
-        if (w.x & bit) {
-            emit(q[i - 1] == tg[j - 1] ? (uint32_t)ISOF_CIGAR_EQ : (uint32_t)ISOF_CIGAR_X, 1);
-            --i; --j;
-        } else if (w.y & bit) {
-            emit(ISOF_CIGAR_I, 1);
-            --i;
-        } else {
-            emit(ISOF_CIGAR_D, 1);
-            --j;
-        }
+    for (int st = 0; st < h.x; ++st) {
+        if ((st & 15) == 0) word = in[st >> 4];
+        const uint32_t code = (word >> (2 * (st & 15))) & 3u;
+        emit(code == 0u ? (uint32_t)ISOF_CIGAR_EQ : code == 1u ? (uint32_t)ISOF_CIGAR_X : code == 2u ? (uint32_t)ISOF_CIGAR_I
+                                                                                                      : (uint32_t)ISOF_CIGAR_D, 1u);
     }
-    if (i > 0) emit(ISOF_CIGAR_I, (uint32_t)i);
-    if (j > 0) emit(ISOF_CIGAR_D, (uint32_t)j);
+    if (h.y > 0) emit(ISOF_CIGAR_I, (uint32_t)h.y);
+    if (h.z > 0) emit(ISOF_CIGAR_D, (uint32_t)h.z);
     emit(0xfeu, 0);                                                    // flush
-    if (!WRITE) nruns64[pair] = count;
 }
 
 int ed_launch_dp(isof_ctx *ctx, EdArgs &a, bool trace, size_t smem_warp, int wpb)
@@ -533,6 +588,13 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     unsigned long long *keys = (unsigned long long *)B[5].p, *keys_out = keys + P;
     int32_t *idx = (int32_t *)B[6].p, *order = idx + P;
     int64_t *task_words = (int64_t *)B[7].p, *task_off = task_words + (P + 1);
+    int64_t *ops_words = nullptr, *ops_off = nullptr;
+    if (want_path) {
+        TRY(dev_reserve(ctx, B[13], sizeof(int64_t) * (size_t)(P + 1) * 2));  // step words per pair | their scan
+        ops_words = (int64_t *)B[13].p;
+        ops_off = ops_words + (P + 1);
+        CUDA_TRY(ctx, cudaMemsetAsync(ops_words + P, 0, sizeof(int64_t), st));
+    }
     CUDA_TRY(ctx, cudaMemsetAsync(present, 0, 512, st));
     CUDA_TRY(ctx, cudaMemsetAsync(lay, 0, sizeof(EdLayout), st));
     {
@@ -551,7 +613,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
-        ed_plan_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_off, n_seqs, d_pa, d_pb, P, pn, pm, keys, idx, cnt, lay);
+        ed_plan_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_off, n_seqs, d_pa, d_pb, P, pn, pm, keys, idx, cnt, lay, ops_words);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     size_t tmp_sort = 0, tmp_scan = 0;
@@ -574,19 +636,24 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
         LaunchTimer lt(ctx, SLOT_OTHER);
         CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(B[8].p, tmp_scan, task_words, task_off, (int)(P + 1), st));
     }
+    if (want_path) {
+        LaunchTimer lt(ctx, SLOT_OTHER);
+        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(B[8].p, tmp_scan, ops_words, ops_off, (int)(P + 1), st));
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     // ---- one read-back: layout + trace total
     EdLayout *h_lay = (EdLayout *)ctx->pinned;
     int64_t *h_total = (int64_t *)((char *)ctx->pinned + 256);
     CUDA_TRY(ctx, cudaMemcpyAsync(h_lay, lay, sizeof(EdLayout), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_total, task_off + P, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (want_path) CUDA_TRY(ctx, cudaMemcpyAsync(h_total + 1, ops_off + P, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (h_lay->err & 1) return isof_fail(ctx, ISOF_ERR_ARG, "pair index outside the sequence pool");
     if (h_lay->err & 2) return isof_fail(ctx, ISOF_ERR_ARG, "sequence longer than 2^31-1");
     const int T = h_lay->task_start[ED_NC];
     const int n_sym = std::max(h_lay->n_sym, 1);
     const int lb_words = h_lay->max_m_multi > 0 ? (((h_lay->max_m_multi + 15) / 16 + 1 + 3) & ~3) : 0;
-    const int64_t total_words = *h_total;
+    const int64_t total_words = *h_total, total_ops = want_path ? h_total[1] : 0;
     const size_t smem_warp = ((size_t)n_sym * 128 + (size_t)lb_words) * sizeof(uint32_t);
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(ED_WARPS, (200 * 1024) / smem_warp));
     const size_t smem = smem_warp * wpb;
@@ -606,8 +673,12 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     // ---- path: trace chunks
     TRY(dev_reserve(ctx, B[9], sizeof(EdDesc) * (size_t)P));
     TRY(dev_reserve(ctx, B[10], sizeof(int64_t) * (size_t)(P + 1)));
+    TRY(dev_reserve(ctx, B[14], sizeof(uint32_t) * (size_t)std::max<int64_t>(total_ops, 1)));
+    TRY(dev_reserve(ctx, B[15], sizeof(int4) * (size_t)P));
     a.desc = (EdDesc *)B[9].p;
     int64_t *nruns64 = (int64_t *)B[10].p;
+    uint32_t *ops = (uint32_t *)B[14].p;
+    int4 *hdr = (int4 *)B[15].p;
     CUDA_TRY(ctx, cudaMemsetAsync(nruns64, 0, sizeof(int64_t) * (size_t)(P + 1), st));
     size_t budget = ctx->trace_budget;
     if (!budget) {
@@ -643,20 +714,23 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     a.trace = (uint2 *)B[11].p;
     a.trace_cap = std::max<int64_t>(need, 1);
     ctx->prof.trace_bytes += total_words * (int64_t)sizeof(uint2);
-    const bool single = cuts.size() == 2;
-    auto run_chunk = [&](size_t x, bool write) -> int {
+    static const int h_lgg[ED_NC] = {5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 0, 0, 0, 0};          // ED_LGG on the host
+    for (size_t x = 0; x + 1 < cuts.size(); ++x) {                     // per chunk: DP with the trace, then the walk
         a.t0 = cuts[x];
         a.t1 = cuts[x + 1];
         a.trace_base = chunk_base[x];
-        if (!write || !single) TRY(ed_launch_dp(ctx, a, true, smem_warp, wpb));
-        const int64_t threads = (int64_t)(a.t1 - a.t0) * 32;
+        TRY(ed_launch_dp(ctx, a, true, smem_warp, wpb));
+        auto first_pair = [&](int t) -> int64_t {                      // sorted position of a task's first pair
+            if (t >= T) return P;
+            int c = 0;
+            while (c + 1 < ED_NC && t >= h_lay->task_start[c + 1]) ++c;
+            return h_lay->cls_start[c] + (int64_t)(t - h_lay->task_start[c]) * (32 >> h_lgg[c]);
+        };
+        const int64_t s0 = first_pair(a.t0), s1 = first_pair(a.t1);
         LaunchTimer lt(ctx, SLOT_TB);
-        if (write) ed_traceback_kernel<true><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a, nruns64, d_cigar_off, d_cigar);
-        else ed_traceback_kernel<false><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a, nruns64, d_cigar_off, d_cigar);
+        ed_traceback_kernel<<<(unsigned)((s1 - s0 + 127) / 128), 128, 0, st>>>(a, s0, s1, nruns64, ops_off, ops, hdr);
         CUDA_TRY(ctx, cudaGetLastError());
-        return ISOF_OK;
-    };
-    for (size_t x = 0; x + 1 < cuts.size(); ++x) TRY(run_chunk(x, false));
+    }
     size_t tmp2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp2, nruns64, d_cigar_off, (int)(P + 1), st);
     TRY(dev_reserve(ctx, B[12], tmp2));
@@ -670,6 +744,10 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     if (!d_cigar || *h_total > cigar_cap)
         return d_cigar ? isof_fail(ctx, ISOF_ERR_CAPACITY, "cigar buffer too small: need %lld runs", (long long)*h_total)
                        : ISOF_OK;
-    for (size_t x = 0; x + 1 < cuts.size(); ++x) TRY(run_chunk(x, true));
+    {
+        LaunchTimer lt(ctx, SLOT_TB);
+        ed_runs_kernel<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(P, ops_off, ops, hdr, d_cigar_off, d_cigar);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     return ISOF_OK;
 }

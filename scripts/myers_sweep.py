@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--lengths", default="50,100,200,500,1000,2000,5000")
     ap.add_argument("--cells", type=float, default=2e11)
     ap.add_argument("--err", type=float, default=0.05)
+    ap.add_argument("--related", type=float, default=0.25, help="fraction of pairs (x, noisy copy of x); the rest are unrelated")
     args = ap.parse_args()
     import oracle
     from isonform_b200 import _lib, hotpath, synth
@@ -33,11 +34,12 @@ def main():
             muts = [synth.mutate(rng, x, args.err) or "A" for x in base]
             pa = (np.arange(n_pairs) % nb).astype(np.int32)
             pb = (nb + (np.arange(n_pairs) * 7 % nb)).astype(np.int32)        # mostly unrelated pairs, 1/nb related
-            pb[::4] = nb + pa[::4]                                              # a quarter: a sequence and its noisy copy
+            rel = rng.random(n_pairs) < args.related                            # a sequence and its noisy copy
+            pb[rel] = nb + pa[rel]
             cat, off = hotpath.pack_sequences(base + muts)
             lens = np.diff(off)
             cells = float((lens[pa].astype(np.int64) * lens[pb]).sum())
-            row = {"len": L, "pairs": n_pairs, "cells": cells}
+            row = {"len": L, "pairs": n_pairs, "cells": cells, "related": args.related}
             for name, want in (("distance", False), ("path", True)):
                 ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=want)
                 ctx.profile_enable(True); ctx.profile_reset()

@@ -191,7 +191,7 @@ def test_path_capacity_protocol_and_chunked_trace(ctx):
     try:
         c2.set_trace_budget(3 << 20)
         r2 = c2.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
-        assert c2.profile()["dp_launches"] > 2
+        assert c2.profile()["dp_launches"] >= 2
     finally:
         c2.close()
     assert (r2["dist"] == ref["dist"]).all() and (r2["cigar_off"] == ref["cigar_off"]).all()
