@@ -499,6 +499,65 @@ def run_c5_points(ctx, lengths=(50, 100, 200, 500, 2000)):
     return rows
 
 
+def run_c5_edit_distance(ctx, int32_peak, hbm_peak, lengths=(50, 100, 200, 500, 1000, 2000, 5000)):
+    """BASELINE config 5, the "vs edlib CPU" column: kernel (b'), unit-cost global edit distance (Myers/Hyyro bit-parallel,
+    csrc/myers.cu) on pairs (x, mutate(x, 5 %)), distances only and with the path, next to the oracle's Myers restatement
+    on all host cores over a bounded sample (edlib itself is absent and has no call site in the reference)."""
+    import oracle
+    from isonform_b200 import hotpath, synth
+    rng = np.random.default_rng(5)
+    threads = os.cpu_count() or 1
+    try:
+        kc = json.load(open(os.path.join(ROOT, "profiles", "ncu_myers_constants.json")))["kernels"]
+    except Exception:
+        kc = None
+    rows = []
+    for L in lengths:
+        nb = 2000 if L <= 1000 else 400
+        n_pairs = int(max(4000, min(2000000, 1e11 / (L * L))))
+        base = [synth.random_dna(rng, L) for _ in range(nb)]
+        muts = [synth.mutate(rng, x, 0.05) or "A" for x in base]
+        pa = (np.arange(n_pairs) % nb).astype(np.int32)
+        pb = (nb + (np.arange(n_pairs) % nb)).astype(np.int32)
+        cat, off = hotpath.pack_sequences(base + muts)
+        lens = np.diff(off)
+        cells = float((lens[pa].astype(np.int64) * lens[pb]).sum())
+        row = {"len": L, "pairs": n_pairs}
+        for name, want in (("distance", False), ("path", True)):
+            ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=want)
+            ctx.profile_enable(True); ctx.profile_reset()
+            t0 = time.perf_counter()
+            res = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=want)
+            wall = time.perf_counter() - t0
+            pr = ctx.profile(); ctx.profile_enable(False)
+            dev_ms = pr["dp_ms"] + pr["traceback_ms"] + pr["other_ms"]
+            row[name] = {"device_ms": dev_ms, "dp_ms": pr["dp_ms"], "traceback_ms": pr["traceback_ms"],
+                         "device_gcups": cells / dev_ms / 1e6, "dp_gcups": cells / pr["dp_ms"] / 1e6,
+                         "device_pairs_per_s": n_pairs / dev_ms * 1e3, "host_pairs_per_s": n_pairs / wall}
+        if kc and int32_peak:
+            # distances only: INT32-ALU bound (ncu: ALU pipe 97 % of active cycles); with the path: bound by the trace write
+            ops = kc["distance"]["alu_lane_ops_per_cell"]
+            row["distance"]["roofline"] = {"bound": "int32_alu", "achieved": row["distance"]["dp_gcups"] * 1e9 * ops / 1e12,
+                                           "peak": int32_peak / 1e12, "unit": "Tlane-op/s",
+                                           "frac": row["distance"]["dp_gcups"] * 1e9 * ops / int32_peak,
+                                           "alu_lane_ops_per_cell": ops}
+            gbs = 0.25 * cells / (row["path"]["dp_ms"] * 1e-3) / 1e9
+            row["path"]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                       "algorithmic_bytes_per_cell": 0.25, "traffic_bytes_per_cell": kc["path"]["dram_bytes_per_cell"]}
+        ns = int(max(200, min(n_pairs, 2e9 / (L * L))))
+        oracle.edit_distance_pairs(cat, off, pa[:ns], pb[:ns], threads=threads)
+        t0 = time.perf_counter()
+        want_d = oracle.edit_distance_pairs(cat, off, pa[:ns], pb[:ns], threads=threads)
+        cw = time.perf_counter() - t0
+        if not (res["dist"][:ns] == want_d).all():
+            raise SystemExit("edit-distance parity failure in the C5 sweep at L=%d" % L)
+        ccells = float((lens[pa[:ns]].astype(np.int64) * lens[pb[:ns]]).sum())
+        row["myers_cpu"] = {"pairs": ns, "threads": threads, "pairs_per_s": ns / cw, "gcups": ccells / cw / 1e9,
+                            "kind": "port (Myers/Hyyro 64-bit blocks, oracle/isof_oracle.c), distances only"}
+        rows.append(row)
+    return rows
+
+
 def run_seam_latency(ctx):
     """Per-call latency of the one-pair seam (consensus.parasail_alignment on a memo miss)."""
     from isonform_b200 import hotpath, synth
@@ -615,6 +674,10 @@ def run_b200(args):
     pairs_all, cells_all, reads_all = allreduce([float(P), float(wl["cells"]), float(R)], "sum")
 
     extras = {}
+    try:
+        hbm_peak_early = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        hbm_peak_early = 6650.0
     if not args.no_extras:
         del step
         torch.cuda.empty_cache()
@@ -623,6 +686,7 @@ def run_b200(args):
             extras["e2e_entry"] = run_entry(ctx, wl)
             extras["seam_latency"] = run_seam_latency(ctx)
             extras["C5"] = run_c5_points(ctx)
+            extras["C5_edit_distance"] = run_c5_edit_distance(ctx, int32_peak, hbm_peak_early)
             extras["C4"] = run_c4_sample(ctx, dev)
 
     # ---- kernel (a) at super-batch scale (the C3 regime: many clusters' reads in one call); rank 0, untimed extra

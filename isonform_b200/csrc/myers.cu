@@ -268,6 +268,10 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
         qb = a.off[a.pa[pair]];
         tb = a.off[a.pb[pair]];
     }
+    // k given: a pair whose lengths differ by more than k is above it whatever the sequences are (every path has at least
+    // | n - m | gap columns) -- reported without running its columns
+    const bool cut = a.k >= 0 && abs(n - m) > a.k;
+    if (cut) m = 0;
     const int m_max = (int)__reduce_max_sync(FULL, (unsigned)m);
     const int ns = (G == 32) ? max(1, (int)(((int64_t)n + 32 * RL - 1) / (32 * RL))) : 1;     // G == 32: one pair per warp, uniform
     const int64_t tbase = TRACE ? a.task_off[t] - a.trace_base : 0;
@@ -395,7 +399,7 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
     }
     if (valid && gl == 0) {
         int dist = m + acc;                                            // D(0,m) = m, then down the last column
-        if (a.k >= 0 && dist > a.k) dist = -1;
+        if (cut || (a.k >= 0 && dist > a.k)) dist = -1;
         a.dist[pair] = dist;
         if (TRACE) a.desc[pair] = EdDesc{tbase, m_max, (slot * G) | (c << 8)};
     }
