@@ -230,3 +230,73 @@ def test_large_batch_checksum_property(ctx):
     sub = rng.integers(0, 200_000, 3000)
     want = oracle.edit_distance_pairs(cat, off, pa[sub], pb[sub], threads=8)
     assert (d_ab[sub] == want).all()
+
+
+def test_debug_build_assertions_stay_silent_for_myers():
+    """The assertion build (-DISOF_CHECK) carries bounds checks on the trace stores / loads and the run writes of
+    kernel (b'): all classes, multi-stripe pairs and a chunked call must leave the violation mask empty."""
+    from isonform_b200 import _lib
+    dctx = _lib.Context(0, debug=True)
+    try:
+        assert dctx.debug_violations() == (0, True)
+        rng = np.random.default_rng(12)
+        seqs = [""]
+        for n in [1, 32, 33, 64, 100, 128, 129, 200, 256, 257, 500, 512, 513, 1024, 1100, 2048, 2100, 4096, 4100, 9000]:
+            s = _rand(rng, n)
+            seqs += [s, _mutate(rng, s, 0.1)]
+        cat, off = _pool(seqs)
+        S = len(seqs)
+        pa = rng.integers(0, S, 400).astype(np.int32)
+        pb = rng.integers(0, S, 400).astype(np.int32)
+        nb = np.arange(S - 1, dtype=np.int32)
+        pa = np.concatenate([pa, nb, nb + 1])
+        pb = np.concatenate([pb, nb + 1, nb])
+        want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+        for budget in (0, 48 << 20):
+            dctx.set_trace_budget(budget)
+            r = dctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+            assert (r["dist"] == want).all()
+            for p in range(0, len(pa), 5):
+                cost, i, j, ok = _apply(r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]], seqs[pa[p]], seqs[pb[p]])
+                assert ok and i == len(seqs[pa[p]]) and j == len(seqs[pb[p]]) and cost == int(want[p])
+            assert dctx.debug_violations()[0] == 0
+        dctx.set_trace_budget(0)
+        assert (dctx.edit_distance_pairs(cat, off, pa, pb, k=30)["dist"] == np.where(want <= 30, want, -1)).all()
+        assert dctx.debug_violations()[0] == 0
+    finally:
+        dctx.close()
+
+
+def test_randomised_differential(ctx):
+    """Seeded random calls: lengths 0-3000 drawn log-uniformly, alphabets of 1-20 symbols, mutation rates 0-50 %, random k,
+    distances always against the oracle's Myers, paths against the plain-matrix traceback when it fits."""
+    import os
+    n_seeds = int(os.environ.get("ISOF_FUZZ_SEEDS", "12"))
+    for seed in range(n_seeds):
+        rng = np.random.default_rng(1000 + seed)
+        alpha = "ACGTNacgtnRYKMSW*-.x"[: int(rng.integers(1, 21))]
+        seqs = []
+        for _ in range(int(rng.integers(2, 60))):
+            n = int(np.exp(rng.uniform(0, np.log(3000)))) - 1
+            s = _rand(rng, n, alpha)
+            seqs += [s, _mutate(rng, s, float(rng.random()) * 0.5, alpha)]
+        cat, off = _pool(seqs)
+        P = int(rng.integers(1, 400))
+        pa = rng.integers(0, len(seqs), P).astype(np.int32)
+        pb = np.where(rng.random(P) < 0.5, pa ^ 1, rng.integers(0, len(seqs), P)).astype(np.int32)
+        want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+        k = int(rng.integers(0, 200)) if seed % 3 == 0 else -1
+        r = ctx.edit_distance_pairs(cat, off, pa, pb, k=k, want_cigar=True)
+        exp = want if k < 0 else np.where(want <= k, want, -1)
+        assert (r["dist"] == exp).all(), seed
+        for p in range(P):
+            runs = r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]]
+            if exp[p] < 0:
+                assert len(runs) == 0
+                continue
+            q, t = seqs[pa[p]], seqs[pb[p]]
+            if len(q) * len(t) <= 400_000:
+                assert runs.tolist() == oracle.edit_path(q, t)[1].tolist(), (seed, p)
+            else:
+                cost, i, j, ok = _apply(runs, q, t)
+                assert ok and i == len(q) and j == len(t) and cost == int(want[p]), (seed, p)
