@@ -114,3 +114,23 @@ class FakeContext:
                 feats[p] = f
         cig = np.concatenate(runs_all).astype(np.uint32) if (want_cigar and runs_all) else (np.zeros(0, np.uint32) if want_cigar else None)
         return {"score": score, "end_q": eq, "end_r": er, "cigar_off": coff, "cigar": cig, "features": feats}
+
+    # ---- (b') unit-cost edit distance: the oracle's Myers restatement and plain-matrix path
+    def edit_distance_pairs(self, cat, off, pair_a, pair_b, k=-1, want_cigar=False):
+        cat = np.asarray(cat, dtype=np.uint8)
+        P = len(pair_a)
+        dist = np.zeros(P, np.int32)
+        coff = np.zeros(P + 1, np.int64)
+        runs_all = []
+        for p in range(P):
+            s1 = bytes(cat[off[pair_a[p]]:off[pair_a[p] + 1]])
+            s2 = bytes(cat[off[pair_b[p]]:off[pair_b[p] + 1]])
+            d, runs = oracle.edit_path(s1, s2)
+            if k >= 0 and d > k:
+                d, runs = -1, runs[:0]
+            dist[p] = d
+            runs_all.append(runs)
+            coff[p + 1] = coff[p] + len(runs)
+        if not want_cigar:
+            return {"dist": dist, "cigar_off": None, "cigar": None}
+        return {"dist": dist, "cigar_off": coff, "cigar": np.concatenate(runs_all).astype(np.uint32) if runs_all else np.zeros(0, np.uint32)}

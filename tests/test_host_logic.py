@@ -169,3 +169,23 @@ def test_host_poa_consensus_properties():
     con = poa.consensus(copies)
     assert con == poa.consensus(list(copies))                       # deterministic
     assert oracle.edit_distance(con, truth) <= 1 < min(oracle.edit_distance(c, truth) for c in copies)
+
+
+def test_edlib_shaped_host_functions_over_the_oracle_double():
+    """hotpath.edlib_align / edit_distance_pairs (edlib's interface; setup.py:81 declares it, nothing calls it): host-side
+    formatting and argument checks over the oracle-backed context double.  The CUDA kernel behind them is tested against
+    the same oracle in tests/test_edit_distance_gpu.py."""
+    import pytest
+    from fake_ctx import FakeContext
+    from isonform_b200 import hotpath
+    ctx = FakeContext()
+    assert hotpath.edlib_align("kitten", "sitting", ctx=ctx) == {"editDistance": 3, "cigar": None}
+    r = hotpath.edlib_align("ACGTACGT", "ACGACGTT", task="path", ctx=ctx)
+    assert r["editDistance"] == 2 and sum(int(x) for x in __import__("re").findall(r"(\d+)[=XI]", r["cigar"])) == 8
+    assert hotpath.edlib_align("AAAA", "TTTTTTTT", k=3, task="path", ctx=ctx) == {"editDistance": -1, "cigar": None}
+    out = hotpath.edit_distance_pairs(["ACGT", "ACGA", ""], [0, 0, 2], [1, 2, 1], task="path", ctx=ctx)
+    assert [o["editDistance"] for o in out] == [1, 4, 4] and out[0]["cigar"] == "3=1X" and out[1]["cigar"] == "4I" and out[2]["cigar"] == "4D"
+    with pytest.raises(ValueError):
+        hotpath.edlib_align("A", "C", mode="HW", ctx=ctx)
+    with pytest.raises(ValueError):
+        hotpath.edit_distance_pairs(["A"], [0], [0], task="locations", ctx=ctx)
