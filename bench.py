@@ -499,13 +499,15 @@ def run_c5_points(ctx, lengths=(50, 100, 200, 500, 2000)):
     return rows
 
 
-def run_c5_edit_distance(ctx, int32_peak, hbm_peak, lengths=(50, 100, 200, 500, 1000, 2000, 5000)):
+def run_c5_edit_distance(ctx, int32_peak, hbm_peak, rank=0, world=1, barrier=None, allreduce=None,
+                         lengths=(50, 100, 200, 500, 1000, 2000, 5000)):
     """BASELINE config 5, the "vs edlib CPU" column: kernel (b'), unit-cost global edit distance (Myers/Hyyro bit-parallel,
     csrc/myers.cu) on pairs (x, mutate(x, 5 %)), distances only and with the path, next to the oracle's Myers restatement
-    on all host cores over a bounded sample (edlib itself is absent and has no call site in the reference)."""
-    import oracle
+    on all host cores over a bounded sample (edlib itself is absent and has no call site in the reference).
+    N > 1 (config 5 asks for 1/2/4/8 GPUs): pairs are independent, every rank runs its own shard of the same size (weak
+    scaling, no collective); the rates are the sum over ranks against the slowest rank's device time."""
     from isonform_b200 import hotpath, synth
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + rank)
     threads = os.cpu_count() or 1
     try:
         kc = json.load(open(os.path.join(ROOT, "profiles", "ncu_myers_constants.json")))["kernels"]
@@ -522,28 +524,38 @@ def run_c5_edit_distance(ctx, int32_peak, hbm_peak, lengths=(50, 100, 200, 500, 
         cat, off = hotpath.pack_sequences(base + muts)
         lens = np.diff(off)
         cells = float((lens[pa].astype(np.int64) * lens[pb]).sum())
-        row = {"len": L, "pairs": n_pairs}
+        row = {"len": L, "pairs": n_pairs * world, "n_gpus": world}
         for name, want in (("distance", False), ("path", True)):
             ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=want)
             ctx.profile_enable(True); ctx.profile_reset()
+            if barrier:
+                barrier()
             t0 = time.perf_counter()
             res = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=want)
             wall = time.perf_counter() - t0
             pr = ctx.profile(); ctx.profile_enable(False)
             dev_ms = pr["dp_ms"] + pr["traceback_ms"] + pr["other_ms"]
-            row[name] = {"device_ms": dev_ms, "dp_ms": pr["dp_ms"], "traceback_ms": pr["traceback_ms"],
-                         "device_gcups": cells / dev_ms / 1e6, "dp_gcups": cells / pr["dp_ms"] / 1e6,
-                         "device_pairs_per_s": n_pairs / dev_ms * 1e3, "host_pairs_per_s": n_pairs / wall}
+            dp_ms, tb_ms = pr["dp_ms"], pr["traceback_ms"]
+            cells_all, pairs_all = cells, float(n_pairs)
+            if allreduce and world > 1:
+                dev_ms, dp_ms, tb_ms, wall = allreduce([dev_ms, dp_ms, tb_ms, wall], "max")
+                cells_all, pairs_all = allreduce([cells, float(n_pairs)], "sum")
+            row[name] = {"device_ms": dev_ms, "dp_ms": dp_ms, "traceback_ms": tb_ms,
+                         "device_gcups": cells_all / dev_ms / 1e6, "dp_gcups": cells_all / dp_ms / 1e6,
+                         "device_pairs_per_s": pairs_all / dev_ms * 1e3, "host_pairs_per_s": pairs_all / wall}
         if kc and int32_peak:
             # distances only: INT32-ALU bound (ncu: ALU pipe 97 % of active cycles); with the path: bound by the trace write
             ops = kc["distance"]["alu_lane_ops_per_cell"]
-            row["distance"]["roofline"] = {"bound": "int32_alu", "achieved": row["distance"]["dp_gcups"] * 1e9 * ops / 1e12,
-                                           "peak": int32_peak / 1e12, "unit": "Tlane-op/s",
-                                           "frac": row["distance"]["dp_gcups"] * 1e9 * ops / int32_peak,
+            row["distance"]["roofline"] = {"bound": "int32_alu", "achieved": row["distance"]["dp_gcups"] * 1e9 * ops / 1e12 / world,
+                                           "peak": int32_peak / 1e12, "unit": "Tlane-op/s per GPU",
+                                           "frac": row["distance"]["dp_gcups"] * 1e9 * ops / int32_peak / world,
                                            "alu_lane_ops_per_cell": ops}
             gbs = 0.25 * cells / (row["path"]["dp_ms"] * 1e-3) / 1e9
             row["path"]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                        "algorithmic_bytes_per_cell": 0.25, "traffic_bytes_per_cell": kc["path"]["dram_bytes_per_cell"]}
+        if rank != 0:
+            continue
+        import oracle
         ns = int(max(200, min(n_pairs, 2e9 / (L * L))))
         oracle.edit_distance_pairs(cat, off, pa[:ns], pb[:ns], threads=threads)
         t0 = time.perf_counter()
@@ -682,11 +694,13 @@ def run_b200(args):
         del step
         torch.cuda.empty_cache()
         extras["config3"] = run_config3(ctx, rank, world, args.config3_clusters, barrier, allreduce)
+        c5e = run_c5_edit_distance(ctx, int32_peak, hbm_peak_early, rank, world, barrier, allreduce)
+        if rank == 0:
+            extras["C5_edit_distance"] = c5e
         if rank == 0 and world == 1:
             extras["e2e_entry"] = run_entry(ctx, wl)
             extras["seam_latency"] = run_seam_latency(ctx)
             extras["C5"] = run_c5_points(ctx)
-            extras["C5_edit_distance"] = run_c5_edit_distance(ctx, int32_peak, hbm_peak_early)
             extras["C4"] = run_c4_sample(ctx, dev)
 
     # ---- kernel (a) at super-batch scale (the C3 regime: many clusters' reads in one call); rank 0, untimed extra
