@@ -166,6 +166,7 @@ int isof_set_traceback_warp(isof_ctx *ctx, int mode)
 {
     if (!ctx || mode < 0 || mode > 2) return ISOF_ERR_ARG;
     ctx->tb_warp = mode;
+    ctx->ed_tb_warp = mode;            // kernel (b') has the same two walks (myers.cu)
     return ISOF_OK;
 }
 

@@ -32,6 +32,7 @@ struct isof_ctx {
     int band_w0 = 1024;               // half-width of the banded trace of long pairs beyond the free-end-gap diagonals; 0 = off
     int tb_warp = 2;                  // traceback of the regular path: 1 = one warp per pair (look-ahead), 0 = one thread per pair,
                                       // 2 = by chunk size (warp per pair up to 4096 pairs)
+    int ed_tb_warp = 2;               // kernel (b') traceback: 0 thread per pair, 1 warp per pair beyond 128 rows, 2 by pair count
     int short_mode = 1;               // short-pair regime: 0 never, 1 when the call is large enough to pay (default), 2 always
     // tie-break table of the restated aligner (isof_set_tiebreak); all zero = the library as restated
     int tb_h_e_before_f = 0, tb_gap_open_on_tie = 0, tb_end_col_first = 0, tb_swap_id = 0;

@@ -147,7 +147,8 @@ __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, 
         const unsigned long long cost = (unsigned long long)stripes * (unsigned long long)m;      // < 2^53
         keys[p] = ((unsigned long long)c << 56) | (0x00ffffffffffffffull - cost);        // ascending: big groups, long targets first
         idx[p] = (int32_t)p;
-        if (ops_words) ops_words[p] = ((n + m + 15) >> 4) + 1;                              // 2 bits per step of the path
+        // path scratch: 2 bits per step for the thread-per-pair walk, a byte per step for pairs that may take the warp walk
+        if (ops_words) ops_words[p] = (n > 128 ? ((n + m + 3) >> 2) : ((n + m + 15) >> 4)) + 1;
         atomicAdd(&s_cnt[c], 1u);
     }
     __syncthreads();
@@ -514,7 +515,75 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
     if (i > 0) count += (cur_op != 2u) ? 1 : 0;
     if (j > 0) count += (cur_op != 3u) ? 1 : 0;
     nruns64[pair] = count;
-    hdr[pair] = make_int4(steps, i, j, 0);
+    hdr[pair] = make_int4(steps, i, j, 0);                           // .w = 0: 2-bit steps
+}
+
+// One WARP per pair: lane k fetches the cell k steps down the diagonal, a ballot of the "diagonal is optimal" bits gives the
+// length of the diagonal stretch, the first lane that is off it holds the gap step -- one trip to DRAM covers up to 32 steps
+// of the walk instead of one to eight.  The look-ahead adapts as in the thread walk.  Steps are left as one BYTE each (lane
+// k writes step k of the stretch).  Taken when the chunk holds few enough pairs beyond 128 rows that a warp each still fills
+// the GPU (a 5 kb x 5 kb pair is 10 k dependent steps for a lone thread).
+__global__ void __launch_bounds__(128) ed_traceback_warp_kernel(const EdArgs a, const int64_t sidx0, const int64_t sidx1,
+                                                                 int64_t *__restrict__ nruns64, const int64_t *__restrict__ ops_off,
+                                                                 uint32_t *__restrict__ ops, int4 *__restrict__ hdr)
+{
+    const int64_t sidx = sidx0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (sidx >= sidx1) return;
+    const int pair = a.order[sidx];
+    if (a.dist[pair] < 0) {
+        if (lane == 0) {
+            nruns64[pair] = 0;
+            hdr[pair] = make_int4(0, 0, 0, 1);
+        }
+        return;
+    }
+    const EdDesc d = a.desc[pair];
+    const int c = d.lane0_cls >> 8;
+    const int W = ED_W[c], lane0 = d.lane0_cls & 255;
+    const int rows_stripe = (32 * W) << ED_LGG[c];
+    const bool multi = ED_LGG[c] == 5;
+    const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
+    int i = a.pn[pair], j = a.pm[pair];
+    uint8_t *out = reinterpret_cast<uint8_t *>(ops + ops_off[pair]);
+    int steps = 0, count = 0, kcur = 1;
+    uint32_t cur = 0xffu;
+    while (i > 0 && j > 0) {
+        const int kmax = min(kcur, min(i, j));
+        bool dg = false, up = false, eq = false;
+        if (lane < kmax) {
+            const int r = i - 1 - lane, jc = j - 1 - lane;
+            const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;
+            const int64_t ti = d.tbase + (((int64_t)s * d.m_max + jc) * 32 + lane0 + wi / W) * W + wi % W;
+            ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
+            const uint2 w = a.trace[ti];
+            const uint32_t bit = 1u << (r & 31);
+            dg = (w.x & bit) != 0;
+            up = (w.y & bit) != 0;
+            eq = q[r] == tg[jc];
+        }
+        const unsigned D = __ballot_sync(FULL, dg), U = __ballot_sync(FULL, up);
+        const int nd = min(kmax, D == FULL ? 32 : __ffs(~D) - 1);       // diagonal steps of this stretch
+        const bool gap = nd < kmax;                                      // lane nd holds a gap step
+        const bool gup = gap && ((U >> nd) & 1u);
+        const int nsteps = nd + (gap ? 1 : 0);
+        const uint32_t code = lane < nd ? (eq ? 0u : 1u) : (up ? 2u : 3u);
+        if (lane < nsteps) out[steps + lane] = (uint8_t)code;
+        uint32_t prev = __shfl_up_sync(FULL, code, 1);
+        if (lane == 0) prev = cur;
+        count += __popc(__ballot_sync(FULL, lane < nsteps && code != prev));
+        cur = __shfl_sync(FULL, code, nsteps - 1);
+        steps += nsteps;
+        i -= nd + (gup ? 1 : 0);
+        j -= nd + ((gap && !gup) ? 1 : 0);
+        kcur = gap ? 1 : min(32, kcur * 2);
+    }
+    if (lane == 0) {
+        if (i > 0) count += (cur != 2u) ? 1 : 0;
+        if (j > 0) count += (cur != 3u) ? 1 : 0;
+        nruns64[pair] = count;
+        hdr[pair] = make_int4(steps, i, j, 1);                           // .w = 1: a byte per step
+    }
 }
 
 __global__ void ed_runs_kernel(int64_t P, const int64_t *__restrict__ ops_off, const uint32_t *__restrict__ ops,
@@ -536,8 +605,14 @@ __global__ void ed_runs_kernel(int64_t P, const int64_t *__restrict__ ops_off, c
         cur_len = len;
     };
     for (int st = 0; st < h.x; ++st) {
-        if ((st & 15) == 0) word = in[st >> 4];
-        const uint32_t code = (word >> (2 * (st & 15))) & 3u;
+        uint32_t code;
+        if (h.w) {
+            if ((st & 3) == 0) word = in[st >> 2];
+            code = (word >> (8 * (st & 3))) & 3u;
+        } else {
+            if ((st & 15) == 0) word = in[st >> 4];
+            code = (word >> (2 * (st & 15))) & 3u;
+        }
         emit(code == 0u ? (uint32_t)ISOF_CIGAR_EQ : code == 1u ? (uint32_t)ISOF_CIGAR_X : code == 2u ? (uint32_t)ISOF_CIGAR_I
                                                                                                       : (uint32_t)ISOF_CIGAR_D, 1u);
     }
@@ -731,8 +806,15 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
             return h_lay->cls_start[c] + (int64_t)(t - h_lay->task_start[c]) * (32 >> h_lgg[c]);
         };
         const int64_t s0 = first_pair(a.t0), s1 = first_pair(a.t1);
+        // pairs beyond 128 rows (classes 0-9, first in the sorted order): a warp each while that still leaves the GPU
+        // enough walkers in flight; the rest one thread each
+        int64_t sw = std::min<int64_t>(s1, std::max<int64_t>(s0, h_lay->cls_start[10]));
+        if (ctx->ed_tb_warp == 0 || (ctx->ed_tb_warp == 2 && sw - s0 > (int64_t)ctx->sm_count * 512)) sw = s0;
         LaunchTimer lt(ctx, SLOT_TB);
-        ed_traceback_kernel<<<(unsigned)((s1 - s0 + 127) / 128), 128, 0, st>>>(a, s0, s1, nruns64, ops_off, ops, hdr);
+        if (sw > s0)
+            ed_traceback_warp_kernel<<<(unsigned)((sw - s0 + 3) / 4), 128, 0, st>>>(a, s0, sw, nruns64, ops_off, ops, hdr);
+        if (s1 > sw)
+            ed_traceback_kernel<<<(unsigned)((s1 - sw + 127) / 128), 128, 0, st>>>(a, sw, s1, nruns64, ops_off, ops, hdr);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     size_t tmp2 = 0;

@@ -19,11 +19,13 @@ def main():
     ap.add_argument("--lengths", default="50,100,200,500,1000,2000,5000")
     ap.add_argument("--cells", type=float, default=2e11)
     ap.add_argument("--err", type=float, default=0.05)
+    ap.add_argument("--tbwarp", type=int, default=2, help="isof_set_traceback_warp mode for the path walk")
     ap.add_argument("--related", type=float, default=0.25, help="fraction of pairs (x, noisy copy of x); the rest are unrelated")
     args = ap.parse_args()
     import oracle
     from isonform_b200 import _lib, hotpath, synth
     ctx = _lib.Context(0)
+    ctx.set_traceback_warp(args.tbwarp)
     rng = np.random.default_rng(5)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as fh:

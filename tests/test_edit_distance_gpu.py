@@ -300,3 +300,41 @@ def test_randomised_differential(ctx):
             else:
                 cost, i, j, ok = _apply(runs, q, t)
                 assert ok and i == len(q) and j == len(t) and cost == int(want[p]), (seed, p)
+
+
+def test_warp_walk_equals_thread_walk(ctx):
+    """The path walk has two forms (one warp per pair with a ballot over the diagonal look-ahead, one thread per pair);
+    isof_set_traceback_warp picks one or lets the pair count decide.  Same runs either way, also for multi-stripe pairs
+    and under a threshold k."""
+    rng = np.random.default_rng(44)
+    seqs = []
+    for n in [129, 130, 200, 255, 256, 400, 512, 513, 900, 1024, 1500, 2048, 3000, 4096, 4097, 7000]:
+        s = _rand(rng, n)
+        seqs += [s, _mutate(rng, s, 0.05), _mutate(rng, s, 0.35), s[: n // 2], _rand(rng, 60)]
+    cat, off = _pool(seqs)
+    S = len(seqs)
+    pa = rng.integers(0, S, 500).astype(np.int32)
+    pb = rng.integers(0, S, 500).astype(np.int32)
+    nb = np.arange(S - 1, dtype=np.int32)
+    pa = np.concatenate([pa, nb, nb + 1])
+    pb = np.concatenate([pb, nb + 1, nb])
+    out = {}
+    try:
+        for mode in (0, 1, 2):
+            ctx.set_traceback_warp(mode)
+            out[mode] = [ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True),
+                         ctx.edit_distance_pairs(cat, off, pa, pb, k=150, want_cigar=True)]
+    finally:
+        ctx.set_traceback_warp(2)
+    for mode in (1, 2):
+        for x in (0, 1):
+            assert (out[mode][x]["dist"] == out[0][x]["dist"]).all()
+            assert (out[mode][x]["cigar_off"] == out[0][x]["cigar_off"]).all()
+            assert (out[mode][x]["cigar"] == out[0][x]["cigar"]).all()
+    want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    assert (out[1][0]["dist"] == want).all()
+    for p in range(0, len(pa), 3):
+        q, t = seqs[pa[p]], seqs[pb[p]]
+        if len(q) * len(t) <= 2_000_000:
+            runs = out[1][0]["cigar"][out[1][0]["cigar_off"][p]:out[1][0]["cigar_off"][p + 1]]
+            assert runs.tolist() == oracle.edit_path(q, t)[1].tolist(), p
