@@ -77,7 +77,7 @@ ISOF_API int isof_set_band(isof_ctx *ctx, int half_width);
  * pair (light, latency-bound: fits the gaps of a pipelined step); mode 2 (default) = warp per pair for chunks of up to 4096
  * pairs (small calls, long reads), thread per pair beyond.  Same results in every mode.  The path walk of
  * isof_edit_distance_pairs follows the same switch (warp per pair for pairs beyond 128 rows; mode 2: while the call holds
- * at most 512 x SMs of them). */
+ * at most 128 x SMs of them). */
 ISOF_API int isof_set_traceback_warp(isof_ctx *ctx, int mode);
 /* Host-buffer calls of at most 32 small pairs (trace <= 200 KB each, i.e. up to ~500 x 500) run as ONE fused launch: base
  * codes, DP, traceback and features in one kernel with the trace in shared memory and inputs / outputs in mapped pinned

@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
 // ---------------------------------------------------------------------------------------------------------------
 // traceback: one thread per pair walks the trace ONCE and leaves the path as 2-bit steps (16 per word, walk order) in a
 // small per-pair scratch plus its run count; after the scan of the counts ed_runs_kernel turns the steps into runs at
-// their final place (alignment order).  The walk is bound by 32-byte sector traffic on a trace that does not fit L2, so
-// it is not repeated -- and a chunked call needs its DP only once.
+// their final place (alignment order).  The walk reads a trace that does not fit L2, so it is not repeated -- and a
+// chunked call needs its DP only once.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const int64_t sidx1, int64_t *__restrict__ nruns64,
                                     const int64_t *__restrict__ ops_off, uint32_t *__restrict__ ops, int4 *__restrict__ hdr)
@@ -470,44 +470,27 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
         acc |= code << (2 * (steps & 15));
         if ((++steps & 15) == 0) { out[(steps >> 4) - 1] = acc; acc = 0u; }
     };
-    // Most steps are diagonal, so the cells of the next steps ALONG THE DIAGONAL are fetched together (independent loads,
-    // one latency) and consumed while the path stays on it; a gap step ends the batch.  The look-ahead doubles after a
-    // batch that was consumed whole and starts over after a gap: unrelated pairs waste no sectors, noisy copies run 8 deep.
-    constexpr int TBK = 8;
+    // A plain dependent walk: fetching the next cells along the diagonal ahead of time (look-ahead 1 -> 8) was measured
+    // slower at every length, related or unrelated pairs (100 bp: 7.0 vs 2.9 ms per 2 M pairs) -- with this many walkers in
+    // flight the kernel is bound by issue slots and occupancy (38 vs 64 registers), not by one walker's latency.  Calls of
+    // few long pairs, where latency does bind, take ed_traceback_warp_kernel.
     const bool multi = ED_LGG[c] == 5;
-    int kcur = 1;
     while (i > 0 && j > 0) {
-        uint2 w[TBK];
-        bool eqc[TBK];
-        const int kmax = min(kcur, min(i, j));
-#pragma unroll
-        for (int k = 0; k < TBK; ++k) {
-            if (k < kmax) {
-                const int r = i - 1 - k;
-                const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;       // word of the stripe
-                const int jc = j - 1 - k;
-                const int64_t ti = d.tbase + (((int64_t)s * d.m_max + jc) * 32 + lane0 + wi / W) * W + wi % W;
-                ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
-                w[k] = a.trace[ti];
-                eqc[k] = q[r] == tg[jc];
-            }
-        }
-        kcur = min(TBK, kcur * 2);
-        bool on = true;                                                // still on the prefetched diagonal
-#pragma unroll
-        for (int k = 0; k < TBK; ++k) {                                // no break: w[] and eqc[] stay in registers
-            if (on && k < kmax) {
-                const uint32_t bit = 1u << ((i - 1) & 31);
-                if (w[k].x & bit) {
-                    step(eqc[k] ? 0u : 1u);
-                    --i; --j;
-                } else {
-                    if (w[k].y & bit) { step(2u); --i; }
-                    else { step(3u); --j; }
-                    kcur = 1;
-                    on = false;
-                }
-            }
+        const int r = i - 1, jc = j - 1;
+        const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;           // word of the stripe
+        const int64_t ti = d.tbase + (((int64_t)s * d.m_max + jc) * 32 + lane0 + wi / W) * W + wi % W;
+        ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
+        const uint2 w = a.trace[ti];
+        const uint32_t bit = 1u << (r & 31);
+        if (w.x & bit) {
+            step(q[r] == tg[jc] ? 0u : 1u);
+            --i; --j;
+        } else if (w.y & bit) {
+            step(2u);
+            --i;
+        } else {
+            step(3u);
+            --j;
         }
     }
     if (steps & 15) out[steps >> 4] = acc;
@@ -521,8 +504,8 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
 // One WARP per pair: lane k fetches the cell k steps down the diagonal, a ballot of the "diagonal is optimal" bits gives the
 // length of the diagonal stretch, the first lane that is off it holds the gap step -- one trip to DRAM covers up to 32 steps
 // of the walk instead of one to eight.  The look-ahead adapts as in the thread walk.  Steps are left as one BYTE each (lane
-// k writes step k of the stretch).  Taken when the chunk holds few enough pairs beyond 128 rows that a warp each still fills
-// the GPU (a 5 kb x 5 kb pair is 10 k dependent steps for a lone thread).
+// k writes step k of the stretch).  Taken when the chunk holds so few pairs beyond 128 rows (at most 128 x SMs) that one
+// thread each would leave the GPU waiting on single walkers (a 5 kb x 5 kb pair is 10 k dependent steps).
 __global__ void __launch_bounds__(128) ed_traceback_warp_kernel(const EdArgs a, const int64_t sidx0, const int64_t sidx1,
                                                                  int64_t *__restrict__ nruns64, const int64_t *__restrict__ ops_off,
                                                                  uint32_t *__restrict__ ops, int4 *__restrict__ hdr)
@@ -809,7 +792,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
         // pairs beyond 128 rows (classes 0-9, first in the sorted order): a warp each while that still leaves the GPU
         // enough walkers in flight; the rest one thread each
         int64_t sw = std::min<int64_t>(s1, std::max<int64_t>(s0, h_lay->cls_start[10]));
-        if (ctx->ed_tb_warp == 0 || (ctx->ed_tb_warp == 2 && sw - s0 > (int64_t)ctx->sm_count * 512)) sw = s0;
+        if (ctx->ed_tb_warp == 0 || (ctx->ed_tb_warp == 2 && sw - s0 > (int64_t)ctx->sm_count * 128)) sw = s0;
         LaunchTimer lt(ctx, SLOT_TB);
         if (sw > s0)
             ed_traceback_warp_kernel<<<(unsigned)((sw - s0 + 3) / 4), 128, 0, st>>>(a, s0, sw, nruns64, ops_off, ops, hdr);
