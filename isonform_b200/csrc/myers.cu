@@ -48,7 +48,7 @@ struct EdLayout {                          // written on the device, read back o
 
 struct EdDesc {                            // where the traceback finds a pair's trace
     int64_t tbase;                         // uint2 index of the task's trace inside the chunk
-    int32_t m_max;                         // column pitch of the task
+    int32_t n_blk;                         // column pitch of the task in blocks of four columns
     int32_t lane0_cls;                     // first lane of the pair's group | class << 8
 };
 
@@ -62,7 +62,7 @@ struct EdArgs {
     int64_t trace_base;                    // task_off of the chunk's first task
     int64_t trace_cap;                     // uint2 elements behind `trace`
     int32_t t0, t1;                        // tasks of this launch
-    int32_t n_sym, lb_words;
+    int32_t n_sym, lb_words, stg_words;     // per-warp shared memory: Eq tables | line buffer | trace staging
     int32_t *dist;
     EdDesc *desc;
     int32_t k;
@@ -190,7 +190,7 @@ __global__ void ed_task_kernel(EdLayout *lay, const int32_t *__restrict__ order,
         int64_t stripes;
         ed_class_of(pn[pair], &stripes);
         if (stripes > 1) atomicMax(&lay->max_m_multi, pm[pair]);
-        if (want_trace) words = stripes * (int64_t)pm[pair] * 32 * ED_W[c];
+        if (want_trace) words = stripes * (int64_t)((pm[pair] + 3) & ~3) * 32 * ED_W[c];      // columns in blocks of four
     }
     task_words[t] = words;
 }
@@ -252,7 +252,7 @@ __device__ __forceinline__ void ed_load_eq(const uint32_t *p, uint32_t (&e)[W])
 
 template <int G, int W, bool TRACE>
 __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const int c, uint32_t *__restrict__ peq,
-                                            uint32_t *__restrict__ lb, const int lane)
+                                            uint32_t *__restrict__ lb, uint4 *__restrict__ stg, const int lane)
 {
     constexpr int PPT = 32 / G;
     constexpr int RL = 32 * W;                                         // rows per lane
@@ -274,6 +274,7 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
     const bool cut = a.k >= 0 && abs(n - m) > a.k;
     if (cut) m = 0;
     const int m_max = (int)__reduce_max_sync(FULL, (unsigned)m);
+    const int n_blk = (m_max + 3) >> 2;                                // trace pitch: blocks of four columns
     const int ns = (G == 32) ? max(1, (int)(((int64_t)n + 32 * RL - 1) / (32 * RL))) : 1;     // G == 32: one pair per warp, uniform
     const int64_t tbase = TRACE ? a.task_off[t] - a.trace_base : 0;
     const uint32_t *codes32 = reinterpret_cast<const uint32_t *>(a.codes);
@@ -305,6 +306,7 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
                     const uint32_t w0 = codes32[ad >> 2], w1 = codes32[(ad >> 2) + 1];
                     c4 = __funnelshift_r(w0, w1, ((unsigned)ad & 3u) * 8u);
                 }
+                uint32_t tdg[TRACE ? 4 : 1][W], tpv[TRACE ? 4 : 1][W];      // the block's trace bits
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j4 + u;
@@ -359,26 +361,40 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
                         if (TRACE) dg[w] = eq0[w] | (ph[w] & ~(pv[w] | mv[w])) | (pv[w] & ~(ph[w] | mh[w]));
                         mv[w] = act ? mvn : mv[w];
                     }
-                    if (TRACE && act) {
-                        // one coalesced row of 256 * W bytes per warp and column.  (Blocks of four columns per 32-byte sector
-                        // cut the traceback's DRAM reads 4x but made these stores 16-byte pieces at a 128-byte stride: the DP
-                        // ran 1.7x slower and the walk, which is latency-bound, gained 15 %.)
-                        const int64_t ti = tbase + (((int64_t)s * m_max + j) * 32 + lane) * W;
-                        ISOF_ASSERT(ti + W <= a.trace_cap, CHK_TRACE_STORE);
-                        if constexpr (W == 4) {
-                            uint4 *dst = reinterpret_cast<uint4 *>(a.trace + ti);
-                            dst[0] = make_uint4(dg[0], pvn[0], dg[1], pvn[1]);
-                            dst[1] = make_uint4(dg[2], pvn[2], dg[3], pvn[3]);
-                        } else if constexpr (W == 2) {
-                            *reinterpret_cast<uint4 *>(a.trace + ti) = make_uint4(dg[0], pvn[0], dg[1], pvn[1]);
-                        } else {
+                    if (TRACE) {
 #pragma unroll
-                            for (int w = 0; w < W; ++w) a.trace[ti + w] = make_uint2(dg[w], pvn[w]);
-                        }
+                        for (int w = 0; w < W; ++w) { tdg[u][w] = dg[w]; tpv[u][w] = pvn[w]; }
                     }
 #pragma unroll
                     for (int w = 0; w < W; ++w) pv[w] = act ? pvn[w] : pv[w];
                     if (G == 32 && wr) hist |= (((t2 >> 7) & 1u) | ((t2 >> 14) & 2u)) << (2 * (j & 15));
+                }
+                if (TRACE) {
+                    // Trace layout [stripe][block of 4 columns][lane][word][column] x (diag, up): the four columns of a
+                    // lane's word share a 32-byte sector, so a diagonal walk reads a quarter of the sectors.  A lane's share
+                    // of the block is 32 W contiguous bytes; stored straight from registers that is 16-byte pieces at a
+                    // 32 W-byte stride (measured: DP 1.7x slower).  So the block goes through shared memory -- each lane
+                    // parks its 2 W chunks of 16 bytes (swizzled by lane: conflict-free per quarter warp), then the warp
+                    // copies the 1024 W bytes out in rows of 512 contiguous bytes.
+                    constexpr int NC = 2 * W;                               // 16-byte chunks per lane
+                    uint4 *dst = reinterpret_cast<uint4 *>(a.trace + tbase) + (((int64_t)s * n_blk + (j4 >> 2)) * 32) * NC;
+                    ISOF_ASSERT(tbase + ((((int64_t)s * n_blk + (j4 >> 2)) * 32) + 32) * NC * 2 <= a.trace_cap, CHK_TRACE_STORE);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const int c0 = 2 * w, c1 = 2 * w + 1;
+                        const int p0 = (NC & (NC - 1)) == 0 ? (c0 ^ (lane & (NC - 1))) : (c0 + lane) % NC;
+                        const int p1 = (NC & (NC - 1)) == 0 ? (c1 ^ (lane & (NC - 1))) : (c1 + lane) % NC;
+                        stg[lane * NC + p0] = make_uint4(tdg[0][w], tpv[0][w], tdg[1][w], tpv[1][w]);
+                        stg[lane * NC + p1] = make_uint4(tdg[2][w], tpv[2][w], tdg[3][w], tpv[3][w]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int rw = 0; rw < NC; ++rw) {
+                        const int p = rw * 32 + lane, lsrc = p / NC, cp = p % NC;
+                        const int cl = (NC & (NC - 1)) == 0 ? (cp ^ (lsrc & (NC - 1))) : (cp + NC - lsrc % NC) % NC;
+                        dst[lsrc * NC + cl] = stg[p];
+                    }
+                    __syncwarp();
                 }
             }
             if (G == 32 && wr) {
@@ -402,7 +418,7 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
         int dist = m + acc;                                            // D(0,m) = m, then down the last column
         if (cut || (a.k >= 0 && dist > a.k)) dist = -1;
         a.dist[pair] = dist;
-        if (TRACE) a.desc[pair] = EdDesc{tbase, m_max, (slot * G) | (c << 8)};
+        if (TRACE) a.desc[pair] = EdDesc{tbase, n_blk, (slot * G) | (c << 8)};
     }
 }
 
@@ -414,24 +430,25 @@ __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = a.t0 + blockIdx.x * (blockDim.x >> 5) + warp;
     if (t >= a.t1) return;
-    uint32_t *peq = ed_smem + (size_t)warp * (a.n_sym * 128 + a.lb_words);       // sized for W = 4; 16-byte aligned (lb_words % 4 == 0)
+    uint32_t *peq = ed_smem + (size_t)warp * (a.n_sym * 128 + a.lb_words + a.stg_words);   // Eq sized for W = 4; all 16-byte aligned
     uint32_t *lb = peq + a.n_sym * 128;
+    uint4 *stg = reinterpret_cast<uint4 *>(lb + a.lb_words);
     const int c = ed_task_class(a.lay, t);
     switch (c) {
-    case 0: ed_run_task<32, 4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 1: ed_run_task<32, 3, TRACE>(a, t, c, peq, lb, lane); break;
-    case 2: ed_run_task<16, 4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 3: ed_run_task<16, 3, TRACE>(a, t, c, peq, lb, lane); break;
-    case 4: ed_run_task<8, 4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 5: ed_run_task<8, 3, TRACE>(a, t, c, peq, lb, lane); break;
-    case 6: ed_run_task<4, 4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 7: ed_run_task<4, 3, TRACE>(a, t, c, peq, lb, lane); break;
-    case 8: ed_run_task<2, 4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 9: ed_run_task<2, 3, TRACE>(a, t, c, peq, lb, lane); break;
-    case 10: ed_run_task<1, 4, TRACE>(a, t, c, peq, lb, lane); break;
-    case 11: ed_run_task<1, 3, TRACE>(a, t, c, peq, lb, lane); break;
-    case 12: ed_run_task<1, 2, TRACE>(a, t, c, peq, lb, lane); break;
-    default: ed_run_task<1, 1, TRACE>(a, t, c, peq, lb, lane); break;
+    case 0: ed_run_task<32, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 1: ed_run_task<32, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 2: ed_run_task<16, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 3: ed_run_task<16, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 4: ed_run_task<8, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 5: ed_run_task<8, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 6: ed_run_task<4, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 7: ed_run_task<4, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 8: ed_run_task<2, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 9: ed_run_task<2, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 10: ed_run_task<1, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 11: ed_run_task<1, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    case 12: ed_run_task<1, 2, TRACE>(a, t, c, peq, lb, stg, lane); break;
+    default: ed_run_task<1, 1, TRACE>(a, t, c, peq, lb, stg, lane); break;
     }
 }
 
@@ -478,7 +495,7 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
     while (i > 0 && j > 0) {
         const int r = i - 1, jc = j - 1;
         const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;           // word of the stripe
-        const int64_t ti = d.tbase + (((int64_t)s * d.m_max + jc) * 32 + lane0 + wi / W) * W + wi % W;
+        const int64_t ti = d.tbase + ((((int64_t)s * d.n_blk + (jc >> 2)) * 32 + lane0 + wi / W) * W + wi % W) * 4 + (jc & 3);
         ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
         const uint2 w = a.trace[ti];
         const uint32_t bit = 1u << (r & 31);
@@ -537,7 +554,7 @@ __global__ void __launch_bounds__(128) ed_traceback_warp_kernel(const EdArgs a, 
         if (lane < kmax) {
             const int r = i - 1 - lane, jc = j - 1 - lane;
             const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;
-            const int64_t ti = d.tbase + (((int64_t)s * d.m_max + jc) * 32 + lane0 + wi / W) * W + wi % W;
+            const int64_t ti = d.tbase + ((((int64_t)s * d.n_blk + (jc >> 2)) * 32 + lane0 + wi / W) * W + wi % W) * 4 + (jc & 3);
             ISOF_ASSERT(ti < a.trace_cap, CHK_TRACE_LOAD);
             const uint2 w = a.trace[ti];
             const uint32_t bit = 1u << (r & 31);
@@ -716,7 +733,8 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     const int n_sym = std::max(h_lay->n_sym, 1);
     const int lb_words = h_lay->max_m_multi > 0 ? (((h_lay->max_m_multi + 15) / 16 + 1 + 3) & ~3) : 0;
     const int64_t total_words = *h_total, total_ops = want_path ? h_total[1] : 0;
-    const size_t smem_warp = ((size_t)n_sym * 128 + (size_t)lb_words) * sizeof(uint32_t);
+    const int stg_words = want_path ? 1024 : 0;                            // 1024 W bytes of trace staging per warp, W <= 4
+    const size_t smem_warp = ((size_t)n_sym * 128 + (size_t)lb_words + (size_t)stg_words) * sizeof(uint32_t);
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(ED_WARPS, (200 * 1024) / smem_warp));
     const size_t smem = smem_warp * wpb;
     if (smem > 200 * 1024)
@@ -728,7 +746,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     EdArgs a;
     a.codes = codes; a.off = d_off; a.pa = d_pa; a.pb = d_pb; a.order = order; a.pn = pn; a.pm = pm; a.lay = lay;
-    a.task_off = task_off; a.trace = nullptr; a.trace_base = 0; a.trace_cap = 0; a.t0 = 0; a.t1 = T; a.n_sym = n_sym; a.lb_words = lb_words;
+    a.task_off = task_off; a.trace = nullptr; a.trace_base = 0; a.trace_cap = 0; a.t0 = 0; a.t1 = T; a.n_sym = n_sym; a.lb_words = lb_words; a.stg_words = stg_words;
     a.dist = d_dist; a.desc = nullptr; a.k = k;
     if (!want_path) return ed_launch_dp(ctx, a, false, smem_warp, wpb);
 
