@@ -338,3 +338,39 @@ def test_warp_walk_equals_thread_walk(ctx):
         if len(q) * len(t) <= 2_000_000:
             runs = out[1][0]["cigar"][out[1][0]["cigar_off"][p]:out[1][0]["cigar_off"][p + 1]]
             assert runs.tolist() == oracle.edit_path(q, t)[1].tolist(), p
+
+
+def test_extreme_shapes(ctx):
+    """Corners of the layout: a 256-symbol pool with paths (one warp per block: 128 KB of match vectors), a multi-stripe
+    query against a much longer target (line buffer of 20 k columns), empty sides in every class, a one-row query against
+    a long target and the transpose."""
+    rng = np.random.default_rng(2)
+    allb = bytes(range(256))
+    seqs = [allb, allb[::-1], bytes(rng.integers(0, 256, 700).astype(np.uint8)), bytes(rng.integers(0, 256, 150).astype(np.uint8))]
+    cat, off = _pool(seqs)
+    pa = np.array([0, 0, 1, 2, 3, 2], np.int32)
+    pb = np.array([1, 0, 2, 3, 2, 2], np.int32)
+    r = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+    for p in range(len(pa)):
+        d, runs = oracle.edit_path(seqs[pa[p]], seqs[pb[p]])
+        assert int(r["dist"][p]) == d
+        assert r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]].tolist() == runs.tolist()
+    big = _rand(rng, 5000)
+    long_t = _mutate(rng, big, 0.1) + _rand(rng, 15000)
+    seqs = [big, long_t, "", "A", _rand(rng, 40), _rand(rng, 200), _rand(rng, 1000), _rand(rng, 4500)]
+    cat, off = _pool(seqs)
+    S = len(seqs)
+    pa = np.repeat(np.arange(S, dtype=np.int32), S)
+    pb = np.tile(np.arange(S, dtype=np.int32), S)
+    want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    for mode in (0, 1):
+        ctx.set_traceback_warp(mode)
+        try:
+            r = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+        finally:
+            ctx.set_traceback_warp(2)
+        assert (r["dist"] == want).all()
+        for p in range(len(pa)):
+            q, t = seqs[pa[p]], seqs[pb[p]]
+            cost, i, j, ok = _apply(r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]], q, t)
+            assert ok and i == len(q) and j == len(t) and cost == int(want[p]), (mode, p)
