@@ -56,6 +56,9 @@ ISOF_API int isof_version(void);
 ISOF_API int isof_init(int device, isof_ctx **ctx);
 ISOF_API int isof_destroy(isof_ctx *ctx);
 ISOF_API const char *isof_last_error(const isof_ctx *ctx);
+/* Device scratch is grow-only (a call that needed a 50 GB trace keeps it for the next one).  This returns all of it to the
+ * device -- after synchronising the ctx's streams -- e.g. between the stages of an in-process run that shares the GPU. */
+ISOF_API int isof_release_scratch(isof_ctx *ctx);
 /* Use an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream, so that
  * the caller's CUDA events bracket the library's kernels.  NULL restores the ctx-owned stream. */
 ISOF_API int isof_set_stream(isof_ctx *ctx, void *cuda_stream);

@@ -35,7 +35,7 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_fused_phases", "isof_set_band", "isof_set_traceback_warp", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
+EXPORTS = ["isof_version", "isof_init", "isof_destroy", "isof_last_error", "isof_release_scratch", "isof_set_stream", "isof_set_trace_budget", "isof_set_packed", "isof_set_overlap", "isof_set_tiebreak", "isof_set_short", "isof_set_fused_small", "isof_debug_fused_phases", "isof_set_band", "isof_set_traceback_warp", "isof_debug_violations", "isof_debug_selftest", "isof_debug_set_span_hash_mask",
            "isof_profile_enable", "isof_profile_reset", "isof_profile_get", "isof_int32_peak", "isof_minimizers_batch",
            "isof_minimizers_batch_dev", "isof_spans_batch", "isof_spans_multi", "isof_spans_batch_dev", "isof_sg_align_pairs", "isof_sg_align_pairs_dev", "isof_sg_align_batch",
            "isof_sg_features_pairs", "isof_edit_distance_pairs", "isof_edit_distance_pairs_dev", "isof_wis_picks", "isof_span_instances", "isof_poa_consensus"]
@@ -63,6 +63,7 @@ def load(debug=False):
     L.isof_destroy.argtypes = [vp]
     L.isof_last_error.argtypes = [vp]
     L.isof_last_error.restype = C.c_char_p
+    L.isof_release_scratch.argtypes = [vp]
     L.isof_set_stream.argtypes = [vp, vp]
     L.isof_set_trace_budget.argtypes = [vp, C.c_size_t]
     L.isof_set_packed.argtypes = [vp, C.c_int]
@@ -156,6 +157,10 @@ class Context:
         return rc
 
     # ------------------------------------------------------------------ plumbing
+    def release_scratch(self):
+        """Return the ctx's grow-only device scratch to the device (synchronises first)."""
+        self._check(self._L.isof_release_scratch(self._h))
+
     def set_stream(self, cuda_stream):
         self._check(self._L.isof_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 

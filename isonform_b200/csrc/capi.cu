@@ -130,6 +130,21 @@ int isof_destroy(isof_ctx *ctx)
     return ISOF_OK;
 }
 
+int isof_release_scratch(isof_ctx *ctx)
+{
+    if (!ctx) return ISOF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &as : ctx->aux_stream) if (as) CUDA_TRY(ctx, cudaStreamSynchronize(as));
+    for (DevBuf *b : ctx->all_bufs()) {
+        if (b->p) CUDA_TRY(ctx, cudaFree(b->p));
+        b->p = nullptr;
+        b->cap = 0;
+    }
+    ctx->trace_free_at_first_use = 0;          // the automatic trace budget is taken again from what is free at the next call
+    return ISOF_OK;
+}
+
 const char *isof_last_error(const isof_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 
 int isof_set_stream(isof_ctx *ctx, void *cuda_stream)

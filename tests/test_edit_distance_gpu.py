@@ -374,3 +374,29 @@ def test_extreme_shapes(ctx):
             q, t = seqs[pa[p]], seqs[pb[p]]
             cost, i, j, ok = _apply(r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]], q, t)
             assert ok and i == len(q) and j == len(t) and cost == int(want[p]), (mode, p)
+
+
+def test_release_scratch_returns_memory_and_calls_still_work():
+    """isof_release_scratch gives the grow-only device scratch back (a traced call of 2 GB here) and the next calls of
+    both aligners simply allocate again with identical results."""
+    import torch
+    from isonform_b200 import _lib, hotpath
+    c = _lib.Context(0)
+    try:
+        rng = np.random.default_rng(3)
+        seqs = [_rand(rng, 2000) for _ in range(64)]
+        cat, off = _pool(seqs)
+        pa = rng.integers(0, 64, 2000).astype(np.int32)
+        pb = rng.integers(0, 64, 2000).astype(np.int32)
+        a = c.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+        b1 = hotpath.align_pairs(seqs, pa[:100], pb[:100], 2, -2, 12, 1, c)
+        free_before = torch.cuda.mem_get_info(0)[0]
+        c.release_scratch()
+        free_after = torch.cuda.mem_get_info(0)[0]
+        assert free_after - free_before > (1 << 30)
+        a2 = c.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+        b2 = hotpath.align_pairs(seqs, pa[:100], pb[:100], 2, -2, 12, 1, c)
+        assert (a["dist"] == a2["dist"]).all() and (a["cigar"] == a2["cigar"]).all()
+        assert (b1["score"] == b2["score"]).all() and (b1["cigar"] == b2["cigar"]).all()
+    finally:
+        c.close()
