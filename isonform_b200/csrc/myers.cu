@@ -30,12 +30,20 @@ namespace {
 
 constexpr int ED_WARPS = 4;                // warps per block of the DP kernel (fewer when the symbol tables are large)
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int ED_NC = 14;                  // classes: (lanes per pair G, words per lane W)
+constexpr int ED_NC = 48;                  // class ids: (5 - lg2 G) * 8 + (8 - W); lanes per pair G = 1..32, words per lane W = 1..8
+constexpr int ED_MAXW_DIST = 8;            // words per lane: distances only
+constexpr int ED_MAXW_PATH = 4;            // with the trace (its block of four columns is buffered in registers)
 
-// class -> lg2(G), W.  Biggest first; a pair of n rows holds ceil(n/32) words: up to 4 stay in ONE thread (G = 1, W = their
-// number), more are spread over the smallest power-of-two group whose lanes then hold 3 or 4 words each.
-__device__ __constant__ const int8_t ED_LGG[ED_NC] = {5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 0, 0, 0, 0};
-__device__ __constant__ const int8_t ED_W[ED_NC] = {4, 3, 4, 3, 4, 3, 4, 3, 4, 3, 4, 3, 2, 1};
+// Biggest first.  A pair of n rows holds ceil(n/32) words: up to max_w stay in ONE thread (G = 1, W = their number), more are
+// spread over the smallest power-of-two group whose lanes then hold more than max_w / 2 words each.
+__host__ __device__ __forceinline__ int ed_lgg(int c) { return 5 - (c >> 3); }
+__host__ __device__ __forceinline__ int ed_w(int c) { return 8 - (c & 7); }
+// widest W of a call: the match vectors Eq[symbol][lane][word] of a warp must fit shared memory (256 symbols x 8 words would
+// be 256 KB), and the traced kernel buffers a block of four columns in registers
+__host__ __device__ __forceinline__ int ed_max_w(int n_sym, bool trace)
+{
+    return trace ? ED_MAXW_PATH : (n_sym <= 64 ? ED_MAXW_DIST : ED_MAXW_PATH);
+}
 
 struct EdLayout {                          // written on the device, read back once per call
     int32_t cls_start[ED_NC + 1];          // sorted position where class c starts
@@ -62,7 +70,7 @@ struct EdArgs {
     int64_t trace_base;                    // task_off of the chunk's first task
     int64_t trace_cap;                     // uint2 elements behind `trace`
     int32_t t0, t1;                        // tasks of this launch
-    int32_t n_sym, lb_words, stg_words;     // per-warp shared memory: Eq tables | line buffer | trace staging
+    int32_t n_sym, eq_words, lb_words, stg_words;     // per-warp shared memory: Eq tables | line buffer | trace staging
     int32_t *dist;
     EdDesc *desc;
     int32_t k;
@@ -111,25 +119,26 @@ __global__ void ed_encode_kernel(const uint8_t *__restrict__ cat, int64_t n_base
 // ---------------------------------------------------------------------------------------------------------------
 // plan: lengths, class (group size, words per lane), sort key
 // ---------------------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int ed_class_of(int64_t n, int64_t *stripes)
+__host__ __device__ __forceinline__ int ed_class_of(int64_t n, int max_w, int64_t *stripes)
 {
     const int64_t wt = (n + 31) >> 5;                                  // words of the query
     *stripes = 1;
-    if (wt <= 4) return wt <= 1 ? 13 : (int)(14 - wt);                // one thread per pair: W = 1..4 -> class 13..10
-    const int64_t ns = (wt + 127) >> 7;                                // stripes of at most 128 words (32 lanes x 4)
-    const int pw = (int)((wt + ns - 1) / ns);                          // words per stripe, 5..128
+    if (wt <= max_w) return 5 * 8 + (8 - (wt < 1 ? 1 : (int)wt));      // one thread per pair
+    const int64_t ns = (wt + 32 * max_w - 1) / (32 * max_w);           // stripes of at most 32 lanes x max_w words
+    const int pw = (int)((wt + ns - 1) / ns);                          // words per stripe
     int lg = 1;
-    while ((4 << lg) < pw) ++lg;                                       // smallest group with <= 4 words per lane
-    const int w = (pw + (1 << lg) - 1) >> lg;                          // 3 or 4
+    while ((max_w << lg) < pw) ++lg;                                   // smallest group with <= max_w words per lane
+    const int w = (pw + (1 << lg) - 1) >> lg;
     *stripes = (n + ((int64_t)1024 * w) - 1) / ((int64_t)1024 * w);    // as the kernel counts them (G = 32 only when > 1)
-    return (5 - lg) * 2 + (4 - w);
+    return (5 - lg) * 8 + (8 - w);
 }
 
 __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, const int32_t *__restrict__ pa,
                                const int32_t *__restrict__ pb, int64_t P, int32_t *__restrict__ pn, int32_t *__restrict__ pm,
                                unsigned long long *__restrict__ keys, int32_t *__restrict__ idx, unsigned int *__restrict__ cnt,
-                               EdLayout *lay, int64_t *__restrict__ ops_words)
+                               EdLayout *lay, int64_t *__restrict__ ops_words, int want_trace)
 {
+    const int max_w = ed_max_w(lay->n_sym, want_trace != 0);
     __shared__ unsigned int s_cnt[ED_NC];
     if (threadIdx.x < ED_NC) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -143,7 +152,7 @@ __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, 
         pn[p] = (int32_t)n;
         pm[p] = (int32_t)m;
         int64_t stripes;
-        const int c = ed_class_of(n, &stripes);
+        const int c = ed_class_of(n, max_w, &stripes);
         const unsigned long long cost = (unsigned long long)stripes * (unsigned long long)m;      // < 2^53
         keys[p] = ((unsigned long long)c << 56) | (0x00ffffffffffffffull - cost);        // ascending: big groups, long targets first
         idx[p] = (int32_t)p;
@@ -161,7 +170,7 @@ __global__ void ed_layout_kernel(const unsigned int *__restrict__ cnt, EdLayout 
     for (int c = 0; c < ED_NC; ++c) {
         lay->cls_start[c] = cs;
         lay->task_start[c] = ts;
-        const int32_t per = 32 >> ED_LGG[c];                                              // pairs per task = 32 / G
+        const int32_t per = 32 >> ed_lgg(c);                                              // pairs per task = 32 / G
         cs += (int32_t)cnt[c];
         ts += ((int32_t)cnt[c] + per - 1) / per;
     }
@@ -186,11 +195,11 @@ __global__ void ed_task_kernel(EdLayout *lay, const int32_t *__restrict__ order,
     int64_t words = 0;
     if (t < lay->task_start[ED_NC]) {
         const int c = ed_task_class(lay, (int)t);
-        const int pair = order[lay->cls_start[c] + ((int)t - lay->task_start[c]) * (32 >> ED_LGG[c])];
+        const int pair = order[lay->cls_start[c] + ((int)t - lay->task_start[c]) * (32 >> ed_lgg(c))];
         int64_t stripes;
-        ed_class_of(pn[pair], &stripes);
+        ed_class_of(pn[pair], ed_max_w(lay->n_sym, want_trace != 0), &stripes);
         if (stripes > 1) atomicMax(&lay->max_m_multi, pm[pair]);
-        if (want_trace) words = stripes * (int64_t)((pm[pair] + 3) & ~3) * 32 * ED_W[c];      // columns in blocks of four
+        if (want_trace) words = stripes * (int64_t)((pm[pair] + 3) & ~3) * 32 * ed_w(c);      // columns in blocks of four
     }
     task_words[t] = words;
 }
@@ -198,7 +207,7 @@ __global__ void ed_task_kernel(EdLayout *lay, const int32_t *__restrict__ order,
 // ---------------------------------------------------------------------------------------------------------------
 // the DP
 // ---------------------------------------------------------------------------------------------------------------
-// s = x + y over W words; returns the carry out of the top word
+// s = x + y over W words; returns the carry out of the top word (one add.cc / addc.cc chain)
 template <int W>
 __device__ __forceinline__ uint32_t ed_add(const uint32_t (&x)[W], const uint32_t (&y)[W], uint32_t (&s)[W])
 {
@@ -206,17 +215,19 @@ __device__ __forceinline__ uint32_t ed_add(const uint32_t (&x)[W], const uint32_
     if constexpr (W == 1)
         asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(s[0]), "=r"(co) : "r"(x[0]), "r"(y[0]));
     else if constexpr (W == 2)
-        asm("add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 %1, %4, %6;\n\taddc.u32 %2, 0, 0;"
-            : "=r"(s[0]), "=r"(s[1]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(y[0]), "r"(y[1]));
+        asm("add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 %1, %4, %6;\n\taddc.u32 %2, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(y[0]), "r"(y[1]));
     else if constexpr (W == 3)
-        asm("add.cc.u32 %0, %4, %7;\n\taddc.cc.u32 %1, %5, %8;\n\taddc.cc.u32 %2, %6, %9;\n\taddc.u32 %3, 0, 0;"
-            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(co)
-            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(y[0]), "r"(y[1]), "r"(y[2]));
-    else
-        asm("add.cc.u32 %0, %5, %9;\n\taddc.cc.u32 %1, %6, %10;\n\taddc.cc.u32 %2, %7, %11;\n\taddc.cc.u32 %3, %8, %12;\n\t"
-            "addc.u32 %4, 0, 0;"
-            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(co)
-            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+        asm("add.cc.u32 %0, %4, %7;\n\taddc.cc.u32 %1, %5, %8;\n\taddc.cc.u32 %2, %6, %9;\n\taddc.u32 %3, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(y[0]), "r"(y[1]), "r"(y[2]));
+    else if constexpr (W == 4)
+        asm("add.cc.u32 %0, %5, %9;\n\taddc.cc.u32 %1, %6, %10;\n\taddc.cc.u32 %2, %7, %11;\n\taddc.cc.u32 %3, %8, %12;\n\taddc.u32 %4, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+    else if constexpr (W == 5)
+        asm("add.cc.u32 %0, %6, %11;\n\taddc.cc.u32 %1, %7, %12;\n\taddc.cc.u32 %2, %8, %13;\n\taddc.cc.u32 %3, %9, %14;\n\taddc.cc.u32 %4, %10, %15;\n\taddc.u32 %5, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]));
+    else if constexpr (W == 6)
+        asm("add.cc.u32 %0, %7, %13;\n\taddc.cc.u32 %1, %8, %14;\n\taddc.cc.u32 %2, %9, %15;\n\taddc.cc.u32 %3, %10, %16;\n\taddc.cc.u32 %4, %11, %17;\n\taddc.cc.u32 %5, %12, %18;\n\taddc.u32 %6, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]));
+    else if constexpr (W == 7)
+        asm("add.cc.u32 %0, %8, %15;\n\taddc.cc.u32 %1, %9, %16;\n\taddc.cc.u32 %2, %10, %17;\n\taddc.cc.u32 %3, %11, %18;\n\taddc.cc.u32 %4, %12, %19;\n\taddc.cc.u32 %5, %13, %20;\n\taddc.cc.u32 %6, %14, %21;\n\taddc.u32 %7, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]));
+    else if constexpr (W == 8)
+        asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\taddc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\taddc.u32 %8, 0, 0;" : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(co) : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
     return co;
 }
 
@@ -230,20 +241,33 @@ __device__ __forceinline__ void ed_add_carry(uint32_t (&s)[W], uint32_t c)
         asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(s[0]), "+r"(s[1]) : "r"(c));
     else if constexpr (W == 3)
         asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 %2, %2, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]) : "r"(c));
-    else
-        asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;"
-            : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]) : "r"(c));
+    else if constexpr (W == 4)
+        asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]) : "r"(c));
+    else if constexpr (W == 5)
+        asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]) : "r"(c));
+    else if constexpr (W == 6)
+        asm("add.cc.u32 %0, %0, %6;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.cc.u32 %4, %4, 0;\n\taddc.u32 %5, %5, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]) : "r"(c));
+    else if constexpr (W == 7)
+        asm("add.cc.u32 %0, %0, %7;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.u32 %6, %6, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]) : "r"(c));
+    else if constexpr (W == 8)
+        asm("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.u32 %7, %7, 0;" : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]) : "r"(c));
 }
 
 template <int W>
 __device__ __forceinline__ void ed_load_eq(const uint32_t *p, uint32_t (&e)[W])
 {
-    if constexpr (W == 4) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(p);
-        e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
-    } else if constexpr (W == 2) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(p);
-        e[0] = v.x; e[1] = v.y;
+    if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int w = 0; w < W; w += 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + w);
+            e[w] = v.x; e[w + 1] = v.y; e[w + 2] = v.z; e[w + 3] = v.w;
+        }
+    } else if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int w = 0; w < W; w += 2) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(p + w);
+            e[w] = v.x; e[w + 1] = v.y;
+        }
     } else {
 #pragma unroll
         for (int w = 0; w < W; ++w) e[w] = p[w];
@@ -430,26 +454,23 @@ __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = a.t0 + blockIdx.x * (blockDim.x >> 5) + warp;
     if (t >= a.t1) return;
-    uint32_t *peq = ed_smem + (size_t)warp * (a.n_sym * 128 + a.lb_words + a.stg_words);   // Eq sized for W = 4; all 16-byte aligned
-    uint32_t *lb = peq + a.n_sym * 128;
+    uint32_t *peq = ed_smem + (size_t)warp * (a.eq_words + a.lb_words + a.stg_words);   // Eq sized for the widest W; all 16-byte aligned
+    uint32_t *lb = peq + a.eq_words;
     uint4 *stg = reinterpret_cast<uint4 *>(lb + a.lb_words);
     const int c = ed_task_class(a.lay, t);
+    // class id -> (G, W); the traced kernel only ever sees W <= ED_MAXW_PATH
+#define ED_CASE(G_, W_)                                                                                        \
+    case ((5 - (G_ == 32 ? 5 : G_ == 16 ? 4 : G_ == 8 ? 3 : G_ == 4 ? 2 : G_ == 2 ? 1 : 0)) * 8 + (8 - W_)):      \
+        if constexpr (!TRACE || W_ <= ED_MAXW_PATH) ed_run_task<G_, W_, TRACE>(a, t, c, peq, lb, stg, lane);        \
+        break;
+#define ED_CASES(G_) ED_CASE(G_, 8) ED_CASE(G_, 7) ED_CASE(G_, 6) ED_CASE(G_, 5) ED_CASE(G_, 4) ED_CASE(G_, 3)
     switch (c) {
-    case 0: ed_run_task<32, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 1: ed_run_task<32, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 2: ed_run_task<16, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 3: ed_run_task<16, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 4: ed_run_task<8, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 5: ed_run_task<8, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 6: ed_run_task<4, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 7: ed_run_task<4, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 8: ed_run_task<2, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 9: ed_run_task<2, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 10: ed_run_task<1, 4, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 11: ed_run_task<1, 3, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    case 12: ed_run_task<1, 2, TRACE>(a, t, c, peq, lb, stg, lane); break;
-    default: ed_run_task<1, 1, TRACE>(a, t, c, peq, lb, stg, lane); break;
+        ED_CASES(32) ED_CASES(16) ED_CASES(8) ED_CASES(4) ED_CASES(2)
+        ED_CASES(1) ED_CASE(1, 2) ED_CASE(1, 1)
+    default: break;
     }
+#undef ED_CASES
+#undef ED_CASE
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -473,8 +494,8 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
         return;
     }
     const EdDesc d = a.desc[pair];
-    const int W = ED_W[c], lane0 = d.lane0_cls & 255;
-    const int rows_stripe = (32 * W) << ED_LGG[c];
+    const int W = ed_w(c), lane0 = d.lane0_cls & 255;
+    const int rows_stripe = (32 * W) << ed_lgg(c);
     const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
     int i = a.pn[pair], j = a.pm[pair];
     uint32_t *out = ops + ops_off[pair];
@@ -491,7 +512,7 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
     // slower at every length, related or unrelated pairs (100 bp: 7.0 vs 2.9 ms per 2 M pairs) -- with this many walkers in
     // flight the kernel is bound by issue slots and occupancy (38 vs 64 registers), not by one walker's latency.  Calls of
     // few long pairs, where latency does bind, take ed_traceback_warp_kernel.
-    const bool multi = ED_LGG[c] == 5;
+    const bool multi = ed_lgg(c) == 5;
     while (i > 0 && j > 0) {
         const int r = i - 1, jc = j - 1;
         const int s = multi ? r / rows_stripe : 0, wi = (r - s * rows_stripe) >> 5;           // word of the stripe
@@ -540,9 +561,9 @@ __global__ void __launch_bounds__(128) ed_traceback_warp_kernel(const EdArgs a, 
     }
     const EdDesc d = a.desc[pair];
     const int c = d.lane0_cls >> 8;
-    const int W = ED_W[c], lane0 = d.lane0_cls & 255;
-    const int rows_stripe = (32 * W) << ED_LGG[c];
-    const bool multi = ED_LGG[c] == 5;
+    const int W = ed_w(c), lane0 = d.lane0_cls & 255;
+    const int rows_stripe = (32 * W) << ed_lgg(c);
+    const bool multi = ed_lgg(c) == 5;
     const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
     int i = a.pn[pair], j = a.pm[pair];
     uint8_t *out = reinterpret_cast<uint8_t *>(ops + ops_off[pair]);
@@ -652,7 +673,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     DevBuf *B = ctx->b_ed;
     TRY(dev_reserve(ctx, B[0], (size_t)n_bases + 32));                       // codes
-    TRY(dev_reserve(ctx, B[1], 512));                                        // present[8] | cnt[ED_NC] | lut[256]
+    TRY(dev_reserve(ctx, B[1], 512));                                        // present[8] | cnt[ED_NC] at +32 B | lut[256] at +256 B
     TRY(dev_reserve(ctx, B[2], sizeof(EdLayout)));
     TRY(dev_reserve(ctx, B[3], sizeof(int32_t) * (size_t)P));                // pn
     TRY(dev_reserve(ctx, B[4], sizeof(int32_t) * (size_t)P));                // pm
@@ -661,7 +682,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     TRY(dev_reserve(ctx, B[7], sizeof(int64_t) * (size_t)(P + 1) * 2));      // task_words | task_off
     uint8_t *codes = (uint8_t *)B[0].p;
     unsigned int *present = (unsigned int *)B[1].p, *cnt = present + 8;
-    uint8_t *lut = (uint8_t *)(present + 32);
+    uint8_t *lut = (uint8_t *)(present + 64);
     EdLayout *lay = (EdLayout *)B[2].p;
     int32_t *pn = (int32_t *)B[3].p, *pm = (int32_t *)B[4].p;
     unsigned long long *keys = (unsigned long long *)B[5].p, *keys_out = keys + P;
@@ -692,16 +713,17 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
-        ed_plan_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_off, n_seqs, d_pa, d_pb, P, pn, pm, keys, idx, cnt, lay, ops_words);
+        ed_plan_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_off, n_seqs, d_pa, d_pb, P, pn, pm, keys, idx, cnt, lay, ops_words,
+                                                                    want_path ? 1 : 0);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     size_t tmp_sort = 0, tmp_scan = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 60, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 62, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, task_words, task_off, (int)(P + 1), st);
     TRY(dev_reserve(ctx, B[8], std::max(tmp_sort, tmp_scan)));
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
-        CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(B[8].p, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 60, st));
+        CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(B[8].p, tmp_sort, keys, keys_out, idx, order, (int)P, 0, 62, st));
     }
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
@@ -722,7 +744,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     CUDA_TRY(ctx, cudaGetLastError());
     // ---- one read-back: layout + trace total
     EdLayout *h_lay = (EdLayout *)ctx->pinned;
-    int64_t *h_total = (int64_t *)((char *)ctx->pinned + 256);
+    int64_t *h_total = (int64_t *)((char *)ctx->pinned + 1024);
     CUDA_TRY(ctx, cudaMemcpyAsync(h_lay, lay, sizeof(EdLayout), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_total, task_off + P, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (want_path) CUDA_TRY(ctx, cudaMemcpyAsync(h_total + 1, ops_off + P, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -734,7 +756,8 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     const int lb_words = h_lay->max_m_multi > 0 ? (((h_lay->max_m_multi + 15) / 16 + 1 + 3) & ~3) : 0;
     const int64_t total_words = *h_total, total_ops = want_path ? h_total[1] : 0;
     const int stg_words = want_path ? 1024 : 0;                            // 1024 W bytes of trace staging per warp, W <= 4
-    const size_t smem_warp = ((size_t)n_sym * 128 + (size_t)lb_words + (size_t)stg_words) * sizeof(uint32_t);
+    const int eq_words = n_sym * 32 * ed_max_w(h_lay->n_sym, want_path);      // Eq[symbol][lane][word] at the widest W
+    const size_t smem_warp = ((size_t)eq_words + (size_t)lb_words + (size_t)stg_words) * sizeof(uint32_t);
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(ED_WARPS, (200 * 1024) / smem_warp));
     const size_t smem = smem_warp * wpb;
     if (smem > 200 * 1024)
@@ -746,7 +769,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     }
     EdArgs a;
     a.codes = codes; a.off = d_off; a.pa = d_pa; a.pb = d_pb; a.order = order; a.pn = pn; a.pm = pm; a.lay = lay;
-    a.task_off = task_off; a.trace = nullptr; a.trace_base = 0; a.trace_cap = 0; a.t0 = 0; a.t1 = T; a.n_sym = n_sym; a.lb_words = lb_words; a.stg_words = stg_words;
+    a.task_off = task_off; a.trace = nullptr; a.trace_base = 0; a.trace_cap = 0; a.t0 = 0; a.t1 = T; a.n_sym = n_sym; a.eq_words = eq_words; a.lb_words = lb_words; a.stg_words = stg_words;
     a.dist = d_dist; a.desc = nullptr; a.k = k;
     if (!want_path) return ed_launch_dp(ctx, a, false, smem_warp, wpb);
 
@@ -794,7 +817,6 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     a.trace = (uint2 *)B[11].p;
     a.trace_cap = std::max<int64_t>(need, 1);
     ctx->prof.trace_bytes += total_words * (int64_t)sizeof(uint2);
-    static const int h_lgg[ED_NC] = {5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 0, 0, 0, 0};          // ED_LGG on the host
     for (size_t x = 0; x + 1 < cuts.size(); ++x) {                     // per chunk: DP with the trace, then the walk
         a.t0 = cuts[x];
         a.t1 = cuts[x + 1];
@@ -804,7 +826,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
             if (t >= T) return P;
             int c = 0;
             while (c + 1 < ED_NC && t >= h_lay->task_start[c + 1]) ++c;
-            return h_lay->cls_start[c] + (int64_t)(t - h_lay->task_start[c]) * (32 >> h_lgg[c]);
+            return h_lay->cls_start[c] + (int64_t)(t - h_lay->task_start[c]) * (32 >> ed_lgg(c));
         };
         const int64_t s0 = first_pair(a.t0), s1 = first_pair(a.t1);
         // pairs beyond 128 rows (classes 0-9, first in the sorted order): a warp each while that still leaves the GPU

@@ -81,8 +81,9 @@ def test_distance_vs_oracle_all_group_sizes_and_stripes(ctx):
     boundaries, ragged targets inside a warp, similar and unrelated pairs."""
     rng = np.random.default_rng(101)
     seqs = [""]
-    edges = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049,
-             3100, 4097]
+    edges = [1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 159, 160, 161, 191, 192, 193, 223, 224, 225, 255, 256,
+             257, 320, 321, 384, 385, 448, 449, 511, 512, 513, 640, 641, 768, 897, 1023, 1024, 1025, 1281, 1537, 1793, 2047,
+             2048, 2049, 2561, 3100, 3585, 4097, 5121, 6145, 7169, 8191, 8192, 8193, 9000]
     for n in edges:
         s = _rand(rng, n)
         seqs += [s, _mutate(rng, s, 0.1), _mutate(rng, s, 0.3)]
@@ -256,6 +257,7 @@ def test_debug_build_assertions_stay_silent_for_myers():
             dctx.set_trace_budget(budget)
             r = dctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
             assert (r["dist"] == want).all()
+            assert (dctx.edit_distance_pairs(cat, off, pa, pb)["dist"] == want).all()
             for p in range(0, len(pa), 5):
                 cost, i, j, ok = _apply(r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]], seqs[pa[p]], seqs[pb[p]])
                 assert ok and i == len(seqs[pa[p]]) and j == len(seqs[pb[p]]) and cost == int(want[p])
@@ -289,6 +291,8 @@ def test_randomised_differential(ctx):
         r = ctx.edit_distance_pairs(cat, off, pa, pb, k=k, want_cigar=True)
         exp = want if k < 0 else np.where(want <= k, want, -1)
         assert (r["dist"] == exp).all(), seed
+        # distances only: another kernel instantiation (up to eight words per lane instead of four)
+        assert (ctx.edit_distance_pairs(cat, off, pa, pb, k=k)["dist"] == exp).all(), seed
         for p in range(P):
             runs = r["cigar"][r["cigar_off"][p]:r["cigar_off"][p + 1]]
             if exp[p] < 0:
@@ -363,6 +367,7 @@ def test_extreme_shapes(ctx):
     pa = np.repeat(np.arange(S, dtype=np.int32), S)
     pb = np.tile(np.arange(S, dtype=np.int32), S)
     want = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    assert (ctx.edit_distance_pairs(cat, off, pa, pb)["dist"] == want).all()
     for mode in (0, 1):
         ctx.set_traceback_warp(mode)
         try:
