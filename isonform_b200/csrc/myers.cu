@@ -374,6 +374,8 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
                     uint32_t dg[W], pvn[W];
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
+                        // (tried: the in-lane shifts of words 1.. as IMAD.HI + IMAD by a run-time 2, to move them from the
+                        // saturated ALU pipe to the idle FMA pipe -- 3 % slower: four instructions for two)
                         const uint32_t ph2 = __funnelshift_l(pcar, ph[w], 1);
                         const uint32_t mh2 = __funnelshift_l(mcar, mh[w], 1);
                         pcar = ph[w];
