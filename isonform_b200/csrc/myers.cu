@@ -6,22 +6,23 @@
 // aligner (sg_align.cu).
 //
 // Layout of the computation.  A pair (query of n rows, target of m columns) is owned by a GROUP of G = 1..32 lanes, lane
-// g holding rows 32g .. 32g+31 of the current stripe as one 32-bit word of the vertical-delta vectors Pv / Mv; a warp
-// carries 32/G pairs ("task"), sorted so that the pairs of a task have about the same m.  The G words are advanced as ONE
-// 32G-bit integer per column, not block by block: the only non-bitwise operations of the column step are
-//   * the addition (Eq & Pv) + Pv -- a multi-word carry chain, resolved with two warp ballots: every lane adds its words,
-//     votes "generates a carry" / "would propagate one", and the carries INTO all lanes fall out of one integer addition of
-//     the two ballot masks (carry-lookahead by the ALU's own adder);
-//   * the shifts Ph << 1, Mh << 1 -- bit 31 of the lane below, one shuffle for both.
-// So there is no wavefront skew, no fill and no drain: a column costs the same ~30 instructions whatever G is.  Queries
-// longer than 1024 rows run as stripes of 1024; the horizontal deltas of a stripe's bottom row (2 bits per column) go to
-// the next stripe through a line buffer in shared memory.  The distance is m + sum of the vertical deltas of the last
-// column (popcounts), no per-column score tracking.
-// Symbols: the bytes of the pool are renumbered densely (only values that occur), the match vectors Eq[symbol][lane] of a
-// stripe sit in shared memory, one conflict-free word load per column.
+// g holding W = 1..8 words (32 rows each) of the vertical-delta vectors Pv / Mv of the current stripe; a warp carries 32/G
+// pairs ("task"), sorted so that the pairs of a task have about the same m.  The G x W words are advanced as ONE wide
+// integer per column, not block by block: the only non-bitwise operations of the column step are
+//   * the addition (Eq & Pv) + Pv -- inside a lane an add.cc / addc.cc chain, across lanes two warp ballots: every lane
+//     votes "my words generate a carry" / "my words would propagate one", and the carries INTO all lanes fall out of one
+//     integer addition of the two ballot masks (carry-lookahead by the ALU's own adder);
+//   * the shifts Ph << 1, Mh << 1 -- bit 31 of the lane below, one shuffle for both, funnel shifts inside the lane.
+// So there is no wavefront skew, no fill and no drain, and the cross-lane part is amortised over up to 256 rows per lane.
+// Queries longer than 32 x 32 x W rows run as stripes; the horizontal deltas of a stripe's bottom row (2 bits per column)
+// go to the next stripe through a line buffer in shared memory.  The distance is m + sum of the vertical deltas of the
+// last column (popcounts), no per-column score tracking.
+// Symbols: the bytes of the pool are renumbered densely (only values that occur), the match vectors Eq[symbol][lane][word]
+// of a stripe sit in shared memory, conflict-free vector loads per column.
 // Path: per cell two bits -- "diagonal move is optimal" (match, or mismatch and D(i,j) = D(i-1,j-1) + 1) and "vertical
-// delta is +1" -- stored as one coalesced row of 256 W bytes per warp and column (0.25 B per cell); the traceback prefers
-// diagonal, then up ('I', consumes the query), then left ('D').
+// delta is +1" -- 0.25 B per cell, four columns of a lane's word per 32-byte sector, written through a shared-memory
+// transpose in rows of 512 contiguous bytes; the traceback prefers diagonal, then up ('I', consumes the query), then left
+// ('D'); one thread per pair, or one warp per pair (ballot over the diagonal look-ahead) for calls of few long pairs.
 #include "common.cuh"
 
 #include <cub/cub.cuh>
