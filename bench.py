@@ -693,8 +693,8 @@ def run_b200(args):
     if not args.no_extras:
         del step
         torch.cuda.empty_cache()
-        ctx.release_scratch()          # the primary step's trace lanes (up to 80 % of HBM for long reads) go back before the companions allocate theirs
         extras["config3"] = run_config3(ctx, rank, world, args.config3_clusters, barrier, allreduce)
+        ctx.release_scratch()          # the primary step's trace lanes (up to 80 % of HBM for long reads) go back before kernel (b') allocates its own
         c5e = run_c5_edit_distance(ctx, int32_peak, hbm_peak_early, rank, world, barrier, allreduce)
         ctx.release_scratch()
         if rank == 0:
