@@ -308,7 +308,8 @@ ISOF_API int isof_sg_features_pairs(isof_ctx *ctx, const uint8_t *seq_cat, const
  * 0.2): this entry point serves BASELINE config 5 (interval-pair sweep against a CPU Myers) and north_star's kernel (b);
  * the reference's decisions stay with isof_sg_* above.  query = pool[pair_a[p]] (rows), target = pool[pair_b[p]].
  * Bytes compare by value (case-sensitive, like edlib without additionalEqualities); empty sequences are allowed.
- *   k            < 0: no bound; else a distance above k is reported as -1 (and the pair gets no path), as edlib does
+ *   k            < 0: no bound; else a distance above k is reported as -1 (and the pair gets no path), as edlib does.  In
+ *                distance-only calls long pairs are then computed inside the band | i - j | <= k only (Ukkonen), exactly
  *   dist         per pair
  *   cigar_off    NULL: distances only (no trace is stored).  Else n_pairs+1 offsets into cigar_runs (filled even on
  *                ISOF_ERR_CAPACITY; cigar_runs may then be NULL to learn the size)

@@ -55,7 +55,7 @@ struct isof_ctx {
     DevBuf b_s_mread, b_s_mkey, b_s_mpolya, b_s_mcnt, b_s_moff, b_s_key1, b_s_key2, b_s_keyt, b_s_keyo, b_s_idx0, b_s_idx1,
         b_s_idx2, b_s_forb, b_s_head, b_s_bid, b_s_sorttmp, b_s_rbatch, b_sh_batchoff;
     DevBuf b_ed[16];                  // kernel (b'), myers.cu: codes, symbols, layout, plan, sort, tasks, trace, runs
-    DevBuf b_h_dist;
+    DevBuf b_h_dist, b_ed_eqg;
     DevBuf b_sh_minpos, b_sh_minoff, b_sh_rread, b_sh_rp1, b_sh_rp2, b_sh_rcount, b_sh_rbucket, b_sh_sorted, b_sh_boff, b_sh_bdrop;
     std::vector<DevBuf *> all_bufs()
     {
@@ -70,6 +70,7 @@ struct isof_ctx {
                 v.push_back(b);
         for (DevBuf &b : b_ed) v.push_back(&b);
         v.push_back(&b_h_dist);
+        v.push_back(&b_ed_eqg);
         return v;
     }
     void *fused_io = nullptr;         // mapped pinned memory of the fused tiny-call path (inputs | outputs)

@@ -17,6 +17,8 @@
 // Queries longer than 32 x 32 x W rows run as stripes; the horizontal deltas of a stripe's bottom row (2 bits per column)
 // go to the next stripe through a line buffer in shared memory.  The distance is m + sum of the vertical deltas of the
 // last column (popcounts), no per-column score tracking.
+// With a bound k (edlib's k) long pairs of distance-only calls run banded: a ring of lanes, one word each, slides down the
+// band | i - j | <= k (ed_run_banded).
 // Symbols: the bytes of the pool are renumbered densely (only values that occur), the match vectors Eq[symbol][lane][word]
 // of a stripe sit in shared memory, conflict-free vector loads per column.
 // Path: per cell two bits -- "diagonal move is optimal" (match, or mismatch and D(i,j) = D(i-1,j-1) + 1) and "vertical
@@ -68,6 +70,8 @@ struct EdArgs {
     const EdLayout *lay;
     const int64_t *task_off;
     uint2 *trace;
+    const uint32_t *eqg;                   // banded classes: match vectors of every pool sequence, [symbol][word], in global memory
+    int64_t eq_tw;                         // words per symbol plane
     int64_t trace_base;                    // task_off of the chunk's first task
     int64_t trace_cap;                     // uint2 elements behind `trace`
     int32_t t0, t1;                        // tasks of this launch
@@ -120,6 +124,23 @@ __global__ void ed_encode_kernel(const uint8_t *__restrict__ cat, int64_t n_base
 // ---------------------------------------------------------------------------------------------------------------
 // plan: lengths, class (group size, words per lane), sort key
 // ---------------------------------------------------------------------------------------------------------------
+// Banded class (Ukkonen): with a bound k only the cells | i - j | <= k can lie on a path of cost <= k, i.e. per column a
+// window of at most (2k >> 5) + 2 words of the query.  Such a pair runs on a RING of G lanes, one word each, that slides
+// down the query (ed_run_banded) -- when that is at least ~3x less work than all its words.  Class id: the unused (G, W = 1).
+__host__ __device__ __forceinline__ int ed_band_class(int64_t n, int64_t m, int k, int n_sym, bool trace)
+{
+    if (k < 0 || trace || n_sym > 8) return -1;
+    const int64_t dlen = n > m ? n - m : m - n;
+    if (dlen > k) return -1;
+    const int64_t bw = ((int64_t)2 * k >> 5) + 2;                      // words a column's window can touch
+    if (bw > 32) return -1;
+    int lg = 1;
+    while ((1 << lg) < bw) ++lg;
+    if (((n + 31) >> 5) < (int64_t)3 << lg) return -1;
+    return (5 - lg) * 8 + 7;
+}
+__host__ __device__ __forceinline__ bool ed_is_band(int c) { return (c & 7) == 7 && c < 40; }
+
 __host__ __device__ __forceinline__ int ed_class_of(int64_t n, int max_w, int64_t *stripes)
 {
     const int64_t wt = (n + 31) >> 5;                                  // words of the query
@@ -137,7 +158,7 @@ __host__ __device__ __forceinline__ int ed_class_of(int64_t n, int max_w, int64_
 __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, const int32_t *__restrict__ pa,
                                const int32_t *__restrict__ pb, int64_t P, int32_t *__restrict__ pn, int32_t *__restrict__ pm,
                                unsigned long long *__restrict__ keys, int32_t *__restrict__ idx, unsigned int *__restrict__ cnt,
-                               EdLayout *lay, int64_t *__restrict__ ops_words, int want_trace)
+                               EdLayout *lay, int64_t *__restrict__ ops_words, int want_trace, int k)
 {
     const int max_w = ed_max_w(lay->n_sym, want_trace != 0);
     __shared__ unsigned int s_cnt[ED_NC];
@@ -153,7 +174,9 @@ __global__ void ed_plan_kernel(const int64_t *__restrict__ off, int32_t n_seqs, 
         pn[p] = (int32_t)n;
         pm[p] = (int32_t)m;
         int64_t stripes;
-        const int c = ed_class_of(n, max_w, &stripes);
+        int c = ed_band_class(n, m, k, lay->n_sym, want_trace != 0);
+        if (c < 0) c = ed_class_of(n, max_w, &stripes);
+        else stripes = 1;
         const unsigned long long cost = (unsigned long long)stripes * (unsigned long long)m;      // < 2^53
         keys[p] = ((unsigned long long)c << 56) | (0x00ffffffffffffffull - cost);        // ascending: big groups, long targets first
         idx[p] = (int32_t)p;
@@ -197,8 +220,8 @@ __global__ void ed_task_kernel(EdLayout *lay, const int32_t *__restrict__ order,
     if (t < lay->task_start[ED_NC]) {
         const int c = ed_task_class(lay, (int)t);
         const int pair = order[lay->cls_start[c] + ((int)t - lay->task_start[c]) * (32 >> ed_lgg(c))];
-        int64_t stripes;
-        ed_class_of(pn[pair], ed_max_w(lay->n_sym, want_trace != 0), &stripes);
+        int64_t stripes = 1;
+        if (!ed_is_band(c)) ed_class_of(pn[pair], ed_max_w(lay->n_sym, want_trace != 0), &stripes);
         if (stripes > 1) atomicMax(&lay->max_m_multi, pm[pair]);
         if (want_trace) words = stripes * (int64_t)((pm[pair] + 3) & ~3) * 32 * ed_w(c);      // columns in blocks of four
     }
@@ -449,6 +472,111 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// banded classes
+// ---------------------------------------------------------------------------------------------------------------
+// Match vectors of every sequence of the pool, once per call: eqg[y * tw + (off[s] >> 5) + s + r] = rows 32r .. 32r+31 of
+// sequence s that hold symbol y (at most 8 symbols).  One warp per sequence.
+__global__ void ed_eqglobal_kernel(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int32_t n_seqs,
+                                   const EdLayout *lay, uint32_t *__restrict__ eqg, int64_t tw)
+{
+    if (lay->n_sym > 8) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t sq = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sq < n_seqs; sq += nwarps) {
+        const int64_t b = off[sq], len = off[sq + 1] - b, o = (b >> 5) + sq;
+        for (int64_t r = lane; r < ((len + 31) >> 5); r += 32) {
+            uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int nv = (int)min((int64_t)32, len - 32 * r);
+            for (int i = 0; i < nv; ++i) {
+                const uint32_t cd = codes[b + 32 * r + i];
+#pragma unroll
+                for (int y = 0; y < 8; ++y) e[y] |= (cd == (uint32_t)y ? 1u : 0u) << i;
+            }
+#pragma unroll
+            for (int y = 0; y < 8; ++y) eqg[y * tw + o + r] = e[y];
+        }
+    }
+}
+
+// One pair on a ring of G lanes, one 32-row word each: the window [ (j-k) >> 5, (j+k) >> 5 ] of query words slides down as
+// the column j advances; word r lives in lane r mod G.  Cells outside the band count as "large" (a word enters with Pv = all
+// ones, the chain's first word takes +1 from above): values never fall below the true ones and are exact wherever the
+// true distance is <= k.  The score is carried along the window's bottom row.
+template <int G>
+__device__ __forceinline__ void ed_run_banded(const EdArgs &a, const int t, const int c, const int lane)
+{
+    constexpr int PPT = 32 / G;
+    constexpr uint32_t GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    const int gl = lane % G, slot = lane / G, gbase = slot * G;
+    const EdLayout *lay = a.lay;
+    const int sidx = lay->cls_start[c] + (t - lay->task_start[c]) * PPT + slot;
+    const bool valid = sidx < lay->cls_start[c + 1];
+    int pair = -1, n = 0, m = 0;
+    int64_t tb = 0, oq = 0;
+    if (valid) {
+        pair = a.order[sidx];
+        n = a.pn[pair];
+        m = a.pm[pair];
+        const int qa = a.pa[pair];
+        oq = (a.off[qa] >> 5) + qa;
+        tb = a.off[a.pb[pair]];
+    }
+    const int k = a.k;
+    const int nw = (n + 31) >> 5;
+    const int m_max = (int)__reduce_max_sync(FULL, (unsigned)m);
+    uint32_t pv = ~0u, mv = 0u;
+    int whi_prev = -1, score = 0;
+    for (int j = 0; j < m_max; ++j) {
+        const bool act = j < m;                                        // uniform inside a group
+        const int wlo = max(j - k, 0) >> 5, whi = min(nw - 1, (j + k) >> 5);
+        const int r = wlo + ((gl - wlo) & (G - 1));                    // the window's word that lives in this lane
+        const bool in = act && r <= whi;
+        if (in && r > whi_prev) { pv = ~0u; mv = 0u; }                 // the word enters the band
+        const uint32_t ch = act ? a.codes[tb + j] : 0u;
+        const uint32_t eq = in ? a.eqg[ch * a.eq_tw + oq + r] : 0u;
+        const int p = r - wlo;                                         // position in the chain, 0 = top of the window
+        const uint32_t x = eq & pv;
+        uint32_t sum = x + pv;
+        const bool top = r == whi;
+        const unsigned gm = __ballot_sync(FULL, in && !top && sum < x);
+        const unsigned pk = __ballot_sync(FULL, in && !top && sum == 0xffffffffu);
+        const int s0 = wlo & (G - 1);                                  // ring -> chain order: rotate the group's votes
+        const uint32_t gs = (gm >> gbase) & GM, ps = (pk >> gbase) & GM;
+        const uint32_t gr = G == 32 ? __funnelshift_r(gs, gs, s0) : (((gs >> s0) | (gs << (G - s0))) & GM);
+        const uint32_t pr = G == 32 ? __funnelshift_r(ps, ps, s0) : (((ps >> s0) | (ps << (G - s0))) & GM);
+        const uint32_t cy = ((pr | gr) + gr) ^ pr;
+        sum += (cy >> p) & 1u;
+        const uint32_t xh = (sum ^ pv) | eq;
+        const uint32_t ph = mv | ~(xh | pv);
+        const uint32_t mh = pv & xh;
+        const uint32_t t2 = (ph >> 31) | ((mh >> 31) << 1);
+        const uint32_t below = __shfl_sync(FULL, t2, gbase + ((gl - 1) & (G - 1)));
+        const uint32_t tbits = __shfl_sync(FULL, t2, gbase + (whi & (G - 1)));
+        const uint32_t up = p == 0 ? 1u : below;                       // above the window: +1 per column
+        const uint32_t ph2 = (ph << 1) | (up & 1u), mh2 = (mh << 1) | (up >> 1);
+        const uint32_t xv = eq | mv;
+        if (in) {
+            pv = mh2 | ~(xv | ph2);
+            mv = ph2 & xv;
+        }
+        if (act) {
+            score += 32 * (whi - whi_prev) + (int)(tbits & 1u) - (int)(tbits >> 1);
+            whi_prev = whi;
+        }
+    }
+    // the last word holds row n-1 (m + k >= n); rows of that word beyond n are padding that never matches
+    const int nvl = n - 32 * (nw - 1);
+    const uint32_t padm = nvl >= 32 ? 0u : ~((1u << nvl) - 1u);
+    const int extra = __popc(pv & padm) - __popc(mv & padm);
+    const int ex = __shfl_sync(FULL, extra, gbase + ((nw - 1) & (G - 1)));
+    if (valid && gl == 0) {
+        int dist = score - ex;
+        if (dist > k) dist = -1;
+        a.dist[pair] = dist;
+    }
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
 {
@@ -470,6 +598,11 @@ __global__ void __launch_bounds__(ED_WARPS * 32) ed_dp_kernel(const EdArgs a)
     switch (c) {
         ED_CASES(32) ED_CASES(16) ED_CASES(8) ED_CASES(4) ED_CASES(2)
         ED_CASES(1) ED_CASE(1, 2) ED_CASE(1, 1)
+    case 0 * 8 + 7: if constexpr (!TRACE) ed_run_banded<32>(a, t, c, lane); break;
+    case 1 * 8 + 7: if constexpr (!TRACE) ed_run_banded<16>(a, t, c, lane); break;
+    case 2 * 8 + 7: if constexpr (!TRACE) ed_run_banded<8>(a, t, c, lane); break;
+    case 3 * 8 + 7: if constexpr (!TRACE) ed_run_banded<4>(a, t, c, lane); break;
+    case 4 * 8 + 7: if constexpr (!TRACE) ed_run_banded<2>(a, t, c, lane); break;
     default: break;
     }
 #undef ED_CASES
@@ -717,7 +850,15 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     {
         LaunchTimer lt(ctx, SLOT_OTHER);
         ed_plan_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_off, n_seqs, d_pa, d_pb, P, pn, pm, keys, idx, cnt, lay, ops_words,
-                                                                    want_path ? 1 : 0);
+                                                                    want_path ? 1 : 0, k);
+    }
+    const bool may_band = k >= 0 && !want_path;
+    const int64_t eq_tw = (n_bases >> 5) + n_seqs + 1;
+    if (may_band) {
+        TRY(dev_reserve(ctx, ctx->b_ed_eqg, sizeof(uint32_t) * 8 * (size_t)eq_tw));
+        LaunchTimer lt(ctx, SLOT_OTHER);
+        const int blocks = (int)std::min<int64_t>(((int64_t)n_seqs * 32 + 255) / 256 + 1, (int64_t)ctx->sm_count * 16);
+        ed_eqglobal_kernel<<<blocks, 256, 0, st>>>(codes, d_off, n_seqs, lay, (uint32_t *)ctx->b_ed_eqg.p, eq_tw);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     size_t tmp_sort = 0, tmp_scan = 0;
@@ -774,6 +915,7 @@ int isof_edit_distance_core(isof_ctx *ctx, const uint8_t *d_cat, const int64_t *
     a.codes = codes; a.off = d_off; a.pa = d_pa; a.pb = d_pb; a.order = order; a.pn = pn; a.pm = pm; a.lay = lay;
     a.task_off = task_off; a.trace = nullptr; a.trace_base = 0; a.trace_cap = 0; a.t0 = 0; a.t1 = T; a.n_sym = n_sym; a.eq_words = eq_words; a.lb_words = lb_words; a.stg_words = stg_words;
     a.dist = d_dist; a.desc = nullptr; a.k = k;
+    a.eqg = may_band ? (const uint32_t *)ctx->b_ed_eqg.p : nullptr; a.eq_tw = eq_tw;
     if (!want_path) return ed_launch_dp(ctx, a, false, smem_warp, wpb);
 
     // ---- path: trace chunks

@@ -405,3 +405,26 @@ def test_release_scratch_returns_memory_and_calls_still_work():
         assert (b1["score"] == b2["score"]).all() and (b1["cigar"] == b2["cigar"]).all()
     finally:
         c.close()
+
+
+def test_banded_classes_under_a_bound_k(ctx):
+    """With a bound k, long pairs of similar length run on a ring of lanes that slides down the band | i - j | <= k
+    (ed_run_banded): exact whenever the distance is <= k, -1 otherwise.  Window widths 2 ... 32 words, words entering and
+    leaving the ring, lengths around word borders, targets shorter and longer than the query, pairs far above the bound."""
+    rng = np.random.default_rng(21)
+    seqs = []
+    for n in [161, 192, 200, 256, 500, 777, 1000, 1024, 1025, 2000, 3001, 4096, 5000, 9000]:
+        s = _rand(rng, n)
+        seqs += [s, _mutate(rng, s, 0.01), _mutate(rng, s, 0.03), _mutate(rng, s, 0.10), s[:-7], "ACG" + s, _rand(rng, n)]
+    cat, off = _pool(seqs)
+    S = len(seqs)
+    base = np.arange(0, S, 7, dtype=np.int32)
+    pa = np.concatenate([np.repeat(base, 7), np.repeat(base, 7) + np.tile(np.arange(7, dtype=np.int32), len(base))])
+    pb = np.concatenate([np.repeat(base, 7) + np.tile(np.arange(7, dtype=np.int32), len(base)), np.repeat(base, 7)])
+    full = oracle.edit_distance_pairs(cat, off, pa, pb, threads=8)
+    assert (ctx.edit_distance_pairs(cat, off, pa, pb)["dist"] == full).all()
+    for k in (0, 1, 3, 15, 16, 17, 31, 47, 64, 100, 200, 480, 495, 496, 600, 5000):
+        got = ctx.edit_distance_pairs(cat, off, pa, pb, k=k)["dist"]
+        want = np.where(full <= k, full, -1)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (k, [(int(p), len(seqs[pa[p]]), len(seqs[pb[p]]), int(got[p]), int(want[p])) for p in bad[:8]])
