@@ -21,8 +21,8 @@
 // band | i - j | <= k (ed_run_banded).
 // Symbols: the bytes of the pool are renumbered densely (only values that occur), the match vectors Eq[symbol][lane][word]
 // of a stripe sit in shared memory, conflict-free vector loads per column.
-// Path: per cell two bits -- "diagonal move is optimal" (match, or mismatch and D(i,j) = D(i-1,j-1) + 1) and "vertical
-// delta is +1" -- 0.25 B per cell, four columns of a lane's word per 32-byte sector, written through a shared-memory
+// Path: per cell two bits -- "diagonal move is optimal" (match, or mismatch and D(i,j) = D(i-1,j-1) + 1) and, on such a
+// cell, "mismatch", elsewhere "vertical delta is +1" -- 0.25 B per cell, four columns of a lane's word per 32-byte sector, written through a shared-memory
 // transpose in rows of 512 contiguous bytes; the traceback prefers diagonal, then up ('I', consumes the query), then left
 // ('D'); one thread per pair, or one warp per pair (ballot over the diagonal look-ahead) for calls of few long pairs.
 #include "common.cuh"
@@ -413,7 +413,9 @@ __device__ __forceinline__ void ed_run_task(const EdArgs &a, const int t, const 
                     }
                     if (TRACE) {
 #pragma unroll
-                        for (int w = 0; w < W; ++w) { tdg[u][w] = dg[w]; tpv[u][w] = pvn[w]; }
+                        // second bit: on a diagonal cell "mismatch", elsewhere "vertical delta is +1" -- the two bits name the
+                        // step (=, X, I, D) without a look at the sequences
+                        for (int w = 0; w < W; ++w) { tdg[u][w] = dg[w]; tpv[u][w] = (dg[w] & ~eq0[w]) | (~dg[w] & pvn[w]); }
                     }
 #pragma unroll
                     for (int w = 0; w < W; ++w) pv[w] = act ? pvn[w] : pv[w];
@@ -632,7 +634,6 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
     const EdDesc d = a.desc[pair];
     const int W = ed_w(c), lane0 = d.lane0_cls & 255;
     const int rows_stripe = (32 * W) << ed_lgg(c);
-    const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
     int i = a.pn[pair], j = a.pm[pair];
     uint32_t *out = ops + ops_off[pair];
     int64_t count = 0;
@@ -657,7 +658,7 @@ __global__ void ed_traceback_kernel(const EdArgs a, const int64_t sidx0, const i
         const uint2 w = a.trace[ti];
         const uint32_t bit = 1u << (r & 31);
         if (w.x & bit) {
-            step(q[r] == tg[jc] ? 0u : 1u);
+            step((w.y & bit) ? 1u : 0u);
             --i; --j;
         } else if (w.y & bit) {
             step(2u);
@@ -700,7 +701,6 @@ __global__ void __launch_bounds__(128) ed_traceback_warp_kernel(const EdArgs a, 
     const int W = ed_w(c), lane0 = d.lane0_cls & 255;
     const int rows_stripe = (32 * W) << ed_lgg(c);
     const bool multi = ed_lgg(c) == 5;
-    const uint8_t *q = a.codes + a.off[a.pa[pair]], *tg = a.codes + a.off[a.pb[pair]];
     int i = a.pn[pair], j = a.pm[pair];
     uint8_t *out = reinterpret_cast<uint8_t *>(ops + ops_off[pair]);
     int steps = 0, count = 0, kcur = 1;
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(128) ed_traceback_warp_kernel(const EdArgs a, 
             const uint32_t bit = 1u << (r & 31);
             dg = (w.x & bit) != 0;
             up = (w.y & bit) != 0;
-            eq = q[r] == tg[jc];
+            eq = !up;                                              // on a diagonal cell the second bit says "mismatch"
         }
         const unsigned D = __ballot_sync(FULL, dg), U = __ballot_sync(FULL, up);
         const int nd = min(kmax, D == FULL ? 32 : __ffs(~D) - 1);       // diagonal steps of this stretch
