@@ -471,10 +471,12 @@ def run_c4_sample(ctx, dev, n_reads=200):
             "band_pairs_retried": ctx.profile()["band_pairs_retried"]}
 
 
-def run_c5_points(ctx, lengths=(50, 100, 200, 500, 2000)):
-    """BASELINE config 5 at three-plus points: pairs (x, mutate(x, 5 %)), bubble scores, all kernels of the call."""
+def run_c5_points(ctx, rank=0, world=1, barrier=None, allreduce=None, lengths=(50, 100, 200, 500, 2000)):
+    """BASELINE config 5 at three-plus points: pairs (x, mutate(x, 5 %)), bubble scores, all kernels of the call.
+    N > 1: every rank aligns its own shard of the same size (pairs are independent: weak scaling, no collective); rates are
+    the sum over ranks against the slowest rank's time."""
     from isonform_b200 import hotpath, synth
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + rank)
     rows = []
     for L in lengths:
         nb = 2000
@@ -488,14 +490,20 @@ def run_c5_points(ctx, lengths=(50, 100, 200, 500, 2000)):
         cells = float((lens[pa].astype(np.int64) * lens[pb]).sum())
         ctx.sg_align_pairs(cat, off, pa, pb, 2, -8, 12, 1)
         ctx.profile_enable(True); ctx.profile_reset()
+        if barrier:
+            barrier()
         t0 = time.perf_counter()
         ctx.sg_align_pairs(cat, off, pa, pb, 2, -8, 12, 1)
         wall = time.perf_counter() - t0
         pr = ctx.profile(); ctx.profile_enable(False)
         dev_ms = pr["dp_ms"] + pr["traceback_ms"] + pr["other_ms"]
-        rows.append({"len": L, "pairs": n_pairs, "device_ms": dev_ms, "device_pairs_per_s": n_pairs / dev_ms * 1e3,
-                     "device_gcups": cells / dev_ms / 1e6, "host_pairs_per_s": n_pairs / wall, "dp_ms": pr["dp_ms"],
-                     "traceback_ms": pr["traceback_ms"]})
+        dp_ms, tb_ms, pairs_all = pr["dp_ms"], pr["traceback_ms"], float(n_pairs)
+        if allreduce and world > 1:
+            dev_ms, dp_ms, tb_ms, wall = allreduce([dev_ms, dp_ms, tb_ms, wall], "max")
+            cells, pairs_all = allreduce([cells, pairs_all], "sum")
+        rows.append({"len": L, "pairs": int(pairs_all), "n_gpus": world, "device_ms": dev_ms, "device_pairs_per_s": pairs_all / dev_ms * 1e3,
+                     "device_gcups": cells / dev_ms / 1e6, "host_pairs_per_s": pairs_all / wall, "dp_ms": dp_ms,
+                     "traceback_ms": tb_ms})
     return rows
 
 
@@ -697,12 +705,14 @@ def run_b200(args):
         ctx.release_scratch()          # the primary step's trace lanes (up to 80 % of HBM for long reads) go back before kernel (b') allocates its own
         c5e = run_c5_edit_distance(ctx, int32_peak, hbm_peak_early, rank, world, barrier, allreduce)
         ctx.release_scratch()
+        c5a = run_c5_points(ctx, rank, world, barrier, allreduce)
+        ctx.release_scratch()
         if rank == 0:
             extras["C5_edit_distance"] = c5e
+            extras["C5"] = c5a
         if rank == 0 and world == 1:
             extras["e2e_entry"] = run_entry(ctx, wl)
             extras["seam_latency"] = run_seam_latency(ctx)
-            extras["C5"] = run_c5_points(ctx)
             extras["C4"] = run_c4_sample(ctx, dev)
 
     # ---- kernel (a) at super-batch scale (the C3 regime: many clusters' reads in one call); rank 0, untimed extra
