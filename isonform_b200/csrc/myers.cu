@@ -752,12 +752,33 @@ __global__ void ed_runs_kernel(int64_t P, const int64_t *__restrict__ ops_off, c
     const uint32_t *in = ops + ops_off[p];
     int64_t wpos = cigar_off[p + 1] - 1;
     uint32_t cur_op = 0xffu, cur_len = 0, word = 0;
+    // Runs go out from the pair's last slot downwards.  One 4-byte store per run is one L2 sector operation each (ncu: 8x the
+    // sectors the bytes need), so four runs are gathered and an aligned group of slots leaves as one 16-byte store; the
+    // ragged groups at either end of the pair's range (shared with its neighbours) are written run by run.
+    const int64_t lo = cigar_off[p];
+    uint32_t g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+    int filled = 0;
+    const bool vec = (reinterpret_cast<uintptr_t>(cigar) & 15) == 0;     // a caller's device buffer need not be 16-byte aligned
+    auto put = [&](uint32_t run) {
+        ISOF_ASSERT(wpos >= lo, CHK_CIGAR_COPY);
+        const int idx = (int)(wpos & 3);
+        g0 = idx == 0 ? run : g0; g1 = idx == 1 ? run : g1; g2 = idx == 2 ? run : g2; g3 = idx == 3 ? run : g3;
+        ++filled;
+        if (idx == 0) {
+            if (filled == 4 && vec) *reinterpret_cast<uint4 *>(cigar + wpos) = make_uint4(g0, g1, g2, g3);
+            else {                                                     // the topmost group of the pair, not full
+                cigar[wpos] = g0;
+                if (filled > 1) cigar[wpos + 1] = g1;
+                if (filled > 2) cigar[wpos + 2] = g2;
+                if (filled > 3) cigar[wpos + 3] = g3;
+            }
+            filled = 0;
+        }
+        --wpos;
+    };
     auto emit = [&](uint32_t op, uint32_t len) {
         if (op == cur_op) { cur_len += len; return; }
-        if (cur_len) {
-            ISOF_ASSERT(wpos >= cigar_off[p], CHK_CIGAR_COPY);
-            cigar[wpos--] = (cur_len << 4) | cur_op;
-        }
+        if (cur_len) put((cur_len << 4) | cur_op);
         cur_op = op;
         cur_len = len;
     };
@@ -776,6 +797,13 @@ __global__ void ed_runs_kernel(int64_t P, const int64_t *__restrict__ ops_off, c
     if (h.y > 0) emit(ISOF_CIGAR_I, (uint32_t)h.y);
     if (h.z > 0) emit(ISOF_CIGAR_D, (uint32_t)h.z);
     emit(0xfeu, 0);                                                    // flush
+    // the lowest group of the pair, not reached down to its aligned start: slots wpos+1 .. wpos+filled
+    if (filled > 0) {
+        const int top = (int)((wpos + filled) & 3);                    // index of the group's highest filled slot
+        if (top == 3) cigar[wpos + filled] = g3;
+        if (top >= 2 && filled > top - 2) cigar[(wpos + filled) - (top - 2)] = g2;
+        if (top >= 1 && filled > top - 1) cigar[(wpos + filled) - (top - 1)] = g1;
+    }
 }
 
 int ed_launch_dp(isof_ctx *ctx, EdArgs &a, bool trace, size_t smem_warp, int wpb)

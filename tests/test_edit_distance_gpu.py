@@ -428,3 +428,37 @@ def test_banded_classes_under_a_bound_k(ctx):
         want = np.where(full <= k, full, -1)
         bad = np.nonzero(got != want)[0]
         assert len(bad) == 0, (k, [(int(p), len(seqs[pa[p]]), len(seqs[pb[p]]), int(got[p]), int(want[p])) for p in bad[:8]])
+
+
+def test_device_pointer_variant_with_an_unaligned_run_buffer(ctx):
+    """isof_edit_distance_pairs_dev on the caller's device buffers; the run buffer starts 4 bytes off a 16-byte boundary, so
+    the runs kernel must fall back from its 16-byte stores."""
+    import torch
+    rng = np.random.default_rng(91)
+    seqs = []
+    for _ in range(40):
+        s = _rand(rng, int(rng.integers(1, 900)))
+        seqs += [s, _mutate(rng, s, 0.2)]
+    cat, off = _pool(seqs)
+    pa = rng.integers(0, len(seqs), 600).astype(np.int32)
+    pb = rng.integers(0, len(seqs), 600).astype(np.int32)
+    ref = ctx.edit_distance_pairs(cat, off, pa, pb, want_cigar=True)
+    dev = torch.device("cuda", 0)
+    d_cat = torch.from_numpy(np.array(cat)).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_pa, d_pb = torch.from_numpy(pa).to(dev), torch.from_numpy(pb).to(dev)
+    d_dist = torch.empty(len(pa), dtype=torch.int32, device=dev)
+    d_coff = torch.empty(len(pa) + 1, dtype=torch.int64, device=dev)
+    cap = len(ref["cigar"]) + 8
+    for shift in (0, 1, 3):
+        d_buf = torch.zeros(cap + 4, dtype=torch.int32, device=dev)
+        d_cig = d_buf[shift:]
+        torch.cuda.synchronize()
+        total = ctx.edit_distance_pairs_dev(d_cat.data_ptr(), d_off.data_ptr(), len(seqs), len(cat), d_pa.data_ptr(), d_pb.data_ptr(),
+                                            len(pa), -1, d_dist.data_ptr(), d_cig.data_ptr(), cap, d_coff.data_ptr())
+        torch.cuda.synchronize()
+        assert total == len(ref["cigar"])
+        assert (d_dist.cpu().numpy() == ref["dist"]).all()
+        assert (d_coff.cpu().numpy() == ref["cigar_off"]).all()
+        assert (d_cig[:total].cpu().numpy().view(np.uint32) == ref["cigar"]).all()
+        assert int(d_buf[:shift].abs().sum()) == 0 and int(d_cig[total:].abs().sum()) == 0      # nothing written outside
