@@ -557,7 +557,10 @@ def run_c5_edit_distance(ctx, int32_peak, hbm_peak, rank=0, world=1, barrier=Non
             row["distance"]["roofline"] = {"bound": "int32_alu", "achieved": row["distance"]["dp_gcups"] * 1e9 * ops / 1e12 / world,
                                            "peak": int32_peak / 1e12, "unit": "Tlane-op/s per GPU",
                                            "frac": row["distance"]["dp_gcups"] * 1e9 * ops / int32_peak / world,
-                                           "alu_lane_ops_per_cell": ops}
+                                           "alu_lane_ops_per_cell": ops,
+                                           "note": "ops per cell from the ncu capture at 1000 bp (eight-word lanes, 4 lanes per pair); "
+                                                   "shorter pairs pad their words (50 bp: 50 of 64 rows) and execute more per useful cell, "
+                                                   "so their frac understates the pipe's occupancy"}
             gbs = 0.25 * cells / (row["path"]["dp_ms"] * 1e-3) / 1e9
             row["path"]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                        "algorithmic_bytes_per_cell": 0.25, "traffic_bytes_per_cell": kc["path"]["dram_bytes_per_cell"]}
