@@ -551,6 +551,20 @@ def run_c5_edit_distance(ctx, int32_peak, hbm_peak, rank=0, world=1, barrier=Non
             row[name] = {"device_ms": dev_ms, "dp_ms": dp_ms, "traceback_ms": tb_ms,
                          "device_gcups": cells_all / dev_ms / 1e6, "dp_gcups": cells_all / dp_ms / 1e6,
                          "device_pairs_per_s": pairs_all / dev_ms * 1e3, "host_pairs_per_s": pairs_all / wall}
+        if L >= 2000:
+            # the same distances under a bound k (edlib's k): long pairs then run inside the Ukkonen band | i - j | <= k
+            kb = int(min(480, 0.12 * L))
+            ctx.edit_distance_pairs(cat, off, pa, pb, k=kb)
+            ctx.profile_enable(True); ctx.profile_reset()
+            rk = ctx.edit_distance_pairs(cat, off, pa, pb, k=kb)
+            prk = ctx.profile(); ctx.profile_enable(False)
+            if not (rk["dist"] == np.where(res["dist"] <= kb, res["dist"], -1)).all():
+                raise SystemExit("banded edit-distance parity failure at L=%d" % L)
+            dpk = prk["dp_ms"]
+            if allreduce and world > 1:
+                dpk = allreduce([dpk], "max")[0]
+            row["distance_bounded"] = {"k": kb, "dp_ms": dpk, "speedup_vs_unbounded": row["distance"]["dp_ms"] / dpk,
+                                       "within_k": float((rk["dist"] >= 0).mean())}
         if kc and int32_peak:
             # distances only: INT32-ALU bound (ncu: ALU pipe 97 % of active cycles); with the path: bound by the trace write
             ops = kc["distance"]["alu_lane_ops_per_cell"]
