@@ -76,6 +76,25 @@ def test_known_answers(ctx):
         assert r["cigar"] == oracle.cigar_runs_to_string(oracle.edit_path(a, b)[1]), (a, b)
 
 
+def test_golden_vectors(ctx):
+    """tests/golden/edit_distance.json (pure-Python Wagner-Fischer, scripts/make_edit_golden.py): distances, paths, and the
+    distances again under a bound."""
+    from conftest import load_golden
+    from isonform_b200 import hotpath
+    g = load_golden("edit_distance.json")["cases"]
+    seqs = [c["query"] for c in g] + [c["target"] for c in g]
+    pa = list(range(len(g)))
+    pb = [len(g) + i for i in pa]
+    got = hotpath.edit_distance_pairs(seqs, pa, pb, task="path", ctx=ctx)
+    for c, r in zip(g, got):
+        assert r["editDistance"] == c["distance"] and r["cigar"] == (c["cigar"] or ""), (len(c["query"]), len(c["target"]))
+    plain = hotpath.edit_distance_pairs(seqs, pa, pb, ctx=ctx)
+    assert [r["editDistance"] for r in plain] == [c["distance"] for c in g]
+    for k in (0, 10, 60):
+        bounded = hotpath.edit_distance_pairs(seqs, pa, pb, k=k, ctx=ctx)
+        assert [r["editDistance"] for r in bounded] == [c["distance"] if c["distance"] <= k else -1 for c in g]
+
+
 def test_distance_vs_oracle_all_group_sizes_and_stripes(ctx):
     """Every class of the kernel (1, 2, 4, 8, 16, 32 lanes per pair; 1 to 4 stripes of 1024 rows), word and stripe
     boundaries, ragged targets inside a warp, similar and unrelated pairs."""

@@ -93,3 +93,15 @@ def test_edit_path_vs_python_and_known_answers():
         want_d, want = _path_py(a, b)
         assert d == want_d == oracle.edit_distance(a, b)
         assert oracle.cigar_runs_to_string(runs) == want
+
+
+def test_oracle_against_the_committed_golden_vectors():
+    """tests/golden/edit_distance.json: distances and paths from the definition (pure-Python Wagner-Fischer,
+    scripts/make_edit_golden.py) -- the oracle's Myers restatement and its path function must reproduce them."""
+    from conftest import load_golden
+    g = load_golden("edit_distance.json")
+    assert len(g["cases"]) >= 50
+    for c in g["cases"]:
+        assert oracle.edit_distance(c["query"], c["target"]) == c["distance"]
+        d, runs = oracle.edit_path(c["query"], c["target"])
+        assert d == c["distance"] and oracle.cigar_runs_to_string(runs) == c["cigar"]
